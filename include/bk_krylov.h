@@ -1,0 +1,189 @@
+/*
+ * bk_krylov.h — C ABI of the B200-native Krylov inner loop (libbk_krylov.so).
+ *
+ * This is the drop-in boundary underneath the reference's Python API
+ * (pytorch_sparse_solver.module_a.cg / bicgstab / gmres).  The reference has no
+ * native boundary of its own (it is 100 % Python on torch ops), so every entry
+ * point below cites the reference *Python* function whose per-iteration work it
+ * replaces (paths relative to the reference checkout,
+ * src/pytorch_sparse_solver/module_a/torch_sparse_linalg.py unless noted).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every function returns 0 on success or a negative bk_error code and never
+ *     throws; bk_last_error() returns a human-readable message for the calling
+ *     thread's last failure.
+ *   - "device pointer" arguments are borrowed for the duration of the call,
+ *     except the three CSR arrays given to bk_csr_create with copy==0, which
+ *     must stay alive until bk_csr_destroy.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     All work is enqueued on it; solver entry points synchronise that stream
+ *     once, at the end, to hand back bk_result (the reference's `info` is a
+ *     Python int, so one sync per solve is part of its contract).
+ *   - a bk_handle is bound to one CUDA device and is not thread-safe.
+ *   - there is NO CPU fallback anywhere in this library.
+ */
+#ifndef BK_KRYLOV_H
+#define BK_KRYLOV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BK_VERSION 100 /* 0.1.0 */
+
+typedef struct bk_handle bk_handle; /* per-device context: scratch, workspaces, graph cache */
+typedef struct bk_csr bk_csr;       /* a registered CSR matrix + its kernel plan */
+typedef struct bk_dist bk_dist;     /* row-partitioned (multi-GPU) matrix + halo plan */
+
+enum bk_error {
+  BK_OK = 0,
+  BK_ERR_ARG = -1,         /* invalid argument (message says which) */
+  BK_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+  BK_ERR_ALLOC = -3,       /* device or host allocation failed */
+  BK_ERR_UNSUPPORTED = -4, /* valid request this build cannot serve */
+  BK_ERR_NCCL = -5         /* NCCL missing or a collective failed */
+};
+
+enum bk_dtype { BK_F64 = 0, BK_F32 = 1 };
+
+/* Device-side loop status, reported in bk_result.status.  The breakdown codes
+ * are the reference's own (k = -10 / -11 at :903, :914, :935). */
+enum bk_status {
+  BK_ST_CONVERGED = 0,       /* recurrence residual met the stop test */
+  BK_ST_MAXITER = 1,         /* maxiter reached */
+  BK_ST_BREAKDOWN_RHO = -10, /* BiCGStab |rho'| < eps |rho|            (:902-904) */
+  BK_ST_BREAKDOWN_AW = -11   /* BiCGStab alpha or omega breakdown      (:913-915, :934-936) */
+};
+
+enum bk_gmres_method { BK_GMRES_BATCHED = 0, BK_GMRES_INCREMENTAL = 1 };
+
+/* How the iteration loop is driven (all variants keep the stop test on the device). */
+enum bk_loop_mode {
+  BK_LOOP_AUTO = 0,
+  BK_LOOP_STREAM = 1, /* plain stream launches, flag polled every `chunk` iterations */
+  BK_LOOP_GRAPH = 2   /* CUDA graph of `chunk` flag-guarded iterations, polled per graph launch */
+};
+
+typedef struct bk_result {
+  int64_t iterations;    /* CG/BiCGStab: iterations done; GMRES: restart cycles done */
+  int64_t matvecs;       /* SpMV launches that did work (excludes the final check) */
+  int32_t info;          /* the reference's `info`: 0 = final TRUE residual within tolerance, -1 otherwise
+                            (_isolve :1008-1016, gmres :766-773) */
+  int32_t status;        /* enum bk_status */
+  double final_residual; /* || b - A x ||_2, recomputed from scratch */
+  double threshold;      /* what final_residual was compared against */
+  double b_norm;         /* || b ||_2 */
+  double x_norm;         /* || x ||_2 (NaN check of the reference) */
+  double rr_last;        /* last recurrence value: CG gamma = r.r, BiCGStab r.r, GMRES residual norm */
+} bk_result;
+
+typedef struct bk_csr_info {
+  int64_t n, nnz;
+  int32_t dtype;        /* enum bk_dtype */
+  int32_t kernel;       /* 0 = row-stream (warp per 32 rows, shared-memory staged), 1 = sub-warp vector */
+  int32_t lanes_per_row;/* for kernel 1 */
+  int32_t max_row_nnz;
+  double mean_row_nnz;
+  int64_t bytes_matrix; /* bytes one SpMV must read for the matrix: nnz*(sizeof val + 4) + (n+1)*4 */
+} bk_csr_info;
+
+/* ---- library / handle ------------------------------------------------------------ */
+int bk_version(void);
+const char* bk_last_error(void);
+/* device: CUDA ordinal.  The handle owns reduction scratch (fixed slots => bitwise
+ * reproducible sums), solver work vectors and cached CUDA graphs. */
+int bk_create(int device, bk_handle** out);
+int bk_destroy(bk_handle* h);
+/* Tunables: "grid_mult" (CTAs per SM of the persistent grids), "loop_mode", "chunk",
+ * "fuse_xpay" (CG: fold p = r + beta p into the next SpMV's gather), "snake"
+ * (alternate sweep direction between kernels for L2 reuse).  Unknown keys -> BK_ERR_ARG. */
+int bk_set_option(bk_handle* h, const char* key, int64_t value);
+int64_t bk_get_option(bk_handle* h, const char* key);
+int bk_device_info(bk_handle* h, int32_t* num_sms, int64_t* l2_bytes, int64_t* mem_bytes);
+
+/* ---- matrix registration ----------------------------------------------------------
+ * Replaces: _normalize_matvec :176-208 (tensor branch; torch.matmul(CSR, v) at :191).
+ * rowptr/col: device arrays of int32 (idx_bits=32) or int64 (idx_bits=64, converted to an
+ * internal int32 copy; n and nnz must be < 2^31).  val: device array of `dtype`.
+ * copy != 0 makes the library keep private copies of all three arrays. */
+int bk_csr_create(bk_handle* h, int64_t n, int64_t nnz, const void* rowptr, const void* col,
+                  int idx_bits, const void* val, int dtype, int copy, void* stream, bk_csr** out);
+int bk_csr_destroy(bk_csr* A);
+int bk_csr_get_info(const bk_csr* A, bk_csr_info* out);
+/* Cached transpose (CSC of A == CSR of A^T) built on the device by a stable LSD radix
+ * sort on the column index — deterministic.  Replaces `A_matrix.T` in
+ * ImplicitAdjointFunction.backward :1245 (which raises for CSR on torch 2.11).
+ * The returned matrix is owned by A and freed with it. */
+int bk_csr_transpose(bk_handle* h, bk_csr* A, void* stream, bk_csr** out);
+/* Export the arrays of a registered matrix (int32 rowptr/col): device pointers, borrowed. */
+int bk_csr_arrays(const bk_csr* A, const void** rowptr, const void** col, const void** val);
+
+/* ---- building blocks (deterministic; also used by the callable-A route) ------------
+ * y = A x                                         (matrix_mv :185-205)            */
+int bk_spmv(bk_handle* h, const bk_csr* A, const void* x, void* y, void* stream);
+/* y = A x and *dot_out(device, fp64) = w . y      (SpMV fused with p.Ap, _cg_solve :844-845) */
+int bk_spmv_dot(bk_handle* h, const bk_csr* A, const void* x, void* y, const void* w,
+                double* dot_out, void* stream);
+/* *out(device, fp64) = x . y                      (_vdot :86-91, _vdot_real_part :100-127) */
+int bk_dot(bk_handle* h, int64_t n, int dtype, const void* x, const void* y, double* out, void* stream);
+/* *out(device, fp64) = sqrt(max(x.x, 0))          (_norm :154-162) */
+int bk_nrm2(bk_handle* h, int64_t n, int dtype, const void* x, double* out, void* stream);
+/* z = a x + b y  (z may alias x or y)             (_add/_sub/_mul :165-173) */
+int bk_axpby(bk_handle* h, int64_t n, int dtype, double a, const void* x, double b, const void* y,
+             void* z, void* stream);
+
+/* ---- solvers ------------------------------------------------------------------------
+ * b: device vector (read only).  x: device vector, in = initial guess when has_x0 != 0
+ * (ignored otherwise: x0 = 0 as in _isolve :975-976), out = solution.
+ * tol/atol are the caller's Python floats; the fp32 rounding of torch.tensor(tol)
+ * (:816, :871, :1010) is reproduced inside.  maxiter < 0 means the default 10*n (:982-984).
+ *
+ * bk_cg       replaces _cg_solve :806-856 + _isolve :967-1016
+ * bk_bicgstab replaces _bicgstab_solve :859-964 + _isolve
+ */
+int bk_cg(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, double tol, double atol,
+          int64_t maxiter, bk_result* result, void* stream);
+int bk_bicgstab(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, double tol,
+                double atol, int64_t maxiter, bk_result* result, void* stream);
+/* bk_gmres replaces gmres :641-784, _gmres_solve_with_method :788-803, _gmres_batched :431-493,
+ * _gmres_incremental :557-638, _kth_arnoldi_iteration :331-388, _iterative_classical_gram_schmidt
+ * :284-328, _givens_rotation :508-518, _safe_normalize :217-273.
+ * tol_eff  = the reference's `adaptive_tol` after its torch.tensor() rounding (:739-747),
+ * atol_eff = max(float32(atol), float32(base_atol)) (:746-748); the device computes
+ * atol = max(tol_eff*||b||, atol_eff) and ptol = ||b|| * min(1, atol/||b||) (:750-753).
+ * maxiter = maximum number of restart cycles (< 0: 10*n, :719-721). */
+int bk_gmres(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, double tol_eff,
+             double atol_eff, int restart, int64_t maxiter, int method, bk_result* result, void* stream);
+
+/* ---- host-buffer entry (end-to-end path: H2D copies + solve + D2H inside) -----------
+ * All pointers are HOST memory (pinned or pageable).  idx_bits 32/64.  method: 0 cg, 1 bicgstab,
+ * 2 gmres (restart/gmres_method used only then; tol/atol are the raw Python floats and the
+ * GMRES CUDA-device constants of :737-741 are applied inside).  x_inout: x0 in (if has_x0) / x out. */
+int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, const void* rowptr, const void* col,
+                  int idx_bits, const void* val, int dtype, const void* b, void* x_inout, int has_x0,
+                  double tol, double atol, int64_t maxiter, int restart, int gmres_method,
+                  bk_result* result);
+
+/* ---- multi-GPU (one process per GPU; 1-D row partition) ------------------
+ * The caller (Python, torch.distributed) owns rendezvous: rank 0 calls bk_dist_unique_id and
+ * broadcasts the 128 bytes; every rank then calls bk_dist_create with its LOCAL rows
+ * [row_begin, row_end) of the global matrix in CSR with GLOBAL column indices (device arrays).
+ * The library splits them into a local block + a ghost block, builds send lists, exchanges
+ * boundary entries of the SpMV input with ncclSend/ncclRecv on a side stream overlapped with
+ * the interior SpMV, and all-reduces the scalar dots with ncclAllReduce. */
+int bk_dist_unique_id(void* id128);
+int bk_dist_create(bk_handle* h, const void* id128, int rank, int nranks, int64_t n_global,
+                   int64_t row_begin, int64_t row_end, int64_t nnz_local, const void* rowptr,
+                   const void* col, int idx_bits, const void* val, int dtype, void* stream, bk_dist** out);
+int bk_dist_destroy(bk_dist* D);
+int bk_dist_spmv(bk_handle* h, bk_dist* D, const void* x_local, void* y_local, void* stream);
+int bk_dist_cg(bk_handle* h, bk_dist* D, const void* b_local, void* x_local, int has_x0, double tol,
+               double atol, int64_t maxiter, bk_result* result, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BK_KRYLOV_H */

@@ -1,0 +1,278 @@
+// bk_bicgstab.cu — BiCGStab with a device-resident loop.
+// Replaces _bicgstab_solve (reference torch_sparse_linalg.py:859-964) + _isolve (:967-1016).
+//
+// Per iteration (the reference's recurrences, operation order and breakdown tests):
+//   K1  p = r + beta (p - omega q)                                              (:906-907)
+//   K2  q = A p  fused with rhat.q ; epilogue alpha = rho'/(rhat.q), |alpha| < eps -> -11  (:909-915)
+//   K3  s = r - alpha q  fused with s.s ; epilogue exit_early = s.s < atol2      (:917-920)
+//   K4  t = A s  fused with t.s, t.t ; epilogue omega (guarded), omega breakdown -> -11 (:923-936)
+//       (skipped when exit_early: neither x nor r depends on t then — SURVEY compatibility ledger)
+//   K5  x += alpha p (+ omega s) ; r = s (- omega t)  fused with r.r and rhat.r ; epilogue: k += 1,
+//       stop tests of the next iteration (:893-904), beta                         (:942-962)
+// The reference pays 5 host syncs per iteration for these tests; here there are none.
+// Algorithmic HBM bytes per iteration: 2*[nnz*(8+4) + (n+1)*4] + 19*n*8  (SURVEY §8d).
+#include "bk_internal.cuh"
+#include "bk_loop.cuh"
+#include "bk_spmv.cuh"
+#include "bk_vec.cuh"
+
+template <typename T>
+struct bk_eps_of {
+  static constexpr double value = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+};
+
+template <typename T>
+struct bk_epi_bicg_alpha {  // alpha = rho' / (rhat . q)
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const {
+    st->rhat_q = s[0];
+    const double alpha = st->rho_new / s[0];
+    st->alpha = alpha;
+    if (fabs(alpha) < bk_eps_of<T>::value) {
+      st->done = 1;
+      st->status = BK_ST_BREAKDOWN_AW;
+    }
+  }
+};
+
+template <typename T>
+struct bk_epi_bicg_omega {  // sums: [0] t.s  [1] t.t
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const {
+    const double eps = bk_eps_of<T>::value;
+    const double omega = (fabs(s[1]) < eps) ? 0.0 : s[0] / s[1];
+    st->omega = omega;
+    if (fabs(omega) < eps && !st->exit_early) {
+      st->done = 1;
+      st->status = BK_ST_BREAKDOWN_AW;
+    }
+  }
+};
+
+// top-of-loop tests of iteration 0 from r0.r0 (rhat = r0 so rho' = r0.r0); rho = alpha = omega = 1 (:884-890)
+template <typename T>
+struct bk_epi_bicg_init {
+  bk_dev_state* st;
+  int has_x0;
+  __device__ __forceinline__ void operator()(const double* s) const {
+    // called from the b.b reduction; r0.r0 already sits in st->rs when has_x0, else equals b.b
+    const double bs = s[0];
+    st->bs = bs;
+    st->atol2 = fmax(st->tolsq32 * bs, st->atolsq32);
+    if (!has_x0) st->rs = bs;
+    const double rs = st->rs;
+    st->rho = 1.0;
+    st->alpha = 1.0;
+    st->omega = 1.0;
+    st->rho_new = rs;
+    if (st->maxiter <= 0) {
+      st->done = 1;
+      st->status = BK_ST_MAXITER;
+      return;
+    }
+    if (rs <= st->atol2) {
+      st->done = 1;
+      st->status = BK_ST_CONVERGED;
+      return;
+    }
+    if (fabs(rs) < bk_eps_of<T>::value * 1.0) {
+      st->done = 1;
+      st->status = BK_ST_BREAKDOWN_RHO;
+      return;
+    }
+    st->beta = rs / 1.0 * 1.0 / 1.0;
+  }
+};
+
+struct bk_epi_set_rs {
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const { st->rs = s[0]; }
+};
+struct bk_epi_final_r2 {
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const { st->rtrue2 = s[0]; }
+};
+struct bk_epi_final_x2 {
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const { st->xx = s[0]; }
+};
+
+template <typename T, typename Epi>
+struct bk_op_dot_epi2 {
+  static constexpr int R = 1;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> a, b;
+  };
+  const T* x;
+  const T* y;
+  Epi epi;
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.a = bk_ld<T, W>(x + i);
+    in.b = bk_ld<T, W>(y + i);
+  }
+  template <int W>
+  __device__ void apply(long long, const In<W>& in, const Ctx&, double (&acc)[1]) const {
+#pragma unroll
+    for (int j = 0; j < W; ++j) acc[0] += (double)in.a.v[j] * (double)in.b.v[j];
+  }
+  __device__ void epilogue(const double* s) const { epi(s); }
+};
+
+template <typename T, typename Epi>
+static int bk_dot_epi2(bk_handle* h, long long n, const void* x, const void* y, Epi epi, int slot, cudaStream_t s) {
+  bk_op_dot_epi2<T, Epi> op;
+  op.x = (const T*)x;
+  op.y = (const T*)y;
+  op.epi = epi;
+  return bk_launch_ew<T>(h, op, n, bk_aligned16(x) && bk_aligned16(y), bk_slot(h, slot), s);
+}
+
+template <typename T>
+struct bk_bicg_vecs {
+  T *x, *r, *rhat, *p, *q, *s, *t;
+};
+
+template <typename T>
+static int bk_bicg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_bicg_vecs<T>& v, cudaStream_t s) {
+  const long long n = A->n;
+  bk_dev_state* st = h->st;
+  {
+    bk_op_bicg_p<T> op;
+    op.r = v.r;
+    op.p = v.p;
+    op.q = v.q;
+    op.st = st;
+    BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), s));
+  }
+  {
+    bk_spmv_args a = bk_spmv_base(A, st);
+    a.x = v.p;
+    a.y = v.q;
+    a.w = v.rhat;
+    a.guard = 1;
+    bk_epi_bicg_alpha<T> epi{st};
+    BK_TRY((bk_launch_spmv<0, 1, 0>(h, A, a, bk_slot(h, 0), epi, s)));
+  }
+  {
+    bk_op_bicg_s<T> op;
+    op.r = v.r;
+    op.q = v.q;
+    op.s = v.s;
+    op.st = st;
+    BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
+  }
+  {
+    bk_spmv_args a = bk_spmv_base(A, st);
+    a.x = v.s;
+    a.y = v.t;
+    a.w = v.s;
+    a.guard = 3;
+    bk_epi_bicg_omega<T> epi{st};
+    BK_TRY((bk_launch_spmv<0, 3, 0>(h, A, a, bk_slot(h, 0), epi, s)));
+  }
+  {
+    bk_op_bicg_xr<T> op;
+    op.x = v.x;
+    op.p = v.p;
+    op.s = v.s;
+    op.t = v.t;
+    op.rhat = v.rhat;
+    op.r = v.r;
+    op.st = st;
+    BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
+  }
+  return BK_OK;
+}
+
+template <typename T>
+static int bk_bicgstab_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, int has_x0, double tol,
+                         double atol, int64_t maxiter, bk_result* res, cudaStream_t s) {
+  const long long n = A->n;
+  const size_t npad = ((size_t)n + 63) & ~(size_t)63;
+  BK_TRY(bk_ws_reserve(h, (size_t)7 * npad * sizeof(T)));
+  bk_bicg_vecs<T> v;
+  v.x = (T*)h->ws;
+  v.r = v.x + npad;
+  v.rhat = v.r + npad;
+  v.p = v.rhat + npad;
+  v.q = v.p + npad;
+  v.s = v.q + npad;
+  v.t = v.s + npad;
+  bk_dev_state* st = h->st;
+  const size_t vbytes = (size_t)n * sizeof(T);
+
+  bk_dev_state init;
+  memset(&init, 0, sizeof(init));
+  init.maxiter = maxiter < 0 ? 10 * n : maxiter;
+  init.status = BK_ST_MAXITER;
+  bk_state_fill_tol(&init, tol, atol);
+  bk_state_set_kernel<<<1, 1, 0, s>>>(st, init);
+  BK_KERNEL_CHECK();
+
+  if (has_x0) {
+    BK_CUDA(cudaMemcpyAsync(v.x, x_user, vbytes, cudaMemcpyDeviceToDevice, s));
+    bk_spmv_args a = bk_spmv_base(A, st);  // r0 = b - A x0 ; rs = r0.r0   (:875)
+    a.x = v.x;
+    a.y = v.r;
+    a.b = b;
+    bk_epi_set_rs epi{st};
+    BK_TRY((bk_launch_spmv<1, 2, 0>(h, A, a, bk_slot(h, 0), epi, s)));
+  } else {
+    BK_CUDA(cudaMemsetAsync(v.x, 0, vbytes, s));
+    BK_CUDA(cudaMemcpyAsync(v.r, b, vbytes, cudaMemcpyDeviceToDevice, s));
+  }
+  {
+    bk_epi_bicg_init<T> epi{st, has_x0};
+    BK_TRY((bk_dot_epi2<T>(h, n, b, b, epi, 1, s)));
+  }
+  // rhat = p = q = r0   (:876, :890)
+  BK_CUDA(cudaMemcpyAsync(v.rhat, v.r, vbytes, cudaMemcpyDeviceToDevice, s));
+  BK_CUDA(cudaMemcpyAsync(v.p, v.r, vbytes, cudaMemcpyDeviceToDevice, s));
+  BK_CUDA(cudaMemcpyAsync(v.q, v.r, vbytes, cudaMemcpyDeviceToDevice, s));
+
+  const double bytes_iter = 2.0 * ((double)A->nnz * (sizeof(T) + 4) + 4.0 * (n + 1)) + 19.0 * n * sizeof(T);
+  const int chunk = bk_pick_chunk(h, bytes_iter, 5);
+  const bool use_graph = h->loop_mode != BK_LOOP_STREAM;
+  uint64_t key[6] = {2 /*bicgstab*/, A->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
+                     (uint64_t)A->dtype | ((uint64_t)chunk << 16),
+                     (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
+  auto enqueue_chunk = [&](cudaStream_t cs) -> int {
+    for (int it = 0; it < chunk; ++it) BK_TRY(bk_bicg_enqueue_iter<T>(h, A, v, cs));
+    return BK_OK;
+  };
+  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk));
+
+  {
+    bk_spmv_args a = bk_spmv_base(A, st);
+    a.x = v.x;
+    a.y = v.t;
+    a.b = b;
+    bk_epi_final_r2 epi{st};
+    BK_TRY((bk_launch_spmv<1, 2, 0>(h, A, a, bk_slot(h, 0), epi, s)));
+    bk_epi_final_x2 epx{st};
+    BK_TRY((bk_dot_epi2<T>(h, n, v.x, v.x, epx, 1, s)));
+  }
+  BK_CUDA(cudaMemcpyAsync(x_user, v.x, vbytes, cudaMemcpyDeviceToDevice, s));
+  BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
+  BK_CUDA(cudaStreamSynchronize(s));
+  const bk_dev_state* fin = &h->st_host[3];
+  bk_fill_result_isolve(fin, res, 2 * fin->k + (has_x0 ? 1 : 0));
+  res->rr_last = fin->rs;
+  return BK_OK;
+}
+
+extern "C" int bk_bicgstab(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, double tol, double atol,
+                           int64_t maxiter, bk_result* result, void* stream) {
+  BK_TRY(bk_solver_args_check("bk_bicgstab", h, A, b, x, result));
+  BK_CUDA(cudaSetDevice(h->device));
+  if (A->n == 0) return BK_OK;
+  if (A->dtype == BK_F64)
+    return bk_bicgstab_t<double>(h, A, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+  return bk_bicgstab_t<float>(h, A, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+}

@@ -1,0 +1,269 @@
+// bk_cg.cu — conjugate gradient with a device-resident loop.
+// Replaces _cg_solve (reference torch_sparse_linalg.py:806-856) and its wrapper _isolve (:967-1016).
+//
+// Per iteration (recurrences and operation order exactly the reference's, :843-853):
+//   K1  Ap = A p            fused with p.Ap ; epilogue: alpha = gamma / p.Ap
+//   K2  x += alpha p ; r -= alpha Ap ; fused with r.r ; epilogue: beta = gamma'/gamma, k += 1,
+//       stop test `k >= maxiter or gamma' <= atol2` (:841) for the next iteration
+//   K3  p = r + beta p
+// With option fuse_xpay K3 disappears: K1 gathers r[c] + beta p_old[c] on the fly (bitwise the
+// same value K3 would have stored) and writes the new p for its own rows (double-buffered p).
+// Algorithmic HBM bytes per iteration: nnz*(8+4) + (n+1)*4 + 11*n*8  (SURVEY §8d).
+#include "bk_internal.cuh"
+#include "bk_loop.cuh"
+#include "bk_spmv.cuh"
+#include "bk_vec.cuh"
+
+// ---- epilogues ---------------------------------------------------------------------------------
+struct bk_epi_cg_pAp {  // alpha = gamma / (p . Ap)   (:845)
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const {
+    st->pAp = s[0];
+    st->alpha = st->gamma / s[0];
+  }
+};
+
+struct bk_epi_set_gamma {  // gamma0 = r0 . r0  (:826)
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const { st->gamma = s[0]; }
+};
+
+struct bk_epi_cg_init {  // bs = b.b ; atol2 = max(tol^2 bs, atol^2) (:815-817) ; first stop test
+  bk_dev_state* st;
+  int has_x0;
+  __device__ __forceinline__ void operator()(const double* s) const {
+    const double bs = s[0];
+    st->bs = bs;
+    st->atol2 = fmax(st->tolsq32 * bs, st->atolsq32);
+    if (!has_x0) st->gamma = bs;  // r0 = b - A*0 = b exactly
+    if (st->maxiter <= 0) {
+      st->done = 1;
+      st->status = BK_ST_MAXITER;
+    }
+    if (st->gamma <= st->atol2) {
+      st->done = 1;
+      st->status = BK_ST_CONVERGED;
+    }
+  }
+};
+
+struct bk_epi_final_r {
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const { st->rtrue2 = s[0]; }
+};
+struct bk_epi_final_x {
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const { st->xx = s[0]; }
+};
+
+template <typename T, typename Epi>
+struct bk_op_dot_epi {
+  static constexpr int R = 1;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> a, b;
+  };
+  const T* x;
+  const T* y;
+  Epi epi;
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.a = bk_ld<T, W>(x + i);
+    in.b = bk_ld<T, W>(y + i);
+  }
+  template <int W>
+  __device__ void apply(long long, const In<W>& in, const Ctx&, double (&acc)[1]) const {
+#pragma unroll
+    for (int j = 0; j < W; ++j) acc[0] += (double)in.a.v[j] * (double)in.b.v[j];
+  }
+  __device__ void epilogue(const double* s) const { epi(s); }
+};
+
+template <typename T, typename Epi>
+static int bk_dot_epi(bk_handle* h, long long n, const void* x, const void* y, Epi epi, int slot, cudaStream_t s) {
+  bk_op_dot_epi<T, Epi> op;
+  op.x = (const T*)x;
+  op.y = (const T*)y;
+  op.epi = epi;
+  return bk_launch_ew<T>(h, op, n, bk_aligned16(x) && bk_aligned16(y), bk_slot(h, slot), s);
+}
+
+// Shared by all solvers: tolerance fields with the reference's fp32 rounding of torch.tensor(tol).
+void bk_state_fill_tol(bk_dev_state* v, double tol, double atol) {
+  const float t = (float)tol, a = (float)atol;
+  v->tol32 = (double)t;
+  v->atol32 = (double)a;
+  v->tolsq32 = (double)(t * t);    // torch.square on an fp32 0-dim tensor
+  v->atolsq32 = (double)(a * a);
+}
+
+// Shared: final true-residual check of _isolve (:1008-1016) from the device state copy.
+void bk_fill_result_isolve(const bk_dev_state* st, bk_result* res, int64_t matvecs) {
+  res->iterations = st->k;
+  res->matvecs = matvecs;
+  res->status = st->status;
+  res->final_residual = sqrt(fmax(st->rtrue2, 0.0));
+  res->b_norm = sqrt(fmax(st->bs, 0.0));
+  res->x_norm = sqrt(fmax(st->xx, 0.0));
+  res->threshold = fmax(st->tol32 * res->b_norm, st->atol32);
+  const bool failed = (res->x_norm != res->x_norm) || (res->final_residual > res->threshold);
+  res->info = failed ? -1 : 0;
+}
+
+template <typename T>
+struct bk_cg_vecs {
+  T* x;
+  T* r;
+  T* p[2];
+  T* ap;
+};
+
+template <typename T>
+static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>& v, int it, bool fuse,
+                              cudaStream_t s) {
+  const long long n = A->n;
+  bk_dev_state* st = h->st;
+  const T* pcur;
+  if (fuse) {
+    const T* pold = v.p[it & 1];
+    T* pnew = v.p[(it + 1) & 1];
+    bk_spmv_args a = bk_spmv_base(A, st);
+    a.x = v.r;
+    a.x2 = pold;
+    a.xout = pnew;
+    a.y = v.ap;
+    a.guard = 1;
+    a.use_parity = h->snake;
+    bk_epi_cg_pAp epi{st};
+    BK_TRY((bk_launch_spmv<0, 1, 1>(h, A, a, bk_slot(h, 0), epi, s)));
+    pcur = pnew;
+  } else {
+    bk_spmv_args a = bk_spmv_base(A, st);
+    a.x = v.p[0];
+    a.w = v.p[0];
+    a.y = v.ap;
+    a.guard = 1;
+    a.use_parity = h->snake;
+    bk_epi_cg_pAp epi{st};
+    BK_TRY((bk_launch_spmv<0, 1, 0>(h, A, a, bk_slot(h, 0), epi, s)));
+    pcur = v.p[0];
+  }
+  {
+    bk_op_cg_update<T> op;
+    op.p = pcur;
+    op.ap = v.ap;
+    op.x = v.x;
+    op.r = v.r;
+    op.st = st;
+    op.snake = h->snake;
+    BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
+  }
+  if (!fuse) {
+    bk_op_xpay<T> op;
+    op.r = v.r;
+    op.p = v.p[0];
+    op.st = st;
+    op.snake = h->snake;
+    BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), s));
+  }
+  return BK_OK;
+}
+
+template <typename T>
+static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, int has_x0, double tol, double atol,
+                   int64_t maxiter, bk_result* res, cudaStream_t s) {
+  const long long n = A->n;
+  const size_t npad = ((size_t)n + 63) & ~(size_t)63;
+  const bool fuse = h->fuse_xpay && A->kernel == 0;
+  BK_TRY(bk_ws_reserve(h, (size_t)5 * npad * sizeof(T)));
+  bk_cg_vecs<T> v;
+  v.x = (T*)h->ws;
+  v.r = v.x + npad;
+  v.p[0] = v.r + npad;
+  v.p[1] = v.p[0] + npad;
+  v.ap = v.p[1] + npad;
+  bk_dev_state* st = h->st;
+  const size_t vbytes = (size_t)n * sizeof(T);
+
+  bk_dev_state init;
+  memset(&init, 0, sizeof(init));
+  init.maxiter = maxiter < 0 ? 10 * n : maxiter;
+  init.status = BK_ST_MAXITER;
+  bk_state_fill_tol(&init, tol, atol);
+  bk_state_set_kernel<<<1, 1, 0, s>>>(st, init);
+  BK_KERNEL_CHECK();
+
+  if (has_x0) {
+    BK_CUDA(cudaMemcpyAsync(v.x, x_user, vbytes, cudaMemcpyDeviceToDevice, s));
+    bk_spmv_args a = bk_spmv_base(A, st);  // r0 = b - A x0, gamma0 = r0.r0   (:820, :826)
+    a.x = v.x;
+    a.y = v.r;
+    a.b = b;
+    bk_epi_set_gamma epi{st};
+    BK_TRY((bk_launch_spmv<1, 2, 0>(h, A, a, bk_slot(h, 0), epi, s)));
+  } else {
+    BK_CUDA(cudaMemsetAsync(v.x, 0, vbytes, s));
+    BK_CUDA(cudaMemcpyAsync(v.r, b, vbytes, cudaMemcpyDeviceToDevice, s));
+  }
+  {
+    bk_epi_cg_init epi{st, has_x0};
+    BK_TRY((bk_dot_epi<T>(h, n, b, b, epi, 1, s)));
+  }
+  if (fuse) {
+    // p_{-1} = 0, beta = 0  =>  the first fused SpMV forms p_0 = r_0 + 0*0 = r_0  (:821)
+    BK_CUDA(cudaMemsetAsync(v.p[0], 0, vbytes, s));
+  } else {
+    BK_CUDA(cudaMemcpyAsync(v.p[0], v.r, vbytes, cudaMemcpyDeviceToDevice, s));
+  }
+
+  const double bytes_iter = (double)A->nnz * (sizeof(T) + 4) + 4.0 * (n + 1) + 11.0 * n * sizeof(T);
+  const int chunk = bk_pick_chunk(h, bytes_iter, fuse ? 2 : 3);
+  const bool use_graph = h->loop_mode != BK_LOOP_STREAM;
+  uint64_t key[6] = {1 /*cg*/, A->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
+                     (uint64_t)A->dtype | ((uint64_t)fuse << 8) | ((uint64_t)h->snake << 9) | ((uint64_t)chunk << 16),
+                     (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
+  auto enqueue_chunk = [&](cudaStream_t cs) -> int {
+    for (int it = 0; it < chunk; ++it) BK_TRY(bk_cg_enqueue_iter<T>(h, A, v, it, fuse, cs));
+    return BK_OK;
+  };
+  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk));
+
+  {  // final true residual  ||b - A x||  and  ||x||   (_isolve :1008-1013)
+    bk_spmv_args a = bk_spmv_base(A, st);
+    a.x = v.x;
+    a.y = v.ap;
+    a.b = b;
+    bk_epi_final_r epi{st};
+    BK_TRY((bk_launch_spmv<1, 2, 0>(h, A, a, bk_slot(h, 0), epi, s)));
+    bk_epi_final_x epx{st};
+    BK_TRY((bk_dot_epi<T>(h, n, v.x, v.x, epx, 1, s)));
+  }
+  BK_CUDA(cudaMemcpyAsync(x_user, v.x, vbytes, cudaMemcpyDeviceToDevice, s));
+  BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
+  BK_CUDA(cudaStreamSynchronize(s));
+  const bk_dev_state* fin = &h->st_host[3];
+  bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
+  res->rr_last = fin->gamma;
+  return BK_OK;
+}
+
+int bk_solver_args_check(const char* who, bk_handle* h, const bk_csr* A, const void* b, void* x, bk_result* res) {
+  if (!h || !A || !res) return bk_fail(BK_ERR_ARG, "%s: null handle/matrix/result", who);
+  if (A->n > 0 && (!b || !x)) return bk_fail(BK_ERR_ARG, "%s: null vector", who);
+  if (A->h != h) return bk_fail(BK_ERR_ARG, "%s: matrix belongs to another handle", who);
+  memset(res, 0, sizeof(*res));
+  return BK_OK;
+}
+
+extern "C" int bk_cg(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, double tol, double atol,
+                     int64_t maxiter, bk_result* result, void* stream) {
+  BK_TRY(bk_solver_args_check("bk_cg", h, A, b, x, result));
+  BK_CUDA(cudaSetDevice(h->device));
+  if (A->n == 0) return BK_OK;
+  if (A->dtype == BK_F64) return bk_cg_t<double>(h, A, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+  return bk_cg_t<float>(h, A, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+}

@@ -1,0 +1,418 @@
+// bk_core.cu — handle, matrix registration, building-block entry points of libbk_krylov.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include "bk_internal.cuh"
+#include "bk_spmv.cuh"
+#include "bk_vec.cuh"
+
+thread_local char bk_err_buf[512] = {0};
+
+int bk_fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(bk_err_buf, sizeof(bk_err_buf), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+extern "C" int bk_version(void) { return BK_VERSION; }
+extern "C" const char* bk_last_error(void) { return bk_err_buf; }
+
+static int64_t bk_env_int(const char* name, int64_t dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return strtoll(v, nullptr, 10);
+}
+
+extern "C" int bk_create(int device, bk_handle** out) {
+  if (!out) return bk_fail(BK_ERR_ARG, "bk_create: out is null");
+  *out = nullptr;
+  int count = 0;
+  BK_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count)
+    return bk_fail(BK_ERR_ARG, "bk_create: device %d out of range (%d CUDA devices)", device, count);
+  BK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BK_CUDA(cudaGetDeviceProperties(&prop, device));
+  bk_handle* h = (bk_handle*)calloc(1, sizeof(bk_handle));
+  if (!h) return bk_fail(BK_ERR_ALLOC, "bk_create: host allocation failed");
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  h->l2_bytes = prop.l2CacheSize;
+  h->mem_bytes = (int64_t)prop.totalGlobalMem;
+  h->grid_mult_vec = (int)bk_env_int("BK_GRID_MULT_VEC", 3);
+  h->grid_mult_spmv = (int)bk_env_int("BK_GRID_MULT_SPMV", 4);
+  h->loop_mode = (int)bk_env_int("BK_LOOP_MODE", BK_LOOP_AUTO);
+  h->chunk = (int)bk_env_int("BK_CHUNK", 0);
+  h->fuse_xpay = (int)bk_env_int("BK_FUSE_XPAY", 0);
+  h->snake = (int)bk_env_int("BK_SNAKE", 0);
+  h->spmv_variant = (int)bk_env_int("BK_SPMV_VARIANT", 0);
+  h->next_uid = 1;
+  cudaError_t e;
+  e = cudaMalloc(&h->partials, sizeof(double) * BK_NSLOT * BK_SLOT_ROWS * BK_MAXB);
+  if (e == cudaSuccess) e = cudaMalloc(&h->counters, sizeof(unsigned int) * 16);
+  if (e == cudaSuccess) e = cudaMemset(h->counters, 0, sizeof(unsigned int) * 16);
+  if (e == cudaSuccess) e = cudaMalloc(&h->st, sizeof(bk_dev_state));
+  if (e == cudaSuccess) e = cudaMemset(h->st, 0, sizeof(bk_dev_state));
+  if (e == cudaSuccess) e = cudaMallocHost(&h->st_host, sizeof(bk_dev_state) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&h->dscratch, sizeof(double) * 64);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    bk_destroy(h);
+    return bk_fail(BK_ERR_CUDA, "bk_create: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return BK_OK;
+}
+
+void bk_graphs_invalidate(bk_handle* h) {
+  for (int i = 0; i < 8; ++i) {
+    if (h->graphs[i].valid && h->graphs[i].exec) cudaGraphExecDestroy(h->graphs[i].exec);
+    h->graphs[i].valid = 0;
+    h->graphs[i].exec = nullptr;
+  }
+}
+
+extern "C" int bk_destroy(bk_handle* h) {
+  if (!h) return BK_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  bk_graphs_invalidate(h);
+  if (h->partials) cudaFree(h->partials);
+  if (h->counters) cudaFree(h->counters);
+  if (h->st) cudaFree(h->st);
+  if (h->st_host) cudaFreeHost(h->st_host);
+  if (h->dscratch) cudaFree(h->dscratch);
+  if (h->ws) cudaFree(h->ws);
+  if (h->gm_small) cudaFree(h->gm_small);
+  if (h->gm_partials) cudaFree(h->gm_partials);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->io_stream) cudaStreamDestroy(h->io_stream);
+  free(h);
+  return BK_OK;
+}
+
+int bk_ws_reserve(bk_handle* h, size_t bytes) {
+  if (bytes <= h->ws_bytes) return BK_OK;
+  bk_graphs_invalidate(h);
+  if (h->ws) {
+    BK_CUDA(cudaDeviceSynchronize());
+    BK_CUDA(cudaFree(h->ws));
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+  }
+  const size_t want = (bytes + 255) & ~(size_t)255;
+  cudaError_t e = cudaMalloc(&h->ws, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return bk_fail(BK_ERR_ALLOC, "workspace of %zu bytes: %s", want, cudaGetErrorString(e));
+  }
+  h->ws_bytes = want;
+  return BK_OK;
+}
+
+struct bk_opt_ref {
+  const char* key;
+  int* field;
+};
+
+static int* bk_opt_field(bk_handle* h, const char* key) {
+  if (!key) return nullptr;
+  if (!strcmp(key, "grid_mult_vec")) return &h->grid_mult_vec;
+  if (!strcmp(key, "grid_mult_spmv")) return &h->grid_mult_spmv;
+  if (!strcmp(key, "grid_mult")) return &h->grid_mult_spmv;
+  if (!strcmp(key, "loop_mode")) return &h->loop_mode;
+  if (!strcmp(key, "chunk")) return &h->chunk;
+  if (!strcmp(key, "fuse_xpay")) return &h->fuse_xpay;
+  if (!strcmp(key, "snake")) return &h->snake;
+  if (!strcmp(key, "spmv_variant")) return &h->spmv_variant;
+  return nullptr;
+}
+
+extern "C" int bk_set_option(bk_handle* h, const char* key, int64_t value) {
+  if (!h) return bk_fail(BK_ERR_ARG, "bk_set_option: null handle");
+  int* f = bk_opt_field(h, key);
+  if (!f) return bk_fail(BK_ERR_ARG, "bk_set_option: unknown key '%s'", key ? key : "(null)");
+  if ((!strcmp(key, "grid_mult_vec") || !strcmp(key, "grid_mult_spmv") || !strcmp(key, "grid_mult")) &&
+      (value < 1 || value * h->num_sms > BK_MAXB))
+    return bk_fail(BK_ERR_ARG, "bk_set_option: %s=%lld out of range", key, (long long)value);
+  if (!strcmp(key, "grid_mult")) h->grid_mult_vec = (int)value;
+  *f = (int)value;
+  bk_graphs_invalidate(h);
+  return BK_OK;
+}
+
+extern "C" int64_t bk_get_option(bk_handle* h, const char* key) {
+  if (!h) return -1;
+  int* f = bk_opt_field(h, key);
+  return f ? *f : -1;
+}
+
+extern "C" int bk_device_info(bk_handle* h, int32_t* num_sms, int64_t* l2_bytes, int64_t* mem_bytes) {
+  if (!h) return bk_fail(BK_ERR_ARG, "bk_device_info: null handle");
+  if (num_sms) *num_sms = h->num_sms;
+  if (l2_bytes) *l2_bytes = h->l2_bytes;
+  if (mem_bytes) *mem_bytes = h->mem_bytes;
+  return BK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// matrix registration
+// ------------------------------------------------------------------------------------------
+__global__ void bk_cvt_i64_i32_kernel(const long long* __restrict__ in, int* __restrict__ out, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int)in[i];
+}
+
+// max row length + validity (monotone rowptr, columns in range) in one pass over rowptr/col
+__global__ void bk_csr_stats_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, long long n,
+                                    long long nnz, int* __restrict__ out /* [0] max len, [1] bad flag */) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int mx = 0;
+  int bad = 0;
+  for (long long i = tid; i < n; i += stride) {
+    const int a = rowptr[i], b = rowptr[i + 1];
+    if (b < a) bad = 1;
+    mx = max(mx, b - a);
+  }
+  for (long long i = tid; i < nnz; i += stride) {
+    const int c = col[i];
+    if (c < 0 || c >= n) bad = 1;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&out[0], mx);
+    if (bad) atomicOr(&out[1], 1);
+  }
+}
+
+static void bk_csr_plan(bk_handle* h, bk_csr* A) {
+  const double mean = A->n > 0 ? (double)A->nnz / (double)A->n : 0.0;
+  A->mean_row_nnz = mean;
+  const double skew_limit = 64.0 * (mean > 8.0 ? mean : 8.0);
+  int kernel = (mean <= 32.0 && (double)A->max_row_nnz <= skew_limit) ? 0 : 1;
+  const int64_t forced = bk_env_int("BK_SPMV_KERNEL", -1);
+  if (forced == 0 || forced == 1) kernel = (int)forced;
+  A->kernel = kernel;
+  A->cap = (mean <= 8.0) ? 256 : 1024;
+  A->lanes_per_row = (mean <= 64.0) ? 8 : (mean <= 128.0 ? 16 : 32);
+  (void)h;
+}
+
+// statistics + validation + kernel plan (one sync at registration time; never on the per-iteration path)
+int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s) {
+  const int64_t n = A->n, nnz = A->nnz;
+  int* dstat = (int*)(h->counters + 8);
+  int hstat[2] = {0, 0};
+  int ends[2] = {0, 0};
+  cudaMemsetAsync(dstat, 0, 2 * sizeof(int), s);
+  if (n > 0) bk_csr_stats_kernel<<<h->num_sms * 8, 256, 0, s>>>(A->rowptr, A->col, n, nnz, dstat);
+  cudaMemcpyAsync(hstat, dstat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(&ends[0], A->rowptr, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(&ends[1], A->rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return bk_fail(BK_ERR_CUDA, "csr registration: %s", cudaGetErrorString(e));
+  if (ends[0] != 0 || ends[1] != (int)nnz || hstat[1] != 0)
+    return bk_fail(BK_ERR_ARG, "malformed CSR (rowptr[0]=%d, rowptr[n]=%d, nnz=%lld, bad=%d)", ends[0], ends[1],
+                   (long long)nnz, hstat[1]);
+  A->max_row_nnz = hstat[0];
+  bk_csr_plan(h, A);
+  return BK_OK;
+}
+
+extern "C" int bk_csr_create(bk_handle* h, int64_t n, int64_t nnz, const void* rowptr, const void* col,
+                             int idx_bits, const void* val, int dtype, int copy, void* stream, bk_csr** out) {
+  if (!h || !out) return bk_fail(BK_ERR_ARG, "bk_csr_create: null handle/out");
+  *out = nullptr;
+  if (n < 0 || nnz < 0) return bk_fail(BK_ERR_ARG, "bk_csr_create: negative size");
+  if (n >= 2147483647LL || nnz >= 2147483647LL)
+    return bk_fail(BK_ERR_UNSUPPORTED, "bk_csr_create: n and nnz must be < 2^31 (int32 indices), got n=%lld nnz=%lld",
+                   (long long)n, (long long)nnz);
+  if (idx_bits != 32 && idx_bits != 64) return bk_fail(BK_ERR_ARG, "bk_csr_create: idx_bits must be 32 or 64");
+  if (dtype != BK_F64 && dtype != BK_F32) return bk_fail(BK_ERR_ARG, "bk_csr_create: dtype must be BK_F64 or BK_F32");
+  if (!rowptr || (nnz > 0 && (!col || !val))) return bk_fail(BK_ERR_ARG, "bk_csr_create: null array");
+  BK_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  bk_csr* A = (bk_csr*)calloc(1, sizeof(bk_csr));
+  if (!A) return bk_fail(BK_ERR_ALLOC, "bk_csr_create: host allocation failed");
+  A->h = h;
+  A->n = n;
+  A->nnz = nnz;
+  A->dtype = dtype;
+  A->uid = h->next_uid++;
+  const size_t vs = bk_dtype_size(dtype);
+  auto fail = [&](int code) {
+    bk_csr_destroy(A);
+    return code;
+  };
+  if (idx_bits == 64) {
+    if (cudaMalloc(&A->own_rowptr, sizeof(int) * (size_t)(n + 1)) != cudaSuccess ||
+        cudaMalloc(&A->own_col, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(bk_fail(BK_ERR_ALLOC, "bk_csr_create: int32 index copy allocation failed"));
+    }
+    bk_cvt_i64_i32_kernel<<<h->num_sms * 8, 256, 0, s>>>((const long long*)rowptr, (int*)A->own_rowptr, n + 1);
+    if (nnz > 0) bk_cvt_i64_i32_kernel<<<h->num_sms * 8, 256, 0, s>>>((const long long*)col, (int*)A->own_col, nnz);
+    A->rowptr = (const int*)A->own_rowptr;
+    A->col = (const int*)A->own_col;
+  } else if (copy) {
+    if (cudaMalloc(&A->own_rowptr, sizeof(int) * (size_t)(n + 1)) != cudaSuccess ||
+        cudaMalloc(&A->own_col, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(bk_fail(BK_ERR_ALLOC, "bk_csr_create: index copy allocation failed"));
+    }
+    cudaMemcpyAsync(A->own_rowptr, rowptr, sizeof(int) * (size_t)(n + 1), cudaMemcpyDeviceToDevice, s);
+    if (nnz > 0) cudaMemcpyAsync(A->own_col, col, sizeof(int) * (size_t)nnz, cudaMemcpyDeviceToDevice, s);
+    A->rowptr = (const int*)A->own_rowptr;
+    A->col = (const int*)A->own_col;
+  } else {
+    A->rowptr = (const int*)rowptr;
+    A->col = (const int*)col;
+  }
+  if (copy) {
+    if (cudaMalloc(&A->own_val, vs * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(bk_fail(BK_ERR_ALLOC, "bk_csr_create: value copy allocation failed"));
+    }
+    if (nnz > 0) cudaMemcpyAsync(A->own_val, val, vs * (size_t)nnz, cudaMemcpyDeviceToDevice, s);
+    A->val = A->own_val;
+  } else {
+    A->val = val;
+  }
+  {
+    int prc = bk_csr_finish_plan(h, A, s);
+    if (prc != BK_OK) return fail(prc);
+  }
+  *out = A;
+  return BK_OK;
+}
+
+extern "C" int bk_csr_destroy(bk_csr* A) {
+  if (!A) return BK_OK;
+  if (A->h) {
+    cudaSetDevice(A->h->device);
+    bk_graphs_invalidate(A->h);
+  }
+  if (A->transpose) bk_csr_destroy(A->transpose);
+  if (A->own_rowptr) cudaFree(A->own_rowptr);
+  if (A->own_col) cudaFree(A->own_col);
+  if (A->own_val) cudaFree(A->own_val);
+  free(A);
+  return BK_OK;
+}
+
+extern "C" int bk_csr_get_info(const bk_csr* A, bk_csr_info* out) {
+  if (!A || !out) return bk_fail(BK_ERR_ARG, "bk_csr_get_info: null argument");
+  out->n = A->n;
+  out->nnz = A->nnz;
+  out->dtype = A->dtype;
+  out->kernel = A->kernel;
+  out->lanes_per_row = A->lanes_per_row;
+  out->max_row_nnz = A->max_row_nnz;
+  out->mean_row_nnz = A->mean_row_nnz;
+  out->bytes_matrix = A->nnz * (int64_t)(bk_dtype_size(A->dtype) + 4) + (A->n + 1) * 4;
+  return BK_OK;
+}
+
+extern "C" int bk_csr_arrays(const bk_csr* A, const void** rowptr, const void** col, const void** val) {
+  if (!A) return bk_fail(BK_ERR_ARG, "bk_csr_arrays: null matrix");
+  if (rowptr) *rowptr = A->rowptr;
+  if (col) *col = A->col;
+  if (val) *val = A->val;
+  return BK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// building blocks
+// ------------------------------------------------------------------------------------------
+struct bk_epi_store {
+  double* out;
+  __device__ __forceinline__ void operator()(const double* s) const { out[0] = s[0]; }
+};
+
+extern "C" int bk_spmv(bk_handle* h, const bk_csr* A, const void* x, void* y, void* stream) {
+  if (!h || !A || !x || !y) return bk_fail(BK_ERR_ARG, "bk_spmv: null argument");
+  if (x == y) return bk_fail(BK_ERR_ARG, "bk_spmv: x and y must not alias");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (A->n == 0) return BK_OK;
+  bk_spmv_args a = bk_spmv_base(A, h->st);
+  a.x = x;
+  a.y = y;
+  return bk_launch_spmv<0, 0, 0>(h, A, a, bk_slot(h, 0), bk_epi_none(), (cudaStream_t)stream);
+}
+
+extern "C" int bk_spmv_dot(bk_handle* h, const bk_csr* A, const void* x, void* y, const void* w, double* dot_out,
+                           void* stream) {
+  if (!h || !A || !x || !y || !w || !dot_out) return bk_fail(BK_ERR_ARG, "bk_spmv_dot: null argument");
+  if (x == y) return bk_fail(BK_ERR_ARG, "bk_spmv_dot: x and y must not alias");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (A->n == 0) {
+    BK_CUDA(cudaMemsetAsync(dot_out, 0, sizeof(double), (cudaStream_t)stream));
+    return BK_OK;
+  }
+  bk_spmv_args a = bk_spmv_base(A, h->st);
+  a.x = x;
+  a.y = y;
+  a.w = w;
+  bk_epi_store epi;
+  epi.out = dot_out;
+  return bk_launch_spmv<0, 1, 0>(h, A, a, bk_slot(h, 0), epi, (cudaStream_t)stream);
+}
+
+template <typename T>
+static int bk_dot_t(bk_handle* h, int64_t n, const void* x, const void* y, double* out, int sqrt_out, cudaStream_t s) {
+  bk_op_dot<T> op;
+  op.x = (const T*)x;
+  op.y = (const T*)y;
+  op.out = out;
+  op.sqrt_out = sqrt_out;
+  return bk_launch_ew<T>(h, op, n, bk_aligned16(x) && bk_aligned16(y), bk_slot(h, 0), s);
+}
+
+extern "C" int bk_dot(bk_handle* h, int64_t n, int dtype, const void* x, const void* y, double* out, void* stream) {
+  if (!h || !out || (n > 0 && (!x || !y))) return bk_fail(BK_ERR_ARG, "bk_dot: null argument");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (dtype == BK_F64) return bk_dot_t<double>(h, n, x, y, out, 0, (cudaStream_t)stream);
+  if (dtype == BK_F32) return bk_dot_t<float>(h, n, x, y, out, 0, (cudaStream_t)stream);
+  return bk_fail(BK_ERR_ARG, "bk_dot: bad dtype %d", dtype);
+}
+
+extern "C" int bk_nrm2(bk_handle* h, int64_t n, int dtype, const void* x, double* out, void* stream) {
+  if (!h || !out || (n > 0 && !x)) return bk_fail(BK_ERR_ARG, "bk_nrm2: null argument");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (dtype == BK_F64) return bk_dot_t<double>(h, n, x, x, out, 1, (cudaStream_t)stream);
+  if (dtype == BK_F32) return bk_dot_t<float>(h, n, x, x, out, 1, (cudaStream_t)stream);
+  return bk_fail(BK_ERR_ARG, "bk_nrm2: bad dtype %d", dtype);
+}
+
+template <typename T>
+static int bk_axpby_t(bk_handle* h, int64_t n, double a, const void* x, double b, const void* y, void* z,
+                      cudaStream_t s) {
+  bk_op_axpby<T> op;
+  op.x = (const T*)x;
+  op.y = (const T*)y;
+  op.z = (T*)z;
+  op.ca = (T)a;
+  op.cb = (T)b;
+  return bk_launch_ew<T>(h, op, n, bk_aligned16(x) && bk_aligned16(y) && bk_aligned16(z), bk_slot(h, 0), s);
+}
+
+extern "C" int bk_axpby(bk_handle* h, int64_t n, int dtype, double a, const void* x, double b, const void* y, void* z,
+                        void* stream) {
+  if (!h || (n > 0 && (!x || !y || !z))) return bk_fail(BK_ERR_ARG, "bk_axpby: null argument");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (n == 0) return BK_OK;
+  if (dtype == BK_F64) return bk_axpby_t<double>(h, n, a, x, b, y, z, (cudaStream_t)stream);
+  if (dtype == BK_F32) return bk_axpby_t<float>(h, n, a, x, b, y, z, (cudaStream_t)stream);
+  return bk_fail(BK_ERR_ARG, "bk_axpby: bad dtype %d", dtype);
+}

@@ -1,0 +1,303 @@
+// bk_internal.cuh — shared internals of libbk_krylov: handle, device state, deterministic
+// reductions, pack loads.  sm_100a only (B200).  Not part of the public ABI (include/bk_krylov.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/bk_krylov.h"
+
+#define BK_BLOCK 256          // threads per CTA of every persistent kernel
+#define BK_WARPS (BK_BLOCK / 32)
+#define BK_MAXB 2048          // upper bound on CTAs of a reducing grid (partials stride)
+#define BK_NSLOT 4            // independent reduction scratch slots per handle
+#define BK_SLOT_ROWS 8        // reductions per slot (fixed-R kernels use <= 8)
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+extern thread_local char bk_err_buf[512];
+int bk_fail(int code, const char* fmt, ...);
+
+#define BK_CUDA(expr)                                                                            \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return bk_fail(BK_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                  \
+                     cudaGetErrorString(_e));                                                    \
+  } while (0)
+
+#define BK_TRY(expr)             \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != BK_OK) return _r;  \
+  } while (0)
+
+#define BK_KERNEL_CHECK() BK_CUDA(cudaGetLastError())
+
+// ------------------------------------------------------------------------------------------
+// device-resident solver state: every scalar of the recurrences lives here, written by the
+// epilogue of the kernel that finishes the corresponding reduction, read by the next kernel.
+// The host only ever reads it (async copy) to poll `done` and to build bk_result.
+// ------------------------------------------------------------------------------------------
+struct bk_dev_state {
+  // loop control
+  long long k;        // iterations (CG/BiCGStab) or restart cycles (GMRES) completed
+  long long maxiter;
+  long long matvecs;
+  int done;           // 1 => every guarded kernel is an exact no-op
+  int status;         // enum bk_status
+  int exit_early;     // BiCGStab: s.s < atol2 (:920)
+  int parity;         // flips every iteration (sweep direction for the "snake" option)
+  // tolerances
+  double tol32;       // (double)(float)tol      — torch.tensor(tol) is fp32 (:816)
+  double atol32;      // (double)(float)atol
+  double tolsq32;     // (double)((float)tol*(float)tol)
+  double atolsq32;
+  double atol2;       // max(tol^2 * b.b, atol^2)  (:815-817, :870-872)
+  double bs;          // b.b
+  // CG
+  double gamma, pAp, alpha, beta;
+  // BiCGStab
+  double rho, omega, rho_new, rs, rhat_q, ss;
+  // final check
+  double rtrue2, xx;
+  // GMRES (scalars; the small dense arrays live in bk_gmres_small)
+  double g_atol, g_ptol, g_tol_eff, g_atol_eff;
+  double g_bnorm, g_resnorm, g_vnorm0, g_err, g_scale;
+  int g_kcur;         // Arnoldi steps taken in the current cycle
+  int g_cycle_over;   // 1 => remaining Arnoldi kernels of this cycle are no-ops
+  int g_use;          // normalisation flag of the last safe_normalize
+  int g_method;
+  int g_restart;
+  int pad0;
+};
+
+struct bk_scratch {
+  double* partials;       // [rows][stride]
+  unsigned int* counter;  // self-resetting ticket (atomicInc wraps at gridDim.x-1)
+  int stride;
+};
+
+// ------------------------------------------------------------------------------------------
+// matrix object
+// ------------------------------------------------------------------------------------------
+struct bk_csr {
+  bk_handle* h;
+  int64_t n, nnz;
+  int dtype;
+  const int* rowptr;  // int32, device
+  const int* col;     // int32, device
+  const void* val;    // dtype, device
+  void* own_rowptr;   // non-null when the library owns (converted / copied) arrays
+  void* own_col;
+  void* own_val;
+  int kernel;         // 0 row-stream, 1 sub-warp vector
+  int lanes_per_row;
+  int cap;            // row-stream: shared-memory products per warp
+  int max_row_nnz;
+  double mean_row_nnz;
+  bk_csr* transpose;  // cached, owned
+  uint64_t uid;       // unique id for graph-cache keys
+};
+
+// ------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------
+struct bk_graph_entry {
+  cudaGraphExec_t exec;
+  uint64_t key[6];
+  int valid;
+};
+
+struct bk_handle {
+  int device;
+  int num_sms;
+  int64_t l2_bytes;
+  int64_t mem_bytes;
+  // options
+  int grid_mult_vec;   // CTAs/SM of elementwise kernels
+  int grid_mult_spmv;  // CTAs/SM of SpMV kernels
+  int loop_mode;
+  int chunk;
+  int fuse_xpay;
+  int snake;
+  int spmv_variant;
+  // reduction scratch
+  double* partials;        // BK_NSLOT * BK_SLOT_ROWS * BK_MAXB
+  unsigned int* counters;  // BK_NSLOT (+ spare)
+  // device state + pinned mirror
+  bk_dev_state* st;        // device
+  bk_dev_state* st_host;   // pinned, 4 entries (poll ring + final)
+  double* dscratch;        // device: a few doubles for the building-block API
+  // work vectors (elements of the largest dtype requested so far)
+  void* ws;
+  size_t ws_bytes;
+  // GMRES small arrays (device)
+  double* gm_small;
+  size_t gm_small_bytes;
+  double* gm_partials;     // (restart+1) x BK_MAXB partial sums for the multi-dot
+  size_t gm_partials_bytes;
+  // poll events
+  cudaEvent_t ev[4];
+  // graph cache
+  bk_graph_entry graphs[8];
+  cudaStream_t cap_stream;
+  cudaStream_t io_stream;   // bk_solve_host: H2D / solve / D2H
+  uint64_t next_uid;
+};
+
+static inline bk_scratch bk_slot(bk_handle* h, int slot) {
+  bk_scratch s;
+  s.partials = h->partials + (size_t)slot * BK_SLOT_ROWS * BK_MAXB;
+  s.counter = h->counters + slot;
+  s.stride = BK_MAXB;
+  return s;
+}
+
+int bk_ws_reserve(bk_handle* h, size_t bytes);  // grows h->ws (invalidates cached graphs)
+void bk_graphs_invalidate(bk_handle* h);
+void bk_state_fill_tol(bk_dev_state* v, double tol, double atol);
+void bk_fill_result_isolve(const bk_dev_state* st, bk_result* res, int64_t matvecs);
+int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s);
+int bk_solver_args_check(const char* who, bk_handle* h, const bk_csr* A, const void* b, void* x, bk_result* res);
+
+static inline int bk_grid_vec(const bk_handle* h) {
+  int g = h->num_sms * h->grid_mult_vec;
+  return g > BK_MAXB ? BK_MAXB : g;
+}
+static inline int bk_grid_spmv(const bk_handle* h) {
+  int g = h->num_sms * h->grid_mult_spmv;
+  return g > BK_MAXB ? BK_MAXB : g;
+}
+static inline size_t bk_dtype_size(int dtype) { return dtype == BK_F32 ? 4 : 8; }
+static inline bool bk_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+// round-to-nearest mul/add that the compiler may NOT contract into an FMA: the reference
+// evaluates x + alpha*p as two separately rounded torch ops (_add/_mul :165-173).
+__device__ __forceinline__ double bk_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double bk_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double bk_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float bk_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float bk_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float bk_sub(float a, float b) { return __fsub_rn(a, b); }
+
+template <typename T, int W>
+struct bk_vec {
+  T v[W];
+};
+
+template <typename T>
+struct bk_native_w {
+  static constexpr int value = 16 / sizeof(T);
+};
+
+// 16-byte vector load/store when W is the native pack width, scalar otherwise.
+template <typename T, int W>
+__device__ __forceinline__ bk_vec<T, W> bk_ld(const T* __restrict__ p) {
+  bk_vec<T, W> r;
+  if constexpr (W == 1) {
+    r.v[0] = *p;
+  } else if constexpr (sizeof(T) == 8) {
+    static_assert(W == 2, "fp64 pack is 2 wide");
+    double2 t = *reinterpret_cast<const double2*>(p);
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+  } else {
+    static_assert(W == 4, "fp32 pack is 4 wide");
+    float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    r.v[2] = t.z;
+    r.v[3] = t.w;
+  }
+  return r;
+}
+
+template <typename T, int W>
+__device__ __forceinline__ void bk_st(T* __restrict__ p, const bk_vec<T, W>& r) {
+  if constexpr (W == 1) {
+    *p = r.v[0];
+  } else if constexpr (sizeof(T) == 8) {
+    double2 t;
+    t.x = r.v[0];
+    t.y = r.v[1];
+    *reinterpret_cast<double2*>(p) = t;
+  } else {
+    float4 t;
+    t.x = r.v[0];
+    t.y = r.v[1];
+    t.z = r.v[2];
+    t.w = r.v[3];
+    *reinterpret_cast<float4*>(p) = t;
+  }
+}
+
+// Block-level sum of R values; result valid in thread 0.  Fixed shuffle tree => the
+// summation order depends only on (blockDim, R), never on scheduling.
+template <int R>
+__device__ __forceinline__ void bk_block_reduce(double (&v)[R], double* sh /* R*BK_WARPS */) {
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[r] += __shfl_down_sync(0xffffffffu, v[r], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) sh[r * BK_WARPS + wid] = v[r];
+  }
+  __syncthreads();
+  if (wid == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double t = (lane < BK_WARPS) ? sh[r * BK_WARPS + lane] : 0.0;
+#pragma unroll
+      for (int o = BK_WARPS / 2; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      v[r] = t;
+    }
+  }
+  __syncthreads();
+}
+
+// Grid-level deterministic sum: every CTA parks its partial in slot [r][blockIdx.x]; the CTA
+// that draws the last ticket adds the partials in index order with the same fixed tree and
+// runs `epi(sums)` on its thread 0 (this is where alpha/beta/stop flags are computed, so no
+// scalar kernels and no host round trip exist).  Bitwise reproducible for a fixed grid size.
+template <int R, typename Epi>
+__device__ __forceinline__ void bk_grid_reduce(double (&v)[R], const bk_scratch sc, Epi epi) {
+  __shared__ double sh[R * BK_WARPS];
+  __shared__ int s_last;
+  bk_block_reduce<R>(v, sh);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) __stcg(&sc.partials[(size_t)r * sc.stride + blockIdx.x], v[r]);
+    __threadfence();
+    const unsigned int t = atomicInc(sc.counter, gridDim.x - 1);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double a = 0.0;
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += BK_BLOCK)
+        a += __ldcg(&sc.partials[(size_t)r * sc.stride + i]);
+      acc[r] = a;
+    }
+    bk_block_reduce<R>(acc, sh);
+    if (threadIdx.x == 0) epi(acc);
+  }
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,292 @@
+// bk_spmv.cuh — CSR SpMV kernels for sm_100a, fused with the dot products that follow them in
+// the Krylov recurrences.  Replaces torch.matmul(CSR, v) (reference torch_sparse_linalg.py:191)
+// + the torch.vdot that consumes its result (:845 p.Ap, :910 rhat.q, :926-930 t.s/t.t).
+//
+// Two kernels, chosen per matrix from its row-length statistics (bk_csr_create):
+//
+//  * row-stream (short rows, mean <= 32 nnz: stencils, FEM/FVM):  a warp owns 32 consecutive
+//    rows.  Their nnz range [rowptr[r0], rowptr[r0+32]) is ONE contiguous span of val/col, so the
+//    warp reads it fully coalesced with streaming (evict-first) loads, multiplies by the gathered
+//    x[col] (served by L1/L2: for a stencil the gathers are 7 contiguous runs) and parks the
+//    products in its private shared-memory strip; then lane l adds the products of row r0+l in
+//    CSR order.  No block barrier, only __syncwarp; rows longer than the strip are handled by
+//    sweeping the strip over the span.  HBM sees each matrix byte exactly once.
+//
+//  * sub-warp vector (long rows: dense-ish matrices the reference tests use): LPR lanes per row,
+//    strided coalesced reads along the row, fixed shuffle tree.
+//
+// Both are persistent (grid = SMs x k, blocked-cyclic over row blocks so the whole chip sweeps
+// one contiguous window of the matrix, which keeps the x-gather window L2 resident) and end in
+// bk_grid_reduce, whose last CTA runs the solver's scalar epilogue.  Summation order is fixed
+// => bitwise reproducible fp64.
+#pragma once
+
+#include "bk_internal.cuh"
+
+struct bk_spmv_args {
+  const int* rowptr;
+  const int* col;
+  const void* val;
+  const void* x;    // SpMV input (XMODE 0) / r (XMODE 1)
+  const void* x2;   // XMODE 1: previous p
+  void* xout;       // XMODE 1: new p = r + beta p, written for the rows this warp owns
+  void* y;
+  const void* b;    // MODE 1: y = b - A x
+  const void* w;    // DOTS bit0: acc0 += w . y   (XMODE 1 uses the new p instead)
+  long long n;
+  int nnz;
+  const bk_dev_state* st;
+  int guard;        // 0 none | 1 st->done | 2 st->done || st->g_cycle_over | 3 st->done || st->exit_early
+  int reverse;      // 1: sweep row blocks from the end (snake order for L2 reuse)
+  int use_parity;   // 1: reverse ^= st->parity
+};
+
+__device__ __forceinline__ bool bk_spmv_skip(const bk_spmv_args& a) {
+  if (a.guard == 0) return false;
+  const bk_dev_state* st = a.st;
+  if (st->done) return true;
+  if (a.guard == 2 && st->g_cycle_over) return true;
+  if (a.guard == 3 && st->exit_early) return true;
+  return false;
+}
+
+template <int DOTS>
+struct bk_ndots {
+  static constexpr int value = ((DOTS & 1) + ((DOTS >> 1) & 1)) > 0 ? ((DOTS & 1) + ((DOTS >> 1) & 1)) : 1;
+};
+
+// MODE: 0 y = A x, 1 y = b - A x.   DOTS: bit0 w.y, bit1 y.y.   XMODE: 0 plain, 1 x := r + beta*p_old.
+template <typename T, int CAP, int MODE, int DOTS, int XMODE, typename Epi>
+__global__ void __launch_bounds__(BK_BLOCK, 4)
+bk_spmv_stream_kernel(const bk_spmv_args a, const bk_scratch sc, Epi epi) {
+  if (bk_spmv_skip(a)) return;
+  extern __shared__ __align__(16) unsigned char bk_smem[];
+  constexpr int UN = 8;
+  constexpr int R = bk_ndots<DOTS>::value;
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  T* __restrict__ prod = reinterpret_cast<T*>(bk_smem) + wid * CAP;
+  const int* __restrict__ rowptr = a.rowptr;
+  const int* __restrict__ col = a.col;
+  const T* __restrict__ val = static_cast<const T*>(a.val);
+  const T* __restrict__ x = static_cast<const T*>(a.x);
+  const T* __restrict__ x2 = static_cast<const T*>(a.x2);
+  T* __restrict__ y = static_cast<T*>(a.y);
+  const long long n = a.n;
+  const int nnz = a.nnz;
+  const long long nblk = (n + BK_BLOCK - 1) / BK_BLOCK;
+  int reverse = a.reverse;
+  if (a.use_parity) reverse ^= (a.st->parity & 1);
+  T beta = T(0);
+  if constexpr (XMODE == 1) beta = static_cast<T>(a.st->beta);
+
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.0;
+
+  auto row_of = [&](long long blk) -> long long {
+    const long long bb = reverse ? (nblk - 1 - blk) : blk;
+    return bb * BK_BLOCK + wid * 32 + lane;
+  };
+
+  long long blk = blockIdx.x;
+  int rs = nnz, re = nnz;
+  if (blk < nblk) {
+    const long long r = row_of(blk);
+    if (r < n) {
+      rs = __ldg(rowptr + r);
+      re = __ldg(rowptr + r + 1);
+    }
+  }
+  for (; blk < nblk; blk += gridDim.x) {
+    const long long row = row_of(blk);
+    // prefetch the next block's row extents so their latency hides behind this block
+    int rs_n = nnz, re_n = nnz;
+    {
+      const long long nb = blk + gridDim.x;
+      if (nb < nblk) {
+        const long long r = row_of(nb);
+        if (r < n) {
+          rs_n = __ldg(rowptr + r);
+          re_n = __ldg(rowptr + r + 1);
+        }
+      }
+    }
+    const int s = __shfl_sync(0xffffffffu, rs, 0);
+    const int e = __shfl_sync(0xffffffffu, re, 31);
+    T sum = T(0);
+    for (int ws = s; ws < e; ws += CAP) {
+      const int we = (e - ws > CAP) ? ws + CAP : e;
+      for (int base = ws; base < we; base += 32 * UN) {
+        int c[UN];
+        T v[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          const int i = base + u * 32 + lane;
+          const bool p = i < we;
+          c[u] = p ? __ldcs(col + i) : -1;
+          v[u] = p ? __ldcs(val + i) : T(0);
+        }
+        T xv[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          xv[u] = T(0);
+          if (c[u] >= 0) {
+            if constexpr (XMODE == 1) {
+              xv[u] = bk_add(__ldg(x + c[u]), bk_mul(beta, __ldg(x2 + c[u])));
+            } else {
+              xv[u] = __ldg(x + c[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+          if (c[u] >= 0) prod[base - ws + u * 32 + lane] = v[u] * xv[u];
+        }
+      }
+      __syncwarp();
+      const int lo = rs > ws ? rs : ws;
+      const int hi = re < we ? re : we;
+      for (int k = lo; k < hi; ++k) sum += prod[k - ws];
+      __syncwarp();
+    }
+    if (row < n) {
+      T out = sum;
+      if constexpr (MODE == 1) out = bk_sub(__ldg(static_cast<const T*>(a.b) + row), sum);
+      y[row] = out;
+      T wv = T(0);
+      if constexpr (XMODE == 1) {
+        wv = bk_add(__ldg(x + row), bk_mul(beta, __ldg(x2 + row)));
+        static_cast<T*>(a.xout)[row] = wv;
+      } else if constexpr ((DOTS & 1) != 0) {
+        wv = __ldg(static_cast<const T*>(a.w) + row);
+      }
+      if constexpr ((DOTS & 1) != 0) acc[0] += static_cast<double>(wv) * static_cast<double>(out);
+      if constexpr ((DOTS & 2) != 0) acc[DOTS & 1] += static_cast<double>(out) * static_cast<double>(out);
+    }
+    rs = rs_n;
+    re = re_n;
+  }
+  if constexpr (DOTS != 0) {
+    bk_grid_reduce<R>(acc, sc, epi);
+  }
+}
+
+template <typename T, int LPR, int MODE, int DOTS, typename Epi>
+__global__ void __launch_bounds__(BK_BLOCK, 4)
+bk_spmv_vector_kernel(const bk_spmv_args a, const bk_scratch sc, Epi epi) {
+  if (bk_spmv_skip(a)) return;
+  constexpr int R = bk_ndots<DOTS>::value;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int sub = lane % LPR;
+  const int rw = lane / LPR;
+  const int* __restrict__ rowptr = a.rowptr;
+  const int* __restrict__ col = a.col;
+  const T* __restrict__ val = static_cast<const T*>(a.val);
+  const T* __restrict__ x = static_cast<const T*>(a.x);
+  T* __restrict__ y = static_cast<T*>(a.y);
+  const long long n = a.n;
+  constexpr long long RPB = BK_WARPS * RPW;
+  const long long nblk = (n + RPB - 1) / RPB;
+  int reverse = a.reverse;
+  if (a.use_parity) reverse ^= (a.st->parity & 1);
+
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.0;
+
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long bb = reverse ? (nblk - 1 - blk) : blk;
+    const long long row = bb * RPB + wid * RPW + rw;
+    T sum = T(0);
+    if (row < n) {
+      const int rs = __ldg(rowptr + row);
+      const int re = __ldg(rowptr + row + 1);
+#pragma unroll 4
+      for (int k = rs + sub; k < re; k += LPR) sum = fma(__ldcs(val + k), __ldg(x + __ldcs(col + k)), sum);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, o, LPR);
+    if (row < n && sub == 0) {
+      T out = sum;
+      if constexpr (MODE == 1) out = bk_sub(__ldg(static_cast<const T*>(a.b) + row), sum);
+      y[row] = out;
+      if constexpr ((DOTS & 1) != 0)
+        acc[0] += static_cast<double>(__ldg(static_cast<const T*>(a.w) + row)) * static_cast<double>(out);
+      if constexpr ((DOTS & 2) != 0) acc[DOTS & 1] += static_cast<double>(out) * static_cast<double>(out);
+    }
+  }
+  if constexpr (DOTS != 0) {
+    bk_grid_reduce<R>(acc, sc, epi);
+  }
+}
+
+struct bk_epi_none {
+  __device__ __forceinline__ void operator()(const double*) const {}
+};
+
+template <typename K>
+static inline int bk_set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    BK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  }
+  return BK_OK;
+}
+
+template <typename T, int MODE, int DOTS, int XMODE, typename Epi>
+static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a, const bk_scratch& sc,
+                            Epi epi, cudaStream_t s) {
+  const int grid = bk_grid_spmv(h);
+  if (A->kernel == 0) {
+    if (A->cap <= 256) {
+      auto k = bk_spmv_stream_kernel<T, 256, MODE, DOTS, XMODE, Epi>;
+      const size_t sm = (size_t)BK_WARPS * 256 * sizeof(T);
+      k<<<grid, BK_BLOCK, sm, s>>>(a, sc, epi);
+    } else {
+      auto k = bk_spmv_stream_kernel<T, 1024, MODE, DOTS, XMODE, Epi>;
+      const size_t sm = (size_t)BK_WARPS * 1024 * sizeof(T);
+      BK_TRY(bk_set_smem(k, sm));
+      k<<<grid, BK_BLOCK, sm, s>>>(a, sc, epi);
+    }
+  } else {
+    if constexpr (XMODE != 0) {
+      return bk_fail(BK_ERR_UNSUPPORTED, "fused p-update needs the row-stream SpMV kernel");
+    } else {
+      switch (A->lanes_per_row) {
+        case 8:
+          bk_spmv_vector_kernel<T, 8, MODE, DOTS, Epi><<<grid, BK_BLOCK, 0, s>>>(a, sc, epi);
+          break;
+        case 16:
+          bk_spmv_vector_kernel<T, 16, MODE, DOTS, Epi><<<grid, BK_BLOCK, 0, s>>>(a, sc, epi);
+          break;
+        default:
+          bk_spmv_vector_kernel<T, 32, MODE, DOTS, Epi><<<grid, BK_BLOCK, 0, s>>>(a, sc, epi);
+          break;
+      }
+    }
+  }
+  BK_KERNEL_CHECK();
+  return BK_OK;
+}
+
+// Fill the matrix part of the argument block.
+static inline bk_spmv_args bk_spmv_base(const bk_csr* A, const bk_dev_state* st) {
+  bk_spmv_args a;
+  memset(&a, 0, sizeof(a));
+  a.rowptr = A->rowptr;
+  a.col = A->col;
+  a.val = A->val;
+  a.n = A->n;
+  a.nnz = (int)A->nnz;
+  a.st = st;
+  return a;
+}
+
+template <int MODE, int DOTS, int XMODE, typename Epi>
+static int bk_launch_spmv(bk_handle* h, const bk_csr* A, const bk_spmv_args& a, const bk_scratch& sc, Epi epi,
+                          cudaStream_t s) {
+  if (A->dtype == BK_F64) return bk_launch_spmv_t<double, MODE, DOTS, XMODE, Epi>(h, A, a, sc, epi, s);
+  return bk_launch_spmv_t<float, MODE, DOTS, XMODE, Epi>(h, A, a, sc, epi, s);
+}

@@ -1,0 +1,461 @@
+// bk_vec.cuh — fused BLAS-1 kernels: every axpy-type update of the recurrences is ONE pass over
+// its vectors with the norm/dot that follows it folded in, ending in the deterministic grid
+// reduction whose last CTA computes the next scalars (alpha, beta, omega, stop flags) on device.
+// Replaces the reference's _add/_sub/_mul temporaries (torch_sparse_linalg.py:165-173) and the
+// separate torch.vdot launches (:86-139).
+//
+// One generic persistent kernel, parameterised by an Op:
+//   Op::R                      number of fused reductions (0 = none)
+//   Op::In<W>                  the input packs of one step
+//   skip()                     device-side guard (flag set by an earlier epilogue)
+//   prepare() -> Ctx           load the scalars of this step from bk_dev_state
+//   load<W>(i, in)             all global loads of pack i (issued for UN packs before any store)
+//   apply<W>(i, in, ctx, acc)  arithmetic + stores + reduction terms
+//   epilogue(sums)             runs once, on the last CTA
+// fp64 packs are double2, fp32 packs float4 (16-byte accesses); W=1 instantiations serve
+// misaligned user pointers and the n % W tail.
+#pragma once
+
+#include "bk_internal.cuh"
+
+template <typename T, int W, typename Op>
+__global__ void __launch_bounds__(BK_BLOCK, 3) bk_ew_kernel(Op op, const long long n, const bk_scratch sc) {
+  if (op.skip()) return;
+  const typename Op::Ctx ctx = op.prepare();
+  constexpr int R = Op::R > 0 ? Op::R : 1;
+  constexpr int UN = 2;
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.0;
+  const long long npack = n / W;
+  const long long stride = (long long)gridDim.x * BK_BLOCK;
+  const bool rev = op.reverse();
+  long long i = (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
+  for (; i + (UN - 1) * stride < npack; i += UN * stride) {
+    typename Op::template In<W> in[UN];
+    long long p[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      p[u] = i + u * stride;
+      if (rev) p[u] = npack - 1 - p[u];
+      op.template load<W>(p[u] * W, in[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) op.template apply<W>(p[u] * W, in[u], ctx, acc);
+  }
+  for (; i < npack; i += stride) {
+    typename Op::template In<W> in;
+    const long long p = rev ? (npack - 1 - i) : i;
+    op.template load<W>(p * W, in);
+    op.template apply<W>(p * W, in, ctx, acc);
+  }
+  if constexpr (W > 1) {
+    const long long t = npack * W + (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
+    if (t < n) {
+      typename Op::template In<1> in;
+      op.template load<1>(t, in);
+      op.template apply<1>(t, in, ctx, acc);
+    }
+  }
+  if constexpr (Op::R > 0) {
+    bk_grid_reduce<R>(acc, sc, [&](const double* s) { op.epilogue(s); });
+  }
+}
+
+template <typename T, typename Op>
+static int bk_launch_ew(bk_handle* h, const Op& op, long long n, bool aligned, const bk_scratch& sc,
+                        cudaStream_t s) {
+  const int grid = bk_grid_vec(h);
+  constexpr int NW = bk_native_w<T>::value;
+  if (aligned) {
+    bk_ew_kernel<T, NW, Op><<<grid, BK_BLOCK, 0, s>>>(op, n, sc);
+  } else {
+    bk_ew_kernel<T, 1, Op><<<grid, BK_BLOCK, 0, s>>>(op, n, sc);
+  }
+  BK_KERNEL_CHECK();
+  return BK_OK;
+}
+
+struct bk_noctx {};
+
+// ---- generic building blocks ---------------------------------------------------------------
+// out[0] = x . y  (sqrt_out: out[0] = sqrt(max(x.y, 0)) — _norm :154-162)
+template <typename T>
+struct bk_op_dot {
+  static constexpr int R = 1;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> a, b;
+  };
+  const T* x;
+  const T* y;
+  double* out;
+  int sqrt_out;
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.a = bk_ld<T, W>(x + i);
+    in.b = bk_ld<T, W>(y + i);
+  }
+  template <int W>
+  __device__ void apply(long long, const In<W>& in, const Ctx&, double (&acc)[1]) const {
+#pragma unroll
+    for (int j = 0; j < W; ++j) acc[0] += (double)in.a.v[j] * (double)in.b.v[j];
+  }
+  __device__ void epilogue(const double* s) const { out[0] = sqrt_out ? sqrt(fmax(s[0], 0.0)) : s[0]; }
+};
+
+// z = a x + b y
+template <typename T>
+struct bk_op_axpby {
+  static constexpr int R = 0;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> a, b;
+  };
+  const T* x;
+  const T* y;
+  T* z;
+  T ca, cb;
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.a = bk_ld<T, W>(x + i);
+    in.b = bk_ld<T, W>(y + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx&, double (&)[1]) const {
+    bk_vec<T, W> o;
+#pragma unroll
+    for (int j = 0; j < W; ++j) o.v[j] = bk_add(bk_mul(ca, in.a.v[j]), bk_mul(cb, in.b.v[j]));
+    bk_st<T, W>(z + i, o);
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
+// ---- CG --------------------------------------------------------------------------------------
+// x += alpha p ; r -= alpha Ap ; gamma' = r.r          (_cg_solve :846-850)
+// epilogue: beta = gamma'/gamma, gamma = gamma', k += 1, stop test of :841 for the NEXT iteration.
+template <typename T>
+struct bk_op_cg_update {
+  static constexpr int R = 1;
+  struct Ctx {
+    T alpha;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> p, ap, x, r;
+  };
+  const T* p;
+  const T* ap;
+  T* x;
+  T* r;
+  bk_dev_state* st;
+  int snake;
+  __device__ bool skip() const { return st->done != 0; }
+  __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.alpha = static_cast<T>(st->alpha);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.p = bk_ld<T, W>(p + i);
+    in.ap = bk_ld<T, W>(ap + i);
+    in.x = bk_ld<T, W>(x + i);
+    in.r = bk_ld<T, W>(r + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&acc)[1]) const {
+    bk_vec<T, W> xo, ro;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      xo.v[j] = bk_add(in.x.v[j], bk_mul(c.alpha, in.p.v[j]));
+      ro.v[j] = bk_sub(in.r.v[j], bk_mul(c.alpha, in.ap.v[j]));
+      acc[0] += (double)ro.v[j] * (double)ro.v[j];
+    }
+    bk_st<T, W>(x + i, xo);
+    bk_st<T, W>(r + i, ro);
+  }
+  __device__ void epilogue(const double* s) const {
+    const double gamma_new = s[0];
+    st->beta = gamma_new / st->gamma;
+    st->gamma = gamma_new;
+    const long long k = st->k + 1;
+    st->k = k;
+    st->parity ^= 1;
+    if (k >= st->maxiter) {
+      st->done = 1;
+      st->status = BK_ST_MAXITER;
+    }
+    if (gamma_new <= st->atol2) {
+      st->done = 1;
+      st->status = BK_ST_CONVERGED;
+    }
+  }
+};
+
+// p = r + beta p                                           (_cg_solve :852)
+template <typename T>
+struct bk_op_xpay {
+  static constexpr int R = 0;
+  struct Ctx {
+    T beta;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> r, p;
+  };
+  const T* r;
+  T* p;
+  const bk_dev_state* st;
+  int snake;
+  __device__ bool skip() const { return st->done != 0; }
+  // parity was flipped by the update kernel's epilogue; sweep the same way as this iteration's SpMV
+  __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.beta = static_cast<T>(st->beta);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.r = bk_ld<T, W>(r + i);
+    in.p = bk_ld<T, W>(p + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
+    bk_vec<T, W> o;
+#pragma unroll
+    for (int j = 0; j < W; ++j) o.v[j] = bk_add(in.r.v[j], bk_mul(c.beta, in.p.v[j]));
+    bk_st<T, W>(p + i, o);
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
+// ---- BiCGStab ----------------------------------------------------------------------------------
+// p = r + beta (p - omega q)                               (_bicgstab_solve :906-907)
+template <typename T>
+struct bk_op_bicg_p {
+  static constexpr int R = 0;
+  struct Ctx {
+    T beta, omega;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> r, p, q;
+  };
+  const T* r;
+  T* p;
+  const T* q;
+  const bk_dev_state* st;
+  __device__ bool skip() const { return st->done != 0; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.beta = static_cast<T>(st->beta);
+    c.omega = static_cast<T>(st->omega);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.r = bk_ld<T, W>(r + i);
+    in.p = bk_ld<T, W>(p + i);
+    in.q = bk_ld<T, W>(q + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
+    bk_vec<T, W> o;
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+      o.v[j] = bk_add(in.r.v[j], bk_mul(c.beta, bk_sub(in.p.v[j], bk_mul(c.omega, in.q.v[j]))));
+    bk_st<T, W>(p + i, o);
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
+// s = r - alpha q ; ss = s.s ; exit_early = ss < atol2      (:917-920)
+template <typename T>
+struct bk_op_bicg_s {
+  static constexpr int R = 1;
+  struct Ctx {
+    T alpha;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> r, q;
+  };
+  const T* r;
+  const T* q;
+  T* s;
+  bk_dev_state* st;
+  __device__ bool skip() const { return st->done != 0; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.alpha = static_cast<T>(st->alpha);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.r = bk_ld<T, W>(r + i);
+    in.q = bk_ld<T, W>(q + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&acc)[1]) const {
+    bk_vec<T, W> o;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      o.v[j] = bk_sub(in.r.v[j], bk_mul(c.alpha, in.q.v[j]));
+      acc[0] += (double)o.v[j] * (double)o.v[j];
+    }
+    bk_st<T, W>(s + i, o);
+  }
+  __device__ void epilogue(const double* sums) const {
+    st->ss = sums[0];
+    st->exit_early = (sums[0] < st->atol2) ? 1 : 0;
+  }
+};
+
+// exit_early ? (x += alpha p ; r = s) : (x += alpha p + omega s ; r = s - omega t)   (:942-950)
+// fused with rs = r.r and rho' = rhat.r for the next iteration's tests (:894-904).
+template <typename T>
+struct bk_op_bicg_xr {
+  static constexpr int R = 2;
+  struct Ctx {
+    T alpha, omega;
+    int early;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> x, p, s, t, rh;
+  };
+  T* x;
+  const T* p;
+  const T* s;
+  const T* t;
+  const T* rhat;
+  T* r;
+  bk_dev_state* st;
+  __device__ bool skip() const { return st->done != 0; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.alpha = static_cast<T>(st->alpha);
+    c.omega = static_cast<T>(st->omega);
+    c.early = st->exit_early;
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.x = bk_ld<T, W>(x + i);
+    in.p = bk_ld<T, W>(p + i);
+    in.s = bk_ld<T, W>(s + i);
+    in.t = bk_ld<T, W>(t + i);
+    in.rh = bk_ld<T, W>(rhat + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&acc)[2]) const {
+    bk_vec<T, W> xo, ro;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const T ap = bk_mul(c.alpha, in.p.v[j]);
+      if (c.early) {
+        xo.v[j] = bk_add(in.x.v[j], ap);
+        ro.v[j] = in.s.v[j];
+      } else {
+        xo.v[j] = bk_add(in.x.v[j], bk_add(ap, bk_mul(c.omega, in.s.v[j])));
+        ro.v[j] = bk_sub(in.s.v[j], bk_mul(c.omega, in.t.v[j]));
+      }
+      acc[0] += (double)ro.v[j] * (double)ro.v[j];
+      acc[1] += (double)in.rh.v[j] * (double)ro.v[j];
+    }
+    bk_st<T, W>(x + i, xo);
+    bk_st<T, W>(r + i, ro);
+  }
+  // End of iteration k and top-of-loop tests of iteration k+1 (:892-905, :952-962).
+  __device__ void epilogue(const double* sums) const {
+    const double eps = (sizeof(T) == 8) ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+    const long long k = st->k + 1;
+    st->k = k;
+    const double rho_prev = st->rho_new;  // rho = rho_new
+    st->rho = rho_prev;
+    if (st->exit_early) {  // "if exit_early: break" (:961-962)
+      st->rs = sums[0];
+      st->done = 1;
+      st->status = BK_ST_CONVERGED;
+      return;
+    }
+    if (k >= st->maxiter) {
+      st->rs = sums[0];
+      st->done = 1;
+      st->status = BK_ST_MAXITER;
+      return;
+    }
+    st->rs = sums[0];
+    if (sums[0] <= st->atol2) {
+      st->done = 1;
+      st->status = BK_ST_CONVERGED;
+      return;
+    }
+    const double rho_new = sums[1];
+    st->rho_new = rho_new;
+    if (fabs(rho_new) < eps * fabs(rho_prev)) {
+      st->done = 1;
+      st->status = BK_ST_BREAKDOWN_RHO;
+      return;
+    }
+    st->beta = rho_new / rho_prev * st->alpha / st->omega;
+  }
+};
+
+// ---- GMRES -------------------------------------------------------------------------------------
+// v = use ? w / norm : 0                                  (_safe_normalize :266-272)
+template <typename T>
+struct bk_op_normalize {
+  static constexpr int R = 0;
+  struct Ctx {
+    T norm;
+    int use;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> w;
+  };
+  const T* w;
+  T* v;
+  const bk_dev_state* st;
+  int guard;  // 0 none | 1 st->done | 2 st->done || st->g_cycle_over
+  __device__ bool skip() const {
+    if (guard == 0) return false;
+    if (st->done) return true;
+    if (guard == 2 && st->g_cycle_over) return true;
+    return false;
+  }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.norm = static_cast<T>(st->g_scale);
+    c.use = st->g_use;
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.w = bk_ld<T, W>(w + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
+    bk_vec<T, W> o;
+#pragma unroll
+    for (int j = 0; j < W; ++j) o.v[j] = c.use ? in.w.v[j] / c.norm : T(0);
+    bk_st<T, W>(v + i, o);
+  }
+  __device__ void epilogue(const double*) const {}
+};

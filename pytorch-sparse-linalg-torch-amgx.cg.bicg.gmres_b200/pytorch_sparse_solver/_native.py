@@ -1,0 +1,433 @@
+"""ctypes binding of libbk_krylov.so (C ABI declared in include/bk_krylov.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every numerical
+operation of the Krylov loop happens inside the hand-written CUDA library.  There is no CPU
+fallback: if the library is missing or there is no CUDA device, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
+from collections import OrderedDict
+from pathlib import Path
+from typing import Optional, Tuple
+
+import torch
+
+_LIB_NAME = "libbk_krylov.so"
+_LIB_DIR = Path(__file__).resolve().parent / "_lib"
+
+BK_F64, BK_F32 = 0, 1
+BK_GMRES_BATCHED, BK_GMRES_INCREMENTAL = 0, 1
+METHOD_CG, METHOD_BICGSTAB, METHOD_GMRES = 0, 1, 2
+
+
+class NativeLibraryError(RuntimeError):
+    """The CUDA library is missing/unloadable or reported an error."""
+
+
+class bk_result(C.Structure):
+    _fields_ = [
+        ("iterations", C.c_int64),
+        ("matvecs", C.c_int64),
+        ("info", C.c_int32),
+        ("status", C.c_int32),
+        ("final_residual", C.c_double),
+        ("threshold", C.c_double),
+        ("b_norm", C.c_double),
+        ("x_norm", C.c_double),
+        ("rr_last", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class bk_csr_info(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64),
+        ("nnz", C.c_int64),
+        ("dtype", C.c_int32),
+        ("kernel", C.c_int32),
+        ("lanes_per_row", C.c_int32),
+        ("max_row_nnz", C.c_int32),
+        ("mean_row_nnz", C.c_double),
+        ("bytes_matrix", C.c_int64),
+    ]
+
+
+# symbol -> (restype, argtypes); kept in one table so tests can check it against the header.
+_VP = C.c_void_p
+_SIGNATURES = {
+    "bk_version": (C.c_int, []),
+    "bk_last_error": (C.c_char_p, []),
+    "bk_create": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "bk_destroy": (C.c_int, [_VP]),
+    "bk_set_option": (C.c_int, [_VP, C.c_char_p, C.c_int64]),
+    "bk_get_option": (C.c_int64, [_VP, C.c_char_p]),
+    "bk_device_info": (C.c_int, [_VP, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "bk_csr_create": (C.c_int, [_VP, C.c_int64, C.c_int64, _VP, _VP, C.c_int, _VP, C.c_int, C.c_int, _VP,
+                                C.POINTER(_VP)]),
+    "bk_csr_destroy": (C.c_int, [_VP]),
+    "bk_csr_get_info": (C.c_int, [_VP, C.POINTER(bk_csr_info)]),
+    "bk_csr_transpose": (C.c_int, [_VP, _VP, _VP, C.POINTER(_VP)]),
+    "bk_csr_arrays": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
+    "bk_spmv": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "bk_spmv_dot": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "bk_dot": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP, _VP, _VP]),
+    "bk_nrm2": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP, _VP]),
+    "bk_axpby": (C.c_int, [_VP, C.c_int64, C.c_int, C.c_double, _VP, C.c_double, _VP, _VP, _VP]),
+    "bk_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(bk_result), _VP]),
+    "bk_bicgstab": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(bk_result),
+                              _VP]),
+    "bk_gmres": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int64, C.c_int,
+                           C.POINTER(bk_result), _VP]),
+    "bk_solve_host": (C.c_int, [_VP, C.c_int, C.c_int64, C.c_int64, _VP, _VP, C.c_int, _VP, C.c_int, _VP, _VP,
+                                C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int, C.POINTER(bk_result)]),
+    "bk_dist_unique_id": (C.c_int, [_VP]),
+    "bk_dist_create": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _VP, _VP,
+                                 C.c_int, _VP, C.c_int, _VP, C.POINTER(_VP)]),
+    "bk_dist_destroy": (C.c_int, [_VP]),
+    "bk_dist_spmv": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "bk_dist_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(bk_result),
+                             _VP]),
+}
+
+_lib = None
+
+
+def library_path() -> Path:
+    return Path(os.environ.get("BK_KRYLOV_LIB", _LIB_DIR / _LIB_NAME))
+
+
+def load_library():
+    """dlopen the C-ABI library and attach signatures.  Raises NativeLibraryError when absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not path.exists():
+        raise NativeLibraryError(
+            f"{path} not found: build it with `python __graft_entry__.py` (or csrc/build.py). "
+            "There is no CPU fallback for the module_a hot path.")
+    try:
+        lib = C.CDLL(str(path))
+    except OSError as e:  # pragma: no cover
+        raise NativeLibraryError(f"cannot load {path}: {e}") from e
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryError(f"{path} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load_library().bk_last_error()
+        raise NativeLibraryError(f"{what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float64:
+        return BK_F64
+    if dt == torch.float32:
+        return BK_F32
+    raise TypeError(f"module_a native path supports float64/float32, got {dt}")
+
+
+class Handle:
+    """One bk_handle per CUDA device (created lazily, lives for the process)."""
+
+    _by_device = {}
+
+    def __init__(self, device_index: int):
+        lib = load_library()
+        if not torch.cuda.is_available():
+            raise NativeLibraryError("a CUDA device is required: module_a has no CPU fallback in this build")
+        torch.cuda.init()
+        with torch.cuda.device(device_index):
+            torch.cuda.current_stream()  # make sure the primary context exists
+            p = _VP()
+            _check(lib.bk_create(device_index, C.byref(p)), "bk_create")
+        self.ptr = p
+        self.device_index = device_index
+        self.lib = lib
+
+    @classmethod
+    def get(cls, device) -> "Handle":
+        idx = torch.device(device).index
+        if idx is None:
+            idx = torch.cuda.current_device()
+        h = cls._by_device.get(idx)
+        if h is None:
+            h = cls(idx)
+            cls._by_device[idx] = h
+        return h
+
+    def set_option(self, key: str, value: int):
+        _check(self.lib.bk_set_option(self.ptr, key.encode(), int(value)), f"bk_set_option({key})")
+
+    def get_option(self, key: str) -> int:
+        return int(self.lib.bk_get_option(self.ptr, key.encode()))
+
+    def device_info(self):
+        sms, l2, mem = C.c_int32(), C.c_int64(), C.c_int64()
+        _check(self.lib.bk_device_info(self.ptr, C.byref(sms), C.byref(l2), C.byref(mem)), "bk_device_info")
+        return {"num_sms": sms.value, "l2_bytes": l2.value, "mem_bytes": mem.value}
+
+
+class CsrMatrix:
+    """A registered CSR matrix.  Holds references to the torch tensors whose memory the library borrows."""
+
+    def __init__(self, handle: Handle, crow: torch.Tensor, col: torch.Tensor, val: torch.Tensor, n: int):
+        assert crow.is_cuda and col.is_cuda and val.is_cuda
+        crow = crow.contiguous()
+        col = col.contiguous()
+        val = val.contiguous()
+        if crow.dtype not in (torch.int32, torch.int64) or col.dtype != crow.dtype:
+            raise TypeError("CSR indices must be int32 or int64")
+        self.handle = handle
+        self.n = int(n)
+        self.nnz = int(val.numel())
+        self.dtype = val.dtype
+        self.device = val.device
+        self._keep = (crow, col, val)
+        p = _VP()
+        with torch.cuda.device(self.device):
+            _check(handle.lib.bk_csr_create(handle.ptr, self.n, self.nnz, crow.data_ptr(), col.data_ptr(),
+                                            32 if crow.dtype == torch.int32 else 64, val.data_ptr(),
+                                            _dtype_code(val.dtype), 0, _stream_ptr(self.device), C.byref(p)),
+                   "bk_csr_create")
+        self.ptr = p
+        self._owned = True
+        self._transpose = None
+        self._finalizer = weakref.finalize(self, CsrMatrix._destroy, handle.lib, p)
+
+    @staticmethod
+    def _destroy(lib, p):
+        try:
+            lib.bk_csr_destroy(p)
+        except Exception:  # pragma: no cover
+            pass
+
+    @classmethod
+    def _wrap(cls, handle: Handle, ptr, n, nnz, dtype, device, keep):
+        obj = cls.__new__(cls)
+        obj.handle, obj.ptr, obj.n, obj.nnz, obj.dtype, obj.device = handle, ptr, n, nnz, dtype, device
+        obj._keep = keep
+        obj._owned = False
+        obj._transpose = None
+        return obj
+
+    def info(self) -> dict:
+        out = bk_csr_info()
+        _check(self.handle.lib.bk_csr_get_info(self.ptr, C.byref(out)), "bk_csr_get_info")
+        return {k: getattr(out, k) for k, _ in out._fields_}
+
+    def transpose(self) -> "CsrMatrix":
+        """Cached A^T (owned by this matrix on the C side)."""
+        if self._transpose is None:
+            p = _VP()
+            with torch.cuda.device(self.device):
+                _check(self.handle.lib.bk_csr_transpose(self.handle.ptr, self.ptr, _stream_ptr(self.device),
+                                                        C.byref(p)), "bk_csr_transpose")
+            self._transpose = CsrMatrix._wrap(self.handle, p, self.n, self.nnz, self.dtype, self.device, (self,))
+        return self._transpose
+
+    def arrays(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Copy the (int32) CSR arrays of this matrix out as torch tensors (testing / debugging)."""
+        rp, cp, vp = _VP(), _VP(), _VP()
+        _check(self.handle.lib.bk_csr_arrays(self.ptr, C.byref(rp), C.byref(cp), C.byref(vp)), "bk_csr_arrays")
+        crow = torch.empty(self.n + 1, dtype=torch.int32, device=self.device)
+        col = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+        val = torch.empty(self.nnz, dtype=self.dtype, device=self.device)
+        cudart = torch.cuda.cudart()
+        torch.cuda.synchronize(self.device)
+        for dst, src in ((crow, rp), (col, cp), (val, vp)):
+            if dst.numel():
+                cudart.cudaMemcpy(dst.data_ptr(), src.value, dst.numel() * dst.element_size(), 3)
+        return crow, col, val
+
+    # ---- building blocks -------------------------------------------------------------------
+    def _vec(self, v: torch.Tensor) -> torch.Tensor:
+        if v.dtype != self.dtype or not v.is_cuda or v.numel() != self.n:
+            raise ValueError(f"vector must be a CUDA {self.dtype} tensor of {self.n} elements")
+        return v.contiguous()
+
+    def spmv(self, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = self._vec(x)
+        y = torch.empty_like(x) if out is None else out
+        with torch.cuda.device(self.device):
+            _check(self.handle.lib.bk_spmv(self.handle.ptr, self.ptr, x.data_ptr(), y.data_ptr(),
+                                           _stream_ptr(self.device)), "bk_spmv")
+        return y
+
+    def spmv_dot(self, x: torch.Tensor, w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        x = self._vec(x)
+        w = self._vec(w)
+        y = torch.empty_like(x)
+        d = torch.empty(1, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self.handle.lib.bk_spmv_dot(self.handle.ptr, self.ptr, x.data_ptr(), y.data_ptr(), w.data_ptr(),
+                                               d.data_ptr(), _stream_ptr(self.device)), "bk_spmv_dot")
+        return y, d[0]
+
+    # ---- solvers -----------------------------------------------------------------------------
+    def _solve(self, which: str, b: torch.Tensor, x0: Optional[torch.Tensor], *args) -> Tuple[torch.Tensor, dict]:
+        b = self._vec(b)
+        if x0 is None:
+            x = torch.empty_like(b)
+            has_x0 = 0
+        else:
+            x = self._vec(x0).clone()
+            has_x0 = 1
+        res = bk_result()
+        lib = self.handle.lib
+        with torch.cuda.device(self.device):
+            s = _stream_ptr(self.device)
+            if which == "cg":
+                tol, atol, maxiter = args
+                rc = lib.bk_cg(self.handle.ptr, self.ptr, b.data_ptr(), x.data_ptr(), has_x0, tol, atol, maxiter,
+                               C.byref(res), s)
+            elif which == "bicgstab":
+                tol, atol, maxiter = args
+                rc = lib.bk_bicgstab(self.handle.ptr, self.ptr, b.data_ptr(), x.data_ptr(), has_x0, tol, atol,
+                                     maxiter, C.byref(res), s)
+            elif which == "gmres":
+                tol_eff, atol_eff, restart, maxiter, method = args
+                rc = lib.bk_gmres(self.handle.ptr, self.ptr, b.data_ptr(), x.data_ptr(), has_x0, tol_eff, atol_eff,
+                                  restart, maxiter, method, C.byref(res), s)
+            else:  # pragma: no cover
+                raise ValueError(which)
+        _check(rc, f"bk_{which}")
+        return x, res.as_dict()
+
+    def cg(self, b, x0, tol, atol, maxiter):
+        return self._solve("cg", b, x0, float(tol), float(atol), -1 if maxiter is None else int(maxiter))
+
+    def bicgstab(self, b, x0, tol, atol, maxiter):
+        return self._solve("bicgstab", b, x0, float(tol), float(atol), -1 if maxiter is None else int(maxiter))
+
+    def gmres(self, b, x0, tol_eff, atol_eff, restart, maxiter, method):
+        return self._solve("gmres", b, x0, float(tol_eff), float(atol_eff), int(restart),
+                           -1 if maxiter is None else int(maxiter), int(method))
+
+
+# ---- building-block vector ops (deterministic reductions) ------------------------------------------
+def dot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    h = Handle.get(x.device)
+    x = x.contiguous()
+    y = y.contiguous()
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(h.lib.bk_dot(h.ptr, x.numel(), _dtype_code(x.dtype), x.data_ptr(), y.data_ptr(), out.data_ptr(),
+                            _stream_ptr(x.device)), "bk_dot")
+    return out[0]
+
+
+def nrm2(x: torch.Tensor) -> torch.Tensor:
+    h = Handle.get(x.device)
+    x = x.contiguous()
+    out = torch.empty(1, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(h.lib.bk_nrm2(h.ptr, x.numel(), _dtype_code(x.dtype), x.data_ptr(), out.data_ptr(),
+                             _stream_ptr(x.device)), "bk_nrm2")
+    return out[0]
+
+
+def axpby(a: float, x: torch.Tensor, b: float, y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    h = Handle.get(x.device)
+    x = x.contiguous()
+    y = y.contiguous()
+    z = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        _check(h.lib.bk_axpby(h.ptr, x.numel(), _dtype_code(x.dtype), float(a), x.data_ptr(), float(b), y.data_ptr(),
+                              z.data_ptr(), _stream_ptr(x.device)), "bk_axpby")
+    return z
+
+
+# ---- matrix ingestion + cache ---------------------------------------------------------------------
+_CACHE: "OrderedDict[tuple, CsrMatrix]" = OrderedDict()
+_CACHE_MAX = 8
+
+
+def _csr_components(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """dense / COO / CSR torch tensor -> (crow, col, values).  Setup-time torch calls (not the hot path)."""
+    if A.layout == torch.sparse_csr:
+        return A.crow_indices(), A.col_indices(), A.values()
+    if A.layout == torch.sparse_coo:
+        A = A.coalesce().to_sparse_csr()
+        return A.crow_indices(), A.col_indices(), A.values()
+    if A.layout == torch.strided:
+        A = A.to_sparse_csr()
+        return A.crow_indices(), A.col_indices(), A.values()
+    A = A.to_sparse_csr()
+    return A.crow_indices(), A.col_indices(), A.values()
+
+
+def register_matrix(A: torch.Tensor, dtype: torch.dtype = torch.float64) -> CsrMatrix:
+    """Register a 2-D CUDA tensor with the library (cached per storage + version)."""
+    if not A.is_cuda:
+        raise NativeLibraryError("register_matrix expects a CUDA tensor")
+    if A.layout == torch.sparse_csr:
+        v = A.values()
+        key = ("csr", A.crow_indices().data_ptr(), A.col_indices().data_ptr(), v.data_ptr(), v._version,
+               tuple(A.shape), v.dtype, dtype, A.device.index)
+    elif A.layout == torch.sparse_coo:
+        v = A._values()
+        key = ("coo", A._indices().data_ptr(), v.data_ptr(), v._version, tuple(A.shape), v.dtype, dtype,
+               A.device.index, A.is_coalesced())
+    else:
+        key = ("dense", A.data_ptr(), A._version, tuple(A.shape), tuple(A.stride()), A.dtype, dtype, A.device.index)
+    hit = _CACHE.get(key)
+    if hit is not None:
+        _CACHE.move_to_end(key)
+        return hit
+    with torch.no_grad():
+        crow, col, val = _csr_components(A.detach())
+        if val.dtype != dtype:
+            val = val.to(dtype)
+    m = CsrMatrix(Handle.get(A.device), crow, col, val, A.shape[0])
+    m._keep = m._keep + (A,)  # keep the source alive so the data_ptr key stays unique
+    _CACHE[key] = m
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)
+    return m
+
+
+def clear_cache():
+    _CACHE.clear()
+
+
+def solve_host(method: int, crow: torch.Tensor, col: torch.Tensor, val: torch.Tensor, b: torch.Tensor,
+               x0: Optional[torch.Tensor], tol: float, atol: float, maxiter: Optional[int], restart: int = 20,
+               gmres_method: int = BK_GMRES_BATCHED, device: Optional[int] = None) -> Tuple[torch.Tensor, dict]:
+    """End-to-end solve from HOST buffers: H2D of matrix and b, the device loop, D2H of x (bk_solve_host)."""
+    for t in (crow, col, val, b):
+        if t.is_cuda:
+            raise ValueError("solve_host takes CPU tensors")
+    h = Handle.get(torch.device("cuda", torch.cuda.current_device() if device is None else device))
+    crow, col, val, b = crow.contiguous(), col.contiguous(), val.contiguous(), b.contiguous()
+    n = b.numel()
+    if x0 is None:
+        x = torch.empty_like(b)
+        has_x0 = 0
+    else:
+        x = x0.to(b.dtype).contiguous().clone()
+        has_x0 = 1
+    res = bk_result()
+    _check(h.lib.bk_solve_host(h.ptr, int(method), n, val.numel(), crow.data_ptr(), col.data_ptr(),
+                               32 if crow.dtype == torch.int32 else 64, val.data_ptr(), _dtype_code(val.dtype),
+                               b.data_ptr(), x.data_ptr(), has_x0, float(tol), float(atol),
+                               -1 if maxiter is None else int(maxiter), int(restart), int(gmres_method),
+                               C.byref(res)), "bk_solve_host")
+    return x, res.as_dict()

@@ -1,0 +1,17 @@
+"""Module A — JAX-style Krylov solvers (cg, bicgstab, gmres) behind the reference's API, running on the
+B200-native CUDA library.  Same exports as the reference module_a/__init__.py:40-63."""
+from .krylov import (
+    cg, bicgstab, gmres,
+    cg_differentiable, bicgstab_differentiable, gmres_differentiable,
+    LinearSolveFunction,
+)
+from .torch_tree_util import tree_leaves, tree_map, tree_flatten, tree_unflatten, Partial
+
+__all__ = [
+    'cg', 'bicgstab', 'gmres',
+    'cg_differentiable', 'bicgstab_differentiable', 'gmres_differentiable',
+    'LinearSolveFunction',
+    'tree_leaves', 'tree_map', 'tree_flatten', 'tree_unflatten', 'Partial',
+]
+
+__version__ = '1.0.0'

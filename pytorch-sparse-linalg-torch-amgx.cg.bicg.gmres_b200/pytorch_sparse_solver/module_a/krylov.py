@@ -1,0 +1,316 @@
+"""module_a front end: the reference's Python API over the B200-native Krylov library.
+
+Mirrors (names, argument meaning, return values, error behaviour) of the reference file
+src/pytorch_sparse_solver/module_a/torch_sparse_linalg.py:
+
+    cg        :1019-1088      bicgstab :1091-1158      gmres :641-784
+    cg/bicgstab/gmres_differentiable :1261-1367        LinearSolveFunction :1161-1224
+    ImplicitAdjointFunction :1227-1248 (here: _ImplicitAdjoint)
+
+What is different underneath: the whole iteration loop of each solver is ONE call into
+libbk_krylov.so (hand-written sm_100a kernels, device-resident loop, deterministic reductions).
+Routes:
+
+  * native   A is a 2-D CUDA tensor (CSR / COO / dense), b a CUDA tensor, M is None
+             -> bk_cg / bk_bicgstab / bk_gmres on the registered CSR matrix.
+  * host     the same with CPU tensors: the arrays are copied to the current CUDA device, solved
+             there and x is copied back (bk_solve_host).  Still the CUDA path — this build has no
+             CPU solver, and raises if no CUDA device exists.
+  * generic  callable A, preconditioner M or pytree b: the reference's recurrences driven from
+             Python (one host sync per iteration, as in the reference) with every dot / axpy done
+             by the library's deterministic kernels (see generic.py).
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Callable, Optional, Tuple, Union
+
+import torch
+
+from .. import _native
+from .torch_tree_util import tree_leaves
+
+__all__ = [
+    "cg", "bicgstab", "gmres",
+    "cg_differentiable", "bicgstab_differentiable", "gmres_differentiable",
+    "LinearSolveFunction",
+]
+
+# Tests comparing against the CPU oracle set this to 'cpu' so that gmres uses the reference's CPU
+# tolerance constants even though the tensors live on a CUDA device (reference :737-744).
+GMRES_TOLERANCE_DEVICE: Optional[str] = None
+
+# Filled by every solve: the native bk_result of the most recent call (iterations, matvecs, ...).
+# The reference returns no iteration count (solver.py:373); this is strictly extra information.
+last_result: dict = {}
+
+
+# --------------------------------------------------------------------------------------------------
+# validation helpers (same exceptions as the reference)
+# --------------------------------------------------------------------------------------------------
+def _check_operator(A):
+    """_normalize_matvec :176-208: ValueError for a non-square tensor, TypeError for junk."""
+    if callable(A) and not isinstance(A, torch.Tensor):
+        return "callable"
+    if isinstance(A, torch.Tensor):
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError(f'linear operator must be a square matrix, but has shape: {A.shape}')
+        return "tensor"
+    raise TypeError(f'linear operator must be either a function or tensor: {A}')
+
+
+def _check_x0(b, x0):
+    """_isolve :992-1002 / gmres :723-727."""
+    b_leaves, x0_leaves = tree_leaves(b), tree_leaves(x0)
+    if len(b_leaves) != len(x0_leaves):
+        raise ValueError('x0 and b must have matching tree structure')
+    for bl, xl in zip(b_leaves, x0_leaves):
+        if bl.shape != xl.shape:
+            raise ValueError(f'arrays in x0 and b must have matching shapes: {xl.shape} vs {bl.shape}')
+
+
+def _route(A, b, x0, M) -> str:
+    kind = _check_operator(A)
+    if kind == "callable" or M is not None or not isinstance(b, torch.Tensor):
+        return "generic"
+    if b.ndim != 1 or b.shape[0] != A.shape[0]:
+        raise ValueError(f"b must be a vector of length {A.shape[0]}, got shape {tuple(b.shape)}")
+    if A.is_complex() or b.is_complex():
+        raise NotImplementedError("complex systems are outside this build's scope (real fp64/fp32 only)")
+    if A.is_cuda != b.is_cuda:
+        raise ValueError("A and b must live on the same device")
+    return "native" if A.is_cuda else "host"
+
+
+def _work_dtype(A: torch.Tensor, b: torch.Tensor) -> torch.dtype:
+    """fp64 unless BOTH A and b are fp32 (the reference always computes in fp64, :979-980; it raises
+    for fp32 A — here that combination selects the native fp32 kernels)."""
+    if A.dtype == torch.float32 and b.dtype == torch.float32:
+        return torch.float32
+    return torch.float64
+
+
+def _use_implicit_diff(A: Any, b: Any) -> bool:
+    """:1251-1258"""
+    return (isinstance(A, torch.Tensor) and isinstance(b, torch.Tensor) and A.ndim == 2
+            and (A.requires_grad or b.requires_grad))
+
+
+def _gmres_effective_tolerances(tol: float, atol: float, size: int, device_type: str) -> Tuple[float, float]:
+    """The host-only part of gmres' tolerance set-up (:733-748), including its fp32 roundings.
+
+    atol_tensor = max(tensor(adaptive_tol) * ||b||, max(tensor(atol), tensor(base_atol)))
+    where torch.tensor(<python float>) is fp32 and torch.tensor(<fp64 tensor>) stays fp64.
+    Returns (tol_eff, atol_eff); the device finishes with ||b||.
+    """
+    if GMRES_TOLERANCE_DEVICE is not None:
+        device_type = GMRES_TOLERANCE_DEVICE
+    eps = torch.finfo(torch.float64).eps
+    root = torch.sqrt(torch.tensor(size, dtype=torch.float64))
+    scaled = (1e-12 if device_type == 'cuda' else 1e-14) * root
+    base_atol = eps * (1000 if device_type == 'cuda' else 100) * size
+    adaptive = max(tol, scaled)  # python max: keeps `tol` (a float) unless the tensor is larger
+    tol_eff = float(torch.tensor(adaptive)) if not isinstance(adaptive, torch.Tensor) else float(adaptive)
+    atol_eff = max(float(torch.tensor(atol)), float(torch.tensor(base_atol)))
+    return tol_eff, atol_eff
+
+
+# --------------------------------------------------------------------------------------------------
+# the three solver cores (no autograd)
+# --------------------------------------------------------------------------------------------------
+def _solve_core(name: str, A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor], tol: float, atol: float,
+                maxiter: Optional[int], restart: int = 20, solve_method: str = 'batched',
+                transpose: bool = False) -> Tuple[torch.Tensor, int]:
+    """Run one solver on (A or A^T).  Returns (x, info) with x of the work dtype on b's device."""
+    global last_result
+    route = "native" if A.is_cuda else "host"
+    wdt = _work_dtype(A, b)
+    if name == "gmres":
+        if solve_method == 'incremental':
+            method = _native.BK_GMRES_INCREMENTAL
+        elif solve_method == 'batched':
+            method = _native.BK_GMRES_BATCHED
+        else:
+            raise ValueError(f"Unsupported solve_method: {solve_method}")
+    with torch.no_grad():
+        bw = b.detach().to(wdt)
+        x0w = None if x0 is None else x0.detach().to(wdt)
+        n = bw.numel()
+        if route == "native":
+            mat = _native.register_matrix(A, wdt)
+            if transpose:
+                mat = mat.transpose()
+            if name == "cg":
+                x, res = mat.cg(bw, x0w, tol, atol, maxiter)
+            elif name == "bicgstab":
+                x, res = mat.bicgstab(bw, x0w, tol, atol, maxiter)
+            else:
+                tol_eff, atol_eff = _gmres_effective_tolerances(tol, atol, n, 'cuda')
+                x, res = mat.gmres(bw, x0w, tol_eff, atol_eff, restart, maxiter, method)
+        else:
+            Ad = A.detach()
+            if transpose:
+                Ad = Ad.t()
+            if Ad.layout != torch.sparse_csr:
+                Ad = (Ad.coalesce() if Ad.layout == torch.sparse_coo else Ad).to_sparse_csr()
+            crow, col, val = Ad.crow_indices(), Ad.col_indices(), Ad.values().to(wdt)
+            if name == "gmres":
+                t, a = _gmres_effective_tolerances(tol, atol, n, 'cpu')
+                x, res = _native.solve_host(_native.METHOD_GMRES, crow, col, val, bw, x0w, t, a, maxiter, restart,
+                                            method)
+            else:
+                code = _native.METHOD_CG if name == "cg" else _native.METHOD_BICGSTAB
+                x, res = _native.solve_host(code, crow, col, val, bw, x0w, tol, atol, maxiter)
+    last_result = dict(res, solver=name, route=route)
+    return x.reshape(b.shape), int(res["info"])
+
+
+class _ImplicitAdjoint(torch.autograd.Function):
+    """Attach the implicit-differentiation backward to a precomputed solution (:1227-1248).
+
+    backward: grad_b = solve(A^T, grad_x) with the forward's x0 / tolerances (:1246); no gradient for
+    A (reference returns None, :1248).  A^T is the library's cached device transpose, so CSR inputs
+    work (the reference's `A.T` raises for CSR on torch 2.11).
+    """
+
+    @staticmethod
+    def forward(ctx, A, b, x, name, x0, tol, atol, restart, maxiter, solve_method):
+        ctx.A = A
+        ctx.meta = (name, x0, tol, atol, restart, maxiter, solve_method)
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        name, x0, tol, atol, restart, maxiter, solve_method = ctx.meta
+        grad_b = None
+        if ctx.needs_input_grad[1]:
+            g, _ = _solve_core(name, ctx.A, grad_output.contiguous(), x0, tol, atol, maxiter, restart, solve_method,
+                               transpose=True)
+            grad_b = g.to(grad_output.dtype)
+        return (None, grad_b) + (None,) * 8
+
+
+def _finish(name, A, b, x, info, x0, tol, atol, restart, maxiter, solve_method):
+    if _use_implicit_diff(A, b):
+        x = _ImplicitAdjoint.apply(A, b, x, name, x0, tol, atol, restart, maxiter, solve_method)
+    return x, info
+
+
+# --------------------------------------------------------------------------------------------------
+# public API
+# --------------------------------------------------------------------------------------------------
+def cg(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any] = None, *, tol: float = 1e-5,
+       atol: float = 0.0, maxiter: Optional[int] = None, M: Optional[Callable[[Any], Any]] = None
+       ) -> Tuple[Any, Optional[int]]:
+    """Conjugate gradient for hermitian positive definite A.  Same contract as reference cg (:1019-1088):
+    returns (x, info), x fp64 (fp32 when A and b are both fp32), info 0 if ||b - A x|| <= max(tol*||b||, atol)
+    else -1; gradients w.r.t. b by implicit differentiation with a second (transposed) solve."""
+    route = _route(A, b, x0, M)
+    if route == "generic":
+        from .generic import generic_cg
+        return generic_cg(A, b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M)
+    if x0 is not None:
+        _check_x0(b, x0)
+    x, info = _solve_core("cg", A, b, x0, tol, atol, maxiter)
+    return _finish("cg", A, b, x, info, x0, tol, atol, 20, maxiter, 'batched')
+
+
+def bicgstab(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any] = None, *, tol: float = 1e-5,
+             atol: float = 0.0, maxiter: Optional[int] = None, M: Optional[Callable[[Any], Any]] = None
+             ) -> Tuple[Any, Optional[int]]:
+    """Bi-conjugate gradient stabilised for general A.  Same contract as reference bicgstab (:1091-1158)."""
+    route = _route(A, b, x0, M)
+    if route == "generic":
+        from .generic import generic_bicgstab
+        return generic_bicgstab(A, b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M)
+    if x0 is not None:
+        _check_x0(b, x0)
+    x, info = _solve_core("bicgstab", A, b, x0, tol, atol, maxiter)
+    return _finish("bicgstab", A, b, x, info, x0, tol, atol, 20, maxiter, 'batched')
+
+
+def gmres(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any] = None, *, tol: float = 1e-5,
+          atol: float = 0.0, restart: int = 20, maxiter: Optional[int] = None,
+          M: Optional[Callable[[Any], Any]] = None, solve_method: str = 'batched') -> Tuple[Any, Optional[int]]:
+    """Restarted GMRES.  Same contract as reference gmres (:641-784): `maxiter` counts restart cycles,
+    solve_method 'batched' (default; always `restart` Arnoldi steps per cycle) or 'incremental' (Givens QR with
+    early exit inside a cycle); info 0 iff ||b - A x|| <= 10*atol_eff and x is finite."""
+    if solve_method not in ('batched', 'incremental'):
+        raise ValueError(f"Unsupported solve_method: {solve_method}")
+    route = _route(A, b, x0, M)
+    if route == "generic":
+        from .generic import generic_gmres
+        return generic_gmres(A, b, x0, tol=tol, atol=atol, restart=restart, maxiter=maxiter, M=M,
+                             solve_method=solve_method)
+    if x0 is not None:
+        _check_x0(b, x0)
+    if restart < 1:
+        raise ValueError("restart must be >= 1")
+    x, info = _solve_core("gmres", A, b, x0, tol, atol, maxiter, restart, solve_method)
+    return _finish("gmres", A, b, x, info, x0, tol, atol, restart, maxiter, solve_method)
+
+
+class LinearSolveFunction(torch.autograd.Function):
+    """Legacy differentiable wrapper with the reference's signature (:1161-1224):
+    forward(A_matrix, b, solve_fn, transpose_solve_fn, *solve_args) -> x ; backward gives only grad_b."""
+
+    @staticmethod
+    def forward(ctx, A_matrix, b, solve_fn, transpose_solve_fn, *solve_args):
+        x, _info = solve_fn(A_matrix, b, *solve_args)
+        ctx.A = A_matrix
+        ctx.transpose_solve_fn = transpose_solve_fn
+        ctx.solve_args = solve_args
+        return x
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad_b = None
+        if ctx.needs_input_grad[1]:
+            grad_b, _ = ctx.transpose_solve_fn(_Transposed(ctx.A), grad_output, *ctx.solve_args)
+        return (None, grad_b, None, None) + (None,) * len(ctx.solve_args)
+
+
+class _Transposed:
+    """Marker handed to a LinearSolveFunction transpose_solve_fn: "solve with A^T" without materialising A.T
+    (which raises for CSR tensors on torch 2.11)."""
+
+    def __init__(self, A):
+        self.A = A
+
+
+def _legacy(name, A, b, x0, tol, atol, maxiter, restart=20):
+    if not isinstance(A, torch.Tensor) or A.ndim != 2:
+        raise ValueError(f"For differentiable {name.upper() if name != 'bicgstab' else 'BiCGStab'}, "
+                         "A must be a 2D tensor")
+
+    def solve_fn(A_mat, rhs, x_init=None, tol_=1e-5, atol_=0.0, *rest):
+        transpose = isinstance(A_mat, _Transposed)
+        A_use = A_mat.A if transpose else A_mat
+        _route(A_use, rhs, x_init, None)
+        if name == "gmres":
+            restart_, maxiter_ = rest
+        else:
+            (maxiter_,) = rest
+            restart_ = 20
+        return _solve_core(name, A_use, rhs, x_init, tol_, atol_, maxiter_, restart_, 'batched', transpose=transpose)
+
+    args = (x0, tol, atol, restart, maxiter) if name == "gmres" else (x0, tol, atol, maxiter)
+    return LinearSolveFunction.apply(A, b, solve_fn, solve_fn, *args)
+
+
+def cg_differentiable(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None, *, tol: float = 1e-5,
+                      atol: float = 0.0, maxiter: Optional[int] = None) -> torch.Tensor:
+    """:1261-1296 — returns x only; gradient of b via an adjoint CG solve."""
+    return _legacy("cg", A, b, x0, tol, atol, maxiter)
+
+
+def bicgstab_differentiable(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None, *,
+                            tol: float = 1e-5, atol: float = 0.0, maxiter: Optional[int] = None) -> torch.Tensor:
+    """:1299-1330"""
+    return _legacy("bicgstab", A, b, x0, tol, atol, maxiter)
+
+
+def gmres_differentiable(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None, *, tol: float = 1e-5,
+                         atol: float = 0.0, restart: int = 20, maxiter: Optional[int] = None) -> torch.Tensor:
+    """:1333-1367"""
+    return _legacy("gmres", A, b, x0, tol, atol, maxiter, restart)

@@ -1,0 +1,34 @@
+"""Backend availability probes (reference utils/availability.py:13-178).  This build ships Module A only:
+module_b (AMGX) and module_c (cuDSS) are outside the hot-path scope and always report unavailable."""
+from functools import lru_cache
+from typing import Dict, List
+
+
+@lru_cache(maxsize=1)
+def check_module_a_available() -> bool:
+    try:
+        from .. import module_a  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def check_module_b_available() -> bool:
+    return False
+
+
+def check_module_c_available() -> bool:
+    return False
+
+
+def get_available_backends() -> Dict[str, bool]:
+    return {'module_a': check_module_a_available(), 'module_b': False, 'module_c': False}
+
+
+def get_available_backend_list() -> List[str]:
+    return [k for k, v in get_available_backends().items() if v]
+
+
+def print_availability_report() -> None:
+    for name, ok in get_available_backends().items():
+        print(f"  {name}: {'available' if ok else 'not available in this build'}")
