@@ -70,6 +70,8 @@ enum bk_loop_mode {
 typedef struct bk_result {
   int64_t iterations;    /* CG/BiCGStab: iterations done; GMRES: restart cycles done */
   int64_t matvecs;       /* SpMV launches that did work (excludes the final check) */
+  int64_t kernel_launches; /* kernels of this library enqueued by the call (graph nodes included; guarded
+                            no-op launches after convergence included) */
   int32_t info;          /* the reference's `info`: 0 = final TRUE residual within tolerance, -1 otherwise
                             (_isolve :1008-1016, gmres :766-773) */
   int32_t status;        /* enum bk_status */

@@ -246,7 +246,8 @@ static int bk_bicgstab_t(bk_handle* h, const bk_csr* A, const void* b, void* x_u
     for (int it = 0; it < chunk; ++it) BK_TRY(bk_bicg_enqueue_iter<T>(h, A, v, cs));
     return BK_OK;
   };
-  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk));
+  int64_t chunks = 0;
+  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
 
   {
     bk_spmv_args a = bk_spmv_base(A, st);
@@ -264,6 +265,7 @@ static int bk_bicgstab_t(bk_handle* h, const bk_csr* A, const void* b, void* x_u
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, 2 * fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->rs;
+  res->kernel_launches = chunks * chunk * 5 + 2 + (has_x0 ? 1 : 0) + 2;
   return BK_OK;
 }
 

@@ -230,7 +230,8 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
     for (int it = 0; it < chunk; ++it) BK_TRY(bk_cg_enqueue_iter<T>(h, A, v, it, fuse, cs));
     return BK_OK;
   };
-  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk));
+  int64_t chunks = 0;
+  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
 
   {  // final true residual  ||b - A x||  and  ||x||   (_isolve :1008-1013)
     bk_spmv_args a = bk_spmv_base(A, st);
@@ -248,6 +249,7 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->gamma;
+  res->kernel_launches = chunks * chunk * (fuse ? 2 : 3) + 2 /*state, b.b*/ + (has_x0 ? 1 : 0) + 2 /*final*/;
   return BK_OK;
 }
 

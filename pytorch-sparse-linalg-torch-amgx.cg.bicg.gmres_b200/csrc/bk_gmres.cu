@@ -509,7 +509,8 @@ static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user
   uint64_t key[6] = {3 /*gmres*/, A->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
                      (uint64_t)A->dtype | ((uint64_t)m << 8) | ((uint64_t)method << 24),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
-  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_cycle));
+  int64_t chunks = 0;
+  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_cycle, &chunks));
 
   // ---- final check (:766-773): the last residual pass already holds ||b - A x||; add ||x|| --------
   BK_TRY(dot_epi(x, x, bk_epi_gm_xx{st}, 1));
@@ -519,6 +520,7 @@ static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user
   const bk_dev_state* fin = &h->st_host[3];
   res->iterations = fin->k;
   res->matvecs = fin->matvecs;
+  res->kernel_launches = chunks * (4 * (int64_t)m + 4) + 5;
   res->status = fin->status;
   res->final_residual = sqrt(fmax(fin->rtrue2, 0.0));
   res->b_norm = fin->g_bnorm;

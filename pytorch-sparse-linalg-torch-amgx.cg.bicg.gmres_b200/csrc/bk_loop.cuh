@@ -70,7 +70,8 @@ static int bk_chunk_graph(bk_handle* h, const uint64_t key[6], F enqueue, cudaGr
 
 // Run chunks until the device reports done.  The poll of chunk i happens after chunk i+1 is enqueued.
 template <typename F>
-static int bk_run_loop(bk_handle* h, cudaStream_t s, bool use_graph, const uint64_t key[6], F enqueue_chunk) {
+static int bk_run_loop(bk_handle* h, cudaStream_t s, bool use_graph, const uint64_t key[6], F enqueue_chunk,
+                       int64_t* chunks_out = nullptr) {
   cudaGraphExec_t exec = nullptr;
   if (use_graph) {
     int rc = bk_chunk_graph(h, key, enqueue_chunk, &exec);
@@ -86,7 +87,9 @@ static int bk_run_loop(bk_handle* h, cudaStream_t s, bool use_graph, const uint6
   }
   int slot = 0, prev = 0;
   bool pending = false;
+  int64_t chunks = 0;
   for (;;) {
+    ++chunks;
     if (exec) {
       BK_CUDA(cudaGraphLaunch(exec, s));
     } else {
@@ -102,6 +105,7 @@ static int bk_run_loop(bk_handle* h, cudaStream_t s, bool use_graph, const uint6
     prev = slot;
     slot ^= 1;
   }
+  if (chunks_out) *chunks_out = chunks;
   return BK_OK;
 }
 

@@ -31,6 +31,7 @@ class bk_result(C.Structure):
     _fields_ = [
         ("iterations", C.c_int64),
         ("matvecs", C.c_int64),
+        ("kernel_launches", C.c_int64),
         ("info", C.c_int32),
         ("status", C.c_int32),
         ("final_residual", C.c_double),
@@ -164,6 +165,9 @@ class Handle:
 
     @classmethod
     def get(cls, device) -> "Handle":
+        load_library()
+        if not torch.cuda.is_available():
+            raise NativeLibraryError("a CUDA device is required: module_a has no CPU fallback in this build")
         idx = torch.device(device).index
         if idx is None:
             idx = torch.cuda.current_device()
@@ -183,6 +187,13 @@ class Handle:
         sms, l2, mem = C.c_int32(), C.c_int64(), C.c_int64()
         _check(self.lib.bk_device_info(self.ptr, C.byref(sms), C.byref(l2), C.byref(mem)), "bk_device_info")
         return {"num_sms": sms.value, "l2_bytes": l2.value, "mem_bytes": mem.value}
+
+
+class _DevPtr:
+    """Minimal __cuda_array_interface__ carrier for a borrowed device pointer."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
 class CsrMatrix:
@@ -247,14 +258,16 @@ class CsrMatrix:
         """Copy the (int32) CSR arrays of this matrix out as torch tensors (testing / debugging)."""
         rp, cp, vp = _VP(), _VP(), _VP()
         _check(self.handle.lib.bk_csr_arrays(self.ptr, C.byref(rp), C.byref(cp), C.byref(vp)), "bk_csr_arrays")
-        crow = torch.empty(self.n + 1, dtype=torch.int32, device=self.device)
-        col = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
-        val = torch.empty(self.nnz, dtype=self.dtype, device=self.device)
-        cudart = torch.cuda.cudart()
         torch.cuda.synchronize(self.device)
-        for dst, src in ((crow, rp), (col, cp), (val, vp)):
-            if dst.numel():
-                cudart.cudaMemcpy(dst.data_ptr(), src.value, dst.numel() * dst.element_size(), 3)
+
+        def view(ptr, count, typestr, dtype):
+            if count == 0:
+                return torch.empty(0, dtype=dtype, device=self.device)
+            return torch.as_tensor(_DevPtr(ptr.value, count, typestr), device=self.device).clone()
+
+        crow = view(rp, self.n + 1, "<i4", torch.int32)
+        col = view(cp, self.nnz, "<i4", torch.int32)
+        val = view(vp, self.nnz, "<f8" if self.dtype == torch.float64 else "<f4", self.dtype)
         return crow, col, val
 
     # ---- building blocks -------------------------------------------------------------------
@@ -415,6 +428,9 @@ def solve_host(method: int, crow: torch.Tensor, col: torch.Tensor, val: torch.Te
     for t in (crow, col, val, b):
         if t.is_cuda:
             raise ValueError("solve_host takes CPU tensors")
+    load_library()
+    if not torch.cuda.is_available():
+        raise NativeLibraryError("a CUDA device is required: module_a has no CPU fallback in this build")
     h = Handle.get(torch.device("cuda", torch.cuda.current_device() if device is None else device))
     crow, col, val, b = crow.contiguous(), col.contiguous(), val.contiguous(), b.contiguous()
     n = b.numel()

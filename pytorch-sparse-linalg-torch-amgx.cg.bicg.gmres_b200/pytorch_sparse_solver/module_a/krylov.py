@@ -266,7 +266,12 @@ class LinearSolveFunction(torch.autograd.Function):
     def backward(ctx, grad_output):
         grad_b = None
         if ctx.needs_input_grad[1]:
-            grad_b, _ = ctx.transpose_solve_fn(_Transposed(ctx.A), grad_output, *ctx.solve_args)
+            fn = ctx.transpose_solve_fn
+            if getattr(fn, "_bk_accepts_transposed", False):
+                A_T = _Transposed(ctx.A)          # library-cached device transpose, works for CSR
+            else:                                 # user-supplied solver: materialise A^T like the reference (:1215)
+                A_T = ctx.A.T.conj() if torch.is_complex(ctx.A) else ctx.A.T
+            grad_b, _ = fn(A_T, grad_output, *ctx.solve_args)
         return (None, grad_b, None, None) + (None,) * len(ctx.solve_args)
 
 
@@ -294,6 +299,7 @@ def _legacy(name, A, b, x0, tol, atol, maxiter, restart=20):
             restart_ = 20
         return _solve_core(name, A_use, rhs, x_init, tol_, atol_, maxiter_, restart_, 'batched', transpose=transpose)
 
+    solve_fn._bk_accepts_transposed = True
     args = (x0, tol, atol, restart, maxiter) if name == "gmres" else (x0, tol, atol, maxiter)
     return LinearSolveFunction.apply(A, b, solve_fn, solve_fn, *args)
 

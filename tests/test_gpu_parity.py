@@ -1,0 +1,413 @@
+"""GPU parity tests: the CUDA path (through the Python API -> ctypes -> C ABI -> sm_100a kernels) against the
+golden vectors of the unmodified reference and against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): solution relative difference <= 1e-10 in fp64, <= 1e-4 in fp32,
+iteration counts within +-2, same `info`.
+"""
+import json
+
+import pytest
+import torch
+
+from conftest import GOLD, build_matrix, load_case, rel_diff
+
+pytestmark = pytest.mark.gpu
+
+FP64_TOL = 1e-10
+FP32_TOL = 1e-4
+
+
+def _names(prefix):
+    with open(GOLD / "manifest.json") as f:
+        return sorted(k for k in json.load(f)["cases"] if k.startswith(prefix))
+
+
+def _rhs_for(name, entry, data, A_cpu):
+    if "b" in data:
+        return data["b"]
+    if "rand" in name:
+        from pytorch_sparse_solver import problems
+        return problems.manufactured_rhs(A_cpu, 0)[0]
+    return torch.ones(entry["n"], dtype=torch.float64)
+
+
+@pytest.fixture(scope="module")
+def ma():
+    from pytorch_sparse_solver import module_a
+    from pytorch_sparse_solver.module_a import krylov
+    krylov.GMRES_TOLERANCE_DEVICE = "cpu"  # goldens were produced by the reference on CPU tensors (:737-744)
+    yield module_a
+    krylov.GMRES_TOLERANCE_DEVICE = None
+
+
+def _last():
+    from pytorch_sparse_solver.module_a import krylov
+    return krylov.last_result
+
+
+# --------------------------------------------------------------------------------------------------
+# SpMV and the building blocks
+# --------------------------------------------------------------------------------------------------
+def _random_csr(n, mean, seed, dtype=torch.float64, empty_rows=False, long_row=False):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(0 if empty_rows else 1, 2 * mean + 1, (n,), generator=g)
+    if long_row:
+        lens[n // 3] = min(n, 3000)
+        lens[n - 1] = min(n, 777)
+    lens = torch.minimum(lens, torch.tensor(n))
+    crow = torch.zeros(n + 1, dtype=torch.int64)
+    crow[1:] = lens.cumsum(0)
+    cols = torch.cat([torch.randperm(n, generator=g)[: int(k)].sort().values for k in lens]) if n else torch.zeros(0)
+    vals = torch.randn(int(crow[-1]), dtype=dtype, generator=g)
+    return torch.sparse_csr_tensor(crow, cols.long(), vals, size=(n, n))
+
+
+SPMV_CASES = [
+    ("p3d12", lambda: build_matrix(dict(matrix="poisson3d", n=12))),
+    ("p2d_33x17", lambda: build_matrix(dict(matrix="poisson2d", nx=33, ny=17))),
+    ("cd3d9", lambda: build_matrix(dict(matrix="convdiff3d", n=9))),
+    ("rand_mean5_empty", lambda: _random_csr(1000, 5, 1, empty_rows=True)),
+    ("rand_mean20", lambda: _random_csr(700, 20, 2)),
+    ("rand_mean60", lambda: _random_csr(513, 60, 3)),
+    ("rand_mean200", lambda: _random_csr(600, 200, 4)),
+    ("rand_longrow", lambda: _random_csr(4000, 4, 5, long_row=True)),
+    ("dense_100", lambda: torch.randn(100, 100, dtype=torch.float64, generator=torch.Generator().manual_seed(6)).to_sparse_csr()),
+    ("one_by_one", lambda: torch.tensor([[3.0]], dtype=torch.float64).to_sparse_csr()),
+    ("n31_tail", lambda: _random_csr(31, 3, 7)),
+]
+
+
+@pytest.mark.parametrize("name,make", SPMV_CASES, ids=[c[0] for c in SPMV_CASES])
+@pytest.mark.parametrize("idx", [torch.int64, torch.int32])
+def test_spmv_matches_cpu(name, make, idx):
+    from pytorch_sparse_solver import _native
+    A = make()
+    n = A.shape[0]
+    x = torch.randn(n, dtype=torch.float64, generator=torch.Generator().manual_seed(11))
+    ref = torch.matmul(A, x)
+    Ad = torch.sparse_csr_tensor(A.crow_indices().to(idx).cuda(), A.col_indices().to(idx).cuda(), A.values().cuda(),
+                                 size=A.shape)
+    m = _native.register_matrix(Ad)
+    y = m.spmv(x.cuda())
+    scale = float(torch.matmul(torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), A.values().abs(),
+                                                       size=A.shape), x.abs()).max()) + 1e-300
+    assert float((y.cpu() - ref).abs().max()) <= 1e-14 * scale * max(1, m.info()["max_row_nnz"]) ** 0.5
+    # fused dot
+    w = torch.randn(n, dtype=torch.float64, generator=torch.Generator().manual_seed(12))
+    y2, d = m.spmv_dot(x.cuda(), w.cuda())
+    assert torch.equal(y2, y)
+    dref = float(torch.dot(w, ref))
+    assert abs(float(d) - dref) <= 1e-12 * float(w.abs() @ ref.abs() + 1e-300)
+
+
+def test_spmv_kernel_selection():
+    from pytorch_sparse_solver import _native
+    m = _native.register_matrix(build_matrix(dict(matrix="poisson3d", n=12), device="cuda"))
+    assert m.info()["kernel"] == 0 and m.info()["max_row_nnz"] == 7
+    m2 = _native.register_matrix(_random_csr(600, 200, 4).cuda())
+    assert m2.info()["kernel"] == 1
+
+
+def test_spmv_fp32():
+    from pytorch_sparse_solver import _native
+    A = build_matrix(dict(matrix="convdiff3d", n=10))
+    x = torch.randn(A.shape[0], dtype=torch.float64, generator=torch.Generator().manual_seed(3))
+    ref = torch.matmul(A, x)
+    m = _native.register_matrix(A.cuda(), torch.float32)
+    y = m.spmv(x.float().cuda())
+    assert y.dtype == torch.float32
+    assert rel_diff(y, ref) <= 1e-6
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 256, 1000, 65537, 1 << 20])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_dot_nrm2_axpby(n, dtype):
+    from pytorch_sparse_solver import _native
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, dtype=torch.float64, generator=g)
+    y = torch.randn(n, dtype=torch.float64, generator=g)
+    xd, yd = x.to(dtype).cuda(), y.to(dtype).cuda()
+    xr, yr = xd.cpu().double(), yd.cpu().double()
+    tol = 1e-13 if dtype == torch.float64 else 1e-6
+    assert abs(float(_native.dot(xd, yd)) - float(xr @ yr)) <= 1e-13 * float(xr.abs() @ yr.abs()) + 1e-300
+    assert abs(float(_native.nrm2(xd)) - float(torch.linalg.norm(xr))) <= 1e-13 * float(torch.linalg.norm(xr))
+    z = _native.axpby(1.5, xd, -0.25, yd)
+    assert rel_diff(z, 1.5 * xr - 0.25 * yr) <= tol
+    # misaligned views take the scalar path
+    if n > 3:
+        assert abs(float(_native.dot(xd[1:], yd[1:])) - float(xr[1:] @ yr[1:])) <= 1e-13 * float(xr.abs() @ yr.abs())
+
+
+def test_reductions_are_bitwise_reproducible():
+    from pytorch_sparse_solver import _native
+    x = torch.randn(3_000_001, dtype=torch.float64, device="cuda")
+    vals = {float(_native.dot(x, x)) for _ in range(5)}
+    assert len(vals) == 1
+
+
+# --------------------------------------------------------------------------------------------------
+# solvers vs the reference goldens
+# --------------------------------------------------------------------------------------------------
+def _solve_case(ma, name, manifest, idx=torch.int64, **override):
+    entry = manifest["cases"][name]
+    data = load_case(name)
+    A_cpu = build_matrix(entry["gen"])
+    b = _rhs_for(name, entry, data, A_cpu)
+    A = torch.sparse_csr_tensor(A_cpu.crow_indices().to(idx).cuda(), A_cpu.col_indices().to(idx).cuda(),
+                                A_cpu.values().cuda(), size=A_cpu.shape)
+    x0 = data["x0"].cuda() if "x0" in data else None
+    kw = dict(entry["kwargs"])
+    kw.update(override)
+    x, info = getattr(ma, entry["kind"])(A, b.cuda(), x0, **kw)
+    return entry, data, x, info
+
+
+def _check_against_golden(entry, data, x, info, tol=FP64_TOL):
+    res = _last()
+    assert x.dtype == torch.float64 and x.is_cuda
+    assert info == entry["info"]
+    assert abs(int(res["iterations"]) - entry["iterations"]) <= 2, (res["iterations"], entry["iterations"])
+    if "x" in data:
+        assert rel_diff(x, data["x"]) <= tol
+    else:
+        idx = data["x_sample_idx"]
+        assert rel_diff(x.cpu()[idx], data["x_sample"]) <= tol
+        assert abs(float(torch.linalg.norm(x)) - entry["x_norm"]) <= tol * entry["x_norm"]
+
+
+@pytest.mark.parametrize("name", _names("cg_"))
+def test_cg_golden(ma, manifest, name):
+    entry, data, x, info = _solve_case(ma, name, manifest)
+    _check_against_golden(entry, data, x, info)
+    if entry["kwargs"].get("tol", 1) == 0.0:  # fixed-iteration window: exact count
+        assert _last()["iterations"] == entry["iterations"]
+
+
+@pytest.mark.parametrize("name", _names("bicgstab_"))
+def test_bicgstab_golden(ma, manifest, name):
+    entry, data, x, info = _solve_case(ma, name, manifest)
+    _check_against_golden(entry, data, x, info)
+
+
+@pytest.mark.parametrize("name", _names("gmres_"))
+def test_gmres_golden(ma, manifest, name):
+    entry, data, x, info = _solve_case(ma, name, manifest)
+    # LDC systems are singular (all-Neumann): compare after removing the constant null-space component too
+    tol = FP64_TOL if "ldc" not in name else 5e-10
+    _check_against_golden(entry, data, x, info, tol=tol)
+    # restart cycles must agree exactly; matvec counts within the +-2 iteration band per cycle
+    assert _last()["iterations"] == entry["iterations"]
+
+
+@pytest.mark.parametrize("name", ["cg_p3d16_rand", "bicgstab_cd3d16_rand", "gmres_cd3d12_batched"])
+def test_int32_indices_and_stream_mode(ma, manifest, name):
+    from pytorch_sparse_solver import _native
+    h = _native.Handle.get(torch.device("cuda"))
+    entry, data, x64, info = _solve_case(ma, name, manifest)
+    try:
+        h.set_option("loop_mode", 1)  # plain stream launches instead of the CUDA graph
+        _native.clear_cache()
+        entry, data, x32, info2 = _solve_case(ma, name, manifest, idx=torch.int32)
+    finally:
+        h.set_option("loop_mode", 0)
+    assert info == info2
+    assert torch.equal(x64, x32), "graph and stream loops must give bitwise identical results"
+
+
+@pytest.mark.parametrize("name", ["cg_p3d16_rand", "bicgstab_cd3d16_rand", "gmres_ldc32_step1_batched"])
+def test_solvers_bitwise_deterministic(ma, manifest, name):
+    xs = [_solve_case(ma, name, manifest)[2] for _ in range(3)]
+    assert torch.equal(xs[0], xs[1]) and torch.equal(xs[0], xs[2])
+
+
+@pytest.mark.parametrize("opts", [dict(fuse_xpay=1), dict(snake=1), dict(fuse_xpay=1, snake=1), dict(chunk=2),
+                                  dict(grid_mult_spmv=2, grid_mult_vec=2)])
+def test_cg_kernel_variants(ma, manifest, opts):
+    from pytorch_sparse_solver import _native
+    h = _native.Handle.get(torch.device("cuda"))
+    saved = {k: h.get_option(k) for k in opts}
+    try:
+        for k, v in opts.items():
+            h.set_option(k, v)
+        for name in ("cg_p3d16_rand", "cg_p2d24x20_x0", "cg_p3d64_ones_digest", "cg_p3d16_fixed10"):
+            entry, data, x, info = _solve_case(ma, name, manifest)
+            _check_against_golden(entry, data, x, info)
+    finally:
+        for k, v in saved.items():
+            h.set_option(k, v)
+
+
+def test_dense_and_coo_inputs(ma, manifest):
+    """The reference's own tests feed dense matrices (test_module_a.py:93-124)."""
+    entry = manifest["cases"]["cg_tridiag100"]
+    data = load_case("cg_tridiag100")
+    A = build_matrix(entry["gen"]).to_dense()
+    for Ain in (A.cuda(), A.to_sparse_coo().cuda()):
+        x, info = ma.cg(Ain, data["b"].cuda(), tol=1e-10, maxiter=1000)
+        assert info == 0 and rel_diff(x, data["x"]) <= 1e-9  # ill-conditioned (kappa ~ 4e3): loose x gate
+
+
+def test_fp32_native_path(ma, manifest):
+    """fp32 A and b select the native fp32 kernels (the reference raises there); parity vs the fp64 golden <= 1e-4."""
+    entry = manifest["cases"]["cg_p3d16_rand"]
+    data = load_case("cg_p3d16_rand")
+    A = build_matrix(entry["gen"])
+    A32 = torch.sparse_csr_tensor(A.crow_indices().cuda(), A.col_indices().cuda(), A.values().float().cuda(),
+                                  size=A.shape)
+    x, info = ma.cg(A32, data["b"].float().cuda(), tol=1e-6)
+    assert x.dtype == torch.float32
+    assert rel_diff(x, data["x"]) <= FP32_TOL
+    entry = manifest["cases"]["bicgstab_cd3d16_rand"]
+    data = load_case("bicgstab_cd3d16_rand")
+    A = build_matrix(entry["gen"])
+    A32 = torch.sparse_csr_tensor(A.crow_indices().cuda(), A.col_indices().cuda(), A.values().float().cuda(),
+                                  size=A.shape)
+    x, info = ma.bicgstab(A32, data["b"].float().cuda(), tol=1e-6)
+    assert rel_diff(x, data["x"]) <= FP32_TOL
+    x, info = ma.gmres(A32, data["b"].float().cuda(), tol=1e-6, restart=30)
+    assert rel_diff(x, data["x"]) <= FP32_TOL
+
+
+def test_upcast_inputs(ma, manifest):
+    """fp32 b / x0 with an fp64 matrix are upcast and x comes back fp64 (reference :979-980)."""
+    entry = manifest["cases"]["cg_p2d32_ones"]
+    data = load_case("cg_p2d32_ones")
+    A = build_matrix(entry["gen"], device="cuda")
+    x, info = ma.cg(A, torch.ones(entry["n"], dtype=torch.float32, device="cuda"), tol=1e-8)
+    assert x.dtype == torch.float64 and info == 0
+    assert rel_diff(x, data["x"]) <= FP64_TOL
+
+
+def test_host_route_cpu_tensors(ma, manifest):
+    """CPU tensors go through bk_solve_host (H2D, CUDA solve, D2H) and return a CPU tensor."""
+    for name in ("cg_p3d16_rand", "bicgstab_cd3d16_rand", "gmres_cd3d12_incremental"):
+        entry = manifest["cases"][name]
+        data = load_case(name)
+        A = build_matrix(entry["gen"])
+        x, info = getattr(ma, entry["kind"])(A, data["b"], **entry["kwargs"])
+        assert not x.is_cuda and info == entry["info"]
+        assert rel_diff(x, data["x"]) <= FP64_TOL
+        assert _last()["route"] == "host"
+
+
+# --------------------------------------------------------------------------------------------------
+# transpose + autograd
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,make", SPMV_CASES, ids=[c[0] for c in SPMV_CASES])
+def test_transpose_matches_cpu(name, make):
+    from pytorch_sparse_solver import _native
+    A = make()
+    m = _native.register_matrix(A.cuda())
+    t = m.transpose()
+    crow, col, val = t.arrays()
+    At = A.to_dense().T.contiguous().to_sparse_csr() if A.shape[0] <= 1200 else None
+    x = torch.randn(A.shape[0], dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    ref = torch.matmul(A.to_dense().T, x) if A.shape[0] <= 4096 else None
+    y = t.spmv(x.cuda())
+    assert rel_diff(y, ref) <= 1e-13
+    # structure: sorted columns inside each row, same nnz, deterministic
+    assert int(crow[-1]) == A.values().numel()
+    crow2, col2, val2 = _native.register_matrix(A.clone().cuda()).transpose().arrays()
+    assert torch.equal(col, col2) and torch.equal(val, val2) and torch.equal(crow, crow2)
+    if At is not None and A.values().numel() == At.values().numel():
+        assert torch.equal(crow.cpu().long(), At.crow_indices())
+        assert torch.equal(col.cpu().long(), At.col_indices())
+        assert torch.equal(val.cpu(), At.values())
+
+
+@pytest.mark.parametrize("kind", ["cg", "bicgstab", "gmres"])
+@pytest.mark.parametrize("layout", ["csr", "dense", "coo"])
+def test_autograd_grad_b(ma, manifest, kind, layout):
+    entry = manifest["autograd"][f"autograd_{kind}"]
+    data = load_case(f"autograd_{kind}")
+    A = build_matrix(entry["gen"])
+    if layout == "dense":
+        Ad = A.to_dense().cuda()
+    elif layout == "coo":
+        Ad = A.to_sparse_coo().cuda()
+    else:
+        Ad = A.cuda()
+    b = data["b"].cuda().requires_grad_(True)
+    x, info = getattr(ma, kind)(Ad, b, **entry["kwargs"])
+    assert info == entry["info"]
+    (x ** 2).sum().backward()
+    assert b.grad is not None and torch.isfinite(b.grad).all()
+    assert rel_diff(b.grad, data["grad_b"]) <= 1e-9
+    assert rel_diff(x, data["x"]) <= FP64_TOL
+
+
+@pytest.mark.parametrize("kind", ["cg", "bicgstab", "gmres"])
+def test_legacy_differentiable(ma, manifest, kind):
+    entry = manifest["autograd"][f"autograd_{kind}"]
+    data = load_case(f"autograd_{kind}")
+    A = build_matrix(entry["gen"], device="cuda")
+    b = data["b"].cuda().requires_grad_(True)
+    x = getattr(ma, f"{kind}_differentiable")(A, b, **entry["kwargs"])
+    (x ** 2).sum().backward()
+    assert rel_diff(b.grad, data["grad_b"]) <= 1e-9
+
+
+# --------------------------------------------------------------------------------------------------
+# router
+# --------------------------------------------------------------------------------------------------
+def test_sparse_solver_module_a(manifest):
+    import pytorch_sparse_solver as pss
+    entry = manifest["cases"]["cg_p2d32_ones"]
+    data = load_case("cg_p2d32_ones")
+    A = build_matrix(entry["gen"], device="cuda")
+    b = torch.ones(entry["n"], dtype=torch.float64, device="cuda")
+    solver = pss.SparseSolver()
+    x, result = solver.solve(A, b, method="cg", backend="module_a", tol=1e-8)
+    assert result.converged and result.backend == "module_a" and result.method == "cg"
+    assert result.residual < 1e-7 and result.iterations == entry["iterations"]
+    assert rel_diff(x, data["x"]) <= FP64_TOL
+    x2, r2 = pss.solve(A, b, method="bicgstab", tol=1e-8)
+    assert r2.converged and rel_diff(x2, data["x"]) <= 1e-7
+    x3, r3 = pss.gmres(A, b, tol=1e-8, restart=30)
+    assert r3.converged
+    with pytest.raises(ValueError):
+        solver.solve(A, b, backend="module_b")
+    with pytest.raises(ValueError):
+        solver.solve(A, b, method="nope", backend="module_a")
+
+
+# --------------------------------------------------------------------------------------------------
+# full-size configs of BASELINE.json (digests measured with the reference at survey time)
+# --------------------------------------------------------------------------------------------------
+def test_cg_poisson3d_256_full_size(ma, manifest):
+    """Config 2: CG fp64, 7-point Poisson 256^3, b = ones, tol 1e-8 — reference: 611 iterations, info 0."""
+    from pytorch_sparse_solver import problems
+    dg = manifest["survey_digests"]["cg_p3d256_ones_tol1e-8"]
+    A = problems.poisson3d_csr(256, device="cuda")
+    b = torch.ones(A.shape[0], dtype=torch.float64, device="cuda")
+    x, info = ma.cg(A, b, tol=1e-8)
+    res = _last()
+    assert info == dg["info"]
+    assert abs(res["iterations"] - dg["iterations"]) <= 2
+    assert abs(float(torch.linalg.norm(x)) - dg["x_norm"]) <= 1e-9 * dg["x_norm"]
+    assert abs(float(x[0]) - dg["x_0"]) <= 1e-8 * abs(dg["x_0"])
+    assert abs(float(x[8388608]) - dg["x_8388608"]) <= 1e-8 * abs(dg["x_8388608"])
+    assert res["final_residual"] / res["b_norm"] <= 1e-8
+    # size-independent property: CG is linear in b for a fixed iteration window
+    x10, _ = ma.cg(A, b, tol=0.0, atol=0.0, maxiter=10)
+    dg10 = manifest["survey_digests"]["cg_p3d256_ones_maxiter10"]
+    assert abs(float(torch.linalg.norm(x10)) - dg10["x_norm"]) <= 1e-10 * dg10["x_norm"]
+    x10s, _ = ma.cg(A, 4.0 * b, tol=0.0, atol=0.0, maxiter=10)
+    assert rel_diff(x10s, 4.0 * x10) <= 1e-13
+
+
+def test_bicgstab_convdiff3d_256_full_size(ma, manifest):
+    """Config 3: BiCGStab fp64, upwind convection-diffusion 256^3, b = A randn(seed 0), tol 1e-8 — reference: 399 its."""
+    from pytorch_sparse_solver import problems
+    dg = manifest["survey_digests"]["bicgstab_cd3d256_rand_tol1e-8"]
+    A = problems.convdiff3d_csr(256, device="cuda")
+    b, xt = problems.manufactured_rhs(A, 0)
+    assert abs(float(torch.linalg.norm(b)) - dg["b_norm"]) <= 1e-12 * dg["b_norm"]
+    x, info = ma.bicgstab(A, b, tol=1e-8)
+    res = _last()
+    assert info == dg["info"]
+    # the reference's own self-noise at tol 1e-8 is a few iterations / 2e-10 in x
+    assert abs(res["iterations"] - dg["iterations"]) <= 8
+    assert abs(float(torch.linalg.norm(x)) - dg["x_norm"]) <= 1e-8 * dg["x_norm"]
+    assert res["final_residual"] / res["b_norm"] <= 1e-8
+    assert rel_diff(x, xt) <= 1e-5

@@ -1,0 +1,140 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header declares,
+argument validation mirrors the reference's exceptions, tolerance helpers mirror the reference's roundings,
+pytree helpers, problem generators.  No compute call is made (there is no GPU here)."""
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_header_symbol():
+    from pytorch_sparse_solver import _native
+    header = (ROOT / "include" / "bk_krylov.h").read_text()
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(bk_[a-z0-9_]+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 25
+    lib = _native.load_library()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/bk_krylov.h but not exported"
+    assert declared == set(_native._SIGNATURES), "ctypes signature table out of sync with the header"
+    assert lib.bk_version() == 100
+
+
+def test_library_result_struct_layout():
+    from pytorch_sparse_solver import _native
+    import ctypes
+    assert ctypes.sizeof(_native.bk_result) == 8 + 8 + 8 + 4 + 4 + 5 * 8
+    assert ctypes.sizeof(_native.bk_csr_info) == 8 + 8 + 4 * 4 + 8 + 8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_cuda():
+    from pytorch_sparse_solver import _native, module_a
+    A = torch.eye(4, dtype=torch.float64).to_sparse_csr()
+    b = torch.ones(4, dtype=torch.float64)
+    with pytest.raises(_native.NativeLibraryError):
+        module_a.cg(A, b)
+    with pytest.raises(_native.NativeLibraryError):
+        module_a.gmres(A, b)
+
+
+def test_argument_validation_matches_reference():
+    from pytorch_sparse_solver import module_a
+    b = torch.ones(4, dtype=torch.float64)
+    with pytest.raises(ValueError, match="square"):
+        module_a.cg(torch.ones(4, 3, dtype=torch.float64), b)
+    with pytest.raises(TypeError):
+        module_a.cg("not a matrix", b)
+    with pytest.raises(ValueError, match="matching shapes"):
+        module_a.bicgstab(torch.eye(4, dtype=torch.float64), b, torch.ones(3, dtype=torch.float64))
+    with pytest.raises(ValueError, match="Unsupported solve_method"):
+        module_a.gmres(torch.eye(4, dtype=torch.float64), b, solve_method="qr")
+    with pytest.raises(ValueError, match="2D tensor"):
+        module_a.cg_differentiable(lambda v: v, b)
+
+
+def test_gmres_tolerance_mirror():
+    """_gmres_effective_tolerances must reproduce the reference's atol_tensor / ptol (oracle copy of :733-753)."""
+    from oracle import krylov_oracle as orc
+    from pytorch_sparse_solver.module_a import krylov
+    import warnings
+    for dev in ("cpu", "cuda"):
+        for tol, atol, n, bn in ((1e-10, 0.0, 10_000, 7071.07), (1e-5, 1e-3, 100, 3.0), (1e-14, 0.0, 16_777_216, 4096.0),
+                                 (1e-8, 0.0, 1024, 0.0)):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                a_ref, p_ref = orc.gmres_tolerances(tol, atol, n, torch.tensor(bn, dtype=torch.float64), dev)
+            t_eff, a_eff = krylov._gmres_effective_tolerances(tol, atol, n, dev)
+            a = max(t_eff * bn, a_eff)
+            assert a == float(a_ref)
+            if bn > 0:
+                assert bn * min(1.0, a / bn) == float(p_ref)
+
+
+def test_fp32_tolerance_rounding_constants():
+    """bk_state_fill_tol reproduces torch.tensor(tol) (fp32) and torch.square on it (reference :816)."""
+    import numpy as np
+    t = np.float32(1e-8)
+    assert float(t) == float(torch.tensor(1e-8))
+    assert float(t * t) == float(torch.square(torch.tensor(1e-8)))
+
+
+def test_tree_utils():
+    from pytorch_sparse_solver.module_a import tree_flatten, tree_leaves, tree_map, tree_unflatten, Partial
+    from pytorch_sparse_solver.module_a.torch_tree_util import tree_reduce, tree_structure
+    t = {"b": [torch.ones(2), (torch.zeros(1), None)], "a": torch.full((3,), 2.0)}
+    leaves, td = tree_flatten(t)
+    assert [tuple(x.shape) for x in leaves] == [(3,), (2,), (1,)]
+    back = tree_unflatten(td, leaves)
+    assert isinstance(back["b"][1], tuple) and back["b"][1][1] is None
+    doubled = tree_map(lambda x: 2 * x, t)
+    assert float(doubled["a"][0]) == 4.0
+    summed = tree_map(lambda x, y: x + y, t, doubled)
+    assert float(summed["a"][0]) == 6.0
+    assert float(tree_reduce(lambda a, c: a + c.sum(), t, 0.0)) == 8.0
+    assert tree_structure(t) == tree_structure(doubled)
+    with pytest.raises(ValueError):
+        tree_map(lambda x, y: x, t, [1, 2])
+    assert Partial(lambda a, b, c=0: a + b + c, 1, c=3)(2) == 6
+    assert len(tree_leaves(None)) == 0
+
+
+def test_generators_match_reference_conventions():
+    import pytorch_sparse_solver as pss
+    from pytorch_sparse_solver import problems
+    A = problems.poisson2d_csr(7, 5)
+    B = pss.create_poisson_2d_sparse_coo(7, 5).to_sparse_csr()
+    assert torch.equal(A.crow_indices(), B.crow_indices()) and torch.equal(A.col_indices(), B.col_indices())
+    assert torch.equal(A.values(), B.values())
+    T = pss.create_tridiagonal_sparse_coo(6).to_dense()
+    assert torch.equal(T, 2 * torch.eye(6, dtype=torch.float64) - torch.diag(torch.ones(5, dtype=torch.float64), 1)
+                       - torch.diag(torch.ones(5, dtype=torch.float64), -1))
+    P = problems.poisson3d_csr(5)
+    D = P.to_dense()
+    assert torch.equal(D, D.T) and P.values().numel() == 7 * 125 - 6 * 25
+    C = problems.convdiff3d_csr(4).to_dense()
+    assert not torch.equal(C, C.T) and float(C.sum(1).min()) >= 0.0        # M-matrix row sums >= 0
+    L = problems.ldc_pressure_csr(6).to_dense()
+    assert torch.equal(L, L.T) and float(L.sum(1).abs().max()) == 0.0       # all-Neumann: singular
+    assert problems.cg_bytes_per_iteration(16_777_216, 117_047_296) == 2_948_071_428
+    assert problems.bicgstab_bytes_per_iteration(16_777_216, 117_047_296) == 5_493_489_672
+    slab = problems.stencil3d_csr(4, nz=2)
+    assert slab.shape[0] == 32
+
+
+def test_router_errors_and_availability():
+    import pytorch_sparse_solver as pss
+    assert pss.get_available_backends() == {"module_a": True, "module_b": False, "module_c": False}
+    s = pss.SparseSolver()
+    assert s.available_backends == ["module_a"]
+    A = torch.eye(3, dtype=torch.float64)
+    b = torch.ones(3, dtype=torch.float64)
+    with pytest.raises(ValueError, match="not available"):
+        s.solve(A, b, backend="module_c")
+    with pytest.raises(ValueError):
+        s.solve(A, b, method="direct")
+    with pytest.raises(ValueError):
+        pss.amg(A, b)
+    assert "module_a" in repr(s)
