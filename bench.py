@@ -253,9 +253,9 @@ def run_single(args):
                    "n": N, "nnz": nnz, "iterations_per_solve": last["iterations"], "info": last["info"],
                    "relres": last["final_residual"] / last["b_norm"],
                    "l2_policy": "inputs (2.9 GB/iteration) exceed L2; no flush needed",
-                   "options": {k: h.get_option(k) for k in ("grid_mult_spmv", "grid_mult_vec", "fuse_xpay", "snake",
-                                                            "loop_mode", "chunk")}},
-        "roofline": {"bound": "hbm", "kernel": "bk_spmv_stream_kernel (SpMV + p.Ap)", "achieved": achieved,
+                   "options": {k: h.get_option(k) for k in ("tma_ctas", "tma_stages", "grid_mult_spmv", "grid_mult_vec",
+                                                            "fuse_xpay", "snake", "loop_mode", "chunk")}},
+        "roofline": {"bound": "hbm", "kernel": "bk_spmv_tma_kernel (CSR SpMV fused with p.Ap)" if m.info()["kernel"] == 2 else "bk_spmv_stream_kernel (CSR SpMV fused with p.Ap)", "achieved": achieved,
                      "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "bytes_per_launch": bytes_k1, "ms_per_launch": k1_ms},
         "iteration": {"bytes_per_iteration": bytes_iter, "achieved_gbs": bytes_iter * value / 1e9,

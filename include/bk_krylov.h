@@ -85,7 +85,7 @@ typedef struct bk_result {
 typedef struct bk_csr_info {
   int64_t n, nnz;
   int32_t dtype;        /* enum bk_dtype */
-  int32_t kernel;       /* 0 = row-stream (warp per 32 rows, shared-memory staged), 1 = sub-warp vector */
+  int32_t kernel;       /* 0 = row-stream (LDG-staged), 1 = sub-warp vector, 2 = row-stream with TMA-staged tiles */
   int32_t lanes_per_row;/* for kernel 1 */
   int32_t max_row_nnz;
   double mean_row_nnz;

@@ -43,6 +43,9 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->mem_bytes = (int64_t)prop.totalGlobalMem;
   h->grid_mult_vec = (int)bk_env_int("BK_GRID_MULT_VEC", 3);
   h->grid_mult_spmv = (int)bk_env_int("BK_GRID_MULT_SPMV", 4);
+  h->tma_ctas = (int)bk_env_int("BK_TMA_CTAS", 4);
+  h->tma_stages = (int)bk_env_int("BK_TMA_STAGES", 0);
+  h->use_tma = (int)bk_env_int("BK_SPMV_TMA", 1);
   h->loop_mode = (int)bk_env_int("BK_LOOP_MODE", BK_LOOP_AUTO);
   h->chunk = (int)bk_env_int("BK_CHUNK", 0);
   h->fuse_xpay = (int)bk_env_int("BK_FUSE_XPAY", 0);
@@ -126,6 +129,9 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "grid_mult_vec")) return &h->grid_mult_vec;
   if (!strcmp(key, "grid_mult_spmv")) return &h->grid_mult_spmv;
   if (!strcmp(key, "grid_mult")) return &h->grid_mult_spmv;
+  if (!strcmp(key, "tma_ctas")) return &h->tma_ctas;
+  if (!strcmp(key, "tma_stages")) return &h->tma_stages;
+  if (!strcmp(key, "use_tma")) return &h->use_tma;
   if (!strcmp(key, "loop_mode")) return &h->loop_mode;
   if (!strcmp(key, "chunk")) return &h->chunk;
   if (!strcmp(key, "fuse_xpay")) return &h->fuse_xpay;
@@ -208,6 +214,62 @@ static void bk_csr_plan(bk_handle* h, bk_csr* A) {
   (void)h;
 }
 
+// widest 16-byte aligned val/col span of any 256-row block: max over blocks of ((e+3)&~3) - (s&~3)
+__global__ void bk_block_span_kernel(const int* __restrict__ rowptr, long long n, long long nblk, int rpb,
+                                     int* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  int mx = 0;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += stride) {
+    const long long r0 = b * rpb;
+    const long long r1 = (r0 + rpb < n) ? r0 + rpb : n;
+    const int s = rowptr[r0], e = rowptr[r1];
+    mx = max(mx, ((e + 3) & ~3) - (s & ~3));
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+
+// Decide whether the TMA row-stream kernel (bk_spmv_tma.cuh) can serve this matrix, size its pipeline and
+// build the 4-entry tail buffers.  Falls back silently to kernel 0 when a requirement is not met.
+static int bk_csr_plan_tma(bk_handle* h, bk_csr* A, cudaStream_t s) {
+  if (A->kernel != 0 || !h->use_tma || A->n == 0 || A->nnz == 0) return BK_OK;
+  if (!bk_aligned16(A->val) || !bk_aligned16(A->col)) return BK_OK;
+  const long long nblk = (A->n + 255) / 256;
+  int* dstat = (int*)(h->counters + 8);
+  int span = 0;
+  cudaMemsetAsync(dstat, 0, sizeof(int), s);
+  bk_block_span_kernel<<<h->num_sms * 4, 256, 0, s>>>(A->rowptr, A->n, nblk, 256, dstat);
+  cudaMemcpyAsync(&span, dstat, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return bk_fail(BK_ERR_CUDA, "csr registration (TMA plan): %s", cudaGetErrorString(e));
+  const int cap = (span + 31) & ~31;
+  const size_t entry = bk_dtype_size(A->dtype) + 4;
+  const size_t budget = 110 * 1024;  // per CTA with two CTAs per SM (the launch picks CTAs/SM and depth)
+  int stages = (int)(budget / ((size_t)cap * entry));
+  if (stages > 8) stages = 8;
+  if (cap <= 0 || stages < 2) return BK_OK;  // blocks too wide for shared memory: keep kernel 0
+  const int tail = (int)(A->nnz & 3);
+  if (tail) {
+    const size_t vs = bk_dtype_size(A->dtype);
+    if (cudaMalloc(&A->tail_val, 4 * vs) != cudaSuccess || cudaMalloc((void**)&A->tail_col, 16) != cudaSuccess) {
+      cudaGetLastError();
+      return bk_fail(BK_ERR_ALLOC, "csr registration: tail buffer allocation failed");
+    }
+    const int64_t base = A->nnz & ~(int64_t)3;
+    cudaMemsetAsync(A->tail_val, 0, 4 * vs, s);
+    cudaMemsetAsync(A->tail_col, 0, 16, s);
+    cudaMemcpyAsync(A->tail_val, (const char*)A->val + base * vs, tail * vs, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(A->tail_col, A->col + base, tail * sizeof(int), cudaMemcpyDeviceToDevice, s);
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return bk_fail(BK_ERR_CUDA, "csr registration (tail): %s", cudaGetErrorString(e));
+  }
+  A->tma_cap = cap;
+  A->tma_stages = stages;
+  A->kernel = 2;
+  return BK_OK;
+}
+
 // statistics + validation + kernel plan (one sync at registration time; never on the per-iteration path)
 int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s) {
   const int64_t n = A->n, nnz = A->nnz;
@@ -227,7 +289,7 @@ int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s) {
                    (long long)nnz, hstat[1]);
   A->max_row_nnz = hstat[0];
   bk_csr_plan(h, A);
-  return BK_OK;
+  return bk_csr_plan_tma(h, A, s);
 }
 
 extern "C" int bk_csr_create(bk_handle* h, int64_t n, int64_t nnz, const void* rowptr, const void* col,
@@ -307,6 +369,8 @@ extern "C" int bk_csr_destroy(bk_csr* A) {
   if (A->own_rowptr) cudaFree(A->own_rowptr);
   if (A->own_col) cudaFree(A->own_col);
   if (A->own_val) cudaFree(A->own_val);
+  if (A->tail_val) cudaFree(A->tail_val);
+  if (A->tail_col) cudaFree(A->tail_col);
   free(A);
   return BK_OK;
 }

@@ -94,9 +94,13 @@ struct bk_csr {
   void* own_rowptr;   // non-null when the library owns (converted / copied) arrays
   void* own_col;
   void* own_val;
-  int kernel;         // 0 row-stream, 1 sub-warp vector
+  int kernel;         // 0 row-stream (LDG staged), 1 sub-warp vector, 2 row-stream with TMA-staged matrix tiles
   int lanes_per_row;
   int cap;            // row-stream: shared-memory products per warp
+  int tma_cap;        // TMA row-stream: entries per pipeline stage (multiple of 4)
+  int tma_stages;     // TMA row-stream: pipeline depth
+  void* tail_val;     // TMA row-stream: the last nnz%4 entries, zero-padded to 4 (own)
+  int* tail_col;
   int max_row_nnz;
   double mean_row_nnz;
   bk_csr* transpose;  // cached, owned
@@ -120,6 +124,9 @@ struct bk_handle {
   // options
   int grid_mult_vec;   // CTAs/SM of elementwise kernels
   int grid_mult_spmv;  // CTAs/SM of SpMV kernels
+  int tma_ctas;        // CTAs/SM of the TMA row-stream SpMV (2..4)
+  int tma_stages;      // 0 = fill shared memory, else cap on the pipeline depth
+  int use_tma;         // allow the TMA row-stream kernel
   int loop_mode;
   int chunk;
   int fuse_xpay;
@@ -240,10 +247,10 @@ __device__ __forceinline__ void bk_st(T* __restrict__ p, const bk_vec<T, W>& r) 
   }
 }
 
-// Block-level sum of R values; result valid in thread 0.  Fixed shuffle tree => the
-// summation order depends only on (blockDim, R), never on scheduling.
-template <int R>
-__device__ __forceinline__ void bk_block_reduce(double (&v)[R], double* sh /* R*BK_WARPS */) {
+// Block-level sum of R values over NW warps; result valid in thread 0.  Fixed shuffle tree => the
+// summation order depends only on (NW, R), never on scheduling.
+template <int R, int NW = BK_WARPS>
+__device__ __forceinline__ void bk_block_reduce(double (&v)[R], double* sh /* R*NW */) {
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
 #pragma unroll
@@ -253,15 +260,16 @@ __device__ __forceinline__ void bk_block_reduce(double (&v)[R], double* sh /* R*
   }
   if (lane == 0) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) sh[r * BK_WARPS + wid] = v[r];
+    for (int r = 0; r < R; ++r) sh[r * NW + wid] = v[r];
   }
   __syncthreads();
   if (wid == 0) {
+    constexpr int TOP = NW <= 2 ? 1 : (NW <= 4 ? 2 : (NW <= 8 ? 4 : (NW <= 16 ? 8 : 16)));
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      double t = (lane < BK_WARPS) ? sh[r * BK_WARPS + lane] : 0.0;
+      double t = (lane < NW) ? sh[r * NW + lane] : 0.0;
 #pragma unroll
-      for (int o = BK_WARPS / 2; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      for (int o = TOP; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
       v[r] = t;
     }
   }
@@ -272,11 +280,11 @@ __device__ __forceinline__ void bk_block_reduce(double (&v)[R], double* sh /* R*
 // that draws the last ticket adds the partials in index order with the same fixed tree and
 // runs `epi(sums)` on its thread 0 (this is where alpha/beta/stop flags are computed, so no
 // scalar kernels and no host round trip exist).  Bitwise reproducible for a fixed grid size.
-template <int R, typename Epi>
+template <int R, typename Epi, int NW = BK_WARPS>
 __device__ __forceinline__ void bk_grid_reduce(double (&v)[R], const bk_scratch sc, Epi epi) {
-  __shared__ double sh[R * BK_WARPS];
+  __shared__ double sh[R * NW];
   __shared__ int s_last;
-  bk_block_reduce<R>(v, sh);
+  bk_block_reduce<R, NW>(v, sh);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int r = 0; r < R; ++r) __stcg(&sc.partials[(size_t)r * sc.stride + blockIdx.x], v[r]);
@@ -291,11 +299,11 @@ __device__ __forceinline__ void bk_grid_reduce(double (&v)[R], const bk_scratch 
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       double a = 0.0;
-      for (int i = threadIdx.x; i < (int)gridDim.x; i += BK_BLOCK)
+      for (int i = threadIdx.x; i < (int)gridDim.x; i += NW * 32)
         a += __ldcg(&sc.partials[(size_t)r * sc.stride + i]);
       acc[r] = a;
     }
-    bk_block_reduce<R>(acc, sh);
+    bk_block_reduce<R, NW>(acc, sh);
     if (threadIdx.x == 0) epi(acc);
   }
 }

@@ -223,9 +223,33 @@ bk_spmv_vector_kernel(const bk_spmv_args a, const bk_scratch sc, Epi epi) {
   }
 }
 
+#include "bk_spmv_tma.cuh"
+
 struct bk_epi_none {
   __device__ __forceinline__ void operator()(const double*) const {}
 };
+
+// Opt a kernel in to > 48 KB of dynamic shared memory once per (kernel, size) — keyed by the kernel's address
+// (all instantiations share one function-pointer TYPE, so a per-type static would be wrong).
+static inline int bk_ensure_dyn_smem(const void* func, size_t bytes) {
+  static const void* funcs[64];
+  static size_t sizes[64];
+  static int count = 0;
+  for (int i = 0; i < count; ++i)
+    if (funcs[i] == func) {
+      if (sizes[i] >= bytes) return BK_OK;
+      BK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      sizes[i] = bytes;
+      return BK_OK;
+    }
+  BK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (count < 64) {
+    funcs[count] = func;
+    sizes[count] = bytes;
+    ++count;
+  }
+  return BK_OK;
+}
 
 template <typename K>
 static inline int bk_set_smem(K kernel, size_t bytes) {
@@ -239,7 +263,41 @@ template <typename T, int MODE, int DOTS, int XMODE, typename Epi>
 static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a, const bk_scratch& sc,
                             Epi epi, cudaStream_t s) {
   const int grid = bk_grid_spmv(h);
-  if (A->kernel == 0) {
+  if (A->kernel == 2 && XMODE == 0) {
+    if constexpr (XMODE == 0) {
+      // CTAs per SM (2..4) trade pipeline depth for consumer warps; stages fill the per-CTA share of shared memory
+      int ctas = h->tma_ctas < 2 ? 2 : (h->tma_ctas > 4 ? 4 : h->tma_ctas);
+      const size_t stage_bytes = (size_t)A->tma_cap * (sizeof(T) + 4);
+      int stages = 0;
+      for (; ctas >= 2; --ctas) {
+        stages = (int)(((size_t)224 * 1024 / ctas - 2048) / stage_bytes);
+        if (stages >= 2) break;
+      }
+      if (stages > BK_TMA_MAX_STAGES) stages = BK_TMA_MAX_STAGES;
+      if (h->tma_stages >= 2 && h->tma_stages < stages) stages = h->tma_stages;
+      const size_t sm = (size_t)stages * stage_bytes;
+      bk_tma_plan plan;
+      plan.cap = A->tma_cap;
+      plan.stages = stages;
+      plan.nnz_al = (int)(A->nnz & ~(int64_t)3);
+      plan.tail_val = A->tail_val;
+      plan.tail_col = A->tail_col;
+      int g = h->num_sms * ctas;
+      if (g > BK_MAXB) g = BK_MAXB;
+      auto launch = [&](auto k) -> int {
+        BK_TRY(bk_ensure_dyn_smem((const void*)k, sm));
+        k<<<g, BK_TMA_THREADS, sm, s>>>(a, plan, sc, epi);
+        return BK_OK;
+      };
+      if (ctas == 2) {
+        BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 2, Epi>));
+      } else if (ctas == 3) {
+        BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 3, Epi>));
+      } else {
+        BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 4, Epi>));
+      }
+    }
+  } else if (A->kernel == 0 || A->kernel == 2) {
     if (A->cap <= 256) {
       auto k = bk_spmv_stream_kernel<T, 256, MODE, DOTS, XMODE, Epi>;
       const size_t sm = (size_t)BK_WARPS * 256 * sizeof(T);

@@ -103,9 +103,38 @@ def test_spmv_matches_cpu(name, make, idx):
 def test_spmv_kernel_selection():
     from pytorch_sparse_solver import _native
     m = _native.register_matrix(build_matrix(dict(matrix="poisson3d", n=12), device="cuda"))
-    assert m.info()["kernel"] == 0 and m.info()["max_row_nnz"] == 7
+    assert m.info()["kernel"] in (0, 2) and m.info()["max_row_nnz"] == 7
     m2 = _native.register_matrix(_random_csr(600, 200, 4).cuda())
     assert m2.info()["kernel"] == 1
+
+
+@pytest.mark.parametrize("name,make", SPMV_CASES[:5] + SPMV_CASES[7:8], ids=[c[0] for c in SPMV_CASES[:5] + SPMV_CASES[7:8]])
+def test_spmv_tma_and_ldg_row_stream_agree(name, make):
+    """The TMA-staged row-stream kernel (kernel 2) against the LDG-staged one (kernel 0) on the same matrix."""
+    from pytorch_sparse_solver import _native
+    h = _native.Handle.get(torch.device("cuda"))
+    A = make().cuda()
+    x = torch.randn(A.shape[0], dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    try:
+        h.set_option("use_tma", 0)
+        _native.clear_cache()
+        m0 = _native.register_matrix(A)
+        y0 = m0.spmv(x)
+        k0 = m0.info()["kernel"]
+        h.set_option("use_tma", 1)
+        _native.clear_cache()
+        m1 = _native.register_matrix(A)
+        y1, d1 = m1.spmv_dot(x, x)
+        k1 = m1.info()["kernel"]
+    finally:
+        h.set_option("use_tma", 1)
+        _native.clear_cache()
+    assert k0 in (0, 1)
+    if k0 == 0 and name != "rand_mean20":
+        assert k1 == 2, "short-row matrices should take the TMA row-stream kernel"
+    scale = float(y0.abs().max()) + 1e-300
+    assert float((y0 - y1).abs().max()) <= 1e-13 * scale
+    assert abs(float(d1) - float(torch.dot(x, y0))) <= 1e-11 * float(x.abs() @ y0.abs() + 1e-300)
 
 
 def test_spmv_fp32():

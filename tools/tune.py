@@ -80,7 +80,14 @@ def main():
         emit(what="bk_axpby", grid_mult_vec=gm, gbs=3 * N * 8 / ms / 1e6, ms=ms)
     h.set_option("grid_mult_vec", 3)
 
-    for gm in (2, 3, 4, 6, 8):
+    for ctas, st in ((2, 0), (2, 2), (2, 3), (3, 0), (3, 2), (4, 0)):
+        h.set_option("tma_ctas", ctas)
+        h.set_option("tma_stages", st)
+        ms = time_gpu(lambda: m.spmv_dot(x, x), reps=10)
+        emit(what="bk_spmv_dot_tma", kernel=m.info()["kernel"], tma_ctas=ctas, tma_stages=st, gbs=bytes_spmv / ms / 1e6, ms=ms)
+    h.set_option("tma_ctas", 4)
+    h.set_option("tma_stages", 0)
+    for gm in (() if m.info()["kernel"] == 2 else (2, 3, 4, 6, 8)):
         h.set_option("grid_mult_spmv", gm)
         ms = time_gpu(lambda: m.spmv(x, out=y), reps=10)
         emit(what="bk_spmv", grid_mult_spmv=gm, gbs=bytes_spmv / ms / 1e6, ms=ms)
@@ -94,12 +101,11 @@ def main():
     def cg_window():
         return m.cg(b, None, 0.0, 0.0, W)
 
-    combos = [dict(), dict(fuse_xpay=1), dict(snake=1), dict(fuse_xpay=1, snake=1), dict(loop_mode=1),
-              dict(grid_mult_vec=2), dict(grid_mult_vec=4), dict(grid_mult_spmv=6), dict(grid_mult_spmv=3),
-              dict(grid_mult_spmv=6, fuse_xpay=1), dict(chunk=16)]
+    combos = [dict(), dict(snake=1), dict(loop_mode=1), dict(grid_mult_vec=2), dict(grid_mult_vec=4),
+              dict(tma_ctas=3), dict(tma_ctas=3, snake=1), dict(chunk=16), dict(fuse_xpay=1)]
     if args.quick:
-        combos = combos[:4]
-    defaults = {k: h.get_option(k) for k in ("fuse_xpay", "snake", "loop_mode", "grid_mult_vec", "grid_mult_spmv", "chunk")}
+        combos = combos[:6]
+    defaults = {k: h.get_option(k) for k in ("fuse_xpay", "snake", "loop_mode", "grid_mult_vec", "grid_mult_spmv", "tma_ctas", "tma_stages", "chunk")}
     for c in combos:
         try:
             for k, v in defaults.items():
