@@ -290,6 +290,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--dist-window", type=int, default=200, help="N>1: CG iterations per timed step")
     ap.add_argument("--ref-window", type=int, default=10, help="--impl reference: CG iterations per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

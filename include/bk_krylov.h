@@ -170,20 +170,31 @@ int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, const void* 
                   bk_result* result);
 
 /* ---- multi-GPU (one process per GPU; 1-D row partition) ------------------
- * The caller (Python, torch.distributed) owns rendezvous: rank 0 calls bk_dist_unique_id and
- * broadcasts the 128 bytes; every rank then calls bk_dist_create with its LOCAL rows
- * [row_begin, row_end) of the global matrix in CSR with GLOBAL column indices (device arrays).
- * The library splits them into a local block + a ghost block, builds send lists, exchanges
- * boundary entries of the SpMV input with ncclSend/ncclRecv on a side stream overlapped with
- * the interior SpMV, and all-reduces the scalar dots with ncclAllReduce. */
+ * No reference counterpart (the reference is single-device).  The caller (Python, torch.distributed) owns
+ * rendezvous and the set-up index work: rank 0 calls bk_dist_unique_id and broadcasts the 128 bytes; every rank
+ * splits its rows into a LOCAL block (columns inside its slab, renumbered from 0) and a GHOST block (columns owned
+ * by peers, renumbered into a compact ghost vector ordered by owner rank) and passes both here, all index arrays
+ * int32 on the device:
+ *   local block : CSR n_local x n_local                      (loc_rowptr, loc_col, loc_val)
+ *   ghost block : CSR over the n_brows boundary rows         (brow_ids = their local row ids, gh_rowptr[n_brows+1],
+ *                                                             gh_col = index into the ghost vector, gh_val)
+ *   halo plan   : peer_ranks/send_counts/recv_counts (HOST arrays, npeers entries; receives land in the ghost
+ *                 vector in peer order), send_idx (DEVICE int32: local indices to send, concatenated per peer).
+ * Run time: boundary entries are packed, exchanged with ncclSend/ncclRecv on a side stream overlapped with the
+ * local-block SpMV, the ghost rows are added afterwards; the scalar dots go through ncclAllReduce. */
 int bk_dist_unique_id(void* id128);
-int bk_dist_create(bk_handle* h, const void* id128, int rank, int nranks, int64_t n_global,
-                   int64_t row_begin, int64_t row_end, int64_t nnz_local, const void* rowptr,
-                   const void* col, int idx_bits, const void* val, int dtype, void* stream, bk_dist** out);
+int bk_dist_create(bk_handle* h, const void* id128, int rank, int nranks, int64_t n_local, int64_t nnz_loc,
+                   const void* loc_rowptr, const void* loc_col, const void* loc_val, int64_t n_brows,
+                   const void* brow_ids, int64_t nnz_gh, const void* gh_rowptr, const void* gh_col,
+                   const void* gh_val, int64_t n_ghost, int npeers, const int32_t* peer_ranks,
+                   const int64_t* send_counts, const int64_t* recv_counts, const void* send_idx, int dtype,
+                   void* stream, bk_dist** out);
 int bk_dist_destroy(bk_dist* D);
+/* y_local = (A x)_local */
 int bk_dist_spmv(bk_handle* h, bk_dist* D, const void* x_local, void* y_local, void* stream);
+/* distributed CG (same recurrences / stop test / info as bk_cg; n_global sets the default maxiter = 10 n) */
 int bk_dist_cg(bk_handle* h, bk_dist* D, const void* b_local, void* x_local, int has_x0, double tol,
-               double atol, int64_t maxiter, bk_result* result, void* stream);
+               double atol, int64_t maxiter, int64_t n_global, bk_result* result, void* stream);
 
 #ifdef __cplusplus
 }

@@ -160,6 +160,7 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
     op.r = v.r;
     op.st = st;
     op.snake = h->snake;
+    op.dist_out = nullptr;
     BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
   }
   if (!fuse) {

@@ -158,6 +158,7 @@ struct bk_op_cg_update {
   T* r;
   bk_dev_state* st;
   int snake;
+  double* dist_out;  // multi-GPU: park the LOCAL r.r here (all-reduced next) instead of finishing the iteration
   __device__ bool skip() const { return st->done != 0; }
   __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
   __device__ Ctx prepare() const {
@@ -185,6 +186,10 @@ struct bk_op_cg_update {
     bk_st<T, W>(r + i, ro);
   }
   __device__ void epilogue(const double* s) const {
+    if (dist_out) {
+      dist_out[0] = s[0];
+      return;
+    }
     const double gamma_new = s[0];
     st->beta = gamma_new / st->gamma;
     st->gamma = gamma_new;

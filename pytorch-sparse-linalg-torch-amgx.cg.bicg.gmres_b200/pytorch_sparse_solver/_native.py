@@ -87,12 +87,13 @@ _SIGNATURES = {
     "bk_solve_host": (C.c_int, [_VP, C.c_int, C.c_int64, C.c_int64, _VP, _VP, C.c_int, _VP, C.c_int, _VP, _VP,
                                 C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int, C.c_int, C.POINTER(bk_result)]),
     "bk_dist_unique_id": (C.c_int, [_VP]),
-    "bk_dist_create": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _VP, _VP,
-                                 C.c_int, _VP, C.c_int, _VP, C.POINTER(_VP)]),
+    "bk_dist_create": (C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int64, C.c_int64, _VP, _VP, _VP, C.c_int64, _VP,
+                                 C.c_int64, _VP, _VP, _VP, C.c_int64, C.c_int, _VP, _VP, _VP, _VP, C.c_int, _VP,
+                                 C.POINTER(_VP)]),
     "bk_dist_destroy": (C.c_int, [_VP]),
     "bk_dist_spmv": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
-    "bk_dist_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(bk_result),
-                             _VP]),
+    "bk_dist_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64,
+                             C.POINTER(bk_result), _VP]),
 }
 
 _lib = None

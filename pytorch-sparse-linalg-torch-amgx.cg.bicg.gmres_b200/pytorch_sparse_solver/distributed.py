@@ -1,0 +1,263 @@
+"""Row-partitioned (multi-GPU) Module A: set-up logic + binding of the bk_dist_* C entries.
+
+One process per GPU (torchrun); `torch.distributed` is used for rendezvous and for the set-up exchange of index
+lists only — the per-iteration halo exchange and scalar all-reduces are issued by the C library on NCCL.
+
+Set-up (device-agnostic torch index arithmetic, exercised on CPU by tests/test_dist_gloo.py with world_size 2):
+  partition_rows      contiguous 1-D row partition
+  split_local_ghost   local rows (CSR, global columns) -> LOCAL block (own columns, renumbered) + GHOST block
+                      (CSR over the boundary rows, columns renumbered into a compact ghost vector ordered by owner)
+  build_halo_plan     who sends which of its entries to whom (the ParCSR / VecScatter pattern)
+The reference has no distributed code at all; nothing here mirrors a reference file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native
+
+
+def partition_rows(n_global: int, world: int) -> List[int]:
+    """Row offsets [o_0=0, ..., o_world=n_global] of a contiguous, balanced 1-D partition."""
+    return [(n_global * r) // world for r in range(world + 1)]
+
+
+@dataclass
+class LocalSplit:
+    n_local: int
+    loc_rowptr: torch.Tensor   # int32 [n_local+1]
+    loc_col: torch.Tensor      # int32, local column ids
+    loc_val: torch.Tensor
+    brow_ids: torch.Tensor     # int32 [n_brows] local row ids that own ghost entries (ascending)
+    gh_rowptr: torch.Tensor    # int32 [n_brows+1]
+    gh_col: torch.Tensor       # int32, index into the ghost vector
+    gh_val: torch.Tensor
+    ghost_ids: torch.Tensor    # int64 [n_ghost] global ids of the ghost vector entries (ascending => grouped by owner)
+
+
+def split_local_ghost(crow: torch.Tensor, col: torch.Tensor, val: torch.Tensor, row_begin: int,
+                      row_end: int) -> LocalSplit:
+    n_local = row_end - row_begin
+    dev = col.device
+    crow = crow.to(torch.int64)
+    col = col.to(torch.int64)
+    lens = crow[1:] - crow[:-1]
+    row_of = torch.repeat_interleave(torch.arange(n_local, device=dev), lens)
+    is_loc = (col >= row_begin) & (col < row_end)
+    # local block
+    loc_counts = torch.zeros(n_local, dtype=torch.int64, device=dev)
+    loc_counts.index_add_(0, row_of, is_loc.to(torch.int64))
+    loc_rowptr = torch.zeros(n_local + 1, dtype=torch.int64, device=dev)
+    loc_rowptr[1:] = loc_counts.cumsum(0)
+    loc_col = (col[is_loc] - row_begin).to(torch.int32)
+    loc_val = val[is_loc].contiguous()
+    # ghost block
+    gmask = ~is_loc
+    gcols = col[gmask]
+    ghost_ids = torch.unique(gcols)  # sorted ascending
+    gh_col = torch.searchsorted(ghost_ids, gcols).to(torch.int32)
+    gh_val = val[gmask].contiguous()
+    gh_rows = row_of[gmask]
+    if gh_rows.numel():
+        brow_ids, counts = torch.unique_consecutive(gh_rows, return_counts=True)
+    else:
+        brow_ids = torch.zeros(0, dtype=torch.int64, device=dev)
+        counts = torch.zeros(0, dtype=torch.int64, device=dev)
+    gh_rowptr = torch.zeros(brow_ids.numel() + 1, dtype=torch.int64, device=dev)
+    gh_rowptr[1:] = counts.cumsum(0)
+    return LocalSplit(n_local, loc_rowptr.to(torch.int32), loc_col, loc_val, brow_ids.to(torch.int32),
+                      gh_rowptr.to(torch.int32), gh_col, gh_val, ghost_ids)
+
+
+@dataclass
+class HaloPlan:
+    peers: List[int]             # ranks exchanged with, ascending
+    send_counts: List[int]       # entries sent to each peer
+    recv_counts: List[int]       # entries received from each peer (ghost vector is the concatenation, in peer order)
+    send_idx: torch.Tensor       # int32: local indices to send, concatenated per peer
+
+
+def build_halo_plan(ghost_ids: torch.Tensor, offsets: Sequence[int], rank: int, world: int, group=None) -> HaloPlan:
+    """Exchange 'which of your entries I need' with every rank (torch.distributed all_gather_object; set-up only)."""
+    import torch.distributed as dist
+    off = torch.tensor(list(offsets[1:]), dtype=torch.int64)
+    gids = ghost_ids.cpu()
+    owner = torch.bucketize(gids, off, right=True)
+    needs = {}
+    for o in torch.unique(owner).tolist():
+        needs[int(o)] = gids[owner == o]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, needs, group=group)
+    else:
+        gathered = [needs]
+    peers = sorted(set(needs.keys()) | {q for q in range(world) if q != rank and rank in gathered[q]})
+    send_counts, recv_counts, send_lists = [], [], []
+    for q in peers:
+        req = gathered[q].get(rank) if q != rank else None
+        if req is None:
+            req = torch.zeros(0, dtype=torch.int64)
+        send_lists.append((req - offsets[rank]).to(torch.int32))
+        send_counts.append(int(req.numel()))
+        recv_counts.append(int(needs[q].numel()) if q in needs else 0)
+    send_idx = torch.cat(send_lists) if send_lists else torch.zeros(0, dtype=torch.int32)
+    return HaloPlan(peers, send_counts, recv_counts, send_idx)
+
+
+class DistMatrix:
+    """A row-partitioned matrix registered with the library on this rank's GPU."""
+
+    def __init__(self, crow: torch.Tensor, col: torch.Tensor, val: torch.Tensor, offsets: Sequence[int], rank: int,
+                 world: int, group=None):
+        import torch.distributed as dist
+        if not val.is_cuda:
+            raise _native.NativeLibraryError("DistMatrix needs CUDA tensors (one GPU per rank)")
+        self.rank, self.world = rank, world
+        self.offsets = list(offsets)
+        self.n_global = int(offsets[-1])
+        self.device = val.device
+        self.dtype = val.dtype
+        sp = split_local_ghost(crow, col, val, offsets[rank], offsets[rank + 1])
+        plan = build_halo_plan(sp.ghost_ids, offsets, rank, world, group)
+        self.split, self.plan = sp, plan
+        self.handle = _native.Handle.get(self.device)
+        lib = self.handle.lib
+        # NCCL unique id: rank 0 creates, everybody receives
+        idbuf = (C.c_char * 128)()
+        if rank == 0:
+            _native._check(lib.bk_dist_unique_id(idbuf), "bk_dist_unique_id")
+        if world > 1:
+            box = [bytes(idbuf.raw)]
+            dist.broadcast_object_list(box, src=0, group=group)
+            idbuf = (C.c_char * 128).from_buffer_copy(box[0])
+        npeers = len(plan.peers)
+        peers = (C.c_int32 * max(npeers, 1))(*plan.peers)
+        sc = (C.c_int64 * max(npeers, 1))(*plan.send_counts)
+        rc = (C.c_int64 * max(npeers, 1))(*plan.recv_counts)
+        self._send_idx = plan.send_idx.to(self.device)
+        self._keep = (sp.loc_rowptr, sp.loc_col, sp.loc_val, sp.brow_ids, sp.gh_rowptr, sp.gh_col, sp.gh_val,
+                      self._send_idx)
+        p = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _native._check(lib.bk_dist_create(
+                self.handle.ptr, idbuf, rank, world, sp.n_local, sp.loc_val.numel(), sp.loc_rowptr.data_ptr(),
+                sp.loc_col.data_ptr(), sp.loc_val.data_ptr(), sp.brow_ids.numel(), sp.brow_ids.data_ptr(),
+                sp.gh_val.numel(), sp.gh_rowptr.data_ptr(), sp.gh_col.data_ptr(), sp.gh_val.data_ptr(),
+                sp.ghost_ids.numel(), npeers, peers, sc, rc, self._send_idx.data_ptr(),
+                _native._dtype_code(self.dtype), _native._stream_ptr(self.device), C.byref(p)), "bk_dist_create")
+        self.ptr = p
+
+    def close(self):
+        if getattr(self, "ptr", None) is not None:
+            self.handle.lib.bk_dist_destroy(self.ptr)
+            self.ptr = None
+
+    def spmv(self, x_local: torch.Tensor) -> torch.Tensor:
+        x = x_local.contiguous()
+        y = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _native._check(self.handle.lib.bk_dist_spmv(self.handle.ptr, self.ptr, x.data_ptr(), y.data_ptr(),
+                                                        _native._stream_ptr(self.device)), "bk_dist_spmv")
+        return y
+
+    def cg(self, b_local: torch.Tensor, x0: Optional[torch.Tensor] = None, tol: float = 1e-5, atol: float = 0.0,
+           maxiter: Optional[int] = None) -> Tuple[torch.Tensor, dict]:
+        b = b_local.to(self.dtype).contiguous()
+        if x0 is None:
+            x, has = torch.empty_like(b), 0
+        else:
+            x, has = x0.to(self.dtype).contiguous().clone(), 1
+        res = _native.bk_result()
+        with torch.cuda.device(self.device):
+            _native._check(self.handle.lib.bk_dist_cg(
+                self.handle.ptr, self.ptr, b.data_ptr(), x.data_ptr(), has, float(tol), float(atol),
+                -1 if maxiter is None else int(maxiter), self.n_global, C.byref(res),
+                _native._stream_ptr(self.device)), "bk_dist_cg")
+        return x, res.as_dict()
+
+
+# ---- weak-scaling benchmark used by bench.py --gpus N --------------------------------------------------------
+def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSampler):
+    """N slabs of n^3 rows each: a (N*n) x n x n Poisson grid, slab q on rank q.  value = N * global iterations/s
+    (n^3-row CG iterations per second summed over ranks)."""
+    import json
+    import time
+    import torch.distributed as dist
+    from . import problems
+    dev = torch.device("cuda", local)
+    n = args.n
+    rows = n ** 3
+    offsets = [q * rows for q in range(world + 1)]
+    crow, col, val = problems.stencil3d_rows(n, world * n, rank * n, (rank + 1) * n, device=dev)
+    nnz_local = val.numel()
+    D = DistMatrix(crow, col, val, offsets, rank, world)
+    del crow, col
+    b = torch.ones(rows, dtype=torch.float64, device=dev)
+    window = args.dist_window
+    for _ in range(max(args.warmup, 3)):
+        D.cg(b, None, 0.0, 0.0, min(window, 50))
+    torch.cuda.synchronize()
+    dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    its = launches = 0
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            x, res = D.cg(b, None, 0.0, 0.0, window)
+            its += res["iterations"]
+            launches += res["kernel_launches"]
+        ev1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    it_s = its / (ms * 1e-3)
+    value = world * it_s
+    bytes_iter = problems.cg_bytes_per_iteration(rows, nnz_local)
+    # end to end: host slab -> device, registration, solve window, x back to host
+    crow_h, col_h, val_h = problems.stencil3d_rows(n, world * n, rank * n, (rank + 1) * n)
+    crow_h, col_h, val_h, b_h = crow_h.pin_memory(), col_h.pin_memory(), val_h.pin_memory(), b.cpu().pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in (crow_h, col_h, val_h, b_h))
+    D.close()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    D2 = DistMatrix(crow_h.to(dev, non_blocking=True), col_h.to(dev, non_blocking=True), val_h.to(dev, non_blocking=True),
+                    offsets, rank, world)
+    xe, re_ = D2.cg(b_h.to(dev, non_blocking=True), None, 0.0, 0.0, window)
+    xh = xe.cpu()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * re_["iterations"] / float(dt), "unit": unit, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": rows * 8, "ms_per_step": 1e3 * float(dt), "steps": 1,
+           "note": "includes partition set-up and NCCL communicator creation"}
+    D2.close()
+    if rank != 0:
+        return None
+    pk, pk_kind = peak
+    return {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"CG fp64, 7-pt Poisson {world * n}x{n}x{n} CSR row-partitioned over {world} GPUs "
+                               f"({n}^3 rows per GPU), b=ones, fixed window of {window} iterations per step",
+                   "value_definition": f"{world} x global iterations/s = {n}^3-row CG iterations per second over all ranks",
+                   "global_iterations_per_second": it_s, "n_local": rows, "nnz_local": nnz_local,
+                   "halo_bytes_per_neighbour": n * n * 8, "peers_rank0": D.plan.peers,
+                   "l2_policy": "inputs exceed L2; no flush needed"},
+        "roofline": {"bound": "hbm", "kernel": "whole distributed CG iteration (per GPU)",
+                     "achieved": bytes_iter * it_s / 1e9, "peak": pk, "peak_kind": pk_kind, "unit": "GB/s",
+                     "frac": bytes_iter * it_s / 1e9 / pk, "traffic": None},
+        "iteration": {"bytes_per_iteration_per_gpu": bytes_iter, "us_per_iteration": 1e3 * ms / its,
+                      "frac_of_8tbs": bytes_iter * it_s / 8e12},
+        "e2e": e2e, "cpu_baseline": None, "gpu_launches": int(launches), "clocks": clk.summary(),
+    }

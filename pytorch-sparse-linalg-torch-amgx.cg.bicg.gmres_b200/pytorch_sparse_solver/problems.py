@@ -40,6 +40,27 @@ def stencil3d_csr(n: int, lower=(-1.0, -1.0, -1.0), upper=(-1.0, -1.0, -1.0), di
     return _csr_from_masked_stencil(N, offsets, values, masks, dtype, index_dtype, device)
 
 
+def stencil3d_rows(n: int, ni_total: int, i_begin: int, i_end: int, lower=(-1.0, -1.0, -1.0),
+                   upper=(-1.0, -1.0, -1.0), diag: float = 6.0, dtype=torch.float64, index_dtype=torch.int64,
+                   device="cpu") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Rows of planes i in [i_begin, i_end) of the 7-point stencil on an ni_total x n x n grid, as CSR arrays
+    (crow, col, val) with GLOBAL column indices — the slab one rank owns in a 1-D row partition."""
+    rows = (i_end - i_begin) * n * n
+    r = torch.arange(i_begin * n * n, i_end * n * n, device=device)
+    k = r % n
+    j = (r // n) % n
+    i = r // (n * n)
+    offs = torch.tensor([-n * n, -n, -1, 0, 1, n, n * n], device=device)
+    vals = torch.tensor([lower[0], lower[1], lower[2], diag, upper[2], upper[1], upper[0]], dtype=dtype, device=device)
+    masks = torch.stack([i > 0, j > 0, k > 0, torch.ones(rows, dtype=torch.bool, device=device), k < n - 1, j < n - 1,
+                         i < ni_total - 1], 1)
+    cols = (r[:, None] + offs[None, :])[masks]
+    v = vals[None, :].expand(rows, 7)[masks]
+    crow = torch.zeros(rows + 1, dtype=torch.int64, device=device)
+    crow[1:] = masks.sum(1).cumsum(0)
+    return crow.to(index_dtype), cols.to(index_dtype), v
+
+
 def poisson3d_csr(n: int, **kw) -> torch.Tensor:
     """P3D-n: diag 6, six off-diagonals -1 (SPD)."""
     return stencil3d_csr(n, **kw)

@@ -1,0 +1,64 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity worker (launched by torchrun, one rank per GPU): distributed SpMV / CG on a row-partitioned
+Poisson slab grid against the single-GPU library solve of the same global system.  Exits non-zero on failure."""
+import os
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "pytorch-sparse-linalg-torch-amgx.cg.bicg.gmres_b200"))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from pytorch_sparse_solver import _native, problems
+    from pytorch_sparse_solver import distributed as bkd
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    rows = n ** 3
+    offsets = [q * rows for q in range(world + 1)]
+    crow, col, val = problems.stencil3d_rows(n, world * n, rank * n, (rank + 1) * n, device=dev)
+    D = bkd.DistMatrix(crow, col, val, offsets, rank, world)
+    assert D.plan.peers == [q for q in (rank - 1, rank + 1) if 0 <= q < world], D.plan.peers
+    A = problems.stencil3d_csr(n, nz=world * n, device=dev)     # every rank also holds the global system (checker)
+    m = _native.register_matrix(A)
+    sl = slice(rank * rows, (rank + 1) * rows)
+
+    def rel(a, b):
+        return float(torch.linalg.norm(a - b) / torch.linalg.norm(b))
+
+    xg = torch.randn(world * rows, dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(5))
+    dist.broadcast(xg, 0)
+    y = D.spmv(xg[sl].contiguous())
+    assert rel(y, m.spmv(xg)[sl]) <= 1e-14, "dist spmv"
+
+    bg = torch.ones(world * rows, dtype=torch.float64, device=dev)
+    x_ref, r_ref = m.cg(bg, None, 1e-8, 0.0, None)
+    for mode in (1, 2):                                   # plain launches, then CUDA-graph captured iterations
+        D.handle.set_option("loop_mode", mode)
+        x, r = D.cg(bg[sl].contiguous(), None, 1e-8, 0.0, None)
+        assert r["info"] == r_ref["info"] == 0, (r, r_ref)
+        assert abs(r["iterations"] - r_ref["iterations"]) <= 2, (r["iterations"], r_ref["iterations"])
+        assert rel(x, x_ref[sl]) <= 1e-10, ("dist cg", mode, rel(x, x_ref[sl]))
+        x2, r2 = D.cg(bg[sl].contiguous(), None, 1e-8, 0.0, None)
+        assert torch.equal(x, x2), "dist cg must be bitwise reproducible"
+    D.handle.set_option("loop_mode", 0)
+    # fixed window + warm start
+    x0 = xg * 0.01
+    x_ref, r_ref = m.cg(bg, x0, 0.0, 0.0, 7)
+    x, r = D.cg(bg[sl].contiguous(), x0[sl].contiguous(), 0.0, 0.0, 7)
+    assert r["iterations"] == 7 and rel(x, x_ref[sl]) <= 1e-12, ("window", rel(x, x_ref[sl]))
+    D.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"dist worker OK: world={world} n={n} iterations={r_ref['iterations']}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -440,3 +440,63 @@ def test_bicgstab_convdiff3d_256_full_size(ma, manifest):
     assert abs(float(torch.linalg.norm(x)) - dg["x_norm"]) <= 1e-8 * dg["x_norm"]
     assert res["final_residual"] / res["b_norm"] <= 1e-8
     assert rel_diff(x, xt) <= 1e-5
+
+
+# --------------------------------------------------------------------------------------------------
+# generic route (callable A, preconditioner M, pytrees) and the row-partitioned path
+# --------------------------------------------------------------------------------------------------
+def test_generic_route_callable_and_preconditioner(ma, manifest):
+    from pytorch_sparse_solver import _native
+    entry = manifest["cases"]["cg_p3d16_rand"]
+    data = load_case("cg_p3d16_rand")
+    A = build_matrix(entry["gen"], device="cuda")
+    m = _native.register_matrix(A)
+    b = data["b"].cuda()
+    x, info = ma.cg(lambda v: m.spmv(v), b, tol=1e-10)
+    assert info == 0 and _last()["route"] == "generic" and _last()["iterations"] == entry["iterations"]
+    assert rel_diff(x, data["x"]) <= FP64_TOL
+    diag = torch.full_like(b, 6.0)
+    xj, info = ma.cg(A, b, tol=1e-10, M=lambda r: r / diag)          # Jacobi preconditioner
+    assert info == 0 and rel_diff(xj, data["x"]) <= 1e-9
+    # pytree right-hand side with a callable operator
+    half = b.numel() // 2
+
+    def op(tree):
+        y = m.spmv(torch.cat([tree["a"], tree["b"]]))
+        return {"a": y[:half], "b": y[half:]}
+    xt, info = ma.cg(op, {"a": b[:half], "b": b[half:]}, tol=1e-10)
+    assert info == 0 and rel_diff(torch.cat([xt["a"], xt["b"]]), data["x"]) <= FP64_TOL
+    for name, fn in (("bicgstab_cd3d16_rand", ma.bicgstab), ("gmres_cd3d12_incremental", ma.gmres),
+                     ("gmres_cd3d12_batched", ma.gmres)):
+        entry = manifest["cases"][name]
+        data = load_case(name)
+        mm = _native.register_matrix(build_matrix(entry["gen"], device="cuda"))
+        xg, info = fn(lambda v, mm=mm: mm.spmv(v), data["b"].cuda(), **entry["kwargs"])
+        assert info == entry["info"] and rel_diff(xg, data["x"]) <= FP64_TOL, name
+
+
+def test_dist_single_rank(manifest):
+    """world_size 1 through the bk_dist_* entries (NCCL communicator of one rank) equals the plain solver."""
+    from pytorch_sparse_solver import _native
+    from pytorch_sparse_solver import distributed as bkd
+    entry = manifest["cases"]["cg_p3d16_rand"]
+    data = load_case("cg_p3d16_rand")
+    A = build_matrix(entry["gen"], device="cuda")
+    D = bkd.DistMatrix(A.crow_indices(), A.col_indices(), A.values(), [0, A.shape[0]], 0, 1)
+    x, res = D.cg(data["b"].cuda(), None, 1e-10, 0.0, None)
+    assert res["info"] == 0 and res["iterations"] == entry["iterations"]
+    assert rel_diff(x, data["x"]) <= FP64_TOL
+    xv = torch.randn(A.shape[0], dtype=torch.float64, device="cuda")
+    assert rel_diff(D.spmv(xv), _native.register_matrix(A).spmv(xv)) <= 1e-15
+    D.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_dist_two_gpus():
+    import subprocess
+    import sys
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29631", str(ROOT / "tests" / "dist_gpu_worker.py"), "16"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "dist worker OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
