@@ -90,6 +90,7 @@ extern "C" int bk_destroy(bk_handle* h) {
   if (h->st_host) cudaFreeHost(h->st_host);
   if (h->dscratch) cudaFree(h->dscratch);
   if (h->ws) cudaFree(h->ws);
+  if (h->stage) cudaFree(h->stage);
   if (h->gm_small) cudaFree(h->gm_small);
   if (h->gm_partials) cudaFree(h->gm_partials);
   for (int i = 0; i < 4; ++i)
@@ -173,6 +174,10 @@ extern "C" int bk_device_info(bk_handle* h, int32_t* num_sms, int64_t* l2_bytes,
 __global__ void bk_cvt_i64_i32_kernel(const long long* __restrict__ in, int* __restrict__ out, long long n) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int)in[i];
+}
+
+void bk_convert_i64_i32(bk_handle* h, const void* in, void* out, long long n, cudaStream_t s) {
+  if (n > 0) bk_cvt_i64_i32_kernel<<<h->num_sms * 8, 256, 0, s>>>((const long long*)in, (int*)out, n);
 }
 
 // max row length + validity (monotone rowptr, columns in range) in one pass over rowptr/col

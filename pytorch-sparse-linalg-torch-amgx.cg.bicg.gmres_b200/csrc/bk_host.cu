@@ -19,25 +19,37 @@ extern "C" int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, c
   if (n == 0) return BK_OK;
   cudaStream_t s = h->io_stream;
   const size_t is = idx_bits / 8, vs = bk_dtype_size(dtype);
-  void *d_rp = nullptr, *d_col = nullptr, *d_val = nullptr, *d_b = nullptr, *d_x = nullptr;
   bk_csr* A = nullptr;
   int rc = BK_OK;
+  // device staging area cached in the handle (grow-only): repeated host solves pay no cudaMalloc/cudaFree
+  const size_t nn = (size_t)(nnz > 0 ? nnz : 1);
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t conv = (idx_bits == 64) ? al(4 * (size_t)(n + 1)) + al(4 * nn) : 0;  // int32 copies of the indices
+  const size_t need = al(is * (size_t)(n + 1)) + al(is * nn) + al(vs * nn) + 2 * al(vs * (size_t)n) + conv;
+  if (need > h->stage_bytes) {
+    if (h->stage) {
+      BK_CUDA(cudaDeviceSynchronize());
+      cudaFree(h->stage);
+      h->stage = nullptr;
+      h->stage_bytes = 0;
+    }
+    if (cudaMalloc(&h->stage, need) != cudaSuccess) {
+      cudaGetLastError();
+      return bk_fail(BK_ERR_ALLOC, "bk_solve_host: device staging allocation of %zu bytes failed", need);
+    }
+    h->stage_bytes = need;
+  }
+  char* base = (char*)h->stage;
+  void* d_rp = base;
+  void* d_col = base + al(is * (size_t)(n + 1));
+  void* d_val = (char*)d_col + al(is * nn);
+  void* d_b = (char*)d_val + al(vs * nn);
+  void* d_x = (char*)d_b + al(vs * (size_t)n);
+  void* d_rp32 = (char*)d_x + al(vs * (size_t)n);
+  void* d_col32 = (char*)d_rp32 + al(4 * (size_t)(n + 1));
   auto cleanup = [&]() {
     if (A) bk_csr_destroy(A);
-    if (d_rp) cudaFree(d_rp);
-    if (d_col) cudaFree(d_col);
-    if (d_val) cudaFree(d_val);
-    if (d_b) cudaFree(d_b);
-    if (d_x) cudaFree(d_x);
   };
-  const size_t nn = (size_t)(nnz > 0 ? nnz : 1);
-  if (cudaMalloc(&d_rp, is * (size_t)(n + 1)) != cudaSuccess || cudaMalloc(&d_col, is * nn) != cudaSuccess ||
-      cudaMalloc(&d_val, vs * nn) != cudaSuccess || cudaMalloc(&d_b, vs * (size_t)n) != cudaSuccess ||
-      cudaMalloc(&d_x, vs * (size_t)n) != cudaSuccess) {
-    cudaGetLastError();
-    cleanup();
-    return bk_fail(BK_ERR_ALLOC, "bk_solve_host: device allocation failed");
-  }
   cudaError_t e = cudaMemcpyAsync(d_rp, rowptr, is * (size_t)(n + 1), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_col, col, is * (size_t)nnz, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_val, val, vs * (size_t)nnz, cudaMemcpyHostToDevice, s);
@@ -47,7 +59,17 @@ extern "C" int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, c
     cleanup();
     return bk_fail(BK_ERR_CUDA, "bk_solve_host: H2D copy failed: %s", cudaGetErrorString(e));
   }
-  rc = bk_csr_create(h, n, nnz, d_rp, d_col, idx_bits, d_val, dtype, 0, s, &A);
+  if (idx_bits == 64) {  // narrow the indices inside the staging area (overlaps the value copy still in flight)
+    if (n >= 2147483647LL || nnz >= 2147483647LL) {
+      cleanup();
+      return bk_fail(BK_ERR_UNSUPPORTED, "bk_solve_host: n and nnz must be < 2^31");
+    }
+    bk_convert_i64_i32(h, d_rp, d_rp32, n + 1, s);
+    bk_convert_i64_i32(h, d_col, d_col32, nnz, s);
+    rc = bk_csr_create(h, n, nnz, d_rp32, d_col32, 32, d_val, dtype, 0, s, &A);
+  } else {
+    rc = bk_csr_create(h, n, nnz, d_rp, d_col, 32, d_val, dtype, 0, s, &A);
+  }
   if (rc == BK_OK) {
     if (method == 0)
       rc = bk_cg(h, A, d_b, d_x, has_x0, tol, atol, maxiter, result, s);

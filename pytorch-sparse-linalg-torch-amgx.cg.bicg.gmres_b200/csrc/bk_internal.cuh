@@ -153,6 +153,8 @@ struct bk_handle {
   bk_graph_entry graphs[8];
   cudaStream_t cap_stream;
   cudaStream_t io_stream;   // bk_solve_host: H2D / solve / D2H
+  void* stage;              // bk_solve_host: cached device staging area
+  size_t stage_bytes;
   uint64_t next_uid;
 };
 
@@ -168,6 +170,7 @@ int bk_ws_reserve(bk_handle* h, size_t bytes);  // grows h->ws (invalidates cach
 void bk_graphs_invalidate(bk_handle* h);
 void bk_state_fill_tol(bk_dev_state* v, double tol, double atol);
 void bk_fill_result_isolve(const bk_dev_state* st, bk_result* res, int64_t matvecs);
+void bk_convert_i64_i32(bk_handle* h, const void* in, void* out, long long n, cudaStream_t s);
 int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s);
 int bk_solver_args_check(const char* who, bk_handle* h, const bk_csr* A, const void* b, void* x, bk_result* res);
 
