@@ -190,6 +190,15 @@ int bk_dist_create(bk_handle* h, const void* id128, int rank, int nranks, int64_
                    const int64_t* send_counts, const int64_t* recv_counts, const void* send_idx, int dtype,
                    void* stream, bk_dist** out);
 int bk_dist_destroy(bk_dist* D);
+/* Peer-memory path (NVLink/NVSwitch, CUDA IPC).  Each rank exports the 64-byte IPC handle of its communication
+ * window (all-reduce slots, halo flags, ghost vector); the caller gathers all handles and every rank maps them.
+ * remote_ghost_offsets[i] = element offset inside halo peer i's ghost vector where this rank's entries land.
+ * Once connected, bk_dist_cg pushes boundary entries straight into the neighbours' ghost vectors from a kernel and
+ * all-reduces the two scalar dots with a one-shot peer-store exchange inside the reducing kernels' epilogues
+ * (no NCCL call and no extra kernel per iteration).  Returns BK_ERR_UNSUPPORTED when peers cannot be mapped; the
+ * NCCL path then stays in use. */
+int bk_dist_p2p_export(bk_dist* D, void* handle64);
+int bk_dist_p2p_connect(bk_dist* D, const void* handles, const int64_t* remote_ghost_offsets);
 /* y_local = (A x)_local */
 int bk_dist_spmv(bk_handle* h, bk_dist* D, const void* x_local, void* y_local, void* stream);
 /* distributed CG (same recurrences / stop test / info as bk_cg; n_global sets the default maxiter = 10 n) */

@@ -161,6 +161,7 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
     op.st = st;
     op.snake = h->snake;
     op.dist_out = nullptr;
+    op.p2p.P = 0;
     BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
   }
   if (!fuse) {

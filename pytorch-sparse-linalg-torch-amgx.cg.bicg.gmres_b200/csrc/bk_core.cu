@@ -46,6 +46,7 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->tma_ctas = (int)bk_env_int("BK_TMA_CTAS", 4);
   h->tma_stages = (int)bk_env_int("BK_TMA_STAGES", 0);
   h->use_tma = (int)bk_env_int("BK_SPMV_TMA", 1);
+  h->dist_p2p = (int)bk_env_int("BK_DIST_P2P", 1);
   h->loop_mode = (int)bk_env_int("BK_LOOP_MODE", BK_LOOP_AUTO);
   h->chunk = (int)bk_env_int("BK_CHUNK", 0);
   h->fuse_xpay = (int)bk_env_int("BK_FUSE_XPAY", 0);
@@ -133,6 +134,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "tma_ctas")) return &h->tma_ctas;
   if (!strcmp(key, "tma_stages")) return &h->tma_stages;
   if (!strcmp(key, "use_tma")) return &h->use_tma;
+  if (!strcmp(key, "dist_p2p")) return &h->dist_p2p;
   if (!strcmp(key, "loop_mode")) return &h->loop_mode;
   if (!strcmp(key, "chunk")) return &h->chunk;
   if (!strcmp(key, "fuse_xpay")) return &h->fuse_xpay;

@@ -17,6 +17,7 @@
 
 #include "bk_internal.cuh"
 #include "bk_loop.cuh"
+#include "bk_p2p.cuh"
 #include "bk_spmv.cuh"
 #include "bk_vec.cuh"
 
@@ -86,8 +87,17 @@ struct bk_dist {
   int64_t send_total;
   const int* send_idx;
   void* sendbuf;
-  void* ghost;
-  double* red;  // [0] p.Ap  [1] r.r  (allreduced in place)  [2..3] spare
+  void* ghost;  // = window + BK_P2P_GHOST_OFF
+  char* window; // IPC-exportable: all-reduce slots, halo flags, ghost vector (bk_p2p.cuh)
+  size_t window_bytes;
+  int p2p_enabled;
+  bk_p2p_ctx p2p;
+  void* peer_mapped[BK_P2P_MAXP];     // cudaIpcOpenMemHandle results (to close)
+  long long* d_seg_start;              // device [npeers+1]: prefix sums of send_counts
+  void** d_remote_ghost;               // device [npeers]: where my entries land in each peer's ghost vector
+  unsigned long long** d_remote_flag;  // device [npeers]: my arrival flag inside each peer's window
+  int* d_peer_ranks;                   // device [npeers]
+  double* red;  // [0] p.Ap  [1] r.r  (allreduced in place)  [2..3] init/final  [4] local-block partial
   bk_nccl_comm comm;
   cudaStream_t comm_stream;
   cudaEvent_t ev_ready, ev_halo;
@@ -112,8 +122,15 @@ extern "C" int bk_dist_destroy(bk_dist* D) {
   }
   if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
   if (D->Aloc) bk_csr_destroy(D->Aloc);
+  for (int q = 0; q < BK_P2P_MAXP; ++q)
+    if (D->peer_mapped[q]) cudaIpcCloseMemHandle(D->peer_mapped[q]);
   if (D->sendbuf) cudaFree(D->sendbuf);
-  if (D->ghost) cudaFree(D->ghost);
+  if (D->window) cudaFree(D->window);
+  if (D->p2p.counters) cudaFree(D->p2p.counters);
+  if (D->d_seg_start) cudaFree(D->d_seg_start);
+  if (D->d_remote_ghost) cudaFree(D->d_remote_ghost);
+  if (D->d_remote_flag) cudaFree(D->d_remote_flag);
+  if (D->d_peer_ranks) cudaFree(D->d_peer_ranks);
   if (D->red) cudaFree(D->red);
   if (D->comm_stream) cudaStreamDestroy(D->comm_stream);
   if (D->ev_ready) cudaEventDestroy(D->ev_ready);
@@ -179,7 +196,12 @@ extern "C" int bk_dist_create(bk_handle* h, const void* id128, int rank, int nra
   D->send_idx = (const int*)send_idx;
   const size_t vs = bk_dtype_size(dtype);
   cudaError_t e = cudaMalloc(&D->sendbuf, vs * (size_t)(D->send_total > 0 ? D->send_total : 1));
-  if (e == cudaSuccess) e = cudaMalloc(&D->ghost, vs * (size_t)(n_ghost > 0 ? n_ghost : 1));
+  D->window_bytes = BK_P2P_GHOST_OFF + ((vs * (size_t)(n_ghost > 0 ? n_ghost : 1) + 255) & ~(size_t)255);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&D->window, D->window_bytes);
+  if (e == cudaSuccess) e = cudaMemset(D->window, 0, D->window_bytes);
+  if (e == cudaSuccess) D->ghost = D->window + BK_P2P_GHOST_OFF;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&D->p2p.counters, sizeof(unsigned int) * 16);
+  if (e == cudaSuccess) e = cudaMemset(D->p2p.counters, 0, sizeof(unsigned int) * 16);
   if (e == cudaSuccess) e = cudaMalloc(&D->red, sizeof(double) * 8);
   if (e == cudaSuccess) e = cudaMemset(D->red, 0, sizeof(double) * 8);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D->comm_stream, cudaStreamNonBlocking);
@@ -200,6 +222,153 @@ extern "C" int bk_dist_create(bk_handle* h, const void* id128, int rank, int nra
   }
   *out = D;
   return BK_OK;
+}
+
+// ---- peer-memory path: export this rank's window, map everybody else's ---------------------------------------
+extern "C" int bk_dist_p2p_export(bk_dist* D, void* handle64) {
+  if (!D || !handle64) return bk_fail(BK_ERR_ARG, "bk_dist_p2p_export: null argument");
+  BK_CUDA(cudaSetDevice(D->h->device));
+  cudaIpcMemHandle_t hd;
+  BK_CUDA(cudaIpcGetMemHandle(&hd, D->window));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &hd, 64);
+  return BK_OK;
+}
+
+// handles: nranks x 64 bytes (rank order).  remote_ghost_offsets[i]: element offset, inside halo peer i's ghost
+// vector, at which the entries this rank sends to it must land (that peer's receive offset for this rank).
+extern "C" int bk_dist_p2p_connect(bk_dist* D, const void* handles, const int64_t* remote_ghost_offsets) {
+  if (!D || !handles) return bk_fail(BK_ERR_ARG, "bk_dist_p2p_connect: null argument");
+  if (D->nranks > BK_P2P_MAXP) return bk_fail(BK_ERR_UNSUPPORTED, "peer-memory path supports up to %d ranks", BK_P2P_MAXP);
+  if (D->npeers > 0 && !remote_ghost_offsets) return bk_fail(BK_ERR_ARG, "bk_dist_p2p_connect: null offsets");
+  BK_CUDA(cudaSetDevice(D->h->device));
+  D->p2p.P = 0;
+  D->p2p.rank = D->rank;
+  for (int q = 0; q < D->nranks; ++q) {
+    if (q == D->rank) {
+      D->p2p.win[q] = D->window;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, (const char*)handles + (size_t)q * 64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return bk_fail(BK_ERR_UNSUPPORTED, "cudaIpcOpenMemHandle(rank %d) failed: %s (falling back to NCCL)", q,
+                     cudaGetErrorString(e));
+    }
+    D->peer_mapped[q] = p;
+    D->p2p.win[q] = (char*)p;
+  }
+  const size_t vs = bk_dtype_size(D->dtype);
+  const int np = D->npeers;
+  long long seg[BK_P2P_MAXP + 1];
+  void* rg[BK_P2P_MAXP];
+  unsigned long long* rf[BK_P2P_MAXP];
+  if (np > BK_P2P_MAXP) return bk_fail(BK_ERR_UNSUPPORTED, "too many halo peers");
+  seg[0] = 0;
+  for (int i = 0; i < np; ++i) {
+    seg[i + 1] = seg[i] + D->send_counts[i];
+    char* w = D->p2p.win[D->peer_ranks[i]];
+    rg[i] = w + BK_P2P_GHOST_OFF + (size_t)remote_ghost_offsets[i] * vs;
+    rf[i] = (unsigned long long*)(w + BK_P2P_FLAG_OFF) + D->rank;
+  }
+  BK_CUDA(cudaMalloc((void**)&D->d_seg_start, sizeof(long long) * (np + 1)));
+  BK_CUDA(cudaMalloc((void**)&D->d_remote_ghost, sizeof(void*) * (np > 0 ? np : 1)));
+  BK_CUDA(cudaMalloc((void**)&D->d_remote_flag, sizeof(void*) * (np > 0 ? np : 1)));
+  BK_CUDA(cudaMalloc((void**)&D->d_peer_ranks, sizeof(int) * (np > 0 ? np : 1)));
+  BK_CUDA(cudaMemcpy(D->d_seg_start, seg, sizeof(long long) * (np + 1), cudaMemcpyHostToDevice));
+  if (np > 0) {
+    BK_CUDA(cudaMemcpy(D->d_remote_ghost, rg, sizeof(void*) * np, cudaMemcpyHostToDevice));
+    BK_CUDA(cudaMemcpy(D->d_remote_flag, rf, sizeof(void*) * np, cudaMemcpyHostToDevice));
+    BK_CUDA(cudaMemcpy(D->d_peer_ranks, D->peer_ranks, sizeof(int) * np, cudaMemcpyHostToDevice));
+  }
+  D->p2p.P = D->nranks;
+  D->p2p_enabled = 1;
+  bk_graphs_invalidate(D->h);
+  return BK_OK;
+}
+
+// push: every boundary entry of x is stored straight into the owning peer's ghost vector (NVLink stores); the last
+// CTA then publishes this rank's arrival flag (sequence number) in every peer's window with release semantics.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bk_halo_push_kernel(const T* __restrict__ x, const int* __restrict__ idx, const long long* __restrict__ seg_start,
+                    void* const* __restrict__ remote_ghost, unsigned long long* const* __restrict__ remote_flag,
+                    int npeers, long long count, unsigned int* counters, const bk_dev_state* st) {
+  if (st->done) return;
+  __shared__ int s_last;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    int p = 0;
+    while (p + 1 < npeers && i >= seg_start[p + 1]) ++p;
+    static_cast<T*>(remote_ghost[p])[i - seg_start[p]] = x[idx[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(&counters[3], gridDim.x - 1);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    const unsigned int seq = counters[1] + 1u;
+    if (threadIdx.x < npeers) bk_st_release_sys_u64(remote_flag[threadIdx.x], (unsigned long long)seq);
+    __syncthreads();
+    if (threadIdx.x == 0) counters[1] = seq;
+  }
+}
+
+// boundary rows with the halo wait in front and the p.Ap all-reduce + alpha behind (peer-memory path of CG's K1b)
+template <typename T>
+__global__ void __launch_bounds__(BK_BLOCK)
+bk_ghost_rows_p2p_kernel(const int* __restrict__ brow_ids, const int* __restrict__ rowptr, const int* __restrict__ col,
+                         const T* __restrict__ val, const T* ghost, T* __restrict__ y, const T* __restrict__ w,
+                         long long n_brows, const bk_scratch sc, const double* local_partial, bk_dev_state* st,
+                         const bk_p2p_ctx p2p, const int* __restrict__ peer_ranks, int npeers) {
+  if (st->done) return;
+  __shared__ int s_fail;
+  if (threadIdx.x == 0) s_fail = 0;
+  __syncthreads();
+  const unsigned int want = p2p.counters[2] + 1u;  // halos consumed so far + 1
+  if (threadIdx.x < npeers) {
+    const unsigned long long* flag =
+        reinterpret_cast<const unsigned long long*>(p2p.win[p2p.rank] + BK_P2P_FLAG_OFF) + peer_ranks[threadIdx.x];
+    const long long t0 = clock64();
+    while ((unsigned int)bk_ld_acquire_sys_u64(flag) != want) {
+      if (clock64() - t0 > BK_P2P_TIMEOUT_CYCLES) {
+        s_fail = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  double acc[1] = {0.0};
+  if (!s_fail) {
+    const long long stride = (long long)gridDim.x * BK_BLOCK;
+    for (long long b = (long long)blockIdx.x * BK_BLOCK + threadIdx.x; b < n_brows; b += stride) {
+      const int r = brow_ids[b];
+      T sum = T(0);
+      for (int k = rowptr[b]; k < rowptr[b + 1]; ++k) sum = fma(val[k], __ldcg(ghost + col[k]), sum);
+      y[r] = y[r] + sum;
+      acc[0] += (double)w[r] * (double)sum;
+    }
+  } else if (threadIdx.x == 0) {
+    p2p.counters[4] = 1u;
+  }
+  bk_grid_reduce<1>(acc, sc, [&](const double* s) {
+    p2p.counters[2] = want;
+    const double total = bk_p2p_allreduce(p2p, local_partial[0] + s[0]);
+    if (p2p.counters[4]) {
+      st->done = 1;
+      st->status = BK_ST_COMM_TIMEOUT;
+      return;
+    }
+    st->pAp = total;
+    st->alpha = st->gamma / total;
+  });
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------
@@ -444,7 +613,57 @@ static int bk_dist_cg_t(bk_handle* h, bk_dist* D, const void* b, void* x_user, i
   BK_KERNEL_CHECK();
   BK_CUDA(cudaMemcpyAsync(p, r, vbytes, cudaMemcpyDeviceToDevice, s));
 
+  const bool p2p = D->p2p_enabled && h->dist_p2p;
+  auto enqueue_iter_p2p = [&](cudaStream_t cs) -> int {
+    if (D->send_total > 0) {
+      int g = (int)((D->send_total + 255) / 256);
+      if (g > h->num_sms * 2) g = h->num_sms * 2;
+      bk_halo_push_kernel<T><<<g, 256, 0, cs>>>(p, D->send_idx, D->d_seg_start, D->d_remote_ghost, D->d_remote_flag,
+                                                D->npeers, D->send_total, D->p2p.counters, st);
+      BK_KERNEL_CHECK();
+    }
+    {
+      bk_spmv_args a = bk_spmv_base(D->Aloc, st);
+      a.x = p;
+      a.y = ap;
+      a.w = p;
+      a.guard = 1;
+      bk_epi_store_pap epi{red + 4};
+      BK_TRY((bk_launch_spmv<0, 1, 0>(h, D->Aloc, a, bk_slot(h, 0), epi, cs)));
+    }
+    {
+      int g = (int)((D->n_brows + BK_BLOCK - 1) / BK_BLOCK);
+      if (g < 1) g = 1;
+      if (g > h->num_sms * 4) g = h->num_sms * 4;
+      bk_ghost_rows_p2p_kernel<T><<<g, BK_BLOCK, 0, cs>>>(D->brow_ids, D->gh_rowptr, D->gh_col, (const T*)D->gh_val,
+                                                         (const T*)D->ghost, ap, p, D->n_brows, bk_slot(h, 3), red + 4,
+                                                         st, D->p2p, D->d_peer_ranks, D->npeers);
+      BK_KERNEL_CHECK();
+    }
+    {
+      bk_op_cg_update<T> op;
+      op.p = p;
+      op.ap = ap;
+      op.x = x;
+      op.r = r;
+      op.st = st;
+      op.snake = 0;
+      op.dist_out = nullptr;
+      op.p2p = D->p2p;
+      BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), cs));
+    }
+    {
+      bk_op_xpay<T> op;
+      op.r = r;
+      op.p = p;
+      op.st = st;
+      op.snake = 0;
+      BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), cs));
+    }
+    return BK_OK;
+  };
   auto enqueue_iter = [&](cudaStream_t cs) -> int {
+    if (p2p) return enqueue_iter_p2p(cs);
     BK_TRY(bk_dist_spmv_t<T>(h, D, p, ap, p, red, 1, cs));                                  // Ap, local p.Ap
     BK_NCCL(g_nccl.AllReduce(red, red, 1, BK_NCCL_F64, BK_NCCL_SUM, D->comm, cs));
     bk_dist_alpha_kernel<<<1, 1, 0, cs>>>(st, red);
@@ -458,6 +677,7 @@ static int bk_dist_cg_t(bk_handle* h, bk_dist* D, const void* b, void* x_user, i
       op.st = st;
       op.snake = 0;
       op.dist_out = red + 1;
+      op.p2p.P = 0;
       BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), cs));
     }
     BK_NCCL(g_nccl.AllReduce(red + 1, red + 1, 1, BK_NCCL_F64, BK_NCCL_SUM, D->comm, cs));
@@ -475,9 +695,9 @@ static int bk_dist_cg_t(bk_handle* h, bk_dist* D, const void* b, void* x_user, i
   };
   const double bytes_iter = (double)D->Aloc->nnz * (sizeof(T) + 4) + 4.0 * (n + 1) + 11.0 * n * sizeof(T);
   const int chunk = bk_pick_chunk(h, bytes_iter, 8);
-  const bool use_graph = h->loop_mode == BK_LOOP_GRAPH;  // plain launches by default: NCCL inside capture is opt-in
+  const bool use_graph = h->loop_mode != BK_LOOP_STREAM;  // NCCL calls are captured into the iteration graph too
   uint64_t key[6] = {4 /*dist cg*/, D->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
-                     (uint64_t)D->dtype | ((uint64_t)chunk << 16), (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
+                     (uint64_t)D->dtype | ((uint64_t)p2p << 8) | ((uint64_t)chunk << 16), (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   auto enqueue_chunk = [&](cudaStream_t cs) -> int {
     for (int it = 0; it < chunk; ++it) BK_TRY(enqueue_iter(cs));
     return BK_OK;
@@ -499,7 +719,9 @@ static int bk_dist_cg_t(bk_handle* h, bk_dist* D, const void* b, void* x_user, i
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->gamma;
-  res->kernel_launches = chunks * chunk * 7 + 12;
+  res->kernel_launches = chunks * chunk * (p2p ? 5 : 7) + 12;
+  if (fin->status == BK_ST_COMM_TIMEOUT)
+    return bk_fail(BK_ERR_NCCL, "bk_dist_cg: a peer did not arrive within the timeout (peer-memory path)");
   return BK_OK;
 }
 

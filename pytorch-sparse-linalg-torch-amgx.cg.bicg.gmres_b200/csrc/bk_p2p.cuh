@@ -1,0 +1,85 @@
+// bk_p2p.cuh — peer-memory (NVLink / NVSwitch) primitives of the multi-GPU path: a one-shot all-reduce of one
+// double and halo-arrival flags, both through windows of device memory that every rank maps with CUDA IPC.
+//
+// Window layout (identical on every rank, so a peer's addresses follow from its base pointer):
+//   [   0,  512)  all-reduce slots: [2 buffers][16 ranks] x 16 bytes, "LL" format — each 8-byte word carries
+//                 32 bits of payload + the 32-bit sequence number, so one atomic 8-byte store publishes data and
+//                 flag together and no fence is needed on the payload path
+//   [ 512,  640)  halo flags: one 64-bit sequence number per SENDER rank (st.release.sys / ld.acquire.sys)
+//   [1024,  ...)  ghost vector (halo landing zone: neighbours store their boundary entries straight into it)
+//
+// All-reduce: every rank stores its value into slot [seq & 1][own rank] of EVERY rank's window, then reads the P
+// slots of its own window in rank order and adds them in that order => the sum is bitwise identical on all ranks
+// and from run to run (the stop test derived from it therefore agrees everywhere).  Two buffers are enough: a rank
+// can be at most one all-reduce ahead of any other because completing all-reduce s needs every rank's value s.
+// Every wait has a ~2 s timeout that turns a lost peer into an error status instead of a hung GPU.
+#pragma once
+
+#include "bk_internal.cuh"
+
+#define BK_P2P_MAXP 16
+#define BK_P2P_AR_OFF 0
+#define BK_P2P_FLAG_OFF 512
+#define BK_P2P_GHOST_OFF 1024
+#define BK_P2P_TIMEOUT_CYCLES 4000000000LL
+#define BK_ST_COMM_TIMEOUT (-20)
+
+struct bk_p2p_ctx {
+  int P;                     // 0 => peer path disabled
+  int rank;
+  unsigned int* counters;    // device-local: [0] all-reduce seq [1] halo send seq [2] halo recv seq [3] push ticket [4] error
+  char* win[BK_P2P_MAXP];    // window base of every rank, own entry included
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void bk_st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long bk_ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void bk_st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long bk_ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// One-shot all-reduce (sum) of one double, executed by ONE thread per rank.  Returns the sum; sets counters[4] on timeout.
+__device__ __forceinline__ double bk_p2p_allreduce(const bk_p2p_ctx& c, double v) {
+  const unsigned int seq = c.counters[0] + 1u;
+  c.counters[0] = seq;
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long w0 = ((unsigned long long)seq << 32) | (bits & 0xffffffffULL);
+  const unsigned long long w1 = ((unsigned long long)seq << 32) | (bits >> 32);
+  const int buf = (int)(seq & 1u);
+  for (int q = 0; q < c.P; ++q) {
+    unsigned long long* slot = reinterpret_cast<unsigned long long*>(c.win[q] + BK_P2P_AR_OFF +
+                                                                     (size_t)(buf * BK_P2P_MAXP + c.rank) * 16);
+    bk_st_volatile_u64(slot, w0);
+    bk_st_volatile_u64(slot + 1, w1);
+  }
+  double sum = 0.0;
+  const long long t0 = clock64();
+  for (int q = 0; q < c.P; ++q) {
+    const unsigned long long* slot = reinterpret_cast<const unsigned long long*>(
+        c.win[c.rank] + BK_P2P_AR_OFF + (size_t)(buf * BK_P2P_MAXP + q) * 16);
+    unsigned long long a, b;
+    for (;;) {
+      a = bk_ld_volatile_u64(slot);
+      b = bk_ld_volatile_u64(slot + 1);
+      if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
+      if (clock64() - t0 > BK_P2P_TIMEOUT_CYCLES) {
+        c.counters[4] = 1u;
+        return __longlong_as_double(0x7ff8000000000000LL);  // NaN: the caller's status handling takes over
+      }
+    }
+    sum += __longlong_as_double((long long)((b << 32) | (a & 0xffffffffULL)));
+  }
+  return sum;
+}
+#endif

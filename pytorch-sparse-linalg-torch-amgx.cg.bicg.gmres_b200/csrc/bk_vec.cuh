@@ -17,6 +17,7 @@
 #pragma once
 
 #include "bk_internal.cuh"
+#include "bk_p2p.cuh"
 
 template <typename T, int W, typename Op>
 __global__ void __launch_bounds__(BK_BLOCK, 3) bk_ew_kernel(Op op, const long long n, const bk_scratch sc) {
@@ -158,7 +159,8 @@ struct bk_op_cg_update {
   T* r;
   bk_dev_state* st;
   int snake;
-  double* dist_out;  // multi-GPU: park the LOCAL r.r here (all-reduced next) instead of finishing the iteration
+  double* dist_out;  // multi-GPU (NCCL path): park the LOCAL r.r here (all-reduced next) instead of finishing the iteration
+  bk_p2p_ctx p2p;    // multi-GPU (peer-memory path, p2p.P > 0): all-reduce r.r right here, then finish the iteration
   __device__ bool skip() const { return st->done != 0; }
   __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
   __device__ Ctx prepare() const {
@@ -190,7 +192,15 @@ struct bk_op_cg_update {
       dist_out[0] = s[0];
       return;
     }
-    const double gamma_new = s[0];
+    double gamma_new = s[0];
+    if (p2p.P > 0) {
+      gamma_new = bk_p2p_allreduce(p2p, s[0]);
+      if (p2p.counters[4]) {
+        st->done = 1;
+        st->status = BK_ST_COMM_TIMEOUT;
+        return;
+      }
+    }
     st->beta = gamma_new / st->gamma;
     st->gamma = gamma_new;
     const long long k = st->k + 1;

@@ -91,6 +91,8 @@ _SIGNATURES = {
                                  C.c_int64, _VP, _VP, _VP, C.c_int64, C.c_int, _VP, _VP, _VP, _VP, C.c_int, _VP,
                                  C.POINTER(_VP)]),
     "bk_dist_destroy": (C.c_int, [_VP]),
+    "bk_dist_p2p_export": (C.c_int, [_VP, _VP]),
+    "bk_dist_p2p_connect": (C.c_int, [_VP, _VP, _VP]),
     "bk_dist_spmv": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "bk_dist_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64,
                              C.POINTER(bk_result), _VP]),

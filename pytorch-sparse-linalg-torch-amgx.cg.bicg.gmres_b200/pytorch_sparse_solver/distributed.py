@@ -150,6 +150,43 @@ class DistMatrix:
                 sp.ghost_ids.numel(), npeers, peers, sc, rc, self._send_idx.data_ptr(),
                 _native._dtype_code(self.dtype), _native._stream_ptr(self.device), C.byref(p)), "bk_dist_create")
         self.ptr = p
+        self.p2p = False
+        import os
+        if os.environ.get("BK_DIST_P2P", "1") != "0":
+            self._connect_peer_memory(plan, group)
+
+    def _connect_peer_memory(self, plan: HaloPlan, group=None):
+        """Exchange CUDA-IPC handles of the communication windows and map every rank's window (NVLink peer memory)."""
+        import warnings
+        import torch.distributed as dist
+        lib = self.handle.lib
+        hbuf = (C.c_char * 64)()
+        try:
+            _native._check(lib.bk_dist_p2p_export(self.ptr, hbuf), "bk_dist_p2p_export")
+        except _native.NativeLibraryError as e:  # pragma: no cover
+            warnings.warn(f"peer-memory path unavailable ({e}); using NCCL")
+            return
+        recv_off, o = {}, 0
+        for q, c in zip(plan.peers, plan.recv_counts):
+            recv_off[q] = o
+            o += c
+        mine = {"handle": bytes(hbuf.raw), "recv_off": recv_off}
+        if self.world > 1:
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, mine, group=group)
+        else:
+            gathered = [mine]
+        handles = b"".join(g["handle"] for g in gathered)
+        roffs = (C.c_int64 * max(len(plan.peers), 1))(*[gathered[q]["recv_off"].get(self.rank, 0) for q in plan.peers])
+        rc = lib.bk_dist_p2p_connect(self.ptr, handles, roffs)
+        ok = torch.tensor([1 if rc == 0 else 0], device=self.device)
+        if self.world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # all ranks or none
+        if int(ok) == 1:
+            self.p2p = True
+        else:
+            warnings.warn("peer-memory path could not be connected on every rank; using NCCL")
+            self.handle.set_option("dist_p2p", 0)
 
     def close(self):
         if getattr(self, "ptr", None) is not None:

@@ -39,8 +39,12 @@ def main():
 
     bg = torch.ones(world * rows, dtype=torch.float64, device=dev)
     x_ref, r_ref = m.cg(bg, None, 1e-8, 0.0, None)
-    for mode in (1, 2):                                   # plain launches, then CUDA-graph captured iterations
+    assert D.p2p or os.environ.get("BK_DIST_P2P") == "0", "peer-memory path should connect on an NVLink box"
+    for mode, p2p in ((1, 0), (2, 0), (1, 1), (2, 1)):   # plain launches / CUDA graph  x  NCCL / peer-memory path
+        if p2p and not D.p2p:
+            continue
         D.handle.set_option("loop_mode", mode)
+        D.handle.set_option("dist_p2p", p2p)
         x, r = D.cg(bg[sl].contiguous(), None, 1e-8, 0.0, None)
         assert r["info"] == r_ref["info"] == 0, (r, r_ref)
         assert abs(r["iterations"] - r_ref["iterations"]) <= 2, (r["iterations"], r_ref["iterations"])
@@ -48,6 +52,7 @@ def main():
         x2, r2 = D.cg(bg[sl].contiguous(), None, 1e-8, 0.0, None)
         assert torch.equal(x, x2), "dist cg must be bitwise reproducible"
     D.handle.set_option("loop_mode", 0)
+    D.handle.set_option("dist_p2p", 1)
     # fixed window + warm start
     x0 = xg * 0.01
     x_ref, r_ref = m.cg(bg, x0, 0.0, 0.0, 7)
