@@ -228,8 +228,13 @@ def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSample
     dev = torch.device("cuda", local)
     n = args.n
     rows = n ** 3
+    # BASELINE config 5 geometry: planes of (2n) x (2n), n/4 planes per GPU (n = 256: 64 planes of 512 x 512, so
+    # 8 GPUs hold exactly the 512^3 system and every halo is one 512^2 plane = 2 MiB); per-GPU rows stay n^3.
+    npl, ppg = 2 * n, max(n // 4, 1)
+    if ppg * npl * npl != rows:
+        npl, ppg = n, n
     offsets = [q * rows for q in range(world + 1)]
-    crow, col, val = problems.stencil3d_rows(n, world * n, rank * n, (rank + 1) * n, device=dev)
+    crow, col, val = problems.stencil3d_rows(npl, world * ppg, rank * ppg, (rank + 1) * ppg, device=dev)
     nnz_local = val.numel()
     D = DistMatrix(crow, col, val, offsets, rank, world)
     del crow, col
@@ -259,7 +264,7 @@ def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSample
     value = world * it_s
     bytes_iter = problems.cg_bytes_per_iteration(rows, nnz_local)
     # end to end: host slab -> device, registration, solve window, x back to host
-    crow_h, col_h, val_h = problems.stencil3d_rows(n, world * n, rank * n, (rank + 1) * n)
+    crow_h, col_h, val_h = problems.stencil3d_rows(npl, world * ppg, rank * ppg, (rank + 1) * ppg)
     crow_h, col_h, val_h, b_h = crow_h.pin_memory(), col_h.pin_memory(), val_h.pin_memory(), b.cpu().pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in (crow_h, col_h, val_h, b_h))
     D.close()
@@ -285,11 +290,14 @@ def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSample
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"CG fp64, 7-pt Poisson {world * n}x{n}x{n} CSR row-partitioned over {world} GPUs "
-                               f"({n}^3 rows per GPU), b=ones, fixed window of {window} iterations per step",
+        "config": {"workload": f"CG fp64, 7-pt Poisson {world * ppg}x{npl}x{npl} CSR row-partitioned over {world} GPUs "
+                               f"({n}^3 rows per GPU; 8 GPUs = BASELINE configs[4] 512^3), b=ones, fixed window of "
+                               f"{window} iterations per step",
+                   "comm": "peer-memory (CUDA IPC over NVLink): kernel halo push + one-shot all-reduce" if D.p2p
+                   else "NCCL send/recv + allreduce",
                    "value_definition": f"{world} x global iterations/s = {n}^3-row CG iterations per second over all ranks",
                    "global_iterations_per_second": it_s, "n_local": rows, "nnz_local": nnz_local,
-                   "halo_bytes_per_neighbour": n * n * 8, "peers_rank0": D.plan.peers,
+                   "halo_bytes_per_neighbour": npl * npl * 8, "peers_rank0": D.plan.peers,
                    "l2_policy": "inputs exceed L2; no flush needed"},
         "roofline": {"bound": "hbm", "kernel": "whole distributed CG iteration (per GPU)",
                      "achieved": bytes_iter * it_s / 1e9, "peak": pk, "peak_kind": pk_kind, "unit": "GB/s",
