@@ -120,6 +120,10 @@ int bk_csr_get_info(const bk_csr* A, bk_csr_info* out);
  * ImplicitAdjointFunction.backward :1245 (which raises for CSR on torch 2.11).
  * The returned matrix is owned by A and freed with it. */
 int bk_csr_transpose(bk_handle* h, bk_csr* A, void* stream, bk_csr** out);
+/* out_vals[k] = -g[row(k)] * x[col[k]] for every stored entry k: the gradient of a loss with respect to the
+ * entries of A on its sparsity pattern, given g = A^-T dL/dx (the adjoint solve) and the solution x.
+ * No reference counterpart in Module A (it returns None for A, :1248); SURVEY §8f-3. */
+int bk_csr_grad_pattern(bk_handle* h, const bk_csr* A, const void* g, const void* x, void* out_vals, void* stream);
 /* Export the arrays of a registered matrix (int32 rowptr/col): device pointers, borrowed. */
 int bk_csr_arrays(const bk_csr* A, const void** rowptr, const void** col, const void** val);
 

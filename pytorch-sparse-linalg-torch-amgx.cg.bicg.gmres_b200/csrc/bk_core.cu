@@ -487,3 +487,36 @@ extern "C" int bk_axpby(bk_handle* h, int64_t n, int dtype, double a, const void
   if (dtype == BK_F32) return bk_axpby_t<float>(h, n, a, x, b, y, z, (cudaStream_t)stream);
   return bk_fail(BK_ERR_ARG, "bk_axpby: bad dtype %d", dtype);
 }
+
+// ---- gradient with respect to the stored entries of A -----------------------------------------
+// For A x = b and a loss L(x):  dL/dA_ij = -(A^-T dL/dx)_i x_j = -g_i x_j, evaluated on the sparsity pattern only
+// (an SDDMM-shaped kernel).  The reference returns no gradient for A (torch_sparse_linalg.py:1248); its Modules B/C
+// compute this product with Python row loops (module_b/torch_amgx.py:444-462).  One warp per row.
+template <typename T>
+__global__ void bk_grad_pattern_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                       const T* __restrict__ g, const T* __restrict__ x, T* __restrict__ out,
+                                       long long n) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    const T gi = -g[r];
+    for (int k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) out[k] = gi * x[col[k]];
+  }
+}
+
+extern "C" int bk_csr_grad_pattern(bk_handle* h, const bk_csr* A, const void* g, const void* x, void* out_vals,
+                                   void* stream) {
+  if (!h || !A || (A->nnz > 0 && (!g || !x || !out_vals))) return bk_fail(BK_ERR_ARG, "bk_csr_grad_pattern: null argument");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (A->n == 0 || A->nnz == 0) return BK_OK;
+  int grid = (int)((A->n * 32 + 255) / 256);
+  if (grid > h->num_sms * 8) grid = h->num_sms * 8;
+  if (A->dtype == BK_F64)
+    bk_grad_pattern_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, (const double*)g,
+                                                                            (const double*)x, (double*)out_vals, A->n);
+  else
+    bk_grad_pattern_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, (const float*)g,
+                                                                           (const float*)x, (float*)out_vals, A->n);
+  BK_KERNEL_CHECK();
+  return BK_OK;
+}

@@ -426,7 +426,7 @@ static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user
   bk_state_set_kernel<<<1, 1, 0, s>>>(st, init);
   BK_KERNEL_CHECK();
 
-  const int grid = bk_grid_vec(h);
+  const int grid = bk_grid_vec_n(h, n, 2 * NW);
   auto dot_epi = [&](const void* a, const void* bb, auto epi, int slot) -> int {
     using E = decltype(epi);
     bk_op_dot_epi3<T, E> op;

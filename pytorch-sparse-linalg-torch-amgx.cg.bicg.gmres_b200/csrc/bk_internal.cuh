@@ -183,6 +183,19 @@ static inline int bk_grid_spmv(const bk_handle* h) {
   int g = h->num_sms * h->grid_mult_spmv;
   return g > BK_MAXB ? BK_MAXB : g;
 }
+// Small problems: do not launch more CTAs than there is work for (cheaper launch, fewer partials in the final
+// reduction).  Depends only on the problem size, so the summation order stays a function of (n, grid options).
+static inline int bk_grid_vec_n(const bk_handle* h, long long n, int elems_per_thread) {
+  const int g = bk_grid_vec(h);
+  long long need = (n + (long long)BK_BLOCK * elems_per_thread - 1) / ((long long)BK_BLOCK * elems_per_thread);
+  if (need < 1) need = 1;
+  return need < g ? (int)need : g;
+}
+static inline int bk_grid_rows(int g, long long n, int rows_per_cta) {
+  long long need = (n + rows_per_cta - 1) / rows_per_cta;
+  if (need < 1) need = 1;
+  return need < g ? (int)need : g;
+}
 static inline size_t bk_dtype_size(int dtype) { return dtype == BK_F32 ? 4 : 8; }
 static inline bool bk_aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 

@@ -262,7 +262,6 @@ static inline int bk_set_smem(K kernel, size_t bytes) {
 template <typename T, int MODE, int DOTS, int XMODE, typename Epi>
 static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a, const bk_scratch& sc,
                             Epi epi, cudaStream_t s) {
-  const int grid = bk_grid_spmv(h);
   if (A->kernel == 2 && XMODE == 0) {
     if constexpr (XMODE == 0) {
       // CTAs per SM (2..4) trade pipeline depth for consumer warps; stages fill the per-CTA share of shared memory
@@ -284,6 +283,7 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
       plan.tail_col = A->tail_col;
       int g = h->num_sms * ctas;
       if (g > BK_MAXB) g = BK_MAXB;
+      g = bk_grid_rows(g, A->n, BK_TMA_RPB);
       auto launch = [&](auto k) -> int {
         BK_TRY(bk_ensure_dyn_smem((const void*)k, sm));
         k<<<g, BK_TMA_THREADS, sm, s>>>(a, plan, sc, epi);
@@ -298,6 +298,7 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
       }
     }
   } else if (A->kernel == 0 || A->kernel == 2) {
+    const int grid = bk_grid_rows(bk_grid_spmv(h), A->n, BK_BLOCK);
     if (A->cap <= 256) {
       auto k = bk_spmv_stream_kernel<T, 256, MODE, DOTS, XMODE, Epi>;
       const size_t sm = (size_t)BK_WARPS * 256 * sizeof(T);
@@ -312,6 +313,7 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
     if constexpr (XMODE != 0) {
       return bk_fail(BK_ERR_UNSUPPORTED, "fused p-update needs the row-stream SpMV kernel");
     } else {
+      const int grid = bk_grid_rows(bk_grid_spmv(h), A->n, BK_WARPS * (32 / A->lanes_per_row));
       switch (A->lanes_per_row) {
         case 8:
           bk_spmv_vector_kernel<T, 8, MODE, DOTS, Epi><<<grid, BK_BLOCK, 0, s>>>(a, sc, epi);

@@ -66,8 +66,8 @@ __global__ void __launch_bounds__(BK_BLOCK, 3) bk_ew_kernel(Op op, const long lo
 template <typename T, typename Op>
 static int bk_launch_ew(bk_handle* h, const Op& op, long long n, bool aligned, const bk_scratch& sc,
                         cudaStream_t s) {
-  const int grid = bk_grid_vec(h);
   constexpr int NW = bk_native_w<T>::value;
+  const int grid = bk_grid_vec_n(h, n, 2 * NW);
   if (aligned) {
     bk_ew_kernel<T, NW, Op><<<grid, BK_BLOCK, 0, s>>>(op, n, sc);
   } else {

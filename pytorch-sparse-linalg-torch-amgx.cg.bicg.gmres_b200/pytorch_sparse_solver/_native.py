@@ -73,6 +73,7 @@ _SIGNATURES = {
     "bk_csr_destroy": (C.c_int, [_VP]),
     "bk_csr_get_info": (C.c_int, [_VP, C.POINTER(bk_csr_info)]),
     "bk_csr_transpose": (C.c_int, [_VP, _VP, _VP, C.POINTER(_VP)]),
+    "bk_csr_grad_pattern": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "bk_csr_arrays": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
     "bk_spmv": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "bk_spmv_dot": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
@@ -296,6 +297,15 @@ class CsrMatrix:
             _check(self.handle.lib.bk_spmv_dot(self.handle.ptr, self.ptr, x.data_ptr(), y.data_ptr(), w.data_ptr(),
                                                d.data_ptr(), _stream_ptr(self.device)), "bk_spmv_dot")
         return y, d[0]
+
+    def grad_pattern(self, g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """-g_i x_j on the stored pattern (values in this matrix's CSR order)."""
+        g, x = self._vec(g), self._vec(x)
+        out = torch.empty(self.nnz, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            _check(self.handle.lib.bk_csr_grad_pattern(self.handle.ptr, self.ptr, g.data_ptr(), x.data_ptr(),
+                                                       out.data_ptr(), _stream_ptr(self.device)), "bk_csr_grad_pattern")
+        return out
 
     # ---- solvers -----------------------------------------------------------------------------
     def _solve(self, which: str, b: torch.Tensor, x0: Optional[torch.Tensor], *args) -> Tuple[torch.Tensor, dict]:

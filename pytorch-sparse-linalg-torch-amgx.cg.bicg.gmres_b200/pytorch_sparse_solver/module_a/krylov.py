@@ -40,6 +40,10 @@ __all__ = [
 # tolerance constants even though the tensors live on a CUDA device (reference :737-744).
 GMRES_TOLERANCE_DEVICE: Optional[str] = None
 
+# Opt-in extension: also return dL/dA = -(A^-T dL/dx) x^T on A's sparsity pattern when A requires grad.
+# Off by default because the reference returns None for A (:1248).
+GRAD_WRT_A: bool = False
+
 # Filled by every solve: the native bk_result of the most recent call (iterations, matvecs, ...).
 # The reference returns no iteration count (solver.py:373); this is strictly extra information.
 last_result: dict = {}
@@ -176,18 +180,40 @@ class _ImplicitAdjoint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, b, x, name, x0, tol, atol, restart, maxiter, solve_method):
         ctx.A = A
+        ctx.x = x.detach()
         ctx.meta = (name, x0, tol, atol, restart, maxiter, solve_method)
         return x.clone()
 
     @staticmethod
     def backward(ctx, grad_output):
         name, x0, tol, atol, restart, maxiter, solve_method = ctx.meta
-        grad_b = None
-        if ctx.needs_input_grad[1]:
+        grad_b = grad_A = None
+        want_A = GRAD_WRT_A and ctx.needs_input_grad[0]
+        if ctx.needs_input_grad[1] or want_A:
             g, _ = _solve_core(name, ctx.A, grad_output.contiguous(), x0, tol, atol, maxiter, restart, solve_method,
                                transpose=True)
-            grad_b = g.to(grad_output.dtype)
-        return (None, grad_b) + (None,) * 8
+            if ctx.needs_input_grad[1]:
+                grad_b = g.to(grad_output.dtype)
+            if want_A:
+                grad_A = _grad_wrt_matrix(ctx.A, g, ctx.x)
+        return (grad_A, grad_b) + (None,) * 8
+
+
+def _grad_wrt_matrix(A: torch.Tensor, g: torch.Tensor, x: torch.Tensor) -> Optional[torch.Tensor]:
+    """dL/dA in A's own layout: -g x^T restricted to the stored pattern for CSR / coalesced COO, dense outer product
+    for strided A."""
+    with torch.no_grad():
+        if A.layout == torch.strided:
+            return -torch.outer(g.to(A.dtype), x.to(A.dtype))
+        if not A.is_cuda:
+            return None
+        wdt = torch.float32 if (A.dtype == torch.float32 and g.dtype == torch.float32) else torch.float64
+        if A.layout == torch.sparse_coo and not A.is_coalesced():
+            return None
+        vals = _native.register_matrix(A, wdt).grad_pattern(g.to(wdt), x.to(wdt)).to(A.dtype)
+        if A.layout == torch.sparse_csr:
+            return torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), vals, size=A.shape)
+        return torch.sparse_coo_tensor(A._indices(), vals, A.shape).coalesce()
 
 
 def _finish(name, A, b, x, info, x0, tol, atol, restart, maxiter, solve_method):

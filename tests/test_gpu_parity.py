@@ -365,6 +365,36 @@ def test_autograd_grad_b(ma, manifest, kind, layout):
     assert rel_diff(x, data["x"]) <= FP64_TOL
 
 
+@pytest.mark.parametrize("layout", ["csr", "coo", "dense"])
+def test_optional_gradient_wrt_matrix(ma, manifest, layout):
+    """Opt-in dL/dA against the analytic -A^-T (dL/dx) x^T on the pattern; default stays None (:1248)."""
+    from pytorch_sparse_solver.module_a import krylov
+    entry = manifest["autograd"]["autograd_bicgstab"]
+    data = load_case("autograd_bicgstab")
+    A_cpu = build_matrix(entry["gen"])
+    Ad = A_cpu.to_dense()
+    x_true = torch.linalg.solve(Ad, data["b"])
+    gA_true = -torch.outer(torch.linalg.solve(Ad.T, 2 * x_true), x_true)
+    A = {"csr": A_cpu.cuda(), "coo": A_cpu.to_sparse_coo().coalesce().cuda(), "dense": Ad.cuda()}[layout]
+    A.requires_grad_(True)
+    b = data["b"].cuda().requires_grad_(True)
+    x, info = ma.bicgstab(A, b, tol=1e-12)
+    (x ** 2).sum().backward()
+    assert A.grad is None and b.grad is not None          # reference behaviour
+    krylov.GRAD_WRT_A = True
+    try:
+        b.grad = None
+        x, info = ma.bicgstab(A, b, tol=1e-12)
+        (x ** 2).sum().backward()
+    finally:
+        krylov.GRAD_WRT_A = False
+    assert A.grad is not None and A.grad.layout == A.layout
+    got = A.grad.to_dense().cpu()
+    mask = (Ad != 0) if layout != "dense" else torch.ones_like(Ad, dtype=torch.bool)
+    assert rel_diff(got[mask], gA_true[mask]) <= 1e-8
+    assert float(got[~mask].abs().max() if (~mask).any() else 0.0) == 0.0
+
+
 @pytest.mark.parametrize("kind", ["cg", "bicgstab", "gmres"])
 def test_legacy_differentiable(ma, manifest, kind):
     entry = manifest["autograd"][f"autograd_{kind}"]
