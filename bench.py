@@ -255,7 +255,7 @@ def run_single(args):
                    "l2_policy": "inputs (2.9 GB/iteration) exceed L2; no flush needed",
                    "options": {k: h.get_option(k) for k in ("tma_ctas", "tma_stages", "grid_mult_spmv", "grid_mult_vec",
                                                             "fuse_xpay", "snake", "loop_mode", "chunk")}},
-        "roofline": {"bound": "hbm", "kernel": "bk_spmv_tma_kernel (CSR SpMV fused with p.Ap)" if m.info()["kernel"] == 2 else "bk_spmv_stream_kernel (CSR SpMV fused with p.Ap)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": {0: "bk_spmv_stream_kernel", 1: "bk_spmv_vector_kernel", 2: "bk_spmv_tma_kernel<int32 columns>", 3: "bk_spmv_tma_kernel<8-bit dictionary-coded columns>"}[m.info()["kernel"]] + " (CSR SpMV fused with p.Ap)", "achieved": achieved,
                      "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "bytes_per_launch": bytes_k1, "ms_per_launch": k1_ms},
         "iteration": {"bytes_per_iteration": bytes_iter, "achieved_gbs": bytes_iter * value / 1e9,

@@ -180,7 +180,7 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
                    int64_t maxiter, bk_result* res, cudaStream_t s) {
   const long long n = A->n;
   const size_t npad = ((size_t)n + 63) & ~(size_t)63;
-  const bool fuse = h->fuse_xpay && (A->kernel == 0 || A->kernel == 2);
+  const bool fuse = h->fuse_xpay && A->kernel != 1;
   BK_TRY(bk_ws_reserve(h, (size_t)5 * npad * sizeof(T)));
   bk_cg_vecs<T> v;
   v.x = (T*)h->ws;

@@ -47,6 +47,7 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->tma_stages = (int)bk_env_int("BK_TMA_STAGES", 0);
   h->use_tma = (int)bk_env_int("BK_SPMV_TMA", 1);
   h->dist_p2p = (int)bk_env_int("BK_DIST_P2P", 1);
+  h->use_compress = (int)bk_env_int("BK_SPMV_COMPRESS", 1);
   h->loop_mode = (int)bk_env_int("BK_LOOP_MODE", BK_LOOP_AUTO);
   h->chunk = (int)bk_env_int("BK_CHUNK", 0);
   h->fuse_xpay = (int)bk_env_int("BK_FUSE_XPAY", 0);
@@ -135,6 +136,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "tma_stages")) return &h->tma_stages;
   if (!strcmp(key, "use_tma")) return &h->use_tma;
   if (!strcmp(key, "dist_p2p")) return &h->dist_p2p;
+  if (!strcmp(key, "use_compress")) return &h->use_compress;
   if (!strcmp(key, "loop_mode")) return &h->loop_mode;
   if (!strcmp(key, "chunk")) return &h->chunk;
   if (!strcmp(key, "fuse_xpay")) return &h->fuse_xpay;
@@ -222,7 +224,7 @@ static void bk_csr_plan(bk_handle* h, bk_csr* A) {
 }
 
 // widest 16-byte aligned val/col span of any 256-row block: max over blocks of ((e+3)&~3) - (s&~3)
-__global__ void bk_block_span_kernel(const int* __restrict__ rowptr, long long n, long long nblk, int rpb,
+__global__ void bk_block_span_kernel(const int* __restrict__ rowptr, long long n, long long nblk, int rpb, int al,
                                      int* __restrict__ out) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   int mx = 0;
@@ -230,10 +232,93 @@ __global__ void bk_block_span_kernel(const int* __restrict__ rowptr, long long n
     const long long r0 = b * rpb;
     const long long r1 = (r0 + rpb < n) ? r0 + rpb : n;
     const int s = rowptr[r0], e = rowptr[r1];
-    mx = max(mx, ((e + 3) & ~3) - (s & ~3));
+    mx = max(mx, ((e + al - 1) & ~(al - 1)) - (s & ~(al - 1)));
   }
   for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) atomicMax(out, mx);
+}
+
+// ---- 8-bit dictionary coding of the column stream (kernel 3) ---------------------------------------------------
+// For every 256-row block collect the distinct (column - row) offsets; if no block has more than 32 of them (all
+// stencil / structured-grid matrices), each column index is replaced by a 1-byte code into its block's dictionary.
+#define BK_DICT_EMPTY ((int)0x80000000)
+__global__ void __launch_bounds__(256)
+bk_build_dict_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, long long n, long long nblk,
+                     int* __restrict__ dict, unsigned char* __restrict__ codes, int* __restrict__ fail) {
+  __shared__ int tab[32];
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    if (threadIdx.x < 32) tab[threadIdx.x] = BK_DICT_EMPTY;
+    __syncthreads();
+    const long long r = blk * 256 + threadIdx.x;
+    if (r < n) {
+      for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+        const int off = col[k] - (int)r;
+        int code = -1;
+        for (int i = 0; i < 32 && code < 0; ++i) {
+          int old = ((volatile int*)tab)[i];
+          if (old == BK_DICT_EMPTY) old = atomicCAS(&tab[i], BK_DICT_EMPTY, off);
+          if (old == BK_DICT_EMPTY || old == off) code = i;
+        }
+        if (code < 0) {
+          *fail = 1;
+          code = 0;
+        }
+        codes[k] = (unsigned char)code;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) dict[blk * 32 + threadIdx.x] = (tab[threadIdx.x] == BK_DICT_EMPTY) ? 0 : tab[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+static int bk_csr_plan_compress(bk_handle* h, bk_csr* A, cudaStream_t s) {
+  if (A->kernel != 2 || !h->use_compress) return BK_OK;
+  const long long nblk = (A->n + 255) / 256;
+  const size_t vs = bk_dtype_size(A->dtype);
+  int* dstat = (int*)(h->counters + 8);
+  int host[2] = {0, 0};
+  if (cudaMalloc((void**)&A->codes, (size_t)A->nnz + 64) != cudaSuccess ||
+      cudaMalloc((void**)&A->dict, sizeof(int) * 32 * (size_t)nblk) != cudaSuccess) {
+    cudaGetLastError();
+    if (A->codes) cudaFree(A->codes);
+    A->codes = nullptr;
+    return BK_OK;  // not enough memory for the coded copy: stay on int32 columns
+  }
+  cudaMemsetAsync(dstat, 0, 2 * sizeof(int), s);
+  int grid = (int)(nblk < (long long)h->num_sms * 8 ? nblk : (long long)h->num_sms * 8);
+  bk_build_dict_kernel<<<grid, 256, 0, s>>>(A->rowptr, A->col, A->n, nblk, A->dict, A->codes, dstat + 1);
+  bk_block_span_kernel<<<h->num_sms * 4, 256, 0, s>>>(A->rowptr, A->n, nblk, 256, 16, dstat);
+  cudaMemcpyAsync(host, dstat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return bk_fail(BK_ERR_CUDA, "csr registration (index coding): %s", cudaGetErrorString(e));
+  const int cap = (host[0] + 31) & ~31;
+  const size_t stage = (size_t)cap * (vs + 1) + 128;
+  if (host[1] != 0 || cap <= 0 || 2 * stage > 110 * 1024) {  // a block with > 32 distinct offsets, or too wide
+    cudaFree(A->codes);
+    cudaFree(A->dict);
+    A->codes = nullptr;
+    A->dict = nullptr;
+    return BK_OK;
+  }
+  const int tail = (int)(A->nnz & 15);
+  if (tail) {
+    if (cudaMalloc(&A->tail_val16, 16 * vs) != cudaSuccess || cudaMalloc((void**)&A->tail_code16, 16) != cudaSuccess) {
+      cudaGetLastError();
+      return bk_fail(BK_ERR_ALLOC, "csr registration: tail buffer allocation failed");
+    }
+    const int64_t base = A->nnz & ~(int64_t)15;
+    cudaMemsetAsync(A->tail_val16, 0, 16 * vs, s);
+    cudaMemsetAsync(A->tail_code16, 0, 16, s);
+    cudaMemcpyAsync(A->tail_val16, (const char*)A->val + base * vs, tail * vs, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(A->tail_code16, A->codes + base, tail, cudaMemcpyDeviceToDevice, s);
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return bk_fail(BK_ERR_CUDA, "csr registration (coded tail): %s", cudaGetErrorString(e));
+  }
+  A->cmp_cap = cap;
+  A->kernel = 3;
+  return BK_OK;
 }
 
 // Decide whether the TMA row-stream kernel (bk_spmv_tma.cuh) can serve this matrix, size its pipeline and
@@ -245,7 +330,7 @@ static int bk_csr_plan_tma(bk_handle* h, bk_csr* A, cudaStream_t s) {
   int* dstat = (int*)(h->counters + 8);
   int span = 0;
   cudaMemsetAsync(dstat, 0, sizeof(int), s);
-  bk_block_span_kernel<<<h->num_sms * 4, 256, 0, s>>>(A->rowptr, A->n, nblk, 256, dstat);
+  bk_block_span_kernel<<<h->num_sms * 4, 256, 0, s>>>(A->rowptr, A->n, nblk, 256, 4, dstat);
   cudaMemcpyAsync(&span, dstat, sizeof(int), cudaMemcpyDeviceToHost, s);
   cudaError_t e = cudaStreamSynchronize(s);
   if (e == cudaSuccess) e = cudaGetLastError();
@@ -274,7 +359,7 @@ static int bk_csr_plan_tma(bk_handle* h, bk_csr* A, cudaStream_t s) {
   A->tma_cap = cap;
   A->tma_stages = stages;
   A->kernel = 2;
-  return BK_OK;
+  return bk_csr_plan_compress(h, A, s);
 }
 
 // statistics + validation + kernel plan (one sync at registration time; never on the per-iteration path)
@@ -378,6 +463,10 @@ extern "C" int bk_csr_destroy(bk_csr* A) {
   if (A->own_val) cudaFree(A->own_val);
   if (A->tail_val) cudaFree(A->tail_val);
   if (A->tail_col) cudaFree(A->tail_col);
+  if (A->codes) cudaFree(A->codes);
+  if (A->dict) cudaFree(A->dict);
+  if (A->tail_val16) cudaFree(A->tail_val16);
+  if (A->tail_code16) cudaFree(A->tail_code16);
   free(A);
   return BK_OK;
 }

@@ -94,13 +94,19 @@ struct bk_csr {
   void* own_rowptr;   // non-null when the library owns (converted / copied) arrays
   void* own_col;
   void* own_val;
-  int kernel;         // 0 row-stream (LDG staged), 1 sub-warp vector, 2 row-stream with TMA-staged matrix tiles
+  int kernel;         // 0 row-stream (LDG staged), 1 sub-warp vector, 2 row-stream with TMA-staged tiles, 3 = 2 + 8-bit column codes
   int lanes_per_row;
   int cap;            // row-stream: shared-memory products per warp
   int tma_cap;        // TMA row-stream: entries per pipeline stage (multiple of 4)
   int tma_stages;     // TMA row-stream: pipeline depth
   void* tail_val;     // TMA row-stream: the last nnz%4 entries, zero-padded to 4 (own)
   int* tail_col;
+  // compressed index stream (kernel 3): 8-bit codes into per-block dictionaries of (column - row) offsets
+  unsigned char* codes;      // nnz (+ padding) bytes, own
+  int* dict;                 // nblk * 32 offsets, own
+  void* tail_val16;          // last nnz%16 entries zero-padded to 16 (own)
+  unsigned char* tail_code16;
+  int cmp_cap;               // entries per stage for the compressed variant
   int max_row_nnz;
   double mean_row_nnz;
   bk_csr* transpose;  // cached, owned
@@ -127,6 +133,7 @@ struct bk_handle {
   int tma_ctas;        // CTAs/SM of the TMA row-stream SpMV (2..4)
   int tma_stages;      // 0 = fill shared memory, else cap on the pipeline depth
   int use_tma;         // allow the TMA row-stream kernel
+  int use_compress;    // allow the 8-bit dictionary-coded column stream (kernel 3)
   int dist_p2p;        // multi-GPU: use the peer-memory path (halo push + one-shot all-reduce) when it is connected
   int loop_mode;
   int chunk;

@@ -262,11 +262,13 @@ static inline int bk_set_smem(K kernel, size_t bytes) {
 template <typename T, int MODE, int DOTS, int XMODE, typename Epi>
 static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a, const bk_scratch& sc,
                             Epi epi, cudaStream_t s) {
-  if (A->kernel == 2 && XMODE == 0) {
+  if ((A->kernel == 2 || A->kernel == 3) && XMODE == 0) {
     if constexpr (XMODE == 0) {
       // CTAs per SM (2..4) trade pipeline depth for consumer warps; stages fill the per-CTA share of shared memory
       int ctas = h->tma_ctas < 2 ? 2 : (h->tma_ctas > 4 ? 4 : h->tma_ctas);
-      const size_t stage_bytes = (size_t)A->tma_cap * (sizeof(T) + 4);
+      const bool cmp = (A->kernel == 3);
+      const int cap = cmp ? A->cmp_cap : A->tma_cap;
+      const size_t stage_bytes = (size_t)cap * (sizeof(T) + (cmp ? 1 : 4)) + (cmp ? 128 : 0);
       int stages = 0;
       for (; ctas >= 2; --ctas) {
         stages = (int)(((size_t)224 * 1024 / ctas - 2048) / stage_bytes);
@@ -276,11 +278,13 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
       if (h->tma_stages >= 2 && h->tma_stages < stages) stages = h->tma_stages;
       const size_t sm = (size_t)stages * stage_bytes;
       bk_tma_plan plan;
-      plan.cap = A->tma_cap;
+      plan.cap = cap;
       plan.stages = stages;
-      plan.nnz_al = (int)(A->nnz & ~(int64_t)3);
-      plan.tail_val = A->tail_val;
-      plan.tail_col = A->tail_col;
+      plan.nnz_al = (int)(A->nnz & ~(int64_t)(cmp ? 15 : 3));
+      plan.tail_val = cmp ? A->tail_val16 : A->tail_val;
+      plan.tail_idx = cmp ? (const void*)A->tail_code16 : (const void*)A->tail_col;
+      plan.idx = cmp ? (const void*)A->codes : (const void*)A->col;
+      plan.dict = A->dict;
       int g = h->num_sms * ctas;
       if (g > BK_MAXB) g = BK_MAXB;
       g = bk_grid_rows(g, A->n, BK_TMA_RPB);
@@ -289,15 +293,23 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
         k<<<g, BK_TMA_THREADS, sm, s>>>(a, plan, sc, epi);
         return BK_OK;
       };
-      if (ctas == 2) {
-        BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 2, Epi>));
+      if (cmp) {
+        if (ctas == 2) {
+          BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 2, 1, Epi>));
+        } else if (ctas == 3) {
+          BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 3, 1, Epi>));
+        } else {
+          BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 4, 1, Epi>));
+        }
+      } else if (ctas == 2) {
+        BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 2, 0, Epi>));
       } else if (ctas == 3) {
-        BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 3, Epi>));
+        BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 3, 0, Epi>));
       } else {
-        BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 4, Epi>));
+        BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 4, 0, Epi>));
       }
     }
-  } else if (A->kernel == 0 || A->kernel == 2) {
+  } else if (A->kernel == 0 || A->kernel == 2 || A->kernel == 3) {
     const int grid = bk_grid_rows(bk_grid_spmv(h), A->n, BK_BLOCK);
     if (A->cap <= 256) {
       auto k = bk_spmv_stream_kernel<T, 256, MODE, DOTS, XMODE, Epi>;

@@ -69,15 +69,22 @@ __device__ __forceinline__ void bk_bulk_g2s(void* dst_smem, const void* src_gmem
 }
 
 struct bk_tma_plan {
-  int cap;            // entries per stage (multiple of 4)
+  int cap;            // entries per stage (multiple of 32)
   int stages;
-  int nnz_al;         // nnz & ~3: entries below come from the caller's arrays, the rest from the tail buffer
+  int nnz_al;         // nnz rounded down to the copy alignment: entries below come from the main arrays, the rest from the tail buffers
   const void* tail_val;
-  const int* tail_col;
+  const void* tail_idx;
+  const void* idx;    // IDX 0: int32 column indices; IDX 1: 8-bit dictionary codes
+  const int* dict;    // IDX 1: per 256-row block, 32 int32 (column - row) offsets
 };
 
+// IDX selects how column indices are stored for this matrix (decided at registration, bk_csr_plan_tma):
+//   0  int32 columns (4 B per entry; the general case)
+//   1  one byte per entry: a code into the block's dictionary of distinct (column - row) offsets (<= 32 per 256-row
+//      block — every stencil / structured-grid matrix qualifies).  The SpMV then moves nnz*(sizeof T + 1) instead of
+//      nnz*(sizeof T + 4) matrix bytes: 20 % less HBM traffic per fp64 SpMV than the algorithmic CSR byte count.
 // MODE: 0 y = A x, 1 y = b - A x.   DOTS: bit0 w.y, bit1 y.y.
-template <typename T, int MODE, int DOTS, int MINB, typename Epi>
+template <typename T, int MODE, int DOTS, int MINB, int IDX, typename Epi>
 __global__ void __launch_bounds__(BK_TMA_THREADS, MINB)
 bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratch sc, Epi epi) {
   if (bk_spmv_skip(a)) return;
@@ -86,11 +93,14 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
   __shared__ __align__(8) uint64_t empty_bar[BK_TMA_MAX_STAGES];
   __shared__ int s_base[BK_TMA_MAX_STAGES];
   constexpr int R = bk_ndots<DOTS>::value;
+  constexpr int AL = IDX ? 16 : 4;        // entries per 16 bytes of the index stream
+  constexpr int IB = IDX ? 1 : 4;         // bytes per index entry
+  constexpr int DICT_BYTES = IDX ? 128 : 0;
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int nstage = plan.stages;
   const int cap = plan.cap;
-  const size_t stage_bytes = (size_t)cap * (sizeof(T) + 4);
+  const size_t stage_bytes = (size_t)cap * (sizeof(T) + IB) + DICT_BYTES;
   const int* __restrict__ rowptr = a.rowptr;
   const long long n = a.n;
   const int nnz = a.nnz;
@@ -120,7 +130,7 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
   if (wid == BK_WARPS) {
     // ------------------------------ producer warp ------------------------------------------------
     const T* __restrict__ val = static_cast<const T*>(a.val);
-    const int* __restrict__ col = a.col;
+    const unsigned char* __restrict__ idx = static_cast<const unsigned char*>(plan.idx);
     const uint64_t pol = bk_policy_evict_first();
     int s_cur = 0, e_cur = 0;  // lane j holds the span of iteration (batch*32 + j)
     for (long long it0 = 0; it0 < my_iters; it0 += 32) {
@@ -141,24 +151,27 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
         if (lane == 0) {
           const int stage = (int)(it % nstage);
           if (it >= nstage) bk_mbar_wait(&empty_bar[stage], (uint32_t)(((it / nstage) - 1) & 1));
-          const int s_al = s & ~3;
-          int e_al = (e + 3) & ~3;
+          const int s_al = s & ~(AL - 1);
+          int e_al = (e + AL - 1) & ~(AL - 1);
           const bool has_tail = e_al > plan.nnz_al;  // this block reaches the unaligned end of the matrix
           if (has_tail) e_al = plan.nnz_al;
           const int main_cnt = e_al > s_al ? e_al - s_al : 0;
-          const int tail_cnt = (has_tail && e > s) ? 4 : 0;
+          const int tail_cnt = (has_tail && e > s) ? AL : 0;
           unsigned char* sv = bk_smem_tma + (size_t)stage * stage_bytes;
-          unsigned char* scol = sv + (size_t)cap * sizeof(T);
+          unsigned char* sidx = sv + (size_t)cap * sizeof(T);
           s_base[stage] = s_al;
-          bk_mbar_expect_tx(&full_bar[stage], (uint32_t)((main_cnt + tail_cnt) * (sizeof(T) + 4)));
+          bk_mbar_expect_tx(&full_bar[stage], (uint32_t)((main_cnt + tail_cnt) * (sizeof(T) + IB) + DICT_BYTES));
           if (main_cnt > 0) {
             bk_bulk_g2s(sv, val + s_al, (uint32_t)(main_cnt * sizeof(T)), &full_bar[stage], pol);
-            bk_bulk_g2s(scol, col + s_al, (uint32_t)(main_cnt * 4), &full_bar[stage], pol);
+            bk_bulk_g2s(sidx, idx + (size_t)s_al * IB, (uint32_t)(main_cnt * IB), &full_bar[stage], pol);
           }
           if (tail_cnt > 0) {
-            const int off = plan.nnz_al - s_al;  // >= 0 because s <= e and e > nnz_al - 4
-            bk_bulk_g2s(sv + (size_t)off * sizeof(T), plan.tail_val, (uint32_t)(4 * sizeof(T)), &full_bar[stage], pol);
-            bk_bulk_g2s(scol + (size_t)off * 4, plan.tail_col, 16u, &full_bar[stage], pol);
+            const int off = plan.nnz_al - s_al;  // >= 0: s_al <= nnz_al whenever the block reaches the tail
+            bk_bulk_g2s(sv + (size_t)off * sizeof(T), plan.tail_val, (uint32_t)(AL * sizeof(T)), &full_bar[stage], pol);
+            bk_bulk_g2s(sidx + (size_t)off * IB, plan.tail_idx, (uint32_t)(AL * IB), &full_bar[stage], pol);
+          }
+          if constexpr (IDX == 1) {
+            bk_bulk_g2s(sidx + (size_t)cap * IB, plan.dict + block_of(it) * 32, 128u, &full_bar[stage], pol);
           }
         }
         __syncwarp();
@@ -188,9 +201,10 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
       }
       const int stage = (int)(it % nstage);
       bk_mbar_wait(&full_bar[stage], (uint32_t)((it / nstage) & 1));
-      const T* __restrict__ sval = reinterpret_cast<const T*>(bk_smem_tma + (size_t)stage * stage_bytes);
-      const int* __restrict__ scol = reinterpret_cast<const int*>(bk_smem_tma + (size_t)stage * stage_bytes +
-                                                                  (size_t)cap * sizeof(T));
+      const unsigned char* sbase = bk_smem_tma + (size_t)stage * stage_bytes;
+      const T* __restrict__ sval = reinterpret_cast<const T*>(sbase);
+      const unsigned char* __restrict__ sidx = sbase + (size_t)cap * sizeof(T);
+      const int* __restrict__ sdict = reinterpret_cast<const int*>(sidx + (size_t)cap * IB);
       const int off = rs - s_base[stage];
       const int len = re - rs;
       T sum = T(0);
@@ -200,7 +214,11 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const bool p = k0 + u < len;
-          c[u] = p ? scol[off + k0 + u] : -1;
+          if constexpr (IDX == 1) {
+            c[u] = p ? (int)row + sdict[sidx[off + k0 + u] & 31] : -1;
+          } else {
+            c[u] = p ? reinterpret_cast<const int*>(sidx)[off + k0 + u] : -1;
+          }
           v[u] = p ? sval[off + k0 + u] : T(0);
         }
         T xv[8];

@@ -103,7 +103,7 @@ def test_spmv_matches_cpu(name, make, idx):
 def test_spmv_kernel_selection():
     from pytorch_sparse_solver import _native
     m = _native.register_matrix(build_matrix(dict(matrix="poisson3d", n=12), device="cuda"))
-    assert m.info()["kernel"] in (0, 2) and m.info()["max_row_nnz"] == 7
+    assert m.info()["kernel"] in (0, 2, 3) and m.info()["max_row_nnz"] == 7
     m2 = _native.register_matrix(_random_csr(600, 200, 4).cuda())
     assert m2.info()["kernel"] == 1
 
@@ -131,10 +131,46 @@ def test_spmv_tma_and_ldg_row_stream_agree(name, make):
         _native.clear_cache()
     assert k0 in (0, 1)
     if k0 == 0 and name != "rand_mean20":
-        assert k1 == 2, "short-row matrices should take the TMA row-stream kernel"
+        assert k1 in (2, 3), "short-row matrices should take the TMA row-stream kernel"
     scale = float(y0.abs().max()) + 1e-300
     assert float((y0 - y1).abs().max()) <= 1e-13 * scale
     assert abs(float(d1) - float(torch.dot(x, y0))) <= 1e-11 * float(x.abs() @ y0.abs() + 1e-300)
+
+
+@pytest.mark.parametrize("gen", [dict(matrix="poisson3d", n=13), dict(matrix="convdiff3d", n=10),
+                                 dict(matrix="poisson2d", nx=40, ny=27), dict(matrix="ldc", nx=23)])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_spmv_dictionary_coded_columns_bitwise(gen, dtype):
+    """Kernel 3 (8-bit dictionary-coded column stream) must equal kernel 2 (int32 columns) bit for bit."""
+    from pytorch_sparse_solver import _native
+    h = _native.Handle.get(torch.device("cuda"))
+    A = build_matrix(gen, device="cuda")
+    x = torch.randn(A.shape[0], dtype=dtype, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+    try:
+        h.set_option("use_compress", 0)
+        _native.clear_cache()
+        m2 = _native.register_matrix(A, dtype)
+        y2, d2 = m2.spmv_dot(x, x)
+        assert m2.info()["kernel"] == 2
+        h.set_option("use_compress", 1)
+        _native.clear_cache()
+        m3 = _native.register_matrix(A, dtype)
+        y3, d3 = m3.spmv_dot(x, x)
+        assert m3.info()["kernel"] == 3, "stencil matrices have <= 32 distinct offsets per block"
+        t3 = m3.transpose()
+        yt = t3.spmv(x)
+    finally:
+        h.set_option("use_compress", 1)
+        _native.clear_cache()
+    assert torch.equal(y2, y3) and float(d2) == float(d3)
+    ref = torch.matmul(A.cpu().to_dense().T.double(), x.cpu().double())
+    assert rel_diff(yt, ref) <= (1e-13 if dtype == torch.float64 else 1e-5)
+
+
+def test_spmv_dictionary_falls_back_on_unstructured():
+    from pytorch_sparse_solver import _native
+    m = _native.register_matrix(_random_csr(1000, 5, 1, empty_rows=True).cuda())
+    assert m.info()["kernel"] == 2
 
 
 def test_spmv_fp32():

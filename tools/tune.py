@@ -87,6 +87,19 @@ def main():
         emit(what="bk_spmv_dot_tma", kernel=m.info()["kernel"], tma_ctas=ctas, tma_stages=st, gbs=bytes_spmv / ms / 1e6, ms=ms)
     h.set_option("tma_ctas", 4)
     h.set_option("tma_stages", 0)
+    for cmp_ in (0, 1):
+        h.set_option("use_compress", cmp_)
+        _native.clear_cache()
+        mm = _native.register_matrix(A)
+        for ctas in (3, 4):
+            h.set_option("tma_ctas", ctas)
+            ms = time_gpu(lambda: mm.spmv_dot(x, x), reps=10)
+            emit(what="bk_spmv_dot_compress", kernel=mm.info()["kernel"], use_compress=cmp_, tma_ctas=ctas,
+                 gbs_algorithmic=bytes_spmv / ms / 1e6, ms=ms)
+    h.set_option("tma_ctas", 4)
+    h.set_option("use_compress", 1)
+    _native.clear_cache()
+    m = _native.register_matrix(A)
     for gm in (() if m.info()["kernel"] == 2 else (2, 3, 4, 6, 8)):
         h.set_option("grid_mult_spmv", gm)
         ms = time_gpu(lambda: m.spmv(x, out=y), reps=10)
