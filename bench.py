@@ -253,7 +253,7 @@ def run_single(args):
                    "n": N, "nnz": nnz, "iterations_per_solve": last["iterations"], "info": last["info"],
                    "relres": last["final_residual"] / last["b_norm"],
                    "l2_policy": "inputs (2.9 GB/iteration) exceed L2; no flush needed",
-                   "options": {k: h.get_option(k) for k in ("tma_ctas", "tma_stages", "grid_mult_spmv", "grid_mult_vec",
+                   "options": {k: h.get_option(k) for k in ("use_tma", "use_compress", "tma_ctas", "tma_stages", "grid_mult_spmv", "grid_mult_vec",
                                                             "fuse_xpay", "snake", "loop_mode", "chunk")}},
         "roofline": {"bound": "hbm", "kernel": {0: "bk_spmv_stream_kernel", 1: "bk_spmv_vector_kernel", 2: "bk_spmv_tma_kernel<int32 columns>", 3: "bk_spmv_tma_kernel<8-bit dictionary-coded columns>"}[m.info()["kernel"]] + " (CSR SpMV fused with p.Ap)", "achieved": achieved,
                      "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": achieved / peak,

@@ -179,28 +179,39 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
     }
   } else {
     // ------------------------------ consumer warps -----------------------------------------------
+    // (32-bit row / block arithmetic: n < 2^31 is guaranteed by bk_csr_create)
     const T* __restrict__ x = static_cast<const T*>(a.x);
     T* __restrict__ y = static_cast<T*>(a.y);
+    const int n32 = (int)n;
+    const int nblk32 = (int)nblk;
+    const int iters32 = (int)my_iters;
+    const int gstep = (int)gridDim.x;
+    const int lane_row = wid * 32 + lane;
+    auto row_of = [&](int it) -> int {
+      const int blk = (int)blockIdx.x + it * gstep;
+      return (reverse ? (nblk32 - 1 - blk) : blk) * BK_TMA_RPB + lane_row;
+    };
     int rs = nnz, re = nnz;
-    if (my_iters > 0) {
-      const long long r = block_of(0) * BK_TMA_RPB + wid * 32 + lane;
-      if (r < n) {
+    if (iters32 > 0) {
+      const int r = row_of(0);
+      if (r < n32) {
         rs = __ldg(rowptr + r);
         re = __ldg(rowptr + r + 1);
       }
     }
-    for (long long it = 0; it < my_iters; ++it) {
-      const long long row = block_of(it) * BK_TMA_RPB + wid * 32 + lane;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < iters32; ++it) {
+      const int row = row_of(it);
       int rs_n = nnz, re_n = nnz;
-      if (it + 1 < my_iters) {  // prefetch the next block's row extents
-        const long long r = block_of(it + 1) * BK_TMA_RPB + wid * 32 + lane;
-        if (r < n) {
+      if (it + 1 < iters32) {  // prefetch the next block's row extents
+        const int r = row_of(it + 1);
+        if (r < n32) {
           rs_n = __ldg(rowptr + r);
           re_n = __ldg(rowptr + r + 1);
         }
       }
-      const int stage = (int)(it % nstage);
-      bk_mbar_wait(&full_bar[stage], (uint32_t)((it / nstage) & 1));
+      bk_mbar_wait(&full_bar[stage], phase);
       const unsigned char* sbase = bk_smem_tma + (size_t)stage * stage_bytes;
       const T* __restrict__ sval = reinterpret_cast<const T*>(sbase);
       const unsigned char* __restrict__ sidx = sbase + (size_t)cap * sizeof(T);
@@ -208,28 +219,36 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
       const int off = rs - s_base[stage];
       const int len = re - rs;
       T sum = T(0);
+      // Branch-free batches of 8 entries: every shared-memory load of a batch is issued before any dependent one
+      // (slots past the row end re-read the row's last entry and contribute 0), then all 8 gathers, then the FMA chain.
+      const int last = off + len - 1;
       for (int k0 = 0; k0 < len; k0 += 8) {
+        int kk[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) kk[u] = min(off + k0 + u, last);
         int c[8];
+        if constexpr (IDX == 1) {
+          unsigned int code[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) code[u] = sidx[kk[u]];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) c[u] = row + sdict[code[u] & 31u];
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) c[u] = reinterpret_cast<const int*>(sidx)[kk[u]];
+        }
         T v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const bool p = k0 + u < len;
-          if constexpr (IDX == 1) {
-            c[u] = p ? (int)row + sdict[sidx[off + k0 + u] & 31] : -1;
-          } else {
-            c[u] = p ? reinterpret_cast<const int*>(sidx)[off + k0 + u] : -1;
-          }
-          v[u] = p ? sval[off + k0 + u] : T(0);
-        }
+        for (int u = 0; u < 8; ++u) v[u] = sval[kk[u]];
         T xv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) xv[u] = (c[u] >= 0) ? __ldg(x + c[u]) : T(0);
+        for (int u = 0; u < 8; ++u) xv[u] = __ldg(x + c[u]);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sum = fma(v[u], xv[u], sum);
+        for (int u = 0; u < 8; ++u) sum = fma((k0 + u < len) ? v[u] : T(0), xv[u], sum);
       }
       __syncwarp();
       if (lane == 0) bk_mbar_arrive(&empty_bar[stage]);
-      if (row < n) {
+      if (row < n32) {
         T out = sum;
         if constexpr (MODE == 1) out = bk_sub(__ldg(static_cast<const T*>(a.b) + row), sum);
         y[row] = out;
@@ -239,6 +258,10 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
       }
       rs = rs_n;
       re = re_n;
+      if (++stage == nstage) {
+        stage = 0;
+        phase ^= 1u;
+      }
     }
   }
   if constexpr (DOTS != 0) {

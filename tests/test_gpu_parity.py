@@ -285,7 +285,7 @@ def test_solvers_bitwise_deterministic(ma, manifest, name):
     assert torch.equal(xs[0], xs[1]) and torch.equal(xs[0], xs[2])
 
 
-@pytest.mark.parametrize("opts", [dict(fuse_xpay=1), dict(snake=1), dict(fuse_xpay=1, snake=1), dict(chunk=2),
+@pytest.mark.parametrize("opts", [dict(fuse_xpay=1), dict(snake=0), dict(fuse_xpay=1, snake=0), dict(chunk=2), dict(use_tma=0), dict(use_compress=0),
                                   dict(grid_mult_spmv=2, grid_mult_vec=2)])
 def test_cg_kernel_variants(ma, manifest, opts):
     from pytorch_sparse_solver import _native
@@ -294,12 +294,14 @@ def test_cg_kernel_variants(ma, manifest, opts):
     try:
         for k, v in opts.items():
             h.set_option(k, v)
+        _native.clear_cache()
         for name in ("cg_p3d16_rand", "cg_p2d24x20_x0", "cg_p3d64_ones_digest", "cg_p3d16_fixed10"):
             entry, data, x, info = _solve_case(ma, name, manifest)
             _check_against_golden(entry, data, x, info)
     finally:
         for k, v in saved.items():
             h.set_option(k, v)
+        _native.clear_cache()
 
 
 def test_dense_and_coo_inputs(ma, manifest):
