@@ -291,6 +291,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--dist-window", type=int, default=200, help="N>1: CG iterations per timed step")
+    ap.add_argument("--strong", action="store_true", help="N>1: split the SAME (2n)^3 system over N GPUs (strong scaling)")
     ap.add_argument("--ref-window", type=int, default=10, help="--impl reference: CG iterations per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -298,7 +299,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if world > 1 or args.gpus > 1:
+    if world > 1 or args.gpus > 1 or args.strong:
         if world == 1:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
         run_dist(args, rank, world)

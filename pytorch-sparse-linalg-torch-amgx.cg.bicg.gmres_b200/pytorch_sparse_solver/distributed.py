@@ -233,6 +233,10 @@ def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSample
     npl, ppg = 2 * n, max(n // 4, 1)
     if ppg * npl * npl != rows:
         npl, ppg = n, n
+    strong = bool(getattr(args, "strong", False))
+    if strong:  # BASELINE configs[4] as written: the SAME (2n)^3 system split over N GPUs (N must divide 2n)
+        ppg = npl // world
+        rows = ppg * npl * npl
     offsets = [q * rows for q in range(world + 1)]
     crow, col, val = problems.stencil3d_rows(npl, world * ppg, rank * ppg, (rank + 1) * ppg, device=dev)
     nnz_local = val.numel()
@@ -261,7 +265,7 @@ def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSample
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
     it_s = its / (ms * 1e-3)
-    value = world * it_s
+    value = it_s * (rows * world) / float(n ** 3)   # n^3-row CG iterations per second over all ranks
     bytes_iter = problems.cg_bytes_per_iteration(rows, nnz_local)
     # end to end: host slab -> device, registration, solve window, x back to host
     crow_h, col_h, val_h = problems.stencil3d_rows(npl, world * ppg, rank * ppg, (rank + 1) * ppg)
@@ -288,7 +292,8 @@ def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSample
     pk, pk_kind = peak
     return {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"CG fp64, 7-pt Poisson {world * ppg}x{npl}x{npl} CSR row-partitioned over {world} GPUs "
                                f"({n}^3 rows per GPU; 8 GPUs = BASELINE configs[4] 512^3), b=ones, fixed window of "
