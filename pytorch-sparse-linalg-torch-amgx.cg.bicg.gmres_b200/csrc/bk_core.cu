@@ -25,6 +25,21 @@ static int64_t bk_env_int(const char* name, int64_t dflt) {
   return strtoll(v, nullptr, 10);
 }
 
+cudaError_t bk_pool_alloc(void** p, size_t bytes, cudaStream_t s) {
+  cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, s);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    *p = nullptr;
+  }
+  return e;
+}
+
+void bk_pool_free(void* p) {
+  // ordered on the legacy default stream: callers have synchronised the streams that used the memory
+  // (solver entry points end with a stream sync; bk_csr_destroy synchronises the device first)
+  if (p) cudaFreeAsync(p, 0);
+}
+
 extern "C" int bk_create(int device, bk_handle** out) {
   if (!out) return bk_fail(BK_ERR_ARG, "bk_create: out is null");
   *out = nullptr;
@@ -35,6 +50,14 @@ extern "C" int bk_create(int device, bk_handle** out) {
   BK_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   BK_CUDA(cudaGetDeviceProperties(&prop, device));
+  {  // keep freed pool memory cached instead of returning it to the driver at every synchronisation
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long thr = ~0ULL;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+  }
   bk_handle* h = (bk_handle*)calloc(1, sizeof(bk_handle));
   if (!h) return bk_fail(BK_ERR_ALLOC, "bk_create: host allocation failed");
   h->device = device;
@@ -278,11 +301,13 @@ static int bk_csr_plan_compress(bk_handle* h, bk_csr* A, cudaStream_t s) {
   const size_t vs = bk_dtype_size(A->dtype);
   int* dstat = (int*)(h->counters + 8);
   int host[2] = {0, 0};
-  if (cudaMalloc((void**)&A->codes, (size_t)A->nnz + 64) != cudaSuccess ||
-      cudaMalloc((void**)&A->dict, sizeof(int) * 32 * (size_t)nblk) != cudaSuccess) {
+  if (bk_pool_alloc((void**)&A->codes, (size_t)A->nnz + 64, s) != cudaSuccess ||
+      bk_pool_alloc((void**)&A->dict, sizeof(int) * 32 * (size_t)nblk, s) != cudaSuccess) {
     cudaGetLastError();
-    if (A->codes) cudaFree(A->codes);
+    if (A->codes) bk_pool_free(A->codes);
+    if (A->dict) bk_pool_free(A->dict);
     A->codes = nullptr;
+    A->dict = nullptr;
     return BK_OK;  // not enough memory for the coded copy: stay on int32 columns
   }
   cudaMemsetAsync(dstat, 0, 2 * sizeof(int), s);
@@ -296,15 +321,15 @@ static int bk_csr_plan_compress(bk_handle* h, bk_csr* A, cudaStream_t s) {
   const int cap = (host[0] + 31) & ~31;
   const size_t stage = (size_t)cap * (vs + 1) + 128;
   if (host[1] != 0 || cap <= 0 || 2 * stage > 110 * 1024) {  // a block with > 32 distinct offsets, or too wide
-    cudaFree(A->codes);
-    cudaFree(A->dict);
+    bk_pool_free(A->codes);
+    bk_pool_free(A->dict);
     A->codes = nullptr;
     A->dict = nullptr;
     return BK_OK;
   }
   const int tail = (int)(A->nnz & 15);
   if (tail) {
-    if (cudaMalloc(&A->tail_val16, 16 * vs) != cudaSuccess || cudaMalloc((void**)&A->tail_code16, 16) != cudaSuccess) {
+    if (bk_pool_alloc(&A->tail_val16, 16 * vs, s) != cudaSuccess || bk_pool_alloc((void**)&A->tail_code16, 16, s) != cudaSuccess) {
       cudaGetLastError();
       return bk_fail(BK_ERR_ALLOC, "csr registration: tail buffer allocation failed");
     }
@@ -344,7 +369,7 @@ static int bk_csr_plan_tma(bk_handle* h, bk_csr* A, cudaStream_t s) {
   const int tail = (int)(A->nnz & 3);
   if (tail) {
     const size_t vs = bk_dtype_size(A->dtype);
-    if (cudaMalloc(&A->tail_val, 4 * vs) != cudaSuccess || cudaMalloc((void**)&A->tail_col, 16) != cudaSuccess) {
+    if (bk_pool_alloc(&A->tail_val, 4 * vs, s) != cudaSuccess || bk_pool_alloc((void**)&A->tail_col, 16, s) != cudaSuccess) {
       cudaGetLastError();
       return bk_fail(BK_ERR_ALLOC, "csr registration: tail buffer allocation failed");
     }
@@ -410,8 +435,8 @@ extern "C" int bk_csr_create(bk_handle* h, int64_t n, int64_t nnz, const void* r
     return code;
   };
   if (idx_bits == 64) {
-    if (cudaMalloc(&A->own_rowptr, sizeof(int) * (size_t)(n + 1)) != cudaSuccess ||
-        cudaMalloc(&A->own_col, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess) {
+    if (bk_pool_alloc(&A->own_rowptr, sizeof(int) * (size_t)(n + 1), s) != cudaSuccess ||
+        bk_pool_alloc(&A->own_col, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1), s) != cudaSuccess) {
       cudaGetLastError();
       return fail(bk_fail(BK_ERR_ALLOC, "bk_csr_create: int32 index copy allocation failed"));
     }
@@ -420,8 +445,8 @@ extern "C" int bk_csr_create(bk_handle* h, int64_t n, int64_t nnz, const void* r
     A->rowptr = (const int*)A->own_rowptr;
     A->col = (const int*)A->own_col;
   } else if (copy) {
-    if (cudaMalloc(&A->own_rowptr, sizeof(int) * (size_t)(n + 1)) != cudaSuccess ||
-        cudaMalloc(&A->own_col, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess) {
+    if (bk_pool_alloc(&A->own_rowptr, sizeof(int) * (size_t)(n + 1), s) != cudaSuccess ||
+        bk_pool_alloc(&A->own_col, sizeof(int) * (size_t)(nnz > 0 ? nnz : 1), s) != cudaSuccess) {
       cudaGetLastError();
       return fail(bk_fail(BK_ERR_ALLOC, "bk_csr_create: index copy allocation failed"));
     }
@@ -434,7 +459,7 @@ extern "C" int bk_csr_create(bk_handle* h, int64_t n, int64_t nnz, const void* r
     A->col = (const int*)col;
   }
   if (copy) {
-    if (cudaMalloc(&A->own_val, vs * (size_t)(nnz > 0 ? nnz : 1)) != cudaSuccess) {
+    if (bk_pool_alloc(&A->own_val, vs * (size_t)(nnz > 0 ? nnz : 1), s) != cudaSuccess) {
       cudaGetLastError();
       return fail(bk_fail(BK_ERR_ALLOC, "bk_csr_create: value copy allocation failed"));
     }
@@ -456,17 +481,18 @@ extern "C" int bk_csr_destroy(bk_csr* A) {
   if (A->h) {
     cudaSetDevice(A->h->device);
     bk_graphs_invalidate(A->h);
+    cudaDeviceSynchronize();  // nothing may still be reading the arrays: the frees below are stream-ordered
   }
   if (A->transpose) bk_csr_destroy(A->transpose);
-  if (A->own_rowptr) cudaFree(A->own_rowptr);
-  if (A->own_col) cudaFree(A->own_col);
-  if (A->own_val) cudaFree(A->own_val);
-  if (A->tail_val) cudaFree(A->tail_val);
-  if (A->tail_col) cudaFree(A->tail_col);
-  if (A->codes) cudaFree(A->codes);
-  if (A->dict) cudaFree(A->dict);
-  if (A->tail_val16) cudaFree(A->tail_val16);
-  if (A->tail_code16) cudaFree(A->tail_code16);
+  if (A->own_rowptr) bk_pool_free(A->own_rowptr);
+  if (A->own_col) bk_pool_free(A->own_col);
+  if (A->own_val) bk_pool_free(A->own_val);
+  if (A->tail_val) bk_pool_free(A->tail_val);
+  if (A->tail_col) bk_pool_free(A->tail_col);
+  if (A->codes) bk_pool_free(A->codes);
+  if (A->dict) bk_pool_free(A->dict);
+  if (A->tail_val16) bk_pool_free(A->tail_val16);
+  if (A->tail_code16) bk_pool_free(A->tail_code16);
   free(A);
   return BK_OK;
 }

@@ -174,6 +174,11 @@ static inline bk_scratch bk_slot(bk_handle* h, int slot) {
   return s;
 }
 
+// Matrix-side allocations (index copies, coded columns, tails, transposes) come from the device's stream-ordered
+// memory pool (cudaMallocAsync) with the release threshold raised, so registering / dropping a matrix costs
+// microseconds instead of the milliseconds cudaMalloc/cudaFree take for hundreds of megabytes.
+cudaError_t bk_pool_alloc(void** p, size_t bytes, cudaStream_t s);
+void bk_pool_free(void* p);
 int bk_ws_reserve(bk_handle* h, size_t bytes);  // grows h->ws (invalidates cached graphs)
 void bk_graphs_invalidate(bk_handle* h);
 void bk_state_fill_tol(bk_dev_state* v, double tol, double atol);

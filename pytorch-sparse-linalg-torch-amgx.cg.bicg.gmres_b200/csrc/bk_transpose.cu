@@ -227,20 +227,22 @@ extern "C" int bk_csr_transpose(bk_handle* h, bk_csr* A, void* stream, bk_csr** 
   const long long hist_n = 256LL * (ntiles > 0 ? ntiles : 1);
   const long long nchunks = (hist_n + SC_CHUNK - 1) / SC_CHUNK;
   auto cleanup = [&]() {
-    if (k0) cudaFree(k0);
-    if (k1) cudaFree(k1);
-    if (v0) cudaFree(v0);
-    if (v1) cudaFree(v1);
-    if (hist) cudaFree(hist);
-    if (sums) cudaFree(sums);
+    if (k0) bk_pool_free(k0);
+    if (k1) bk_pool_free(k1);
+    if (v0) bk_pool_free(v0);
+    if (v1) bk_pool_free(v1);
+    if (hist) bk_pool_free(hist);
+    if (sums) bk_pool_free(sums);
   };
-  bool ok = cudaMalloc(&Tm->own_rowptr, sizeof(int) * (size_t)(n + 1)) == cudaSuccess &&
-            cudaMalloc(&Tm->own_col, sizeof(int) * nn) == cudaSuccess &&
-            cudaMalloc(&Tm->own_val, vs * nn) == cudaSuccess && cudaMalloc(&k0, sizeof(int) * nn) == cudaSuccess &&
-            cudaMalloc(&k1, sizeof(int) * nn) == cudaSuccess && cudaMalloc(&v0, sizeof(int) * nn) == cudaSuccess &&
-            cudaMalloc(&v1, sizeof(int) * nn) == cudaSuccess &&
-            cudaMalloc(&hist, sizeof(unsigned int) * (size_t)hist_n) == cudaSuccess &&
-            cudaMalloc(&sums, sizeof(unsigned int) * (size_t)(nchunks + 1)) == cudaSuccess;
+  bool ok = bk_pool_alloc(&Tm->own_rowptr, sizeof(int) * (size_t)(n + 1), s) == cudaSuccess &&
+            bk_pool_alloc(&Tm->own_col, sizeof(int) * nn, s) == cudaSuccess &&
+            bk_pool_alloc(&Tm->own_val, vs * nn, s) == cudaSuccess &&
+            bk_pool_alloc((void**)&k0, sizeof(int) * nn, s) == cudaSuccess &&
+            bk_pool_alloc((void**)&k1, sizeof(int) * nn, s) == cudaSuccess &&
+            bk_pool_alloc((void**)&v0, sizeof(int) * nn, s) == cudaSuccess &&
+            bk_pool_alloc((void**)&v1, sizeof(int) * nn, s) == cudaSuccess &&
+            bk_pool_alloc((void**)&hist, sizeof(unsigned int) * (size_t)hist_n, s) == cudaSuccess &&
+            bk_pool_alloc((void**)&sums, sizeof(unsigned int) * (size_t)(nchunks + 1), s) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
     cleanup();
