@@ -285,6 +285,7 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
       plan.tail_idx = cmp ? (const void*)A->tail_code16 : (const void*)A->tail_col;
       plan.idx = cmp ? (const void*)A->codes : (const void*)A->col;
       plan.dict = A->dict;
+      plan.prefetch_x = h->prefetch_x && bk_aligned16(a.x);
       int g = h->num_sms * ctas;
       if (g > BK_MAXB) g = BK_MAXB;
       g = bk_grid_rows(g, A->n, BK_TMA_RPB);

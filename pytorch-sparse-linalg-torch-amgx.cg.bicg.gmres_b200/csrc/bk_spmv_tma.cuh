@@ -68,6 +68,11 @@ __device__ __forceinline__ void bk_bulk_g2s(void* dst_smem, const void* src_gmem
       : "memory");
 }
 
+// L2 bulk prefetch (no data returned to the SM; SASS: UBLKPF)
+__device__ __forceinline__ void bk_bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
 struct bk_tma_plan {
   int cap;            // entries per stage (multiple of 32)
   int stages;
@@ -76,6 +81,7 @@ struct bk_tma_plan {
   const void* tail_idx;
   const void* idx;    // IDX 0: int32 column indices; IDX 1: 8-bit dictionary codes
   const int* dict;    // IDX 1: per 256-row block, 32 int32 (column - row) offsets
+  int prefetch_x;     // IDX 1: the producer warp prefetches the x ranges of each block's forward diagonals into L2
 };
 
 // IDX selects how column indices are stored for this matrix (decided at registration, bk_csr_plan_tma):
@@ -133,6 +139,12 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
     const unsigned char* __restrict__ idx = static_cast<const unsigned char*>(plan.idx);
     const uint64_t pol = bk_policy_evict_first();
     int s_cur = 0, e_cur = 0;  // lane j holds the span of iteration (batch*32 + j)
+    // x-gather prefetch (IDX 1): lane l owns dictionary entry l of the block being staged; for every forward
+    // diagonal (offset > 0: the entries no earlier block has touched yet) it asks the L2 for the 256-row x range
+    // that block will gather from, ~NSTAGE block-times before the consumers need it.
+    const T* __restrict__ xpf = static_cast<const T*>(a.x);
+    int d_next = 0;
+    if (IDX == 1 && plan.prefetch_x && my_iters > 0) d_next = __ldg(plan.dict + block_of(0) * 32 + lane);
     for (long long it0 = 0; it0 < my_iters; it0 += 32) {
       {
         const long long it = it0 + lane;
@@ -148,6 +160,24 @@ bk_spmv_tma_kernel(const bk_spmv_args a, const bk_tma_plan plan, const bk_scratc
         const long long it = it0 + j;
         const int s = __shfl_sync(0xffffffffu, s_cur, j);
         const int e = __shfl_sync(0xffffffffu, e_cur, j);
+        if constexpr (IDX == 1) {
+          if (plan.prefetch_x) {
+            const int d = d_next;
+            if (it + 1 < my_iters) d_next = __ldg(plan.dict + block_of(it + 1) * 32 + lane);
+            if (reverse ? (d < 0) : (d > 0)) {  // diagonals pointing at rows this sweep has not reached yet
+              constexpr long long EA = 16 / sizeof(T);                    // elements per 16 bytes
+              long long lo = block_of(it) * BK_TMA_RPB + d;
+              if (lo < 0) lo = 0;
+              lo &= ~(EA - 1);
+              long long hi = block_of(it) * BK_TMA_RPB + BK_TMA_RPB + d;
+              const long long nal = n & ~(EA - 1);
+              if (hi > nal) hi = nal;
+              hi = (hi + EA - 1) & ~(EA - 1);
+              if (hi > nal) hi = nal;
+              if (hi > lo) bk_bulk_prefetch_l2(xpf + lo, (uint32_t)((hi - lo) * sizeof(T)));
+            }
+          }
+        }
         if (lane == 0) {
           const int stage = (int)(it % nstage);
           if (it >= nstage) bk_mbar_wait(&empty_bar[stage], (uint32_t)(((it / nstage) - 1) & 1));

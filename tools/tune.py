@@ -87,6 +87,10 @@ def main():
         emit(what="bk_spmv_dot_tma", kernel=m.info()["kernel"], tma_ctas=ctas, tma_stages=st, gbs=bytes_spmv / ms / 1e6, ms=ms)
     h.set_option("tma_ctas", 4)
     h.set_option("tma_stages", 0)
+    for pf in (0, 1):
+        h.set_option("prefetch_x", pf)
+        ms = time_gpu(lambda: m.spmv_dot(x, x), reps=10)
+        emit(what="bk_spmv_dot_prefetch", prefetch_x=pf, kernel=m.info()["kernel"], gbs_algorithmic=bytes_spmv / ms / 1e6, ms=ms)
     for cmp_ in (0, 1):
         h.set_option("use_compress", cmp_)
         _native.clear_cache()
@@ -114,11 +118,11 @@ def main():
     def cg_window():
         return m.cg(b, None, 0.0, 0.0, W)
 
-    combos = [dict(), dict(snake=1), dict(loop_mode=1), dict(grid_mult_vec=2), dict(grid_mult_vec=4),
+    combos = [dict(), dict(prefetch_x=0), dict(snake=0), dict(snake=0, prefetch_x=0), dict(loop_mode=1), dict(grid_mult_vec=2), dict(grid_mult_vec=4),
               dict(tma_ctas=3), dict(tma_ctas=3, snake=1), dict(chunk=16), dict(fuse_xpay=1)]
     if args.quick:
         combos = combos[:6]
-    defaults = {k: h.get_option(k) for k in ("fuse_xpay", "snake", "loop_mode", "grid_mult_vec", "grid_mult_spmv", "tma_ctas", "tma_stages", "chunk")}
+    defaults = {k: h.get_option(k) for k in ("fuse_xpay", "snake", "loop_mode", "grid_mult_vec", "grid_mult_spmv", "tma_ctas", "tma_stages", "chunk", "prefetch_x")}
     for c in combos:
         try:
             for k, v in defaults.items():
