@@ -300,7 +300,7 @@ def main():
         run_reference(args, rank, world)
         return
     if world > 1 or args.gpus > 1 or args.strong:
-        if world == 1:
+        if "RANK" not in os.environ:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
         run_dist(args, rank, world)
     else:
