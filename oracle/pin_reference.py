@@ -225,6 +225,20 @@ def main():
                           gen=(dict(matrix="poisson2d", nx=12, ny=12) if kind == "cg" else dict(matrix="convdiff3d", n=6)),
                           grad_vs_exact=float((g_ref - g_exact).abs().max() / g_exact.abs().max()))
         print(f"  pinned {name}: grad rel err vs analytic {auto[name]['grad_vs_exact']:.2e}")
+    # BASELINE configs[3]: GMRES(30) on the LDC pressure system with autograd backward (reference needs COO A: CSR .T raises)
+    A = problems.ldc_pressure_csr(32)
+    with np.load(GOLD / "gmres_ldc32_step1_batched.npz") as z:
+        b0 = torch.from_numpy(z["b"].copy())
+    kw = dict(tol=1e-10, maxiter=1000, restart=30)
+    b1 = b0.clone().requires_grad_(True)
+    x, info = ref.gmres(A.to_sparse_coo(), b1, **kw)
+    (x ** 2).sum().backward()
+    xo, _, _ = orc.gmres(A, b0, None, **kw)
+    g_orc = orc.adjoint_grad_b("gmres", A, 2.0 * xo, None, **kw)
+    assert torch.equal(b1.grad, g_orc), "oracle adjoint differs from the reference on LDC-32"
+    np.savez_compressed(GOLD / "autograd_gmres_ldc32.npz", b=b0.numpy(), grad_b=b1.grad.numpy(), x=x.detach().numpy())
+    auto["autograd_gmres_ldc32"] = dict(kind="gmres", info=int(info), kwargs=kw, n=int(b0.numel()), gen=dict(matrix="ldc", nx=32),
+                                        note="GMRES(30) on the LDC pressure system with autograd backward; reference run with COO A")
     manifest["autograd"] = auto
 
     # ---- full-size digests measured with the reference at survey time (3-6 CPU-minutes each,

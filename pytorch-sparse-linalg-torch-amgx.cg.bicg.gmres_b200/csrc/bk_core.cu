@@ -74,7 +74,7 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->prefetch_x = (int)bk_env_int("BK_SPMV_PREFETCH_X", 0);  // measured: 5 % slower on P3D-256, kept as an experiment
   h->loop_mode = (int)bk_env_int("BK_LOOP_MODE", BK_LOOP_AUTO);
   h->chunk = (int)bk_env_int("BK_CHUNK", 0);
-  h->fuse_xpay = (int)bk_env_int("BK_FUSE_XPAY", 0);
+  h->fuse_xpay = (int)bk_env_int("BK_FUSE_XPAY", -1);  // -1 auto, 0 off, 1 on
   h->snake = (int)bk_env_int("BK_SNAKE", 1);
   h->spmv_variant = (int)bk_env_int("BK_SPMV_VARIANT", 0);
   h->next_uid = 1;

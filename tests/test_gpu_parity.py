@@ -433,6 +433,20 @@ def test_optional_gradient_wrt_matrix(ma, manifest, layout):
     assert float(got[~mask].abs().max() if (~mask).any() else 0.0) == 0.0
 
 
+@pytest.mark.parametrize("solve_method", ["batched", "incremental"])
+def test_autograd_ldc_gmres_config4(ma, manifest, solve_method):
+    """BASELINE configs[3]: GMRES(30) on the LDC pressure system (CSR input) with the implicit-diff backward."""
+    entry = manifest["autograd"]["autograd_gmres_ldc32"]
+    data = load_case("autograd_gmres_ldc32")
+    A = build_matrix(entry["gen"], device="cuda")
+    b = data["b"].cuda().requires_grad_(True)
+    x, info = ma.gmres(A, b, solve_method=solve_method, **entry["kwargs"])
+    assert info == entry["info"]
+    (x ** 2).sum().backward()
+    assert rel_diff(x, data["x"]) <= (5e-10 if solve_method == "batched" else 1e-7)
+    assert rel_diff(b.grad, data["grad_b"]) <= (1e-8 if solve_method == "batched" else 1e-6)
+
+
 @pytest.mark.parametrize("kind", ["cg", "bicgstab", "gmres"])
 def test_legacy_differentiable(ma, manifest, kind):
     entry = manifest["autograd"][f"autograd_{kind}"]

@@ -61,6 +61,15 @@ def test_oracle_adjoint_matches_reference_autograd(kind, manifest):
     assert rel_diff(x, data["x"]) <= 1e-12
 
 
+def test_oracle_adjoint_ldc_gmres(manifest):
+    entry = manifest["autograd"]["autograd_gmres_ldc32"]
+    data = load_case("autograd_gmres_ldc32")
+    A = build_matrix(entry["gen"])
+    x, info, _ = orc.gmres(A, data["b"], None, **entry["kwargs"])
+    g = orc.adjoint_grad_b("gmres", A, 2.0 * x, None, **entry["kwargs"])
+    assert info == entry["info"] and rel_diff(g, data["grad_b"]) <= 1e-12 and rel_diff(x, data["x"]) <= 1e-12
+
+
 def test_oracle_tolerance_quirk_fp32():
     """torch.tensor(tol) is fp32 (reference :816): 1e-8 -> 9.99999993922529e-09, squared in fp32."""
     t = torch.tensor(1e-8)
