@@ -99,9 +99,18 @@ const char* bk_last_error(void);
  * reproducible sums), solver work vectors and cached CUDA graphs. */
 int bk_create(int device, bk_handle** out);
 int bk_destroy(bk_handle* h);
-/* Tunables: "grid_mult" (CTAs per SM of the persistent grids), "loop_mode", "chunk",
- * "fuse_xpay" (CG: fold p = r + beta p into the next SpMV's gather), "snake"
- * (alternate sweep direction between kernels for L2 reuse).  Unknown keys -> BK_ERR_ARG. */
+/* Tunables (all also readable from the environment at bk_create, BK_<UPPERCASE KEY>; unknown keys -> BK_ERR_ARG):
+ *   loop_mode      0 auto (= graph) | 1 plain stream launches | 2 CUDA graph of `chunk` flag-guarded iterations
+ *   chunk          iterations per graph / poll (0 = sized for ~2 ms of GPU work)
+ *   use_tma        1: short-row matrices use the TMA-staged row-stream SpMV (kernel 2/3), 0: LDG-staged (kernel 0)
+ *   use_compress   1: stream column indices as 8-bit dictionary codes when the matrix allows it (kernel 3)
+ *   tma_ctas       CTAs per SM of the TMA SpMV (2..4), tma_stages: cap on its pipeline depth (0 = fill shared memory)
+ *   prefetch_x     kernel 3: L2 bulk prefetch of the forward-diagonal x ranges (experiment, default 0)
+ *   grid_mult_vec / grid_mult_spmv   CTAs per SM of the BLAS-1 kernels / the non-TMA SpMV kernels
+ *   fuse_xpay      CG: fold p = r + beta p into the next SpMV's gather (-1 auto: only for launch-bound small systems)
+ *   snake          CG: alternate the sweep direction of consecutive kernels so the tail of one is still in L2
+ *   dist_p2p       multi-GPU: use the peer-memory path when it is connected (0 = NCCL path)
+ * Registration-time options (use_tma, use_compress) apply to matrices registered afterwards. */
 int bk_set_option(bk_handle* h, const char* key, int64_t value);
 int64_t bk_get_option(bk_handle* h, const char* key);
 int bk_device_info(bk_handle* h, int32_t* num_sms, int64_t* l2_bytes, int64_t* mem_bytes);

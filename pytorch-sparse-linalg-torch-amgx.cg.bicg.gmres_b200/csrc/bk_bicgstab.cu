@@ -97,42 +97,6 @@ struct bk_epi_final_x2 {
   __device__ __forceinline__ void operator()(const double* s) const { st->xx = s[0]; }
 };
 
-template <typename T, typename Epi>
-struct bk_op_dot_epi2 {
-  static constexpr int R = 1;
-  using Ctx = bk_noctx;
-  template <int W>
-  struct In {
-    bk_vec<T, W> a, b;
-  };
-  const T* x;
-  const T* y;
-  Epi epi;
-  __device__ bool skip() const { return false; }
-  __device__ bool reverse() const { return false; }
-  __device__ Ctx prepare() const { return Ctx(); }
-  template <int W>
-  __device__ void load(long long i, In<W>& in) const {
-    in.a = bk_ld<T, W>(x + i);
-    in.b = bk_ld<T, W>(y + i);
-  }
-  template <int W>
-  __device__ void apply(long long, const In<W>& in, const Ctx&, double (&acc)[1]) const {
-#pragma unroll
-    for (int j = 0; j < W; ++j) acc[0] += (double)in.a.v[j] * (double)in.b.v[j];
-  }
-  __device__ void epilogue(const double* s) const { epi(s); }
-};
-
-template <typename T, typename Epi>
-static int bk_dot_epi2(bk_handle* h, long long n, const void* x, const void* y, Epi epi, int slot, cudaStream_t s) {
-  bk_op_dot_epi2<T, Epi> op;
-  op.x = (const T*)x;
-  op.y = (const T*)y;
-  op.epi = epi;
-  return bk_launch_ew<T>(h, op, n, bk_aligned16(x) && bk_aligned16(y), bk_slot(h, slot), s);
-}
-
 template <typename T>
 struct bk_bicg_vecs {
   T *x, *r, *rhat, *p, *q, *s, *t;
@@ -229,7 +193,7 @@ static int bk_bicgstab_t(bk_handle* h, const bk_csr* A, const void* b, void* x_u
   }
   {
     bk_epi_bicg_init<T> epi{st, has_x0};
-    BK_TRY((bk_dot_epi2<T>(h, n, b, b, epi, 1, s)));
+    BK_TRY((bk_dot_epi<T>(h, n, b, b, epi, 1, s)));
   }
   // rhat = p = q = r0   (:876, :890)
   BK_CUDA(cudaMemcpyAsync(v.rhat, v.r, vbytes, cudaMemcpyDeviceToDevice, s));
@@ -257,7 +221,7 @@ static int bk_bicgstab_t(bk_handle* h, const bk_csr* A, const void* b, void* x_u
     bk_epi_final_r2 epi{st};
     BK_TRY((bk_launch_spmv<1, 2, 0>(h, A, a, bk_slot(h, 0), epi, s)));
     bk_epi_final_x2 epx{st};
-    BK_TRY((bk_dot_epi2<T>(h, n, v.x, v.x, epx, 1, s)));
+    BK_TRY((bk_dot_epi<T>(h, n, v.x, v.x, epx, 1, s)));
   }
   BK_CUDA(cudaMemcpyAsync(x_user, v.x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));

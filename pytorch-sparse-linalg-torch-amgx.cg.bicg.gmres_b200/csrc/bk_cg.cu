@@ -56,42 +56,6 @@ struct bk_epi_final_x {
   __device__ __forceinline__ void operator()(const double* s) const { st->xx = s[0]; }
 };
 
-template <typename T, typename Epi>
-struct bk_op_dot_epi {
-  static constexpr int R = 1;
-  using Ctx = bk_noctx;
-  template <int W>
-  struct In {
-    bk_vec<T, W> a, b;
-  };
-  const T* x;
-  const T* y;
-  Epi epi;
-  __device__ bool skip() const { return false; }
-  __device__ bool reverse() const { return false; }
-  __device__ Ctx prepare() const { return Ctx(); }
-  template <int W>
-  __device__ void load(long long i, In<W>& in) const {
-    in.a = bk_ld<T, W>(x + i);
-    in.b = bk_ld<T, W>(y + i);
-  }
-  template <int W>
-  __device__ void apply(long long, const In<W>& in, const Ctx&, double (&acc)[1]) const {
-#pragma unroll
-    for (int j = 0; j < W; ++j) acc[0] += (double)in.a.v[j] * (double)in.b.v[j];
-  }
-  __device__ void epilogue(const double* s) const { epi(s); }
-};
-
-template <typename T, typename Epi>
-static int bk_dot_epi(bk_handle* h, long long n, const void* x, const void* y, Epi epi, int slot, cudaStream_t s) {
-  bk_op_dot_epi<T, Epi> op;
-  op.x = (const T*)x;
-  op.y = (const T*)y;
-  op.epi = epi;
-  return bk_launch_ew<T>(h, op, n, bk_aligned16(x) && bk_aligned16(y), bk_slot(h, slot), s);
-}
-
 // Shared by all solvers: tolerance fields with the reference's fp32 rounding of torch.tensor(tol).
 void bk_state_fill_tol(bk_dev_state* v, double tol, double atol) {
   const float t = (float)tol, a = (float)atol;

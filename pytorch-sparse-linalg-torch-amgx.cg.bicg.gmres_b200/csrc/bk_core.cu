@@ -76,7 +76,6 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->chunk = (int)bk_env_int("BK_CHUNK", 0);
   h->fuse_xpay = (int)bk_env_int("BK_FUSE_XPAY", -1);  // -1 auto, 0 off, 1 on
   h->snake = (int)bk_env_int("BK_SNAKE", 1);
-  h->spmv_variant = (int)bk_env_int("BK_SPMV_VARIANT", 0);
   h->next_uid = 1;
   cudaError_t e;
   e = cudaMalloc(&h->partials, sizeof(double) * BK_NSLOT * BK_SLOT_ROWS * BK_MAXB);
@@ -85,7 +84,6 @@ extern "C" int bk_create(int device, bk_handle** out) {
   if (e == cudaSuccess) e = cudaMalloc(&h->st, sizeof(bk_dev_state));
   if (e == cudaSuccess) e = cudaMemset(h->st, 0, sizeof(bk_dev_state));
   if (e == cudaSuccess) e = cudaMallocHost(&h->st_host, sizeof(bk_dev_state) * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&h->dscratch, sizeof(double) * 64);
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking);
@@ -114,7 +112,6 @@ extern "C" int bk_destroy(bk_handle* h) {
   if (h->counters) cudaFree(h->counters);
   if (h->st) cudaFree(h->st);
   if (h->st_host) cudaFreeHost(h->st_host);
-  if (h->dscratch) cudaFree(h->dscratch);
   if (h->ws) cudaFree(h->ws);
   if (h->stage) cudaFree(h->stage);
   if (h->gm_small) cudaFree(h->gm_small);
@@ -146,11 +143,6 @@ int bk_ws_reserve(bk_handle* h, size_t bytes) {
   return BK_OK;
 }
 
-struct bk_opt_ref {
-  const char* key;
-  int* field;
-};
-
 static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!key) return nullptr;
   if (!strcmp(key, "grid_mult_vec")) return &h->grid_mult_vec;
@@ -166,7 +158,6 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "chunk")) return &h->chunk;
   if (!strcmp(key, "fuse_xpay")) return &h->fuse_xpay;
   if (!strcmp(key, "snake")) return &h->snake;
-  if (!strcmp(key, "spmv_variant")) return &h->spmv_variant;
   return nullptr;
 }
 

@@ -454,11 +454,6 @@ __global__ void bk_dist_final_kernel(bk_dev_state* st, const double* red) {  // 
   st->xx = red[3];
 }
 
-struct bk_epi_to {
-  double* out;
-  __device__ __forceinline__ void operator()(const double* s) const { out[0] = s[0]; }
-};
-
 template <typename T>
 struct bk_op_dot_to {
   static constexpr int R = 1;

@@ -108,33 +108,6 @@ struct bk_epi_gm_xx {
   __device__ __forceinline__ void operator()(const double* s) const { st->xx = s[0]; }
 };
 
-template <typename T, typename Epi>
-struct bk_op_dot_epi3 {
-  static constexpr int R = 1;
-  using Ctx = bk_noctx;
-  template <int W>
-  struct In {
-    bk_vec<T, W> a, b;
-  };
-  const T* x;
-  const T* y;
-  Epi epi;
-  __device__ bool skip() const { return false; }
-  __device__ bool reverse() const { return false; }
-  __device__ Ctx prepare() const { return Ctx(); }
-  template <int W>
-  __device__ void load(long long i, In<W>& in) const {
-    in.a = bk_ld<T, W>(x + i);
-    in.b = bk_ld<T, W>(y + i);
-  }
-  template <int W>
-  __device__ void apply(long long, const In<W>& in, const Ctx&, double (&acc)[1]) const {
-#pragma unroll
-    for (int j = 0; j < W; ++j) acc[0] += (double)in.a.v[j] * (double)in.b.v[j];
-  }
-  __device__ void epilogue(const double* s) const { epi(s); }
-};
-
 // ---- A2: h_i = v_i . w for i < count ---------------------------------------------------------------
 // Tall-skinny multi-vector GEMV: one pass over w per group of 8 basis vectors, 9 independent 16-byte
 // loads in flight per thread; per-CTA partials land in fixed slots, the last CTA adds them in index
@@ -428,12 +401,7 @@ static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user
 
   const int grid = bk_grid_vec_n(h, n, 2 * NW);
   auto dot_epi = [&](const void* a, const void* bb, auto epi, int slot) -> int {
-    using E = decltype(epi);
-    bk_op_dot_epi3<T, E> op;
-    op.x = (const T*)a;
-    op.y = (const T*)bb;
-    op.epi = epi;
-    return bk_launch_ew<T>(h, op, n, bk_aligned16(a) && bk_aligned16(bb), bk_slot(h, slot), s);
+    return bk_dot_epi<T>(h, n, a, bb, epi, slot, s);
   };
   auto normalize = [&](const T* src, T* dst, int guard, cudaStream_t cs) -> int {
     bk_op_normalize<T> op;

@@ -140,14 +140,12 @@ struct bk_handle {
   int chunk;
   int fuse_xpay;
   int snake;
-  int spmv_variant;
   // reduction scratch
   double* partials;        // BK_NSLOT * BK_SLOT_ROWS * BK_MAXB
   unsigned int* counters;  // BK_NSLOT (+ spare)
   // device state + pinned mirror
   bk_dev_state* st;        // device
   bk_dev_state* st_host;   // pinned, 4 entries (poll ring + final)
-  double* dscratch;        // device: a few doubles for the building-block API
   // work vectors (elements of the largest dtype requested so far)
   void* ws;
   size_t ws_bytes;

@@ -15,11 +15,6 @@
 
 static __global__ void bk_state_set_kernel(bk_dev_state* st, const bk_dev_state v) { *st = v; }
 
-static inline uint64_t bk_mix(uint64_t a, uint64_t b) {
-  a ^= b + 0x9e3779b97f4a7c15ULL + (a << 6) + (a >> 2);
-  return a;
-}
-
 // Look up / build the graph of one chunk.  `enqueue` must enqueue the chunk on the stream it is given.
 template <typename F>
 static int bk_chunk_graph(bk_handle* h, const uint64_t key[6], F enqueue, cudaGraphExec_t* out) {

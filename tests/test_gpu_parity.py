@@ -285,7 +285,7 @@ def test_solvers_bitwise_deterministic(ma, manifest, name):
     assert torch.equal(xs[0], xs[1]) and torch.equal(xs[0], xs[2])
 
 
-@pytest.mark.parametrize("opts", [dict(fuse_xpay=1), dict(snake=0), dict(fuse_xpay=1, snake=0), dict(chunk=2), dict(use_tma=0), dict(use_compress=0),
+@pytest.mark.parametrize("opts", [dict(fuse_xpay=1), dict(fuse_xpay=0), dict(snake=0), dict(fuse_xpay=1, snake=0), dict(chunk=2), dict(use_tma=0), dict(use_compress=0),
                                   dict(grid_mult_spmv=2, grid_mult_vec=2)])
 def test_cg_kernel_variants(ma, manifest, opts):
     from pytorch_sparse_solver import _native
@@ -643,3 +643,29 @@ def test_zero_size_and_shape_errors(ma):
         ma.cg(A, torch.ones(20, dtype=torch.float64))            # device mismatch
     with pytest.raises(ValueError):
         ma.gmres(A, torch.ones(20, dtype=torch.float64, device="cuda"), restart=0)
+
+
+def test_c_abi_argument_validation_on_gpu():
+    import ctypes as C
+    from pytorch_sparse_solver import _native
+    h = _native.Handle.get(torch.device("cuda"))
+    lib = h.lib
+    A = build_matrix(dict(matrix="poisson2d", nx=6, ny=5), device="cuda")
+    crow, col, val = A.crow_indices().int(), A.col_indices().int(), A.values()
+    out = C.c_void_p()
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.bk_csr_create(h.ptr, 30, val.numel(), crow.data_ptr(), col.data_ptr(), 16, val.data_ptr(), 0, 0, s, C.byref(out)) == -1
+    assert lib.bk_csr_create(h.ptr, 30, val.numel(), crow.data_ptr(), col.data_ptr(), 32, val.data_ptr(), 7, 0, s, C.byref(out)) == -1
+    bad = col.clone()
+    bad[3] = 1000                                        # column out of range -> malformed CSR
+    assert lib.bk_csr_create(h.ptr, 30, val.numel(), crow.data_ptr(), bad.data_ptr(), 32, val.data_ptr(), 0, 0, s, C.byref(out)) == -1
+    assert b"malformed" in lib.bk_last_error()
+    assert lib.bk_set_option(h.ptr, b"no_such_option", 1) == -1
+    m = _native.register_matrix(A)
+    res = _native.bk_result()
+    b = torch.ones(30, dtype=torch.float64, device="cuda")
+    x = torch.empty_like(b)
+    assert lib.bk_gmres(h.ptr, m.ptr, b.data_ptr(), x.data_ptr(), 0, 1e-8, 0.0, 0, -1, 0, C.byref(res), s) == -4   # restart 0
+    assert lib.bk_gmres(h.ptr, m.ptr, b.data_ptr(), x.data_ptr(), 0, 1e-8, 0.0, 1000, -1, 0, C.byref(res), s) == -4  # > 256
+    assert lib.bk_gmres(h.ptr, m.ptr, b.data_ptr(), x.data_ptr(), 0, 1e-8, 0.0, 10, -1, 5, C.byref(res), s) == -1   # method
+    assert lib.bk_spmv(h.ptr, m.ptr, b.data_ptr(), b.data_ptr(), s) == -1                                        # aliasing

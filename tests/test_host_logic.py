@@ -138,3 +138,27 @@ def test_router_errors_and_availability():
     with pytest.raises(ValueError):
         pss.amg(A, b)
     assert "module_a" in repr(s)
+
+
+def test_c_abi_error_paths_without_gpu():
+    """Argument validation of the C ABI: negative bk_error codes + a message, never a crash.  (No compute call.)"""
+    import ctypes as C
+    from pytorch_sparse_solver import _native
+    lib = _native.load_library()
+    h = C.c_void_p()
+    rc = lib.bk_create(0, None)
+    assert rc == -1 and b"out is null" in lib.bk_last_error()
+    if not torch.cuda.is_available():
+        rc = lib.bk_create(0, C.byref(h))
+        assert rc < 0 and h.value is None and len(lib.bk_last_error()) > 0
+    assert lib.bk_set_option(None, b"chunk", 4) == -1
+    assert lib.bk_get_option(None, b"chunk") == -1
+    out = C.c_void_p()
+    assert lib.bk_csr_create(None, 4, 4, None, None, 32, None, 0, 0, None, C.byref(out)) == -1
+    assert lib.bk_spmv(None, None, None, None, None) == -1
+    res = _native.bk_result()
+    assert lib.bk_cg(None, None, None, None, 0, 1e-5, 0.0, -1, C.byref(res), None) == -1
+    assert lib.bk_gmres(None, None, None, None, 0, 1e-5, 0.0, 20, -1, 0, C.byref(res), None) == -1
+    assert lib.bk_solve_host(None, 0, 4, 4, None, None, 32, None, 0, None, None, 0, 1e-5, 0.0, -1, 20, 0, C.byref(res)) == -1
+    assert lib.bk_dist_p2p_export(None, None) == -1
+    assert lib.bk_csr_destroy(None) == 0 and lib.bk_destroy(None) == 0 and lib.bk_dist_destroy(None) == 0
