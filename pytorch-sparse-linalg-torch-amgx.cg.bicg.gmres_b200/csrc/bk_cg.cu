@@ -78,6 +78,125 @@ void bk_fill_result_isolve(const bk_dev_state* st, bk_result* res, int64_t matve
   res->info = failed ? -1 : 0;
 }
 
+// ---- persistent cooperative CG for launch-latency-bound (small) systems ------------------------------------
+// One cooperative kernel runs the WHOLE iteration loop: three grid-wide barriers per iteration replace three
+// kernel launches (which cost ~5 us each at n = 65k even inside a CUDA graph).  Every CTA re-adds the per-CTA
+// partials of a dot product in the same fixed order after the barrier, so all threads hold bitwise identical
+// alpha/beta/gamma and take the reference's stop test (`k >= maxiter or gamma <= atol2`, :841) uniformly — the
+// convergence flag never leaves the device.  Thread-per-row SpMV is fine here: the matrix and vectors are L2
+// resident at these sizes.  Same recurrences and rounding (separate mul/add) as the multi-kernel path.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+__device__ __forceinline__ double bk_sum_partials(const double* partials, int count, double* sh) {
+  // executed by all threads of the CTA; result identical in every CTA (fixed order)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (wid == 0) {
+    double a = 0.0;
+    for (int i = lane; i < count; i += 32) a += __ldcg(partials + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) sh[0] = a;
+  }
+  __syncthreads();
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BK_BLOCK)
+bk_cg_persistent_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const T* __restrict__ val,
+                        T* x, T* r, T* p, T* ap, const long long n, bk_dev_state* st, double* partials) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double sh_red[BK_WARPS];
+  __shared__ double sh_one[1];
+  const long long tid = (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
+  const long long nth = (long long)gridDim.x * BK_BLOCK;
+  double gamma = st->gamma;
+  const double atol2 = st->atol2;
+  const long long maxiter = st->maxiter;
+  long long k = 0;
+  int status = BK_ST_MAXITER;
+  if (st->done) return;  // uniform: set by the init epilogue (zero rhs / maxiter 0)
+  for (;;) {
+    if (k >= maxiter) {
+      status = BK_ST_MAXITER;
+      break;
+    }
+    if (gamma <= atol2) {
+      status = BK_ST_CONVERGED;
+      break;
+    }
+    // phase 1: Ap = A p, partial p.Ap
+    double acc[1] = {0.0};
+    for (long long row = tid; row < n; row += nth) {
+      T sum = T(0);
+      for (int e = rowptr[row]; e < rowptr[row + 1]; ++e) sum = fma(val[e], p[col[e]], sum);
+      ap[row] = sum;
+      acc[0] += (double)p[row] * (double)sum;
+    }
+    bk_block_reduce<1>(acc, sh_red);
+    if (threadIdx.x == 0) __stcg(partials + blockIdx.x, acc[0]);
+    grid.sync();
+    const double pAp = bk_sum_partials(partials, (int)gridDim.x, sh_one);
+    const double alpha_d = gamma / pAp;
+    const T alpha = (T)alpha_d;
+    // phase 2: x += alpha p ; r -= alpha Ap ; partial r.r
+    acc[0] = 0.0;
+    for (long long row = tid; row < n; row += nth) {
+      x[row] = bk_add(x[row], bk_mul(alpha, p[row]));
+      const T rn = bk_sub(r[row], bk_mul(alpha, ap[row]));
+      r[row] = rn;
+      acc[0] += (double)rn * (double)rn;
+    }
+    bk_block_reduce<1>(acc, sh_red);
+    if (threadIdx.x == 0) __stcg(partials + BK_MAXB + blockIdx.x, acc[0]);
+    grid.sync();
+    const double gamma_new = bk_sum_partials(partials + BK_MAXB, (int)gridDim.x, sh_one);
+    const T beta = (T)(gamma_new / gamma);
+    gamma = gamma_new;
+    ++k;
+    // phase 3: p = r + beta p   (the barrier makes the new p visible to the next SpMV's gathers)
+    for (long long row = tid; row < n; row += nth) p[row] = bk_add(r[row], bk_mul(beta, p[row]));
+    grid.sync();
+  }
+  if (tid == 0) {
+    st->k = k;
+    st->gamma = gamma;
+    st->done = 1;
+    st->status = status;
+  }
+}
+
+template <typename T>
+static int bk_cg_try_persistent(bk_handle* h, const bk_csr* A, T* x, T* r, T* p, T* ap, cudaStream_t s, bool* used) {
+  *used = false;
+  if (!h->persistent || A->n > (long long)h->persistent_max_n) return BK_OK;
+  int coop = 0;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+  if (!coop) return BK_OK;
+  int per_sm = 0;
+  BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk_cg_persistent_kernel<T>, BK_BLOCK, 0));
+  long long grid = (A->n + BK_BLOCK - 1) / BK_BLOCK;
+  const long long cap = (long long)per_sm * h->num_sms;
+  if (grid > cap) grid = cap;
+  if (grid > BK_MAXB) grid = BK_MAXB;
+  if (grid < 1) return BK_OK;
+  const int* rowptr = A->rowptr;
+  const int* col = A->col;
+  const T* val = (const T*)A->val;
+  long long n = A->n;
+  bk_dev_state* st = h->st;
+  double* partials = h->partials;  // slots 0 and 1 (BK_MAXB apart)
+  void* args[] = {(void*)&rowptr, (void*)&col, (void*)&val, (void*)&x, (void*)&r, (void*)&p, (void*)&ap,
+                  (void*)&n, (void*)&st, (void*)&partials};
+  BK_CUDA(cudaLaunchCooperativeKernel((const void*)bk_cg_persistent_kernel<T>, dim3((unsigned)grid), dim3(BK_BLOCK),
+                                      args, 0, s));
+  *used = true;
+  return BK_OK;
+}
+
 template <typename T>
 struct bk_cg_vecs {
   T* x;
@@ -146,7 +265,8 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   const size_t npad = ((size_t)n + 63) & ~(size_t)63;
   // fused p-update: 2 kernels per iteration instead of 3 — a win while the iteration is launch-latency bound
   // (measured: -17 % at n = 65k, +13 % at n = 1M), so 'auto' (-1) enables it for small systems only
-  const bool fuse = A->kernel != 1 && (h->fuse_xpay > 0 || (h->fuse_xpay < 0 && n <= 300000));
+  const bool persist_ok = h->persistent && n <= (long long)h->persistent_max_n;  // one cooperative kernel runs the loop
+  const bool fuse = !persist_ok && A->kernel != 1 && (h->fuse_xpay > 0 || (h->fuse_xpay < 0 && n <= 300000));
   BK_TRY(bk_ws_reserve(h, (size_t)5 * npad * sizeof(T)));
   bk_cg_vecs<T> v;
   v.x = (T*)h->ws;
@@ -199,7 +319,9 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
     return BK_OK;
   };
   int64_t chunks = 0;
-  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
+  bool persistent = false;
+  BK_TRY(bk_cg_try_persistent<T>(h, A, v.x, v.r, v.p[0], v.ap, s, &persistent));
+  if (!persistent) BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
 
   {  // final true residual  ||b - A x||  and  ||x||   (_isolve :1008-1013)
     bk_spmv_args a = bk_spmv_base(A, st);
@@ -217,7 +339,7 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->gamma;
-  res->kernel_launches = chunks * chunk * (fuse ? 2 : 3) + 2 /*state, b.b*/ + (has_x0 ? 1 : 0) + 2 /*final*/;
+  res->kernel_launches = (persistent ? 1 : chunks * chunk * (fuse ? 2 : 3)) + 2 /*state, b.b*/ + (has_x0 ? 1 : 0) + 2 /*final*/;
   return BK_OK;
 }
 

@@ -71,6 +71,8 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->use_tma = (int)bk_env_int("BK_SPMV_TMA", 1);
   h->dist_p2p = (int)bk_env_int("BK_DIST_P2P", 1);
   h->use_compress = (int)bk_env_int("BK_SPMV_COMPRESS", 1);
+  h->persistent = (int)bk_env_int("BK_PERSISTENT", 1);
+  h->persistent_max_n = (int)bk_env_int("BK_PERSISTENT_MAX_N", 200000);
   h->prefetch_x = (int)bk_env_int("BK_SPMV_PREFETCH_X", 0);  // measured: 5 % slower on P3D-256, kept as an experiment
   h->loop_mode = (int)bk_env_int("BK_LOOP_MODE", BK_LOOP_AUTO);
   h->chunk = (int)bk_env_int("BK_CHUNK", 0);
@@ -153,6 +155,8 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "use_tma")) return &h->use_tma;
   if (!strcmp(key, "dist_p2p")) return &h->dist_p2p;
   if (!strcmp(key, "use_compress")) return &h->use_compress;
+  if (!strcmp(key, "persistent")) return &h->persistent;
+  if (!strcmp(key, "persistent_max_n")) return &h->persistent_max_n;
   if (!strcmp(key, "prefetch_x")) return &h->prefetch_x;
   if (!strcmp(key, "loop_mode")) return &h->loop_mode;
   if (!strcmp(key, "chunk")) return &h->chunk;

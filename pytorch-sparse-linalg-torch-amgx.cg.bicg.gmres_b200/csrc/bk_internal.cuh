@@ -134,6 +134,8 @@ struct bk_handle {
   int tma_stages;      // 0 = fill shared memory, else cap on the pipeline depth
   int use_tma;         // allow the TMA row-stream kernel
   int prefetch_x;      // kernel 3: L2 bulk prefetch of the forward-diagonal x ranges
+  int persistent;      // CG: run small systems in ONE cooperative persistent kernel (grid barriers instead of launches)
+  int persistent_max_n;
   int use_compress;    // allow the 8-bit dictionary-coded column stream (kernel 3)
   int dist_p2p;        // multi-GPU: use the peer-memory path (halo push + one-shot all-reduce) when it is connected
   int loop_mode;

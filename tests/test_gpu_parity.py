@@ -285,8 +285,8 @@ def test_solvers_bitwise_deterministic(ma, manifest, name):
     assert torch.equal(xs[0], xs[1]) and torch.equal(xs[0], xs[2])
 
 
-@pytest.mark.parametrize("opts", [dict(fuse_xpay=1), dict(fuse_xpay=0), dict(snake=0), dict(fuse_xpay=1, snake=0), dict(chunk=2), dict(use_tma=0), dict(use_compress=0),
-                                  dict(grid_mult_spmv=2, grid_mult_vec=2)])
+@pytest.mark.parametrize("opts", [dict(persistent=0), dict(persistent=0, fuse_xpay=1), dict(persistent=0, fuse_xpay=0), dict(persistent=0, snake=0), dict(persistent=0, fuse_xpay=1, snake=0), dict(persistent=0, chunk=2), dict(persistent=0, use_tma=0), dict(persistent=0, use_compress=0),
+                                  dict(persistent=0, grid_mult_spmv=2, grid_mult_vec=2), dict(persistent=1)])
 def test_cg_kernel_variants(ma, manifest, opts):
     from pytorch_sparse_solver import _native
     h = _native.Handle.get(torch.device("cuda"))

@@ -42,13 +42,15 @@ def main():
     h = _native.Handle.get(dev)
     A = problems.poisson2d_csr(256, 256, device=dev)
     b = torch.ones(A.shape[0], dtype=torch.float64, device=dev)
-    for mode in (0, 1):
+    for mode, pers in ((0, 1), (0, 0), (1, 0)):
         h.set_option("loop_mode", mode)
+        h.set_option("persistent", pers)
         dt, (x, info) = timed(lambda: module_a.cg(A, b, tol=1e-8))
         r = krylov.last_result
-        emit(what="cg_p2d256", loop_mode=mode, ms=1e3 * dt, iterations=r["iterations"], it_s=r["iterations"] / dt,
+        emit(what="cg_p2d256", loop_mode=mode, persistent=pers, ms=1e3 * dt, iterations=r["iterations"], it_s=r["iterations"] / dt,
              us_per_iter=1e6 * dt / r["iterations"], info=info, launches=r["kernel_launches"])
     h.set_option("loop_mode", 0)
+    h.set_option("persistent", 1)
     for nx, step in ((32, 1), (100, 0), (100, 1)):
         name = f"gmres_ldc{nx}_step{step}_batched"
         z = np.load(ROOT / "tests" / "golden" / f"{name}.npz")
