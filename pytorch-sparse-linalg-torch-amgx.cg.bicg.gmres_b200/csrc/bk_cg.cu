@@ -104,21 +104,30 @@ __device__ __forceinline__ double bk_sum_partials(const double* partials, int co
   return r;
 }
 
+#define BK_PERSIST_BLOCK 1024
+#define BK_PERSIST_WARPS (BK_PERSIST_BLOCK / 32)
+
+// Two grid barriers per iteration: the p-update is folded into the SpMV gather (p_new[c] = r[c] + beta p_old[c] is
+// recomputed on the fly with the same two roundings the stand-alone update would use, and stored once per owned row
+// into the other p buffer), so only the two dot products need a barrier.  1024-thread CTAs keep the barrier small.
 template <typename T>
-__global__ void __launch_bounds__(BK_BLOCK)
+__global__ void __launch_bounds__(BK_PERSIST_BLOCK, 1)
 bk_cg_persistent_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const T* __restrict__ val,
-                        T* x, T* r, T* p, T* ap, const long long n, bk_dev_state* st, double* partials) {
+                        T* x, T* r, T* p0, T* p1, T* ap, const long long n, bk_dev_state* st, double* partials) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double sh_red[BK_WARPS];
+  __shared__ double sh_red[BK_PERSIST_WARPS];
   __shared__ double sh_one[1];
-  const long long tid = (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
-  const long long nth = (long long)gridDim.x * BK_BLOCK;
+  const long long tid = (long long)blockIdx.x * BK_PERSIST_BLOCK + threadIdx.x;
+  const long long nth = (long long)gridDim.x * BK_PERSIST_BLOCK;
   double gamma = st->gamma;
   const double atol2 = st->atol2;
   const long long maxiter = st->maxiter;
   long long k = 0;
   int status = BK_ST_MAXITER;
   if (st->done) return;  // uniform: set by the init epilogue (zero rhs / maxiter 0)
+  T beta = T(0);         // p_{-1} = 0 (buffer p0 is zero-filled), so the first gather forms p_0 = r_0 exactly
+  T* pold = p0;
+  T* pnew = p1;
   for (;;) {
     if (k >= maxiter) {
       status = BK_ST_MAXITER;
@@ -128,38 +137,42 @@ bk_cg_persistent_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
       status = BK_ST_CONVERGED;
       break;
     }
-    // phase 1: Ap = A p, partial p.Ap
+    // phase 1: p_new = r + beta p_old (own rows), Ap = A p_new, partial p.Ap
     double acc[1] = {0.0};
     for (long long row = tid; row < n; row += nth) {
       T sum = T(0);
-      for (int e = rowptr[row]; e < rowptr[row + 1]; ++e) sum = fma(val[e], p[col[e]], sum);
+      for (int e = rowptr[row]; e < rowptr[row + 1]; ++e) {
+        const int c = col[e];
+        sum = fma(val[e], bk_add(r[c], bk_mul(beta, pold[c])), sum);
+      }
+      const T pr = bk_add(r[row], bk_mul(beta, pold[row]));
+      pnew[row] = pr;
       ap[row] = sum;
-      acc[0] += (double)p[row] * (double)sum;
+      acc[0] += (double)pr * (double)sum;
     }
-    bk_block_reduce<1>(acc, sh_red);
+    bk_block_reduce<1, BK_PERSIST_WARPS>(acc, sh_red);
     if (threadIdx.x == 0) __stcg(partials + blockIdx.x, acc[0]);
     grid.sync();
     const double pAp = bk_sum_partials(partials, (int)gridDim.x, sh_one);
-    const double alpha_d = gamma / pAp;
-    const T alpha = (T)alpha_d;
+    const T alpha = (T)(gamma / pAp);
     // phase 2: x += alpha p ; r -= alpha Ap ; partial r.r
     acc[0] = 0.0;
     for (long long row = tid; row < n; row += nth) {
-      x[row] = bk_add(x[row], bk_mul(alpha, p[row]));
+      x[row] = bk_add(x[row], bk_mul(alpha, pnew[row]));
       const T rn = bk_sub(r[row], bk_mul(alpha, ap[row]));
       r[row] = rn;
       acc[0] += (double)rn * (double)rn;
     }
-    bk_block_reduce<1>(acc, sh_red);
+    bk_block_reduce<1, BK_PERSIST_WARPS>(acc, sh_red);
     if (threadIdx.x == 0) __stcg(partials + BK_MAXB + blockIdx.x, acc[0]);
-    grid.sync();
+    grid.sync();  // also publishes the new r (and p_new) to the next iteration's gathers
     const double gamma_new = bk_sum_partials(partials + BK_MAXB, (int)gridDim.x, sh_one);
-    const T beta = (T)(gamma_new / gamma);
+    beta = (T)(gamma_new / gamma);
     gamma = gamma_new;
     ++k;
-    // phase 3: p = r + beta p   (the barrier makes the new p visible to the next SpMV's gathers)
-    for (long long row = tid; row < n; row += nth) p[row] = bk_add(r[row], bk_mul(beta, p[row]));
-    grid.sync();
+    T* t = pold;
+    pold = pnew;
+    pnew = t;
   }
   if (tid == 0) {
     st->k = k;
@@ -170,15 +183,16 @@ bk_cg_persistent_kernel(const int* __restrict__ rowptr, const int* __restrict__ 
 }
 
 template <typename T>
-static int bk_cg_try_persistent(bk_handle* h, const bk_csr* A, T* x, T* r, T* p, T* ap, cudaStream_t s, bool* used) {
+static int bk_cg_try_persistent(bk_handle* h, const bk_csr* A, T* x, T* r, T* p0, T* p1, T* ap, cudaStream_t s,
+                                bool* used) {
   *used = false;
   if (!h->persistent || A->n > (long long)h->persistent_max_n) return BK_OK;
   int coop = 0;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
   if (!coop) return BK_OK;
   int per_sm = 0;
-  BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk_cg_persistent_kernel<T>, BK_BLOCK, 0));
-  long long grid = (A->n + BK_BLOCK - 1) / BK_BLOCK;
+  BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk_cg_persistent_kernel<T>, BK_PERSIST_BLOCK, 0));
+  long long grid = (A->n + BK_PERSIST_BLOCK - 1) / BK_PERSIST_BLOCK;
   const long long cap = (long long)per_sm * h->num_sms;
   if (grid > cap) grid = cap;
   if (grid > BK_MAXB) grid = BK_MAXB;
@@ -189,10 +203,10 @@ static int bk_cg_try_persistent(bk_handle* h, const bk_csr* A, T* x, T* r, T* p,
   long long n = A->n;
   bk_dev_state* st = h->st;
   double* partials = h->partials;  // slots 0 and 1 (BK_MAXB apart)
-  void* args[] = {(void*)&rowptr, (void*)&col, (void*)&val, (void*)&x, (void*)&r, (void*)&p, (void*)&ap,
-                  (void*)&n, (void*)&st, (void*)&partials};
-  BK_CUDA(cudaLaunchCooperativeKernel((const void*)bk_cg_persistent_kernel<T>, dim3((unsigned)grid), dim3(BK_BLOCK),
-                                      args, 0, s));
+  void* args[] = {(void*)&rowptr, (void*)&col, (void*)&val, (void*)&x,  (void*)&r,       (void*)&p0,
+                  (void*)&p1,     (void*)&ap,  (void*)&n,   (void*)&st, (void*)&partials};
+  BK_CUDA(cudaLaunchCooperativeKernel((const void*)bk_cg_persistent_kernel<T>, dim3((unsigned)grid),
+                                      dim3(BK_PERSIST_BLOCK), args, 0, s));
   *used = true;
   return BK_OK;
 }
@@ -301,7 +315,7 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
     bk_epi_cg_init epi{st, has_x0};
     BK_TRY((bk_dot_epi<T>(h, n, b, b, epi, 1, s)));
   }
-  if (fuse) {
+  if (fuse || persist_ok) {
     // p_{-1} = 0, beta = 0  =>  the first fused SpMV forms p_0 = r_0 + 0*0 = r_0  (:821)
     BK_CUDA(cudaMemsetAsync(v.p[0], 0, vbytes, s));
   } else {
@@ -320,8 +334,12 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   };
   int64_t chunks = 0;
   bool persistent = false;
-  BK_TRY(bk_cg_try_persistent<T>(h, A, v.x, v.r, v.p[0], v.ap, s, &persistent));
-  if (!persistent) BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
+  BK_TRY(bk_cg_try_persistent<T>(h, A, v.x, v.r, v.p[0], v.p[1], v.ap, s, &persistent));
+  if (!persistent) {
+    if (persist_ok)  // cooperative launch unavailable after all: the unfused loop expects p = r0
+      BK_CUDA(cudaMemcpyAsync(v.p[0], v.r, vbytes, cudaMemcpyDeviceToDevice, s));
+    BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
+  }
 
   {  // final true residual  ||b - A x||  and  ||x||   (_isolve :1008-1013)
     bk_spmv_args a = bk_spmv_base(A, st);
