@@ -109,6 +109,7 @@ int bk_destroy(bk_handle* h);
  *   grid_mult_vec / grid_mult_spmv   CTAs per SM of the BLAS-1 kernels / the non-TMA SpMV kernels
  *   fuse_xpay      CG: fold p = r + beta p into the next SpMV's gather (-1 auto: only for launch-bound small systems)
  *   snake          CG: alternate the sweep direction of consecutive kernels so the tail of one is still in L2
+ *   persistent     CG: run systems with n <= persistent_max_n (200000) in one cooperative persistent kernel
  *   dist_p2p       multi-GPU: use the peer-memory path when it is connected (0 = NCCL path)
  * Registration-time options (use_tma, use_compress) apply to matrices registered afterwards. */
 int bk_set_option(bk_handle* h, const char* key, int64_t value);

@@ -12,7 +12,7 @@
 // slots of its own window in rank order and adds them in that order => the sum is bitwise identical on all ranks
 // and from run to run (the stop test derived from it therefore agrees everywhere).  Two buffers are enough: a rank
 // can be at most one all-reduce ahead of any other because completing all-reduce s needs every rank's value s.
-// Every wait has a ~2 s timeout that turns a lost peer into an error status instead of a hung GPU.
+// Every wait has a ~10 s timeout that turns a lost peer into an error status instead of a hung GPU.
 #pragma once
 
 #include "bk_internal.cuh"
@@ -21,7 +21,7 @@
 #define BK_P2P_AR_OFF 0
 #define BK_P2P_FLAG_OFF 512
 #define BK_P2P_GHOST_OFF 1024
-#define BK_P2P_TIMEOUT_CYCLES 4000000000LL
+#define BK_P2P_TIMEOUT_CYCLES 20000000000LL
 #define BK_ST_COMM_TIMEOUT (-20)
 
 struct bk_p2p_ctx {
