@@ -60,8 +60,41 @@ def main():
     assert r["iterations"] == 7 and rel(x, x_ref[sl]) <= 1e-12, ("window", rel(x, x_ref[sl]))
     D.close()
     dist.barrier()
+
+    # ---- all-to-all coupling: every rank exchanges halos with every other rank (SPD: diagonally dominant, symmetric)
+    N = 6000 * world
+    i = torch.arange(N, device=dev)
+    rows_, cols_, vals_ = [i], [i], [torch.full((N,), 8.0, dtype=torch.float64, device=dev)]
+    for shift, v in ((1, -1.0), (N // world + 7, -0.7), (N // 2 + 3, -0.5), (3 * (N // world) + 11, -0.3)):
+        j = (i + shift) % N
+        rows_ += [i, j]
+        cols_ += [j, i]
+        vals_ += [torch.full((N,), v, dtype=torch.float64, device=dev)] * 2
+    G = torch.sparse_coo_tensor(torch.stack([torch.cat(rows_), torch.cat(cols_)]), torch.cat(vals_), (N, N)).coalesce()
+    G = G.to_sparse_csr()
+    offs = bkd.partition_rows(N, world)
+    rb, re_ = offs[rank], offs[rank + 1]
+    gc = G.crow_indices()
+    lo, hi = int(gc[rb]), int(gc[re_])
+    D2 = bkd.DistMatrix((gc[rb:re_ + 1] - gc[rb]).contiguous(), G.col_indices()[lo:hi].contiguous(),
+                        G.values()[lo:hi].contiguous(), offs, rank, world)
+    if world > 2:
+        assert len(D2.plan.peers) == world - 1, D2.plan.peers
+    mg = _native.register_matrix(G)
+    bg2 = torch.randn(N, dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(9))
+    dist.broadcast(bg2, 0)
+    assert rel(D2.spmv(bg2[rb:re_].contiguous()), mg.spmv(bg2)[rb:re_]) <= 1e-14, "dist spmv (all-to-all)"
+    xr2, rr2 = mg.cg(bg2, None, 1e-10, 0.0, None)
+    for p2p in ((0, 1) if D2.p2p else (0,)):
+        D2.handle.set_option("dist_p2p", p2p)
+        x2, r2 = D2.cg(bg2[rb:re_].contiguous(), None, 1e-10, 0.0, None)
+        assert r2["info"] == rr2["info"] == 0 and abs(r2["iterations"] - rr2["iterations"]) <= 2, (r2, rr2)
+        assert rel(x2, xr2[rb:re_]) <= 1e-10, ("dist cg all-to-all", p2p, rel(x2, xr2[rb:re_]))
+    D2.handle.set_option("dist_p2p", 1)
+    D2.close()
+    dist.barrier()
     if rank == 0:
-        print(f"dist worker OK: world={world} n={n} iterations={r_ref['iterations']}")
+        print(f"dist worker OK: world={world} n={n} iterations={r_ref['iterations']} all-to-all iterations={rr2['iterations']}")
     dist.destroy_process_group()
 
 
