@@ -85,7 +85,9 @@ typedef struct bk_result {
 typedef struct bk_csr_info {
   int64_t n, nnz;
   int32_t dtype;        /* enum bk_dtype */
-  int32_t kernel;       /* 0 = row-stream (LDG-staged), 1 = sub-warp vector, 2 = row-stream with TMA-staged tiles */
+  int32_t kernel;       /* 0 row-stream (LDG-staged) | 1 sub-warp vector | 2 row-stream, TMA-staged tiles, int32 columns |
+                           3 = 2 with 8-bit dictionary-coded columns | 4 long rows split into virtual rows (skewed
+                           matrices) + ordered per-row reduction */
   int32_t lanes_per_row;/* for kernel 1 */
   int32_t max_row_nnz;
   double mean_row_nnz;
@@ -103,6 +105,7 @@ int bk_destroy(bk_handle* h);
  *   loop_mode      0 auto (= graph) | 1 plain stream launches | 2 CUDA graph of `chunk` flag-guarded iterations
  *   chunk          iterations per graph / poll (0 = sized for ~2 ms of GPU work)
  *   use_tma        1: short-row matrices use the TMA-staged row-stream SpMV (kernel 2/3), 0: LDG-staged (kernel 0)
+ *   use_split      1: matrices with a short mean row but a few very long rows are run on a virtual-row view (kernel 4)
  *   use_compress   1: stream column indices as 8-bit dictionary codes when the matrix allows it (kernel 3)
  *   tma_ctas       CTAs per SM of the TMA SpMV (2..4), tma_stages: cap on its pipeline depth (0 = fill shared memory)
  *   prefetch_x     kernel 3: L2 bulk prefetch of the forward-diagonal x ranges (experiment, default 0)

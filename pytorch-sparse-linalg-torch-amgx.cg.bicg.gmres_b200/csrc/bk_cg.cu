@@ -280,7 +280,7 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   // fused p-update: 2 kernels per iteration instead of 3 — a win while the iteration is launch-latency bound
   // (measured: -17 % at n = 65k, +13 % at n = 1M), so 'auto' (-1) enables it for small systems only
   const bool persist_ok = h->persistent && n <= (long long)h->persistent_max_n;  // one cooperative kernel runs the loop
-  const bool fuse = !persist_ok && A->kernel != 1 && (h->fuse_xpay > 0 || (h->fuse_xpay < 0 && n <= 300000));
+  const bool fuse = !persist_ok && A->kernel != 1 && A->split == nullptr && (h->fuse_xpay > 0 || (h->fuse_xpay < 0 && n <= 300000));
   BK_TRY(bk_ws_reserve(h, (size_t)5 * npad * sizeof(T)));
   bk_cg_vecs<T> v;
   v.x = (T*)h->ws;

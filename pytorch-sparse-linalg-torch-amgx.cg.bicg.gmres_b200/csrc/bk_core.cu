@@ -71,6 +71,7 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->use_tma = (int)bk_env_int("BK_SPMV_TMA", 1);
   h->dist_p2p = (int)bk_env_int("BK_DIST_P2P", 1);
   h->use_compress = (int)bk_env_int("BK_SPMV_COMPRESS", 1);
+  h->use_split = (int)bk_env_int("BK_SPMV_SPLIT", 1);
   h->persistent = (int)bk_env_int("BK_PERSISTENT", 1);
   h->persistent_max_n = (int)bk_env_int("BK_PERSISTENT_MAX_N", 200000);
   h->prefetch_x = (int)bk_env_int("BK_SPMV_PREFETCH_X", 0);  // measured: 5 % slower on P3D-256, kept as an experiment
@@ -155,6 +156,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "use_tma")) return &h->use_tma;
   if (!strcmp(key, "dist_p2p")) return &h->dist_p2p;
   if (!strcmp(key, "use_compress")) return &h->use_compress;
+  if (!strcmp(key, "use_split")) return &h->use_split;
   if (!strcmp(key, "persistent")) return &h->persistent;
   if (!strcmp(key, "persistent_max_n")) return &h->persistent_max_n;
   if (!strcmp(key, "prefetch_x")) return &h->prefetch_x;
@@ -241,6 +243,77 @@ static void bk_csr_plan(bk_handle* h, bk_csr* A) {
   A->cap = (mean <= 8.0) ? 256 : 1024;
   A->lanes_per_row = (mean <= 64.0) ? 8 : (mean <= 128.0 ? 16 : 32);
   (void)h;
+}
+
+// ---- long-row splitting for skewed row-length distributions --------------------------------------------------
+// count[r] = number of virtual rows of real row r (at least 1, so empty rows keep a slot)
+__global__ void bk_vrow_count_kernel(const int* __restrict__ rowptr, long long n, unsigned int* __restrict__ cnt) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r <= n; r += stride) {
+    if (r == n) {
+      cnt[r] = 0;
+    } else {
+      const int len = rowptr[r + 1] - rowptr[r];
+      cnt[r] = len <= BK_SPLIT_LEN ? 1u : (unsigned int)((len + BK_SPLIT_LEN - 1) / BK_SPLIT_LEN);
+    }
+  }
+}
+// vrowptr: virtual row v of real row r covers entries [rowptr[r] + i*L, min(rowptr[r] + (i+1)*L, rowptr[r+1]))
+__global__ void bk_vrow_fill_kernel(const int* __restrict__ rowptr, const int* __restrict__ vstart, long long n,
+                                    int* __restrict__ vrowptr) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const int s = rowptr[r], e = rowptr[r + 1];
+    const int v0 = vstart[r], v1 = vstart[r + 1];
+    for (int v = v0; v < v1; ++v) vrowptr[v] = s + (v - v0) * BK_SPLIT_LEN;
+    if (r == n - 1) vrowptr[v1] = e;
+  }
+}
+
+static int bk_csr_plan_split(bk_handle* h, bk_csr* A, cudaStream_t s) {
+  // only for short-mean matrices with a few very long rows (the row-stream kernels would serialise on them and
+  // the warp-per-row kernel wastes 31 lanes on every short row)
+  const double mean = A->mean_row_nnz;
+  if (A->is_view || !h->use_split || A->n == 0 || mean > 32.0) return BK_OK;
+  if ((double)A->max_row_nnz <= 64.0 * (mean > 8.0 ? mean : 8.0)) return BK_OK;
+  const long long n = A->n;
+  unsigned int* cnt = nullptr;
+  if (bk_pool_alloc((void**)&cnt, sizeof(unsigned int) * (size_t)(n + 1), s) != cudaSuccess)
+    return bk_fail(BK_ERR_ALLOC, "row splitting: allocation failed");
+  const int g = h->num_sms * 8;
+  bk_vrow_count_kernel<<<g, 256, 0, s>>>(A->rowptr, n, cnt);
+  int rc = bk_exclusive_scan_u32(cnt, n + 1, s);
+  if (rc != BK_OK) {
+    bk_pool_free(cnt);
+    return rc;
+  }
+  unsigned int nv_u = 0;
+  cudaMemcpyAsync(&nv_u, cnt + n, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) {
+    bk_pool_free(cnt);
+    return bk_fail(BK_ERR_CUDA, "row splitting: %s", cudaGetErrorString(e));
+  }
+  const long long nv = (long long)nv_u;
+  A->vstart = (int*)cnt;  // exclusive scan of the counts == first virtual row of every real row (n+1 entries)
+  bk_csr* S = (bk_csr*)calloc(1, sizeof(bk_csr));
+  if (!S) return bk_fail(BK_ERR_ALLOC, "row splitting: host allocation failed");
+  S->h = h;
+  S->n = nv;
+  S->nnz = A->nnz;
+  S->dtype = A->dtype;
+  S->col = A->col;
+  S->val = A->val;
+  S->is_view = 1;
+  S->uid = h->next_uid++;
+  A->split = S;
+  if (bk_pool_alloc(&S->own_rowptr, sizeof(int) * (size_t)(nv + 1), s) != cudaSuccess ||
+      bk_pool_alloc(&A->yv, bk_dtype_size(A->dtype) * (size_t)(nv > 0 ? nv : 1), s) != cudaSuccess)
+    return bk_fail(BK_ERR_ALLOC, "row splitting: allocation failed");
+  S->rowptr = (const int*)S->own_rowptr;
+  bk_vrow_fill_kernel<<<g, 256, 0, s>>>(A->rowptr, A->vstart, n, (int*)S->own_rowptr);
+  A->kernel = 4;
+  return bk_csr_finish_plan(h, S, s);  // statistics + kernel choice (row-stream / TMA) for the virtual rows
 }
 
 // widest 16-byte aligned val/col span of any 256-row block: max over blocks of ((e+3)&~3) - (s&~3)
@@ -403,6 +476,8 @@ int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s) {
                    (long long)nnz, hstat[1]);
   A->max_row_nnz = hstat[0];
   bk_csr_plan(h, A);
+  BK_TRY(bk_csr_plan_split(h, A, s));
+  if (A->split) return BK_OK;  // the virtual-row view carries the kernel plan
   return bk_csr_plan_tma(h, A, s);
 }
 
@@ -481,6 +556,9 @@ extern "C" int bk_csr_destroy(bk_csr* A) {
     cudaDeviceSynchronize();  // nothing may still be reading the arrays: the frees below are stream-ordered
   }
   if (A->transpose) bk_csr_destroy(A->transpose);
+  if (A->split) bk_csr_destroy(A->split);
+  if (A->vstart) bk_pool_free(A->vstart);
+  if (A->yv) bk_pool_free(A->yv);
   if (A->own_rowptr) bk_pool_free(A->own_rowptr);
   if (A->own_col) bk_pool_free(A->own_col);
   if (A->own_val) bk_pool_free(A->own_val);

@@ -110,6 +110,12 @@ struct bk_csr {
   int max_row_nnz;
   double mean_row_nnz;
   bk_csr* transpose;  // cached, owned
+  // long-row splitting (skewed matrices): `split` views the same col/val arrays through a finer row pointer in which
+  // every row longer than BK_SPLIT_LEN is cut into virtual rows; vstart[r] = first virtual row of real row r
+  bk_csr* split;      // owned (its rowptr only)
+  int* vstart;        // n+1, own
+  void* yv;           // nv partial sums of the virtual rows, own
+  int is_view;        // this object borrows col/val/tails from a parent (do not free them)
   uint64_t uid;       // unique id for graph-cache keys
 };
 
@@ -136,6 +142,7 @@ struct bk_handle {
   int prefetch_x;      // kernel 3: L2 bulk prefetch of the forward-diagonal x ranges
   int persistent;      // CG: run small systems in ONE cooperative persistent kernel (grid barriers instead of launches)
   int persistent_max_n;
+  int use_split;       // split very long rows into virtual rows (skewed matrices)
   int use_compress;    // allow the 8-bit dictionary-coded column stream (kernel 3)
   int dist_p2p;        // multi-GPU: use the peer-memory path (halo push + one-shot all-reduce) when it is connected
   int loop_mode;
@@ -185,6 +192,8 @@ void bk_graphs_invalidate(bk_handle* h);
 void bk_state_fill_tol(bk_dev_state* v, double tol, double atol);
 void bk_fill_result_isolve(const bk_dev_state* st, bk_result* res, int64_t matvecs);
 void bk_convert_i64_i32(bk_handle* h, const void* in, void* out, long long n, cudaStream_t s);
+int bk_exclusive_scan_u32(unsigned int* data, long long n, cudaStream_t s);
+#define BK_SPLIT_LEN 256
 int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s);
 int bk_solver_args_check(const char* who, bk_handle* h, const bk_csr* A, const void* b, void* x, bk_result* res);
 

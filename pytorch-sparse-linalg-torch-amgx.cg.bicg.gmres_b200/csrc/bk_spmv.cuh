@@ -225,6 +225,34 @@ bk_spmv_vector_kernel(const bk_spmv_args a, const bk_scratch sc, Epi epi) {
 
 #include "bk_spmv_tma.cuh"
 
+// Second half of the long-row path: y[r] = (b[r] -) sum of the partial sums of r's virtual rows, added in order
+// (deterministic), fused with the requested dots and the solver's scalar epilogue.
+template <typename T, int MODE, int DOTS, typename Epi>
+__global__ void __launch_bounds__(BK_BLOCK)
+bk_vrow_reduce_kernel(const bk_spmv_args a, const int* __restrict__ vstart, const T* __restrict__ yv,
+                      const bk_scratch sc, Epi epi) {
+  if (bk_spmv_skip(a)) return;
+  constexpr int R = bk_ndots<DOTS>::value;
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.0;
+  T* __restrict__ y = static_cast<T*>(a.y);
+  const long long stride = (long long)gridDim.x * BK_BLOCK;
+  for (long long row = (long long)blockIdx.x * BK_BLOCK + threadIdx.x; row < a.n; row += stride) {
+    T sum = T(0);
+    for (int v = vstart[row]; v < vstart[row + 1]; ++v) sum += yv[v];
+    T out = sum;
+    if constexpr (MODE == 1) out = bk_sub(__ldg(static_cast<const T*>(a.b) + row), sum);
+    y[row] = out;
+    if constexpr ((DOTS & 1) != 0)
+      acc[0] += static_cast<double>(__ldg(static_cast<const T*>(a.w) + row)) * static_cast<double>(out);
+    if constexpr ((DOTS & 2) != 0) acc[DOTS & 1] += static_cast<double>(out) * static_cast<double>(out);
+  }
+  if constexpr (DOTS != 0) {
+    bk_grid_reduce<R>(acc, sc, epi);
+  }
+}
+
 struct bk_epi_none {
   __device__ __forceinline__ void operator()(const double*) const {}
 };
@@ -261,7 +289,36 @@ static inline int bk_set_smem(K kernel, size_t bytes) {
 
 template <typename T, int MODE, int DOTS, int XMODE, typename Epi>
 static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a, const bk_scratch& sc,
+                            Epi epi, cudaStream_t s);
+
+// Skewed matrices: SpMV over the virtual-row view (every lane's work bounded by BK_SPLIT_LEN entries), then the
+// ordered per-row reduction of the partial sums.
+template <typename T, int MODE, int DOTS, typename Epi>
+static int bk_launch_spmv_split(bk_handle* h, const bk_csr* A, const bk_spmv_args& a, const bk_scratch& sc, Epi epi,
+                                cudaStream_t s) {
+  bk_spmv_args av = a;
+  av.rowptr = A->split->rowptr;
+  av.n = A->split->n;
+  av.y = A->yv;
+  av.b = nullptr;
+  av.w = nullptr;
+  BK_TRY((bk_launch_spmv_t<T, 0, 0, 0, bk_epi_none>(h, A->split, av, sc, bk_epi_none(), s)));
+  const int grid = bk_grid_rows(bk_grid_vec(h), A->n, BK_BLOCK);
+  bk_vrow_reduce_kernel<T, MODE, DOTS, Epi><<<grid, BK_BLOCK, 0, s>>>(a, A->vstart, (const T*)A->yv, sc, epi);
+  BK_KERNEL_CHECK();
+  return BK_OK;
+}
+
+template <typename T, int MODE, int DOTS, int XMODE, typename Epi>
+static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a, const bk_scratch& sc,
                             Epi epi, cudaStream_t s) {
+  if (A->split != nullptr) {
+    if constexpr (XMODE != 0) {
+      return bk_fail(BK_ERR_UNSUPPORTED, "fused p-update is not available for row-split matrices");
+    } else {
+      return bk_launch_spmv_split<T, MODE, DOTS, Epi>(h, A, a, sc, epi, s);
+    }
+  }
   if ((A->kernel == 2 || A->kernel == 3) && XMODE == 0) {
     if constexpr (XMODE == 0) {
       // CTAs per SM (2..4) trade pipeline depth for consumer warps; stages fill the per-CTA share of shared memory

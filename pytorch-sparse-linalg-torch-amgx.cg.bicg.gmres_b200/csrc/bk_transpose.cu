@@ -113,6 +113,22 @@ bk_scan_apply_kernel(unsigned int* __restrict__ data, long long n, const unsigne
   }
 }
 
+// In-place exclusive scan of `n` uint32 values (set-up helper shared with the long-row splitter).
+int bk_exclusive_scan_u32(unsigned int* data, long long n, cudaStream_t s) {
+  if (n <= 0) return BK_OK;
+  const long long nchunks = (n + SC_CHUNK - 1) / SC_CHUNK;
+  unsigned int* sums = nullptr;
+  if (bk_pool_alloc((void**)&sums, sizeof(unsigned int) * (size_t)(nchunks + 1), s) != cudaSuccess)
+    return bk_fail(BK_ERR_ALLOC, "scan scratch allocation failed");
+  bk_scan_sums_kernel<<<(unsigned)nchunks, BK_BLOCK, 0, s>>>(data, n, sums);
+  bk_scan_serial_kernel<<<1, BK_BLOCK, 0, s>>>(sums, nchunks);
+  bk_scan_apply_kernel<<<(unsigned)nchunks, BK_BLOCK, 0, s>>>(data, n, sums);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(sums, s);
+  if (e != cudaSuccess) return bk_fail(BK_ERR_CUDA, "scan: %s", cudaGetErrorString(e));
+  return BK_OK;
+}
+
 // stable scatter of one tile: position = scanned_hist[digit][tile] + rank of the item among the
 // tile's earlier items with the same digit (tile order = warp, then iteration, then lane).
 __global__ void __launch_bounds__(BK_BLOCK)

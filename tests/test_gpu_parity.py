@@ -129,7 +129,7 @@ def test_spmv_tma_and_ldg_row_stream_agree(name, make):
     finally:
         h.set_option("use_tma", 1)
         _native.clear_cache()
-    assert k0 in (0, 1)
+    assert k0 in (0, 1, 4)
     if k0 == 0 and name != "rand_mean20":
         assert k1 in (2, 3), "short-row matrices should take the TMA row-stream kernel"
     scale = float(y0.abs().max()) + 1e-300
@@ -171,6 +171,42 @@ def test_spmv_dictionary_falls_back_on_unstructured():
     from pytorch_sparse_solver import _native
     m = _native.register_matrix(_random_csr(1000, 5, 1, empty_rows=True).cuda())
     assert m.info()["kernel"] == 2
+
+
+def _arrowhead(n, dtype=torch.float64):
+    """SPD arrowhead: dense first row/column + strong diagonal — mean row length ~3, one row of n entries."""
+    i = torch.arange(1, n)
+    rows = torch.cat([torch.arange(n), torch.zeros(n - 1, dtype=torch.long), i])
+    cols = torch.cat([torch.arange(n), i, torch.zeros(n - 1, dtype=torch.long)])
+    vals = torch.cat([torch.full((n,), 4.0, dtype=dtype), torch.full((2 * (n - 1),), -1.0 / n ** 0.5, dtype=dtype)])
+    vals[0] = 6.0
+    return torch.sparse_coo_tensor(torch.stack([rows, cols]), vals, (n, n)).coalesce().to_sparse_csr()
+
+
+@pytest.mark.parametrize("n", [700, 5000, 70000])
+def test_skewed_matrix_row_splitting(ma, n):
+    """A few very long rows among short ones: kernel 4 (virtual rows + ordered reduction) vs CPU, and CG vs the oracle."""
+    from oracle import krylov_oracle as orc
+    from pytorch_sparse_solver import _native
+    A = _arrowhead(n)
+    m = _native.register_matrix(A.cuda())
+    assert m.info()["kernel"] == 4 and m.info()["max_row_nnz"] == n
+    x = torch.randn(n, dtype=torch.float64, generator=torch.Generator().manual_seed(4))
+    ref = torch.matmul(A, x)
+    y, d = m.spmv_dot(x.cuda(), x.cuda())
+    assert rel_diff(y, ref) <= 1e-13
+    assert abs(float(d) - float(x @ ref)) <= 1e-11 * float(x.abs() @ ref.abs())
+    yt = m.transpose().spmv(x.cuda())                     # symmetric: A^T x == A x
+    assert rel_diff(yt, ref) <= 1e-13
+    b = torch.matmul(A, torch.ones(n, dtype=torch.float64))
+    x_ref, info_ref, st = orc.cg(A, b, tol=1e-10)
+    xs, info = ma.cg(A.cuda(), b.cuda(), tol=1e-10)
+    assert info == info_ref == 0 and abs(_last()["iterations"] - st["iterations"]) <= 2
+    assert rel_diff(xs, x_ref) <= FP64_TOL
+    xb, info = ma.bicgstab(A.cuda(), b.cuda(), tol=1e-10)
+    assert info == 0 and rel_diff(xb, x_ref) <= 1e-8
+    xg, info = ma.gmres(A.cuda(), b.cuda(), tol=1e-10, restart=20)
+    assert info == 0 and rel_diff(xg, x_ref) <= 1e-8
 
 
 def test_spmv_fp32():
