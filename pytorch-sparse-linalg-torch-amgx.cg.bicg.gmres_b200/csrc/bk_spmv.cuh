@@ -260,22 +260,17 @@ struct bk_epi_none {
 // Opt a kernel in to > 48 KB of dynamic shared memory once per (kernel, size) — keyed by the kernel's address
 // (all instantiations share one function-pointer TYPE, so a per-type static would be wrong).
 static inline int bk_ensure_dyn_smem(const void* func, size_t bytes) {
-  static const void* funcs[64];
-  static size_t sizes[64];
+  // This header is compiled into several translation units, each with its own table, while the attribute is
+  // per kernel and process-wide: always opt in to one fixed ceiling (the most a 2-CTA/SM plan can ask for, leaving
+  // room for static shared memory) so that no unit can lower another's limit.
+  constexpr size_t kMaxOptIn = 112 * 1024;
+  static const void* funcs[128];
   static int count = 0;
+  if (bytes > kMaxOptIn) return bk_fail(BK_ERR_ARG, "dynamic shared memory request exceeds 112 KB");
   for (int i = 0; i < count; ++i)
-    if (funcs[i] == func) {
-      if (sizes[i] >= bytes) return BK_OK;
-      BK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-      sizes[i] = bytes;
-      return BK_OK;
-    }
-  BK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  if (count < 64) {
-    funcs[count] = func;
-    sizes[count] = bytes;
-    ++count;
-  }
+    if (funcs[i] == func) return BK_OK;
+  BK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxOptIn));
+  if (count < 128) funcs[count++] = func;
   return BK_OK;
 }
 
