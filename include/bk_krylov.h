@@ -114,7 +114,7 @@ int bk_destroy(bk_handle* h);
  *   snake          CG: alternate the sweep direction of consecutive kernels so the tail of one is still in L2
  *   persistent     CG: run systems with n <= persistent_max_n (200000) in one cooperative persistent kernel
  *   dist_p2p       multi-GPU: use the peer-memory path when it is connected (0 = NCCL path)
- * Registration-time options (use_tma, use_compress) apply to matrices registered afterwards. */
+ * Registration-time options (use_tma, use_compress, use_split) apply to matrices registered afterwards. */
 int bk_set_option(bk_handle* h, const char* key, int64_t value);
 int64_t bk_get_option(bk_handle* h, const char* key);
 int bk_device_info(bk_handle* h, int32_t* num_sms, int64_t* l2_bytes, int64_t* mem_bytes);
