@@ -221,6 +221,16 @@ int bk_dist_spmv(bk_handle* h, bk_dist* D, const void* x_local, void* y_local, v
 /* distributed CG (same recurrences / stop test / info as bk_cg; n_global sets the default maxiter = 10 n) */
 int bk_dist_cg(bk_handle* h, bk_dist* D, const void* b_local, void* x_local, int has_x0, double tol,
                double atol, int64_t maxiter, int64_t n_global, bk_result* result, void* stream);
+/* distributed BiCGStab / GMRES: the single-GPU drivers (bk_bicgstab, bk_gmres — same recurrences, breakdown codes,
+ * restart logic and info) run on the row-partitioned matrix; every dot product becomes a global sum (NCCL path:
+ * ncclAllReduce + a one-thread scalar kernel; peer-memory path: all-reduced inside the reducing kernel's epilogue,
+ * GMRES's projection coefficients V^T w as one vector all-reduce of j+1 doubles).  The GMRES small dense problem is
+ * replicated on every rank.  Reference: _bicgstab_solve :859-964, gmres :641-784; SURVEY section 8e. */
+int bk_dist_bicgstab(bk_handle* h, bk_dist* D, const void* b_local, void* x_local, int has_x0, double tol,
+                     double atol, int64_t maxiter, int64_t n_global, bk_result* result, void* stream);
+int bk_dist_gmres(bk_handle* h, bk_dist* D, const void* b_local, void* x_local, int has_x0, double tol_eff,
+                  double atol_eff, int restart, int64_t maxiter, int method, int64_t n_global, bk_result* result,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,8 @@
 #include "bk_internal.cuh"
 #include "bk_loop.cuh"
 #include "bk_spmv.cuh"
+#include "bk_sys.cuh"
+#include "bk_dist.cuh"
 #include "bk_vec.cuh"
 
 template <typename T>
@@ -102,44 +104,27 @@ struct bk_bicg_vecs {
   T *x, *r, *rhat, *p, *q, *s, *t;
 };
 
-template <typename T>
-static int bk_bicg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_bicg_vecs<T>& v, cudaStream_t s) {
-  const long long n = A->n;
-  bk_dev_state* st = h->st;
+template <typename T, typename Sys>
+static int bk_bicg_enqueue_iter(const Sys& sys, const bk_bicg_vecs<T>& v, cudaStream_t s) {
+  bk_dev_state* st = sys.h->st;
   {
     bk_op_bicg_p<T> op;
     op.r = v.r;
     op.p = v.p;
     op.q = v.q;
     op.st = st;
-    BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), s));
+    BK_TRY(sys.template ew<T>(op, true, 2, s));
   }
-  {
-    bk_spmv_args a = bk_spmv_base(A, st);
-    a.x = v.p;
-    a.y = v.q;
-    a.w = v.rhat;
-    a.guard = 1;
-    bk_epi_bicg_alpha<T> epi{st};
-    BK_TRY((bk_launch_spmv<0, 1, 0>(h, A, a, bk_slot(h, 0), epi, s)));
-  }
+  BK_TRY((sys.template matvec<T, 0, 1>(v.p, v.q, v.rhat, nullptr, 1, bk_epi_bicg_alpha<T>{st}, s)));
   {
     bk_op_bicg_s<T> op;
     op.r = v.r;
     op.q = v.q;
     op.s = v.s;
     op.st = st;
-    BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
+    BK_TRY(sys.template ew<T>(op, true, 1, s));
   }
-  {
-    bk_spmv_args a = bk_spmv_base(A, st);
-    a.x = v.s;
-    a.y = v.t;
-    a.w = v.s;
-    a.guard = 3;
-    bk_epi_bicg_omega<T> epi{st};
-    BK_TRY((bk_launch_spmv<0, 3, 0>(h, A, a, bk_slot(h, 0), epi, s)));
-  }
+  BK_TRY((sys.template matvec<T, 0, 3>(v.s, v.t, v.s, nullptr, 3, bk_epi_bicg_omega<T>{st}, s)));
   {
     bk_op_bicg_xr<T> op;
     op.x = v.x;
@@ -149,15 +134,16 @@ static int bk_bicg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_bicg_vec
     op.rhat = v.rhat;
     op.r = v.r;
     op.st = st;
-    BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
+    BK_TRY(sys.template ew<T>(op, true, 1, s));
   }
   return BK_OK;
 }
 
-template <typename T>
-static int bk_bicgstab_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, int has_x0, double tol,
-                         double atol, int64_t maxiter, bk_result* res, cudaStream_t s) {
-  const long long n = A->n;
+template <typename T, typename Sys>
+static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0, double tol, double atol,
+                         int64_t maxiter, bk_result* res, cudaStream_t s) {
+  bk_handle* h = sys.h;
+  const long long n = sys.n();
   const size_t npad = ((size_t)n + 63) & ~(size_t)63;
   BK_TRY(bk_ws_reserve(h, (size_t)7 * npad * sizeof(T)));
   bk_bicg_vecs<T> v;
@@ -173,7 +159,7 @@ static int bk_bicgstab_t(bk_handle* h, const bk_csr* A, const void* b, void* x_u
 
   bk_dev_state init;
   memset(&init, 0, sizeof(init));
-  init.maxiter = maxiter < 0 ? 10 * n : maxiter;
+  init.maxiter = maxiter < 0 ? 10 * sys.n_global() : maxiter;
   init.status = BK_ST_MAXITER;
   bk_state_fill_tol(&init, tol, atol);
   bk_state_set_kernel<<<1, 1, 0, s>>>(st, init);
@@ -181,48 +167,33 @@ static int bk_bicgstab_t(bk_handle* h, const bk_csr* A, const void* b, void* x_u
 
   if (has_x0) {
     BK_CUDA(cudaMemcpyAsync(v.x, x_user, vbytes, cudaMemcpyDeviceToDevice, s));
-    bk_spmv_args a = bk_spmv_base(A, st);  // r0 = b - A x0 ; rs = r0.r0   (:875)
-    a.x = v.x;
-    a.y = v.r;
-    a.b = b;
-    bk_epi_set_rs epi{st};
-    BK_TRY((bk_launch_spmv<1, 2, 0>(h, A, a, bk_slot(h, 0), epi, s)));
+    // r0 = b - A x0 ; rs = r0.r0   (:875)
+    BK_TRY((sys.template matvec<T, 1, 2>(v.x, v.r, nullptr, b, 0, bk_epi_set_rs{st}, s)));
   } else {
     BK_CUDA(cudaMemsetAsync(v.x, 0, vbytes, s));
     BK_CUDA(cudaMemcpyAsync(v.r, b, vbytes, cudaMemcpyDeviceToDevice, s));
   }
-  {
-    bk_epi_bicg_init<T> epi{st, has_x0};
-    BK_TRY((bk_dot_epi<T>(h, n, b, b, epi, 1, s)));
-  }
+  BK_TRY((sys.template dot<T>(b, b, bk_epi_bicg_init<T>{st, has_x0}, 1, s)));
   // rhat = p = q = r0   (:876, :890)
   BK_CUDA(cudaMemcpyAsync(v.rhat, v.r, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(v.p, v.r, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(v.q, v.r, vbytes, cudaMemcpyDeviceToDevice, s));
 
-  const double bytes_iter = 2.0 * ((double)A->nnz * (sizeof(T) + 4) + 4.0 * (n + 1)) + 19.0 * n * sizeof(T);
+  const double bytes_iter = 2.0 * sys.matrix_bytes() + 19.0 * n * sizeof(T);
   const int chunk = bk_pick_chunk(h, bytes_iter, 5);
   const bool use_graph = h->loop_mode != BK_LOOP_STREAM;
-  uint64_t key[6] = {2 /*bicgstab*/, A->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
-                     (uint64_t)A->dtype | ((uint64_t)chunk << 16),
+  uint64_t key[6] = {2 /*bicgstab*/, sys.uid(), (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
+                     (uint64_t)sys.dtype() | ((uint64_t)chunk << 16),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   auto enqueue_chunk = [&](cudaStream_t cs) -> int {
-    for (int it = 0; it < chunk; ++it) BK_TRY(bk_bicg_enqueue_iter<T>(h, A, v, cs));
+    for (int it = 0; it < chunk; ++it) BK_TRY((bk_bicg_enqueue_iter<T, Sys>(sys, v, cs)));
     return BK_OK;
   };
   int64_t chunks = 0;
   BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
 
-  {
-    bk_spmv_args a = bk_spmv_base(A, st);
-    a.x = v.x;
-    a.y = v.t;
-    a.b = b;
-    bk_epi_final_r2 epi{st};
-    BK_TRY((bk_launch_spmv<1, 2, 0>(h, A, a, bk_slot(h, 0), epi, s)));
-    bk_epi_final_x2 epx{st};
-    BK_TRY((bk_dot_epi<T>(h, n, v.x, v.x, epx, 1, s)));
-  }
+  BK_TRY((sys.template matvec<T, 1, 2>(v.x, v.t, nullptr, b, 0, bk_epi_final_r2{st}, s)));
+  BK_TRY((sys.template dot<T>(v.x, v.x, bk_epi_final_x2{st}, 1, s)));
   BK_CUDA(cudaMemcpyAsync(x_user, v.x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
   BK_CUDA(cudaStreamSynchronize(s));
@@ -230,7 +201,7 @@ static int bk_bicgstab_t(bk_handle* h, const bk_csr* A, const void* b, void* x_u
   bk_fill_result_isolve(fin, res, 2 * fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->rs;
   res->kernel_launches = chunks * chunk * 5 + 2 + (has_x0 ? 1 : 0) + 2;
-  return BK_OK;
+  return sys.check_comm(fin, "bicgstab");
 }
 
 extern "C" int bk_bicgstab(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, double tol, double atol,
@@ -238,7 +209,21 @@ extern "C" int bk_bicgstab(bk_handle* h, const bk_csr* A, const void* b, void* x
   BK_TRY(bk_solver_args_check("bk_bicgstab", h, A, b, x, result));
   BK_CUDA(cudaSetDevice(h->device));
   if (A->n == 0) return BK_OK;
+  const bk_sys_local sys{h, A};
   if (A->dtype == BK_F64)
-    return bk_bicgstab_t<double>(h, A, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
-  return bk_bicgstab_t<float>(h, A, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+    return bk_bicgstab_t<double>(sys, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+  return bk_bicgstab_t<float>(sys, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+}
+
+// Row-partitioned BiCGStab: same driver, every reduction made global ("BiCGStab: 3 allreduce points").
+extern "C" int bk_dist_bicgstab(bk_handle* h, bk_dist* D, const void* b_local, void* x_local, int has_x0, double tol,
+                                double atol, int64_t maxiter, int64_t n_global, bk_result* result, void* stream) {
+  if (!h || !D || !result) return bk_fail(BK_ERR_ARG, "bk_dist_bicgstab: null handle/matrix/result");
+  if (D->n_local > 0 && (!b_local || !x_local)) return bk_fail(BK_ERR_ARG, "bk_dist_bicgstab: null vector");
+  memset(result, 0, sizeof(*result));
+  BK_CUDA(cudaSetDevice(h->device));
+  const bk_sys_dist sys{h, D, D->p2p_enabled && h->dist_p2p, n_global};
+  if (D->dtype == BK_F64)
+    return bk_bicgstab_t<double>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+  return bk_bicgstab_t<float>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
 }

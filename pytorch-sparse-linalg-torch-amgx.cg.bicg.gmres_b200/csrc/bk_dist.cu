@@ -20,24 +20,9 @@
 #include "bk_p2p.cuh"
 #include "bk_spmv.cuh"
 #include "bk_vec.cuh"
+#include "bk_dist.cuh"
 
-// ---- minimal NCCL surface (nccl.h is not required at build time) -------------------------------------
-typedef struct { char internal[128]; } bk_nccl_id;
-typedef void* bk_nccl_comm;
-struct bk_nccl_api {
-  void* lib;
-  int (*GetUniqueId)(bk_nccl_id*);
-  int (*CommInitRank)(bk_nccl_comm*, int, bk_nccl_id, int);
-  int (*CommDestroy)(bk_nccl_comm);
-  int (*AllReduce)(const void*, void*, size_t, int, int, bk_nccl_comm, cudaStream_t);
-  int (*Send)(const void*, size_t, int, int, bk_nccl_comm, cudaStream_t);
-  int (*Recv)(void*, size_t, int, int, bk_nccl_comm, cudaStream_t);
-  int (*GroupStart)();
-  int (*GroupEnd)();
-  const char* (*GetErrorString)(int);
-};
-static bk_nccl_api g_nccl = {nullptr};
-enum { BK_NCCL_SUM = 0, BK_NCCL_F32 = 7, BK_NCCL_F64 = 8 };
+bk_nccl_api g_nccl = {nullptr};
 
 static int bk_nccl_load() {
   if (g_nccl.lib) return BK_OK;
@@ -62,47 +47,6 @@ static int bk_nccl_load() {
   g_nccl.lib = lib;
   return BK_OK;
 }
-
-#define BK_NCCL(expr)                                                                                   \
-  do {                                                                                                  \
-    int _r = (expr);                                                                                    \
-    if (_r != 0) return bk_fail(BK_ERR_NCCL, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,             \
-                                g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");              \
-  } while (0)
-
-struct bk_dist {
-  bk_handle* h;
-  int rank, nranks;
-  int64_t n_local, n_ghost, n_brows, nnz_gh;
-  int dtype;
-  bk_csr* Aloc;
-  const int* brow_ids;
-  const int* gh_rowptr;
-  const int* gh_col;
-  const void* gh_val;
-  int npeers;
-  int* peer_ranks;
-  int64_t* send_counts;
-  int64_t* recv_counts;
-  int64_t send_total;
-  const int* send_idx;
-  void* sendbuf;
-  void* ghost;  // = window + BK_P2P_GHOST_OFF
-  char* window; // IPC-exportable: all-reduce slots, halo flags, ghost vector (bk_p2p.cuh)
-  size_t window_bytes;
-  int p2p_enabled;
-  bk_p2p_ctx p2p;
-  void* peer_mapped[BK_P2P_MAXP];     // cudaIpcOpenMemHandle results (to close)
-  long long* d_seg_start;              // device [npeers+1]: prefix sums of send_counts
-  void** d_remote_ghost;               // device [npeers]: where my entries land in each peer's ghost vector
-  unsigned long long** d_remote_flag;  // device [npeers]: my arrival flag inside each peer's window
-  int* d_peer_ranks;                   // device [npeers]
-  double* red;  // [0] p.Ap  [1] r.r  (allreduced in place)  [2..3] init/final  [4] local-block partial
-  bk_nccl_comm comm;
-  cudaStream_t comm_stream;
-  cudaEvent_t ev_ready, ev_halo;
-  uint64_t uid;
-};
 
 extern "C" int bk_dist_unique_id(void* id128) {
   if (!id128) return bk_fail(BK_ERR_ARG, "bk_dist_unique_id: null buffer");
@@ -202,8 +146,8 @@ extern "C" int bk_dist_create(bk_handle* h, const void* id128, int rank, int nra
   if (e == cudaSuccess) D->ghost = D->window + BK_P2P_GHOST_OFF;
   if (e == cudaSuccess) e = cudaMalloc((void**)&D->p2p.counters, sizeof(unsigned int) * 16);
   if (e == cudaSuccess) e = cudaMemset(D->p2p.counters, 0, sizeof(unsigned int) * 16);
-  if (e == cudaSuccess) e = cudaMalloc(&D->red, sizeof(double) * 8);
-  if (e == cudaSuccess) e = cudaMemset(D->red, 0, sizeof(double) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&D->red, sizeof(double) * BK_DIST_RED_DOUBLES);
+  if (e == cudaSuccess) e = cudaMemset(D->red, 0, sizeof(double) * BK_DIST_RED_DOUBLES);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&D->comm_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&D->ev_ready, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&D->ev_halo, cudaEventDisableTiming);
@@ -290,37 +234,6 @@ extern "C" int bk_dist_p2p_connect(bk_dist* D, const void* handles, const int64_
   return BK_OK;
 }
 
-// push: every boundary entry of x is stored straight into the owning peer's ghost vector (NVLink stores); the last
-// CTA then publishes this rank's arrival flag (sequence number) in every peer's window with release semantics.
-template <typename T>
-__global__ void __launch_bounds__(256)
-bk_halo_push_kernel(const T* __restrict__ x, const int* __restrict__ idx, const long long* __restrict__ seg_start,
-                    void* const* __restrict__ remote_ghost, unsigned long long* const* __restrict__ remote_flag,
-                    int npeers, long long count, unsigned int* counters, const bk_dev_state* st) {
-  if (st->done) return;
-  __shared__ int s_last;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
-    int p = 0;
-    while (p + 1 < npeers && i >= seg_start[p + 1]) ++p;
-    static_cast<T*>(remote_ghost[p])[i - seg_start[p]] = x[idx[i]];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int t = atomicInc(&counters[3], gridDim.x - 1);
-    s_last = (t == gridDim.x - 1) ? 1 : 0;
-  }
-  __syncthreads();
-  if (s_last) {
-    __threadfence_system();
-    const unsigned int seq = counters[1] + 1u;
-    if (threadIdx.x < npeers) bk_st_release_sys_u64(remote_flag[threadIdx.x], (unsigned long long)seq);
-    __syncthreads();
-    if (threadIdx.x == 0) counters[1] = seq;
-  }
-}
-
 // boundary rows with the halo wait in front and the p.Ap all-reduce + alpha behind (peer-memory path of CG's K1b)
 template <typename T>
 __global__ void __launch_bounds__(BK_BLOCK)
@@ -372,14 +285,6 @@ bk_ghost_rows_p2p_kernel(const int* __restrict__ brow_ids, const int* __restrict
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------
-template <typename T>
-__global__ void bk_halo_pack_kernel(const T* __restrict__ x, const int* __restrict__ idx, T* __restrict__ out,
-                                    long long count, const bk_dev_state* st, int guard) {
-  if (guard && st->done) return;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) out[i] = x[idx[i]];
-}
-
 struct bk_epi_dist_store {  // out[0] = base[0] + s   (adds the local-block partial to the ghost-block partial)
   double* out;
   const double* base;
@@ -389,7 +294,7 @@ struct bk_epi_dist_store {  // out[0] = base[0] + s   (adds the local-block part
 // boundary rows: y[r] += sum_k gh_val[k] * ghost[gh_col[k]] ; optional dot partial w[r] * sum
 template <typename T, int DOT>
 __global__ void __launch_bounds__(BK_BLOCK)
-bk_ghost_rows_kernel(const int* __restrict__ brow_ids, const int* __restrict__ rowptr, const int* __restrict__ col,
+bk_ghost_rows_cg_kernel(const int* __restrict__ brow_ids, const int* __restrict__ rowptr, const int* __restrict__ col,
                      const T* __restrict__ val, const T* __restrict__ ghost, T* __restrict__ y, const T* __restrict__ w,
                      long long n_brows, const bk_scratch sc, bk_epi_dist_store epi, const bk_dev_state* st, int guard) {
   if (guard && st->done) return;
@@ -532,11 +437,11 @@ static int bk_dist_spmv_t(bk_handle* h, bk_dist* D, const T* x, T* y, const T* w
     if (g > h->num_sms * 4) g = h->num_sms * 4;
     bk_epi_dist_store epi{dot_out, D->red + 4};
     if (dot_out) {
-      bk_ghost_rows_kernel<T, 1><<<g, BK_BLOCK, 0, s>>>(D->brow_ids, D->gh_rowptr, D->gh_col, (const T*)D->gh_val,
+      bk_ghost_rows_cg_kernel<T, 1><<<g, BK_BLOCK, 0, s>>>(D->brow_ids, D->gh_rowptr, D->gh_col, (const T*)D->gh_val,
                                                        (const T*)D->ghost, y, w, D->n_brows, bk_slot(h, 3), epi, st,
                                                        guard);
     } else if (D->n_brows > 0) {
-      bk_ghost_rows_kernel<T, 0><<<g, BK_BLOCK, 0, s>>>(D->brow_ids, D->gh_rowptr, D->gh_col, (const T*)D->gh_val,
+      bk_ghost_rows_cg_kernel<T, 0><<<g, BK_BLOCK, 0, s>>>(D->brow_ids, D->gh_rowptr, D->gh_col, (const T*)D->gh_val,
                                                        (const T*)D->ghost, y, w, D->n_brows, bk_slot(h, 3), epi, st,
                                                        guard);
     }
@@ -614,7 +519,7 @@ static int bk_dist_cg_t(bk_handle* h, bk_dist* D, const void* b, void* x_user, i
       int g = (int)((D->send_total + 255) / 256);
       if (g > h->num_sms * 2) g = h->num_sms * 2;
       bk_halo_push_kernel<T><<<g, 256, 0, cs>>>(p, D->send_idx, D->d_seg_start, D->d_remote_ghost, D->d_remote_flag,
-                                                D->npeers, D->send_total, D->p2p.counters, st);
+                                                D->npeers, D->send_total, D->p2p.counters, st, 1);
       BK_KERNEL_CHECK();
     }
     {

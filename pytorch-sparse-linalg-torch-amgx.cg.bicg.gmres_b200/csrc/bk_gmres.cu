@@ -21,6 +21,8 @@
 #include "bk_internal.cuh"
 #include "bk_loop.cuh"
 #include "bk_spmv.cuh"
+#include "bk_sys.cuh"
+#include "bk_dist.cuh"
 #include "bk_vec.cuh"
 
 #define BK_GM_MAXM 256  // largest supported restart
@@ -115,8 +117,8 @@ struct bk_epi_gm_xx {
 template <typename T, int W>
 __global__ void __launch_bounds__(BK_BLOCK, 3)
 bk_multidot_kernel(const T* __restrict__ V, const size_t ldv, const int count, const T* __restrict__ w, const long long n,
-                   double* __restrict__ partials, unsigned int* counter, const bk_dev_state* st,
-                   double* __restrict__ hout) {
+                   double* __restrict__ partials, unsigned int* counter, bk_dev_state* st,
+                   double* __restrict__ hout, const bk_gsum gs) {
   if (st->done || st->g_cycle_over) return;
   constexpr int NV = 8;
   __shared__ double sh[NV * BK_WARPS];
@@ -170,6 +172,19 @@ bk_multidot_kernel(const T* __restrict__ V, const size_t ldv, const int count, c
       for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
       if (lane == 0) hout[r] = a;
     }
+    if (gs.mode == 1) {  // peer memory: make the coefficients global right here (mode 2: ncclAllReduce follows)
+      __syncthreads();
+      const unsigned int seq = gs.p2p.counters[5] + 1u;
+      bk_p2p_allreduce_vec(gs.p2p, seq, hout, hout, count, threadIdx.x, BK_BLOCK);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        gs.p2p.counters[5] = seq;
+        if (gs.p2p.counters[4]) {
+          st->done = 1;
+          st->status = BK_ST_COMM_TIMEOUT;
+        }
+      }
+    }
   }
 }
 
@@ -187,12 +202,55 @@ __device__ __forceinline__ void bk_givens(double a, double b, double& cs, double
   sn = a_lt_b ? r : r * t;
 }
 
+// The small dense work of Arnoldi step j, on ONE thread: hc = h_0..h_j (shared), s_c/s_s = the stored rotations,
+// ww = GLOBAL ||w||^2 after the projection.
+template <typename T>
+__device__ __forceinline__ void bk_gm_dense_step(bk_dev_state* st, const bk_gm_small& sm, const int j, const double ww,
+                                                 double* hc, const double* s_c, const double* s_s) {
+  const double eps = bk_gm_eps<T>::value;
+  const int m = sm.m;
+  const double norm1 = sqrt(fmax(ww, 0.0));
+  const double thresh = eps * st->g_vnorm0;  // tol = eps * v_norm_0   (:358)
+  const int use = norm1 > thresh;
+  const double vnorm1 = use ? norm1 : 0.0;
+  st->g_scale = norm1;
+  st->g_use = use;
+  const bool breakdown = (vnorm1 == 0.0);  // :387
+  // new Hessenberg column (h_0..h_j, v_norm_1), rotated by the stored Givens rotations (:599-603)
+  hc[j + 1] = vnorm1;
+  for (int i = 0; i < j; ++i) {
+    const double t = s_c[i] * hc[i] - s_s[i] * hc[i + 1];
+    hc[i + 1] = s_s[i] * hc[i] + s_c[i] * hc[i + 1];
+    hc[i] = t;
+  }
+  double c_new, s_new;
+  bk_givens(hc[j], hc[j + 1], c_new, s_new);  // :606
+  sm.cs[j] = c_new;
+  sm.sn[j] = s_new;
+  hc[j] = c_new * hc[j] - s_new * hc[j + 1];  // :611
+  hc[j + 1] = 0.0;
+  double* Rcol = sm.R + (size_t)j * (m + 1);
+  for (int i = 0; i <= j; ++i) Rcol[i] = hc[i];  // :615
+  const double gj = sm.g[j], gj1 = sm.g[j + 1];
+  const double t = c_new * gj - s_new * gj1;  // :618-620
+  const double gnext = s_new * gj + c_new * gj1;
+  sm.g[j] = t;
+  sm.g[j + 1] = gnext;
+  const double err = fabs(gnext);
+  st->g_err = err;
+  const int kcur = j + 1;
+  st->g_kcur = kcur;
+  bool over = breakdown || (kcur >= m);
+  if (st->g_method == BK_GMRES_INCREMENTAL && !(err > st->g_ptol)) over = true;  // :591
+  st->g_cycle_over = over ? 1 : 0;
+}
+
 // ---- A3 (MODE 0): w -= sum_i h_i v_i, ||w||^2, then the step's small dense update
 // ---- C2 (MODE 1): x += sum_{i<kcur} y_i v_i
 template <typename T, int W, int MODE>
 __global__ void __launch_bounds__(BK_BLOCK, 3)
 bk_multiaxpy_kernel(const T* __restrict__ V, const size_t ldv, const int count_arg, T* __restrict__ w, const long long n,
-                    const bk_scratch sc, bk_dev_state* st, const bk_gm_small sm, const int step) {
+                    const bk_scratch sc, bk_dev_state* st, const bk_gm_small sm, const int step, const bk_gsum gs) {
   if (st->done) return;
   if (MODE == 0 && st->g_cycle_over) return;
   __shared__ double s_coef[BK_GM_MAXM + 1];
@@ -274,43 +332,26 @@ bk_multiaxpy_kernel(const T* __restrict__ V, const size_t ldv, const int count_a
   }
   __syncthreads();
   if (threadIdx.x != 0) return;
-  const double eps = bk_gm_eps<T>::value;
-  const int m = sm.m;
-  const double norm1 = sqrt(fmax(tot[0], 0.0));
-  const double thresh = eps * st->g_vnorm0;  // tol = eps * v_norm_0   (:358)
-  const int use = norm1 > thresh;
-  const double vnorm1 = use ? norm1 : 0.0;
-  st->g_scale = norm1;
-  st->g_use = use;
-  const bool breakdown = (vnorm1 == 0.0);  // :387
-  // new Hessenberg column (h_0..h_j, v_norm_1), rotated by the stored Givens rotations (:599-603)
-  double* hc = s_coef;
-  hc[j + 1] = vnorm1;
-  for (int i = 0; i < j; ++i) {
-    const double t = s_c[i] * hc[i] - s_s[i] * hc[i + 1];
-    hc[i + 1] = s_s[i] * hc[i] + s_c[i] * hc[i + 1];
-    hc[i] = t;
+  double ww[1];
+  if (!bk_gsum_finish<1>(gs, st, tot, ww)) return;  // NCCL path: bk_gm_step_kernel finishes the step
+  bk_gm_dense_step<T>(st, sm, j, ww[0], s_coef, s_c, s_s);
+}
+
+// NCCL path: the dense step after ncclAllReduce of ||w||^2 (red[0])
+template <typename T>
+__global__ void __launch_bounds__(BK_BLOCK) bk_gm_step_kernel(bk_dev_state* st, const bk_gm_small sm, const int j,
+                                                            const double* red) {
+  if (st->done || st->g_cycle_over) return;
+  __shared__ double s_coef[BK_GM_MAXM + 1];
+  __shared__ double s_c[BK_GM_MAXM];
+  __shared__ double s_s[BK_GM_MAXM];
+  for (int i = threadIdx.x; i <= j; i += BK_BLOCK) s_coef[i] = sm.hcol[i];
+  for (int i = threadIdx.x; i < j; i += BK_BLOCK) {
+    s_c[i] = sm.cs[i];
+    s_s[i] = sm.sn[i];
   }
-  double c_new, s_new;
-  bk_givens(hc[j], hc[j + 1], c_new, s_new);  // :606
-  sm.cs[j] = c_new;
-  sm.sn[j] = s_new;
-  hc[j] = c_new * hc[j] - s_new * hc[j + 1];  // :611
-  hc[j + 1] = 0.0;
-  double* Rcol = sm.R + (size_t)j * (m + 1);
-  for (int i = 0; i <= j; ++i) Rcol[i] = hc[i];  // :615
-  const double gj = sm.g[j], gj1 = sm.g[j + 1];
-  const double t = c_new * gj - s_new * gj1;  // :618-620
-  const double gnext = s_new * gj + c_new * gj1;
-  sm.g[j] = t;
-  sm.g[j + 1] = gnext;
-  const double err = fabs(gnext);
-  st->g_err = err;
-  const int kcur = j + 1;
-  st->g_kcur = kcur;
-  bool over = breakdown || (kcur >= m);
-  if (st->g_method == BK_GMRES_INCREMENTAL && !(err > st->g_ptol)) over = true;  // :591
-  st->g_cycle_over = over ? 1 : 0;
+  __syncthreads();
+  if (threadIdx.x == 0) bk_gm_dense_step<T>(st, sm, j, red[0], s_coef, s_c, s_s);
 }
 
 // ---- C1: y = R[:k,:k]^-1 g[:k] (back substitution on one warp), then clear g[1..m] for the next cycle
@@ -332,10 +373,11 @@ __global__ void bk_gm_solve_kernel(bk_dev_state* st, const bk_gm_small sm) {
   for (int i = 1 + lane; i <= m; i += 32) sm.g[i] = 0.0;
 }
 
-template <typename T>
-static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, int has_x0, double tol_eff,
-                      double atol_eff, int restart, int64_t maxiter, int method, bk_result* res, cudaStream_t s) {
-  const long long n = A->n;
+template <typename T, typename Sys>
+static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, double tol_eff, double atol_eff,
+                      int restart, int64_t maxiter, int method, bk_result* res, cudaStream_t s) {
+  bk_handle* h = sys.h;
+  const long long n = sys.n();
   const int m = restart;
   const size_t npad = ((size_t)n + 63) & ~(size_t)63;
   BK_TRY(bk_ws_reserve(h, (size_t)(m + 4) * npad * sizeof(T)));
@@ -346,6 +388,7 @@ static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user
   bk_dev_state* st = h->st;
   const size_t vbytes = (size_t)n * sizeof(T);
   constexpr int NW = bk_native_w<T>::value;
+  const bk_gsum gs = sys.gsum();
 
   // small dense arrays
   const size_t small_doubles = (size_t)(m + 1) * m + 2 * (size_t)m + 2 * (size_t)(m + 1) + m + 16;
@@ -390,7 +433,7 @@ static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user
 
   bk_dev_state init;
   memset(&init, 0, sizeof(init));
-  init.maxiter = maxiter < 0 ? 10 * n : maxiter;
+  init.maxiter = maxiter < 0 ? 10 * sys.n_global() : maxiter;
   init.status = BK_ST_MAXITER;
   init.g_tol_eff = tol_eff;
   init.g_atol_eff = atol_eff;
@@ -400,30 +443,22 @@ static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user
   BK_KERNEL_CHECK();
 
   const int grid = bk_grid_vec_n(h, n, 2 * NW);
-  auto dot_epi = [&](const void* a, const void* bb, auto epi, int slot) -> int {
-    return bk_dot_epi<T>(h, n, a, bb, epi, slot, s);
-  };
   auto normalize = [&](const T* src, T* dst, int guard, cudaStream_t cs) -> int {
     bk_op_normalize<T> op;
     op.w = src;
     op.v = dst;
     op.st = st;
     op.guard = guard;
-    return bk_launch_ew<T>(h, op, n, true, bk_slot(h, 3), cs);
+    return sys.template ew<T>(op, true, 3, cs);
   };
 
   // ---- set-up: ||b||, tolerances, r0, v_0 ----------------------------------------------------------
   BK_CUDA(cudaMemcpyAsync(bw, b, vbytes, cudaMemcpyDeviceToDevice, s));
   b = bw;
-  BK_TRY(dot_epi(b, b, bk_epi_gm_tol{st}, 1));
+  BK_TRY((sys.template dot<T>(b, b, bk_epi_gm_tol{st}, 1, s)));
   if (has_x0) {
     BK_CUDA(cudaMemcpyAsync(x, x_user, vbytes, cudaMemcpyDeviceToDevice, s));
-    bk_spmv_args a = bk_spmv_base(A, st);
-    a.x = x;
-    a.y = w;
-    a.b = b;
-    bk_epi_gm_resid<T> epi{st, sm, 1};
-    BK_TRY((bk_launch_spmv<1, 2, 0>(h, A, a, bk_slot(h, 0), epi, s)));
+    BK_TRY((sys.template matvec<T, 1, 2>(x, w, nullptr, b, 0, bk_epi_gm_resid<T>{st, sm, 1}, s)));
   } else {
     BK_CUDA(cudaMemsetAsync(x, 0, vbytes, s));
     BK_CUDA(cudaMemcpyAsync(w, b, vbytes, cudaMemcpyDeviceToDevice, s));
@@ -435,53 +470,37 @@ static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user
   // ---- one restart cycle ------------------------------------------------------------------------
   auto enqueue_cycle = [&](cudaStream_t cs) -> int {
     for (int j = 0; j < m; ++j) {
-      {
-        bk_spmv_args a = bk_spmv_base(A, st);
-        a.x = V + (size_t)j * npad;
-        a.y = w;
-        a.guard = 2;
-        bk_epi_gm_vnorm0<T> epi{st};
-        BK_TRY((bk_launch_spmv<0, 2, 0>(h, A, a, bk_slot(h, 0), epi, cs)));
-      }
+      BK_TRY((sys.template matvec<T, 0, 2>(V + (size_t)j * npad, w, nullptr, nullptr, 2, bk_epi_gm_vnorm0<T>{st}, cs)));
       bk_multidot_kernel<T, NW><<<grid, BK_BLOCK, 0, cs>>>(V, npad, j + 1, w, n, h->gm_partials, h->counters + 4, st,
-                                                            sm.hcol);
+                                                            sm.hcol, gs);
       BK_KERNEL_CHECK();
-      bk_multiaxpy_kernel<T, NW, 0><<<grid, BK_BLOCK, 0, cs>>>(V, npad, j + 1, w, n, bk_slot(h, 1), st, sm, j);
+      if (gs.mode == 2) BK_TRY(sys.allreduce(sm.hcol, j + 1, cs));
+      bk_multiaxpy_kernel<T, NW, 0><<<grid, BK_BLOCK, 0, cs>>>(V, npad, j + 1, w, n, bk_slot(h, 1), st, sm, j, gs);
       BK_KERNEL_CHECK();
-      {
-        bk_op_normalize<T> op;
-        op.w = w;
-        op.v = V + (size_t)(j + 1) * npad;
-        op.st = st;
-        op.guard = 2;
-        BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 3), cs));
+      if (gs.mode == 2) {
+        BK_TRY(sys.allreduce(gs.red, 1, cs));
+        bk_gm_step_kernel<T><<<1, BK_BLOCK, 0, cs>>>(st, sm, j, gs.red);
+        BK_KERNEL_CHECK();
       }
+      BK_TRY(normalize(w, V + (size_t)(j + 1) * npad, 2, cs));
     }
     bk_gm_solve_kernel<<<1, 32, 0, cs>>>(st, sm);
     BK_KERNEL_CHECK();
-    bk_multiaxpy_kernel<T, NW, 1><<<grid, BK_BLOCK, 0, cs>>>(V, npad, 0, x, n, bk_slot(h, 1), st, sm, 0);
+    bk_multiaxpy_kernel<T, NW, 1><<<grid, BK_BLOCK, 0, cs>>>(V, npad, 0, x, n, bk_slot(h, 1), st, sm, 0, gs);
     BK_KERNEL_CHECK();
-    {
-      bk_spmv_args a = bk_spmv_base(A, st);
-      a.x = x;
-      a.y = w;
-      a.b = b;
-      a.guard = 1;
-      bk_epi_gm_resid<T> epi{st, sm, 0};
-      BK_TRY((bk_launch_spmv<1, 2, 0>(h, A, a, bk_slot(h, 0), epi, cs)));
-    }
+    BK_TRY((sys.template matvec<T, 1, 2>(x, w, nullptr, b, 1, bk_epi_gm_resid<T>{st, sm, 0}, cs)));
     BK_TRY(normalize(w, V, 1, cs));
     return BK_OK;
   };
   const bool use_graph = h->loop_mode != BK_LOOP_STREAM;
-  uint64_t key[6] = {3 /*gmres*/, A->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
-                     (uint64_t)A->dtype | ((uint64_t)m << 8) | ((uint64_t)method << 24),
+  uint64_t key[6] = {3 /*gmres*/, sys.uid(), (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
+                     (uint64_t)sys.dtype() | ((uint64_t)m << 8) | ((uint64_t)method << 24),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   int64_t chunks = 0;
   BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_cycle, &chunks));
 
   // ---- final check (:766-773): the last residual pass already holds ||b - A x||; add ||x|| --------
-  BK_TRY(dot_epi(x, x, bk_epi_gm_xx{st}, 1));
+  BK_TRY((sys.template dot<T>(x, x, bk_epi_gm_xx{st}, 1, s)));
   BK_CUDA(cudaMemcpyAsync(x_user, x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
   BK_CUDA(cudaStreamSynchronize(s));
@@ -497,21 +516,45 @@ static int bk_gmres_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user
   res->rr_last = fin->g_resnorm;
   const bool failed = (res->x_norm != res->x_norm) || (res->final_residual > res->threshold);
   res->info = failed ? -1 : 0;
+  return sys.check_comm(fin, "gmres");
+}
+
+static int bk_gmres_args_check(const char* who, int restart, int method) {
+  if (restart < 1 || restart > BK_GM_MAXM)
+    return bk_fail(BK_ERR_UNSUPPORTED, "%s: restart must be in [1, %d], got %d", who, BK_GM_MAXM, restart);
+  if (method != BK_GMRES_BATCHED && method != BK_GMRES_INCREMENTAL)
+    return bk_fail(BK_ERR_ARG, "%s: unknown method %d", who, method);
   return BK_OK;
 }
 
 extern "C" int bk_gmres(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, double tol_eff,
                         double atol_eff, int restart, int64_t maxiter, int method, bk_result* result, void* stream) {
   BK_TRY(bk_solver_args_check("bk_gmres", h, A, b, x, result));
-  if (restart < 1 || restart > BK_GM_MAXM)
-    return bk_fail(BK_ERR_UNSUPPORTED, "bk_gmres: restart must be in [1, %d], got %d", BK_GM_MAXM, restart);
-  if (method != BK_GMRES_BATCHED && method != BK_GMRES_INCREMENTAL)
-    return bk_fail(BK_ERR_ARG, "bk_gmres: unknown method %d", method);
+  BK_TRY(bk_gmres_args_check("bk_gmres", restart, method));
   BK_CUDA(cudaSetDevice(h->device));
   if (A->n == 0) return BK_OK;
+  const bk_sys_local sys{h, A};
   if (A->dtype == BK_F64)
-    return bk_gmres_t<double>(h, A, b, x, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
+    return bk_gmres_t<double>(sys, b, x, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
                               (cudaStream_t)stream);
-  return bk_gmres_t<float>(h, A, b, x, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
+  return bk_gmres_t<float>(sys, b, x, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
+                           (cudaStream_t)stream);
+}
+
+// Row-partitioned GMRES: the basis is partitioned like every vector; V^T w is one all-reduce of j+1 doubles and the
+// small dense problem is replicated (identical on every rank because the all-reduced sums are) — SURVEY §8e.
+extern "C" int bk_dist_gmres(bk_handle* h, bk_dist* D, const void* b_local, void* x_local, int has_x0, double tol_eff,
+                             double atol_eff, int restart, int64_t maxiter, int method, int64_t n_global,
+                             bk_result* result, void* stream) {
+  if (!h || !D || !result) return bk_fail(BK_ERR_ARG, "bk_dist_gmres: null handle/matrix/result");
+  if (D->n_local > 0 && (!b_local || !x_local)) return bk_fail(BK_ERR_ARG, "bk_dist_gmres: null vector");
+  BK_TRY(bk_gmres_args_check("bk_dist_gmres", restart, method));
+  memset(result, 0, sizeof(*result));
+  BK_CUDA(cudaSetDevice(h->device));
+  const bk_sys_dist sys{h, D, D->p2p_enabled && h->dist_p2p, n_global};
+  if (D->dtype == BK_F64)
+    return bk_gmres_t<double>(sys, b_local, x_local, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
+                              (cudaStream_t)stream);
+  return bk_gmres_t<float>(sys, b_local, x_local, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
                            (cudaStream_t)stream);
 }

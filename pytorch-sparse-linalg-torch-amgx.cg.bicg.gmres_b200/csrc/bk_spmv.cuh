@@ -41,14 +41,14 @@ struct bk_spmv_args {
   int use_parity;   // 1: reverse ^= st->parity
 };
 
-__device__ __forceinline__ bool bk_spmv_skip(const bk_spmv_args& a) {
-  if (a.guard == 0) return false;
-  const bk_dev_state* st = a.st;
+__device__ __forceinline__ bool bk_guard_skip(const bk_dev_state* st, int guard) {
+  if (guard == 0) return false;
   if (st->done) return true;
-  if (a.guard == 2 && st->g_cycle_over) return true;
-  if (a.guard == 3 && st->exit_early) return true;
+  if (guard == 2 && st->g_cycle_over) return true;
+  if (guard == 3 && st->exit_early) return true;
   return false;
 }
+__device__ __forceinline__ bool bk_spmv_skip(const bk_spmv_args& a) { return bk_guard_skip(a.st, a.guard); }
 
 template <int DOTS>
 struct bk_ndots {

@@ -121,7 +121,15 @@ struct bk_op_dot_epi {
   const T* x;
   const T* y;
   Epi epi;
-  __device__ bool skip() const { return false; }
+  const bk_dev_state* st = nullptr;  // with guard != 0: skip like the other guarded kernels (bk_guard_skip)
+  int guard = 0;
+  __device__ bool skip() const {
+    if (guard == 0) return false;
+    if (st->done) return true;
+    if (guard == 2 && st->g_cycle_over) return true;
+    if (guard == 3 && st->exit_early) return true;
+    return false;
+  }
   __device__ bool reverse() const { return false; }
   __device__ Ctx prepare() const { return Ctx(); }
   template <int W>

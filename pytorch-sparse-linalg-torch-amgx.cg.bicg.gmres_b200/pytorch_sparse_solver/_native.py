@@ -97,6 +97,10 @@ _SIGNATURES = {
     "bk_dist_spmv": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "bk_dist_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64,
                              C.POINTER(bk_result), _VP]),
+    "bk_dist_bicgstab": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64,
+                                   C.POINTER(bk_result), _VP]),
+    "bk_dist_gmres": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int64, C.c_int,
+                                C.c_int64, C.POINTER(bk_result), _VP]),
 }
 
 _lib = None

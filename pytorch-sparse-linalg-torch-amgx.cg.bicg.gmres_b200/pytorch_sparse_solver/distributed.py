@@ -216,6 +216,44 @@ class DistMatrix:
                 _native._stream_ptr(self.device)), "bk_dist_cg")
         return x, res.as_dict()
 
+    def _vectors(self, b_local, x0):
+        b = b_local.to(self.dtype).contiguous()
+        if x0 is None:
+            return b, torch.empty_like(b), 0
+        return b, x0.to(self.dtype).contiguous().clone(), 1
+
+    def bicgstab(self, b_local: torch.Tensor, x0: Optional[torch.Tensor] = None, tol: float = 1e-5,
+                 atol: float = 0.0, maxiter: Optional[int] = None) -> Tuple[torch.Tensor, dict]:
+        """Row-partitioned BiCGStab (reference _bicgstab_solve :859-964 on the global system)."""
+        b, x, has = self._vectors(b_local, x0)
+        res = _native.bk_result()
+        with torch.cuda.device(self.device):
+            _native._check(self.handle.lib.bk_dist_bicgstab(
+                self.handle.ptr, self.ptr, b.data_ptr(), x.data_ptr(), has, float(tol), float(atol),
+                -1 if maxiter is None else int(maxiter), self.n_global, C.byref(res),
+                _native._stream_ptr(self.device)), "bk_dist_bicgstab")
+        return x, res.as_dict()
+
+    def gmres(self, b_local: torch.Tensor, x0: Optional[torch.Tensor] = None, tol: float = 1e-5, atol: float = 0.0,
+              restart: int = 20, maxiter: Optional[int] = None,
+              solve_method: str = 'batched') -> Tuple[torch.Tensor, dict]:
+        """Row-partitioned restarted GMRES (reference gmres :641-784 on the global system; the tolerance constants
+        use the GLOBAL size, as one process holding the whole matrix would)."""
+        from .module_a.krylov import _gmres_effective_tolerances
+        if solve_method not in ('batched', 'incremental'):
+            raise ValueError(f"invalid solve_method {solve_method}, must be either 'incremental' or 'batched'")
+        method = 1 if solve_method == 'incremental' else 0
+        restart = min(int(restart), self.n_global)
+        tol_eff, atol_eff = _gmres_effective_tolerances(tol, atol, self.n_global, 'cuda')
+        b, x, has = self._vectors(b_local, x0)
+        res = _native.bk_result()
+        with torch.cuda.device(self.device):
+            _native._check(self.handle.lib.bk_dist_gmres(
+                self.handle.ptr, self.ptr, b.data_ptr(), x.data_ptr(), has, float(tol_eff), float(atol_eff),
+                restart, -1 if maxiter is None else int(maxiter), method, self.n_global, C.byref(res),
+                _native._stream_ptr(self.device)), "bk_dist_gmres")
+        return x, res.as_dict()
+
 
 # ---- weak-scaling benchmark used by bench.py --gpus N --------------------------------------------------------
 def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSampler):

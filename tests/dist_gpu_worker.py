@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Multi-GPU parity worker (launched by torchrun, one rank per GPU): distributed SpMV / CG on a row-partitioned
+"""Multi-GPU parity worker (launched by torchrun, one rank per GPU): distributed SpMV / CG / BiCGStab / GMRES on a row-partitioned
 Poisson slab grid against the single-GPU library solve of the same global system.  Exits non-zero on failure."""
 import os
 import sys
@@ -61,6 +61,53 @@ def main():
     D.close()
     dist.barrier()
 
+    # ---- BiCGStab / GMRES on a non-symmetric slab system (convection-diffusion, SURVEY config 3 at test size)
+    from pytorch_sparse_solver.module_a.krylov import _gmres_effective_tolerances
+    g3 = (1.0, 0.5, 0.25)
+    cd = dict(lower=(-(1 + g3[0]), -(1 + g3[1]), -(1 + g3[2])), diag=6 + sum(g3))
+    crow, col, val = problems.stencil3d_rows(n, world * n, rank * n, (rank + 1) * n, device=dev, **cd)
+    Dc = bkd.DistMatrix(crow, col, val, offsets, rank, world)
+    Ac = problems.stencil3d_csr(n, nz=world * n, device=dev, **cd)
+    mc = _native.register_matrix(Ac)
+    bc = mc.spmv(xg)                                            # manufactured right-hand side
+    Ng = world * rows
+    xb_ref, rb_ref = mc.bicgstab(bc, None, 1e-10, 0.0, None)
+    te, ae = _gmres_effective_tolerances(1e-10, 0.0, Ng, 'cuda')
+    xg_ref, rg_ref = mc.gmres(bc, None, te, ae, 30, 1000, _native.BK_GMRES_BATCHED)
+    xi_ref, ri_ref = mc.gmres(bc, None, te, ae, 30, 1000, _native.BK_GMRES_INCREMENTAL)
+    x0c = xg * 0.5
+    xw_ref, rw_ref = mc.bicgstab(bc, x0c, 0.0, 0.0, 6)
+    xgw_ref, rgw_ref = mc.gmres(bc, x0c, *_gmres_effective_tolerances(0.0, 0.0, Ng, 'cuda'), 12, 2,
+                                _native.BK_GMRES_BATCHED)
+    for mode, p2p in ((1, 0), (2, 0), (1, 1), (2, 1)):
+        if p2p and not Dc.p2p:
+            continue
+        Dc.handle.set_option("loop_mode", mode)
+        Dc.handle.set_option("dist_p2p", p2p)
+        tag = ("mode", mode, "p2p", p2p)
+        x, r = Dc.bicgstab(bc[sl].contiguous(), None, 1e-10, 0.0, None)
+        assert r["info"] == rb_ref["info"] == 0, (tag, r, rb_ref)
+        assert abs(r["iterations"] - rb_ref["iterations"]) <= 2, (tag, r["iterations"], rb_ref["iterations"])
+        assert rel(x, xb_ref[sl]) <= 1e-9, ("dist bicgstab", tag, rel(x, xb_ref[sl]))
+        x2, _ = Dc.bicgstab(bc[sl].contiguous(), None, 1e-10, 0.0, None)
+        assert torch.equal(x, x2), ("dist bicgstab must be bitwise reproducible", tag)
+        x, r = Dc.bicgstab(bc[sl].contiguous(), x0c[sl].contiguous(), 0.0, 0.0, 6)
+        assert r["iterations"] == 6 and rel(x, xw_ref[sl]) <= 1e-11, ("bicgstab window", tag, rel(x, xw_ref[sl]))
+        for sm_name, (xr_, rr_) in (("batched", (xg_ref, rg_ref)), ("incremental", (xi_ref, ri_ref))):
+            x, r = Dc.gmres(bc[sl].contiguous(), None, 1e-10, 0.0, 30, 1000, sm_name)
+            assert r["info"] == rr_["info"] == 0, (tag, sm_name, r, rr_)
+            assert abs(r["iterations"] - rr_["iterations"]) <= 1, (tag, sm_name, r["iterations"], rr_["iterations"])
+            assert abs(r["matvecs"] - rr_["matvecs"]) <= 2, (tag, sm_name, r["matvecs"], rr_["matvecs"])
+            assert rel(x, xr_[sl]) <= 1e-10, ("dist gmres", tag, sm_name, rel(x, xr_[sl]))
+        x2, _ = Dc.gmres(bc[sl].contiguous(), None, 1e-10, 0.0, 30, 1000, "incremental")
+        assert torch.equal(x, x2), ("dist gmres must be bitwise reproducible", tag)
+        x, r = Dc.gmres(bc[sl].contiguous(), x0c[sl].contiguous(), 0.0, 0.0, 12, 2, "batched")
+        assert r["iterations"] == 2 and rel(x, xgw_ref[sl]) <= 1e-11, ("gmres window", tag, rel(x, xgw_ref[sl]))
+    Dc.handle.set_option("loop_mode", 0)
+    Dc.handle.set_option("dist_p2p", 1)
+    Dc.close()
+    dist.barrier()
+
     # ---- all-to-all coupling: every rank exchanges halos with every other rank (SPD: diagonally dominant, symmetric)
     N = 6000 * world
     i = torch.arange(N, device=dev)
@@ -90,6 +137,16 @@ def main():
         x2, r2 = D2.cg(bg2[rb:re_].contiguous(), None, 1e-10, 0.0, None)
         assert r2["info"] == rr2["info"] == 0 and abs(r2["iterations"] - rr2["iterations"]) <= 2, (r2, rr2)
         assert rel(x2, xr2[rb:re_]) <= 1e-10, ("dist cg all-to-all", p2p, rel(x2, xr2[rb:re_]))
+        # the same couplings drive BiCGStab and GMRES (all-to-all halos, fp64)
+        xb2, rb2 = mg.bicgstab(bg2, None, 1e-10, 0.0, None)
+        x2, r2 = D2.bicgstab(bg2[rb:re_].contiguous(), None, 1e-10, 0.0, None)
+        assert r2["info"] == rb2["info"] == 0 and abs(r2["iterations"] - rb2["iterations"]) <= 2, (r2, rb2)
+        assert rel(x2, xb2[rb:re_]) <= 1e-9, ("dist bicgstab all-to-all", p2p, rel(x2, xb2[rb:re_]))
+        te2, ae2 = _gmres_effective_tolerances(1e-10, 0.0, N, 'cuda')
+        xq2, rq2 = mg.gmres(bg2, None, te2, ae2, 20, 1000, _native.BK_GMRES_BATCHED)
+        x2, r2 = D2.gmres(bg2[rb:re_].contiguous(), None, 1e-10, 0.0, 20, 1000)
+        assert r2["info"] == rq2["info"] == 0 and abs(r2["iterations"] - rq2["iterations"]) <= 1, (r2, rq2)
+        assert rel(x2, xq2[rb:re_]) <= 1e-10, ("dist gmres all-to-all", p2p, rel(x2, xq2[rb:re_]))
     D2.handle.set_option("dist_p2p", 1)
     D2.close()
     dist.barrier()
