@@ -12,6 +12,8 @@
 #include "bk_internal.cuh"
 #include "bk_loop.cuh"
 #include "bk_spmv.cuh"
+#include "bk_sys.cuh"
+#include "bk_dist.cuh"
 #include "bk_vec.cuh"
 
 // ---- epilogues ---------------------------------------------------------------------------------
@@ -257,8 +259,6 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
     op.r = v.r;
     op.st = st;
     op.snake = h->snake;
-    op.dist_out = nullptr;
-    op.p2p.P = 0;
     BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
   }
   if (!fuse) {
@@ -376,4 +376,100 @@ extern "C" int bk_cg(bk_handle* h, const bk_csr* A, const void* b, void* x, int 
   if (A->n == 0) return BK_OK;
   if (A->dtype == BK_F64) return bk_cg_t<double>(h, A, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
   return bk_cg_t<float>(h, A, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+}
+
+// ---- row-partitioned CG --------------------------------------------------------------------------
+// The 3-kernel iteration above on the distributed system: K1's halo exchange overlaps the local-block SpMV, p.Ap and
+// r.r become global sums (peer path: inside the epilogues of the boundary-row kernel and of K2; NCCL path:
+// ncclAllReduce + a one-thread scalar kernel each).
+template <typename T>
+static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int has_x0, double tol, double atol,
+                        int64_t maxiter, bk_result* res, cudaStream_t s) {
+  bk_handle* h = sys.h;
+  const long long n = sys.n();
+  const size_t npad = ((size_t)n + 63) & ~(size_t)63;
+  BK_TRY(bk_ws_reserve(h, (size_t)4 * npad * sizeof(T)));
+  T* x = (T*)h->ws;
+  T* r = x + npad;
+  T* p = r + npad;
+  T* ap = p + npad;
+  bk_dev_state* st = h->st;
+  const size_t vbytes = (size_t)n * sizeof(T);
+
+  bk_dev_state init;
+  memset(&init, 0, sizeof(init));
+  init.maxiter = maxiter < 0 ? 10 * sys.n_global() : maxiter;
+  init.status = BK_ST_MAXITER;
+  bk_state_fill_tol(&init, tol, atol);
+  bk_state_set_kernel<<<1, 1, 0, s>>>(st, init);
+  BK_KERNEL_CHECK();
+
+  if (has_x0) {
+    BK_CUDA(cudaMemcpyAsync(x, x_user, vbytes, cudaMemcpyDeviceToDevice, s));
+    BK_TRY((sys.matvec<T, 1, 2>(x, r, nullptr, b, 0, bk_epi_set_gamma{st}, s)));  // r0 = b - A x0, gamma0 (:820, :826)
+  } else {
+    BK_CUDA(cudaMemsetAsync(x, 0, vbytes, s));
+    BK_CUDA(cudaMemcpyAsync(r, b, vbytes, cudaMemcpyDeviceToDevice, s));
+  }
+  BK_TRY((sys.dot<T>(b, b, bk_epi_cg_init{st, has_x0}, 1, s)));
+  BK_CUDA(cudaMemcpyAsync(p, r, vbytes, cudaMemcpyDeviceToDevice, s));
+
+  auto enqueue_iter = [&](cudaStream_t cs) -> int {
+    BK_TRY((sys.matvec<T, 0, 1>(p, ap, p, nullptr, 1, bk_epi_cg_pAp{st}, cs)));
+    {
+      bk_op_cg_update<T> op;
+      op.p = p;
+      op.ap = ap;
+      op.x = x;
+      op.r = r;
+      op.st = st;
+      op.snake = 0;
+      BK_TRY(sys.ew<T>(op, true, 1, cs));
+    }
+    {
+      bk_op_xpay<T> op;
+      op.r = r;
+      op.p = p;
+      op.st = st;
+      op.snake = 0;
+      BK_TRY(sys.ew<T>(op, true, 2, cs));
+    }
+    return BK_OK;
+  };
+  const double bytes_iter = sys.matrix_bytes() + 11.0 * n * sizeof(T);
+  const int chunk = bk_pick_chunk(h, bytes_iter, 8);
+  const bool use_graph = h->loop_mode != BK_LOOP_STREAM;  // NCCL calls are captured into the iteration graph too
+  uint64_t key[6] = {4 /*dist cg*/, sys.uid(), (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
+                     (uint64_t)sys.dtype() | ((uint64_t)chunk << 16),
+                     (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
+  auto enqueue_chunk = [&](cudaStream_t cs) -> int {
+    for (int it = 0; it < chunk; ++it) BK_TRY(enqueue_iter(cs));
+    return BK_OK;
+  };
+  int64_t chunks = 0;
+  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
+
+  // final true residual and ||x|| (global)
+  BK_TRY((sys.matvec<T, 1, 2>(x, ap, nullptr, b, 0, bk_epi_final_r{st}, s)));
+  BK_TRY((sys.dot<T>(x, x, bk_epi_final_x{st}, 1, s)));
+  BK_CUDA(cudaMemcpyAsync(x_user, x, vbytes, cudaMemcpyDeviceToDevice, s));
+  BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
+  BK_CUDA(cudaStreamSynchronize(s));
+  const bk_dev_state* fin = &h->st_host[3];
+  bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
+  res->rr_last = fin->gamma;
+  res->kernel_launches = chunks * chunk * (sys.p2p ? 5 : 7) + 12;
+  return sys.check_comm(fin, "bk_dist_cg");
+}
+
+extern "C" int bk_dist_cg(bk_handle* h, bk_dist* D, const void* b_local, void* x_local, int has_x0, double tol,
+                          double atol, int64_t maxiter, int64_t n_global, bk_result* result, void* stream) {
+  if (!h || !D || !result) return bk_fail(BK_ERR_ARG, "bk_dist_cg: null handle/matrix/result");
+  if (D->n_local > 0 && (!b_local || !x_local)) return bk_fail(BK_ERR_ARG, "bk_dist_cg: null vector");
+  memset(result, 0, sizeof(*result));
+  BK_CUDA(cudaSetDevice(h->device));
+  const bk_sys_dist sys{h, D, D->p2p_enabled && h->dist_p2p, n_global};
+  if (D->dtype == BK_F64)
+    return bk_dist_cg_t<double>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+  return bk_dist_cg_t<float>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
 }

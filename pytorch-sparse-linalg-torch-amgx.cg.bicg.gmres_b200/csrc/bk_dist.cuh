@@ -235,6 +235,87 @@ struct bk_sys_dist {
     return BK_OK;
   }
 
+  // start the halo exchange of x: peer path = push kernel on `cs`; NCCL path = pack on `cs`, send/recv on the side stream
+  template <typename T>
+  int halo_begin(const void* x, int guard, bool peer, cudaStream_t cs) const {
+    if (D->npeers == 0) return BK_OK;
+    bk_dev_state* st = h->st;
+    int g = (int)((D->send_total + 255) / 256);
+    if (g < 1) g = 1;
+    if (peer) {
+      if (g > h->num_sms * 2) g = h->num_sms * 2;
+      bk_halo_push_kernel<T><<<g, 256, 0, cs>>>((const T*)x, D->send_idx, D->d_seg_start, D->d_remote_ghost,
+                                                D->d_remote_flag, D->npeers, D->send_total, D->p2p.counters, st, guard);
+      BK_KERNEL_CHECK();
+      return BK_OK;
+    }
+    if (g > h->num_sms * 4) g = h->num_sms * 4;
+    if (D->send_total > 0) {
+      bk_halo_pack_kernel<T><<<g, 256, 0, cs>>>((const T*)x, D->send_idx, (T*)D->sendbuf, D->send_total, st, guard);
+      BK_KERNEL_CHECK();
+    }
+    BK_CUDA(cudaEventRecord(D->ev_ready, cs));
+    BK_CUDA(cudaStreamWaitEvent(D->comm_stream, D->ev_ready, 0));
+    const int nt = sizeof(T) == 8 ? BK_NCCL_F64 : BK_NCCL_F32;
+    BK_NCCL(g_nccl.GroupStart());
+    int64_t so = 0, ro = 0;
+    for (int i = 0; i < D->npeers; ++i) {
+      if (D->send_counts[i] > 0)
+        BK_NCCL(g_nccl.Send((const T*)D->sendbuf + so, (size_t)D->send_counts[i], nt, D->peer_ranks[i], D->comm,
+                            D->comm_stream));
+      if (D->recv_counts[i] > 0)
+        BK_NCCL(g_nccl.Recv((T*)D->ghost + ro, (size_t)D->recv_counts[i], nt, D->peer_ranks[i], D->comm,
+                            D->comm_stream));
+      so += D->send_counts[i];
+      ro += D->recv_counts[i];
+    }
+    BK_NCCL(g_nccl.GroupEnd());
+    BK_CUDA(cudaEventRecord(D->ev_halo, D->comm_stream));
+    return BK_OK;
+  }
+
+  // boundary rows once the halo is there (NCCL path: stream wait; peer path: the kernel waits for the flags itself)
+  template <typename T, int MODE, int KD, typename Epi>
+  int ghost_rows(void* y, const void* w, int guard, bool peer, Epi epi, cudaStream_t cs) const {
+    if (!peer && D->npeers > 0) BK_CUDA(cudaStreamWaitEvent(cs, D->ev_halo, 0));
+    int g = (int)((D->n_brows + BK_BLOCK - 1) / BK_BLOCK);
+    if (g < 1) g = 1;
+    if (g > h->num_sms * 4) g = h->num_sms * 4;
+    bk_ghost_args<T> ga;
+    ga.brow_ids = D->brow_ids;
+    ga.rowptr = D->gh_rowptr;
+    ga.col = D->gh_col;
+    ga.val = (const T*)D->gh_val;
+    ga.ghost = (const T*)D->ghost;
+    ga.y = (T*)y;
+    ga.w = (const T*)w;
+    ga.n_brows = D->n_brows;
+    ga.peer_ranks = D->d_peer_ranks;
+    ga.npeers = D->npeers;
+    bk_gsum gs = gsum();
+    if (!peer) gs.mode = 2;
+    const double* part = D->red + 8;
+    if (peer) {
+      bk_ghost_rows_kernel<T, MODE, KD, true, Epi><<<g, BK_BLOCK, 0, cs>>>(ga, bk_slot(h, 3), part, gs, h->st, guard, epi);
+    } else if (KD != 0 || D->n_brows > 0) {
+      bk_ghost_rows_kernel<T, MODE, KD, false, Epi><<<g, BK_BLOCK, 0, cs>>>(ga, bk_slot(h, 3), part, gs, h->st, guard, epi);
+    }
+    BK_KERNEL_CHECK();
+    return BK_OK;
+  }
+
+  // y = A x without any reduction (bk_dist_spmv).  Always the NCCL exchange: the peer path needs an all-reduce
+  // between two halo exchanges to know that every neighbour has consumed the previous one.
+  template <typename T>
+  int spmv(const void* x, void* y, cudaStream_t cs) const {
+    BK_TRY(halo_begin<T>(x, 0, false, cs));
+    bk_spmv_args a = bk_spmv_base(D->Aloc, h->st);
+    a.x = x;
+    a.y = y;
+    BK_TRY((bk_launch_spmv_t<T, 0, 0, 0>(h, D->Aloc, a, bk_slot(h, 0), bk_epi_none(), cs)));
+    return ghost_rows<T, 0, 0>(y, nullptr, 0, false, bk_epi_none(), cs);
+  }
+
   template <typename T, int MODE, int DOTS, typename Epi>
   int matvec(const void* x, void* y, const void* w, const void* b, int guard, Epi epi, cudaStream_t cs) const {
     static_assert(DOTS != 0, "distributed solver matvecs always carry a reduction");
@@ -244,41 +325,7 @@ struct bk_sys_dist {
     constexpr int KD = (MODE == 1) ? 0 : DOTS;
     constexpr int R = bk_ndots<KD>::value;
     bk_dev_state* st = h->st;
-    double* part = D->red + 8;
-    if (D->npeers > 0) {
-      int g = (int)((D->send_total + 255) / 256);
-      if (g < 1) g = 1;
-      if (p2p) {
-        if (g > h->num_sms * 2) g = h->num_sms * 2;
-        bk_halo_push_kernel<T><<<g, 256, 0, cs>>>((const T*)x, D->send_idx, D->d_seg_start, D->d_remote_ghost,
-                                                  D->d_remote_flag, D->npeers, D->send_total, D->p2p.counters, st,
-                                                  guard);
-        BK_KERNEL_CHECK();
-      } else {
-        if (g > h->num_sms * 4) g = h->num_sms * 4;
-        if (D->send_total > 0) {
-          bk_halo_pack_kernel<T><<<g, 256, 0, cs>>>((const T*)x, D->send_idx, (T*)D->sendbuf, D->send_total, st, guard);
-          BK_KERNEL_CHECK();
-        }
-        BK_CUDA(cudaEventRecord(D->ev_ready, cs));
-        BK_CUDA(cudaStreamWaitEvent(D->comm_stream, D->ev_ready, 0));
-        const int nt = sizeof(T) == 8 ? BK_NCCL_F64 : BK_NCCL_F32;
-        BK_NCCL(g_nccl.GroupStart());
-        int64_t so = 0, ro = 0;
-        for (int i = 0; i < D->npeers; ++i) {
-          if (D->send_counts[i] > 0)
-            BK_NCCL(g_nccl.Send((const T*)D->sendbuf + so, (size_t)D->send_counts[i], nt, D->peer_ranks[i], D->comm,
-                                D->comm_stream));
-          if (D->recv_counts[i] > 0)
-            BK_NCCL(g_nccl.Recv((T*)D->ghost + ro, (size_t)D->recv_counts[i], nt, D->peer_ranks[i], D->comm,
-                                D->comm_stream));
-          so += D->send_counts[i];
-          ro += D->recv_counts[i];
-        }
-        BK_NCCL(g_nccl.GroupEnd());
-        BK_CUDA(cudaEventRecord(D->ev_halo, D->comm_stream));
-      }
-    }
+    BK_TRY(halo_begin<T>(x, guard, p2p, cs));
     {  // local block (overlaps the exchange)
       bk_spmv_args a = bk_spmv_base(D->Aloc, st);
       a.x = x;
@@ -287,36 +334,13 @@ struct bk_sys_dist {
       a.b = b;
       a.guard = guard;
       if constexpr (KD != 0) {
-        bk_epi_store_n<R> store{part};
+        bk_epi_store_n<R> store{D->red + 8};
         BK_TRY((bk_launch_spmv_t<T, MODE, KD, 0>(h, D->Aloc, a, bk_slot(h, 0), store, cs)));
       } else {
         BK_TRY((bk_launch_spmv_t<T, MODE, 0, 0>(h, D->Aloc, a, bk_slot(h, 0), bk_epi_none(), cs)));
       }
     }
-    if (!p2p && D->npeers > 0) BK_CUDA(cudaStreamWaitEvent(cs, D->ev_halo, 0));
-    {
-      int g = (int)((D->n_brows + BK_BLOCK - 1) / BK_BLOCK);
-      if (g < 1) g = 1;
-      if (g > h->num_sms * 4) g = h->num_sms * 4;
-      bk_ghost_args<T> ga;
-      ga.brow_ids = D->brow_ids;
-      ga.rowptr = D->gh_rowptr;
-      ga.col = D->gh_col;
-      ga.val = (const T*)D->gh_val;
-      ga.ghost = (const T*)D->ghost;
-      ga.y = (T*)y;
-      ga.w = (const T*)w;
-      ga.n_brows = D->n_brows;
-      ga.peer_ranks = D->d_peer_ranks;
-      ga.npeers = D->npeers;
-      const bk_gsum gs = gsum();
-      if (p2p) {
-        bk_ghost_rows_kernel<T, MODE, KD, true, Epi><<<g, BK_BLOCK, 0, cs>>>(ga, bk_slot(h, 3), part, gs, st, guard, epi);
-      } else if (KD != 0 || D->n_brows > 0) {
-        bk_ghost_rows_kernel<T, MODE, KD, false, Epi><<<g, BK_BLOCK, 0, cs>>>(ga, bk_slot(h, 3), part, gs, st, guard, epi);
-      }
-      BK_KERNEL_CHECK();
-    }
+    BK_TRY((ghost_rows<T, MODE, KD>(y, w, guard, p2p, epi, cs)));
     if constexpr (KD == 0) {
       bk_op_dot_epi<T, Epi> op;
       op.x = (const T*)y;

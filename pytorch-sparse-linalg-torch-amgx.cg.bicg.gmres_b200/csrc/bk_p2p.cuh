@@ -1,18 +1,17 @@
-// bk_p2p.cuh — peer-memory (NVLink / NVSwitch) primitives of the multi-GPU path: a one-shot all-reduce of one
-// double and halo-arrival flags, both through windows of device memory that every rank maps with CUDA IPC.
+// bk_p2p.cuh — peer-memory (NVLink / NVSwitch) primitives of the multi-GPU path: a one-shot all-reduce of a few
+// doubles and halo-arrival flags, both through windows of device memory that every rank maps with CUDA IPC.
 //
 // Window layout (identical on every rank, so a peer's addresses follow from its base pointer):
-//   [   0,  512)  all-reduce slots: [2 buffers][16 ranks] x 16 bytes, "LL" format — each 8-byte word carries
-//                 32 bits of payload + the 32-bit sequence number, so one atomic 8-byte store publishes data and
-//                 flag together and no fence is needed on the payload path
-//   [ 512,  640)  halo flags: one 64-bit sequence number per SENDER rank (st.release.sys / ld.acquire.sys)
-//   [1024, 140288) vector all-reduce slots: [2 buffers][16 ranks][272 values] x 16 bytes, same LL format — used by
-//                 the reductions that carry more than one value (BiCGStab's pairs, GMRES's projection coefficients)
+//   [   0,  512)   reserved
+//   [ 512,  640)   halo flags: one 64-bit sequence number per SENDER rank (st.release.sys / ld.acquire.sys)
+//   [1024, 140288) all-reduce slots: [2 buffers][16 ranks][272 values] x 16 bytes, "LL" format — each 8-byte word
+//                  carries 32 bits of payload + the 32-bit sequence number, so one atomic 8-byte store publishes data
+//                  and flag together and no fence is needed on the payload path
 //   [140288, ...)  ghost vector (halo landing zone: neighbours store their boundary entries straight into it)
 //
-// All-reduce: every rank stores its value into slot [seq & 1][own rank] of EVERY rank's window, then reads the P
-// slots of its own window in rank order and adds them in that order => the sum is bitwise identical on all ranks
-// and from run to run (the stop test derived from it therefore agrees everywhere).  Two buffers are enough: a rank
+// All-reduce: every rank stores its values into slot [seq & 1][own rank] of EVERY rank's window, then reads the P
+// slots of its own window in rank order and adds them in that order => the sums are bitwise identical on all ranks
+// and from run to run (the stop tests derived from them therefore agree everywhere).  Two buffers are enough: a rank
 // can be at most one all-reduce ahead of any other because completing all-reduce s needs every rank's value s.
 // Every wait has a ~10 s timeout that turns a lost peer into an error status instead of a hung GPU.
 #pragma once
@@ -20,7 +19,6 @@
 #include "bk_internal.cuh"
 
 #define BK_P2P_MAXP 16
-#define BK_P2P_AR_OFF 0
 #define BK_P2P_FLAG_OFF 512
 #define BK_P2P_VEC_OFF 1024
 #define BK_P2P_VEC_MAX 272  // >= largest GMRES restart + 1
@@ -31,8 +29,8 @@
 struct bk_p2p_ctx {
   int P;                     // 0 => peer path disabled
   int rank;
-  unsigned int* counters;    // device-local: [0] all-reduce seq [1] halo send seq [2] halo recv seq [3] push ticket [4] error
-                             //               [5] vector all-reduce seq
+  unsigned int* counters;    // device-local: [1] halo send seq [2] halo recv seq [3] push ticket [4] error
+                             //               [5] all-reduce seq
   char* win[BK_P2P_MAXP];    // window base of every rank, own entry included
 };
 
@@ -54,44 +52,10 @@ __device__ __forceinline__ unsigned long long bk_ld_acquire_sys_u64(const unsign
   return v;
 }
 
-// One-shot all-reduce (sum) of one double, executed by ONE thread per rank.  Returns the sum; sets counters[4] on timeout.
-__device__ __forceinline__ double bk_p2p_allreduce(const bk_p2p_ctx& c, double v) {
-  const unsigned int seq = c.counters[0] + 1u;
-  c.counters[0] = seq;
-  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-  const unsigned long long w0 = ((unsigned long long)seq << 32) | (bits & 0xffffffffULL);
-  const unsigned long long w1 = ((unsigned long long)seq << 32) | (bits >> 32);
-  const int buf = (int)(seq & 1u);
-  for (int q = 0; q < c.P; ++q) {
-    unsigned long long* slot = reinterpret_cast<unsigned long long*>(c.win[q] + BK_P2P_AR_OFF +
-                                                                     (size_t)(buf * BK_P2P_MAXP + c.rank) * 16);
-    bk_st_volatile_u64(slot, w0);
-    bk_st_volatile_u64(slot + 1, w1);
-  }
-  double sum = 0.0;
-  const long long t0 = clock64();
-  for (int q = 0; q < c.P; ++q) {
-    const unsigned long long* slot = reinterpret_cast<const unsigned long long*>(
-        c.win[c.rank] + BK_P2P_AR_OFF + (size_t)(buf * BK_P2P_MAXP + q) * 16);
-    unsigned long long a, b;
-    for (;;) {
-      a = bk_ld_volatile_u64(slot);
-      b = bk_ld_volatile_u64(slot + 1);
-      if ((unsigned int)(a >> 32) == seq && (unsigned int)(b >> 32) == seq) break;
-      if (clock64() - t0 > BK_P2P_TIMEOUT_CYCLES) {
-        c.counters[4] = 1u;
-        return __longlong_as_double(0x7ff8000000000000LL);  // NaN: the caller's status handling takes over
-      }
-    }
-    sum += __longlong_as_double((long long)((b << 32) | (a & 0xffffffffULL)));
-  }
-  return sum;
-}
-
 // All-reduce (sum) of `count` <= BK_P2P_VEC_MAX doubles, run by `nthreads` threads of ONE CTA per rank: thread `tid`
 // owns elements tid, tid + nthreads, ...  `seq` is this all-reduce's sequence number (counters[5] + 1; the caller
-// publishes it afterwards).  Same LL format, rank-ordered summation and timeout as the scalar version; `in` and `out`
-// may alias.  Two vector all-reduces must be separated by a kernel boundary or a block barrier.
+// publishes it afterwards).  `in` and `out` may alias.  Two all-reduces must be separated by a kernel boundary or a
+// block barrier.
 __device__ __forceinline__ void bk_p2p_allreduce_vec(const bk_p2p_ctx& c, unsigned int seq, const double* in,
                                                      double* out, int count, int tid, int nthreads) {
   const size_t buf = (size_t)(seq & 1u);

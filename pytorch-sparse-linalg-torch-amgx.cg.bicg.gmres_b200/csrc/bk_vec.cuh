@@ -204,8 +204,6 @@ struct bk_op_cg_update {
   T* r;
   bk_dev_state* st;
   int snake;
-  double* dist_out;  // multi-GPU (NCCL path): park the LOCAL r.r here (all-reduced next) instead of finishing the iteration
-  bk_p2p_ctx p2p;    // multi-GPU (peer-memory path, p2p.P > 0): all-reduce r.r right here, then finish the iteration
   __device__ bool skip() const { return st->done != 0; }
   __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
   __device__ Ctx prepare() const {
@@ -233,19 +231,7 @@ struct bk_op_cg_update {
     bk_st<T, W>(r + i, ro);
   }
   __device__ void epilogue(const double* s) const {
-    if (dist_out) {
-      dist_out[0] = s[0];
-      return;
-    }
-    double gamma_new = s[0];
-    if (p2p.P > 0) {
-      gamma_new = bk_p2p_allreduce(p2p, s[0]);
-      if (p2p.counters[4]) {
-        st->done = 1;
-        st->status = BK_ST_COMM_TIMEOUT;
-        return;
-      }
-    }
+    const double gamma_new = s[0];
     st->beta = gamma_new / st->gamma;
     st->gamma = gamma_new;
     const long long k = st->k + 1;
