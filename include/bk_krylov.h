@@ -87,7 +87,8 @@ typedef struct bk_csr_info {
   int32_t dtype;        /* enum bk_dtype */
   int32_t kernel;       /* 0 row-stream (LDG-staged) | 1 sub-warp vector | 2 row-stream, TMA-staged tiles, int32 columns |
                            3 = 2 with 8-bit dictionary-coded columns | 4 long rows split into virtual rows (skewed
-                           matrices) + ordered per-row reduction */
+                           matrices) + ordered per-row reduction | 5 = 2 with 8-bit codes of (column - row, value)
+                           PAIRS and no value stream (constant-coefficient stencils; lossless, bit-identical) */
   int32_t lanes_per_row;/* for kernel 1 */
   int32_t max_row_nnz;
   double mean_row_nnz;
@@ -106,7 +107,8 @@ int bk_destroy(bk_handle* h);
  *   chunk          iterations per graph / poll (0 = sized for ~2 ms of GPU work)
  *   use_tma        1: short-row matrices use the TMA-staged row-stream SpMV (kernel 2/3), 0: LDG-staged (kernel 0)
  *   use_split      1: matrices with a short mean row but a few very long rows are run on a virtual-row view (kernel 4)
- *   use_compress   1: stream column indices as 8-bit dictionary codes when the matrix allows it (kernel 3)
+ *   use_compress   0: off | 1: stream column indices as 8-bit dictionary codes when the matrix allows it (kernel 3)
+ *                  | 2 (default): first try 8-bit codes of (column - row, value) pairs (kernel 5), then kernel 3
  *   tma_ctas       CTAs per SM of the TMA SpMV (2..4), tma_stages: cap on its pipeline depth (0 = fill shared memory)
  *   prefetch_x     kernel 3: L2 bulk prefetch of the forward-diagonal x ranges (experiment, default 0)
  *   grid_mult_vec / grid_mult_spmv   CTAs per SM of the BLAS-1 kernels / the non-TMA SpMV kernels

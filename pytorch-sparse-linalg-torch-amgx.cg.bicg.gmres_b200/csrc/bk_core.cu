@@ -67,10 +67,11 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->grid_mult_vec = (int)bk_env_int("BK_GRID_MULT_VEC", 3);
   h->grid_mult_spmv = (int)bk_env_int("BK_GRID_MULT_SPMV", 4);
   h->tma_ctas = (int)bk_env_int("BK_TMA_CTAS", 4);
+  h->pair_ctas = (int)bk_env_int("BK_PAIR_CTAS", 4);
   h->tma_stages = (int)bk_env_int("BK_TMA_STAGES", 0);
   h->use_tma = (int)bk_env_int("BK_SPMV_TMA", 1);
   h->dist_p2p = (int)bk_env_int("BK_DIST_P2P", 1);
-  h->use_compress = (int)bk_env_int("BK_SPMV_COMPRESS", 1);
+  h->use_compress = (int)bk_env_int("BK_SPMV_COMPRESS", 2);
   h->use_split = (int)bk_env_int("BK_SPMV_SPLIT", 1);
   h->persistent = (int)bk_env_int("BK_PERSISTENT", 1);
   h->persistent_max_n = (int)bk_env_int("BK_PERSISTENT_MAX_N", 200000);
@@ -152,6 +153,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "grid_mult_spmv")) return &h->grid_mult_spmv;
   if (!strcmp(key, "grid_mult")) return &h->grid_mult_spmv;
   if (!strcmp(key, "tma_ctas")) return &h->tma_ctas;
+  if (!strcmp(key, "pair_ctas")) return &h->pair_ctas;
   if (!strcmp(key, "tma_stages")) return &h->tma_stages;
   if (!strcmp(key, "use_tma")) return &h->use_tma;
   if (!strcmp(key, "dist_p2p")) return &h->dist_p2p;
@@ -416,6 +418,176 @@ static int bk_csr_plan_compress(bk_handle* h, bk_csr* A, cudaStream_t s) {
   return BK_OK;
 }
 
+// ---- 8-bit coding of (column - row, value) PAIRS, SELL-32-4 layout (kernel 5, bk_spmv_pair.cuh) ---------------
+// bytes of every 256-row block's span: 128-byte header + per 32-row chunk (longest row rounded up to 4) x 32 lanes
+__global__ void bk_pair_block_bytes_kernel(const int* __restrict__ rowptr, long long n, long long nblk,
+                                           unsigned int* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long blk = warp0; blk < nblk; blk += nwarps) {
+    unsigned int units = BK_PAIR_HDR_BYTES / 128;
+    for (int pass = 0; pass < 8; ++pass) {
+      const long long r = blk * 256 + pass * 32 + lane;
+      int len = (r < n) ? rowptr[r + 1] - rowptr[r] : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+      units += (unsigned int)((len + 3) >> 2);
+    }
+    if (lane == 0) out[blk] = units * 128u;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[nblk] = 0u;
+}
+
+// One warp per 256-row block.  Lane i keeps dictionary entry i in registers; the warp walks its 8 chunks of 32 rows,
+// entry position by entry position: the (offset, value-bits) pairs of the 32 lanes are grouped (leader broadcast +
+// ballot), each group is looked up in / appended to the dictionary by one ballot, and every lane stores the code of
+// its entry at its SELL position.  A block with more than 31 distinct pairs sets `fail` (slot 31 is the zero entry).
+template <typename T>
+__global__ void __launch_bounds__(256)
+bk_build_pair_dict_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const T* __restrict__ val,
+                          long long n, long long nblk, const int* __restrict__ bptr,
+                          bk_pair_entry* __restrict__ dict, unsigned char* __restrict__ codes, int* __restrict__ fail) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (long long blk = warp0; blk < nblk; blk += nwarps) {
+    int t_off = 0;
+    unsigned long long t_val = 0ull;
+    int count = 0;
+    bool bad = false;
+    unsigned char* span = codes + bptr[blk];
+    unsigned int unit = BK_PAIR_HDR_BYTES / 128;  // running chunk start, in 128-byte units from the span start
+    for (int pass = 0; pass < 8; ++pass) {
+      const long long r = blk * 256 + pass * 32 + lane;
+      int s = 0, e = 0;
+      if (r < n) {
+        s = rowptr[r];
+        e = rowptr[r + 1];
+      }
+      int maxlen = e - s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+      const unsigned int words = (unsigned int)((maxlen + 3) >> 2);
+      if (lane == 0) reinterpret_cast<unsigned int*>(span)[pass] = ((unit + words) << 16) | unit;
+      unsigned char* out = span + (size_t)unit * 128 + lane * 4;
+      unit += words;
+      for (int k = 0; k < maxlen && !bad; ++k) {
+        const bool active = k < e - s;
+        int off = 0;
+        unsigned long long vb = 0ull;
+        if (active) {
+          off = col[s + k] - (int)r;
+          if (sizeof(T) == 8) vb = (unsigned long long)__double_as_longlong((double)val[s + k]);
+          else vb = (unsigned long long)__float_as_uint((float)val[s + k]);
+        }
+        unsigned int remaining = __ballot_sync(0xffffffffu, active);
+        int code = 0;
+        while (remaining) {
+          const int leader = __ffs(remaining) - 1;
+          const int lo = __shfl_sync(0xffffffffu, off, leader);
+          const unsigned long long lv = __shfl_sync(0xffffffffu, vb, leader);
+          const bool same = active && off == lo && vb == lv;
+          const unsigned int grp = __ballot_sync(0xffffffffu, same);
+          const unsigned int hit = __ballot_sync(0xffffffffu, lane < count && t_off == lo && t_val == lv);
+          int idx;
+          if (hit) {
+            idx = __ffs(hit) - 1;
+          } else {
+            idx = count;
+            if (count >= BK_PAIR_ZERO) {
+              bad = true;
+              idx = 0;
+            } else {
+              if (lane == count) {
+                t_off = lo;
+                t_val = lv;
+              }
+              ++count;
+            }
+          }
+          if (same) code = idx;
+          remaining &= ~grp;
+        }
+        if (active) out[(k >> 2) * 128 + (k & 3)] = (unsigned char)code;
+      }
+    }
+    if (bad && lane == 0) *fail = 1;
+    bk_pair_entry ent;
+    ent.val = (lane < count) ? t_val : 0ull;
+    ent.off = (lane < count) ? t_off : 0;
+    ent.pad = 0;
+    dict[blk * 32 + lane] = ent;
+  }
+}
+
+// Try the pair-coded stream (kernel 5); on success one SpMV reads neither val, col nor rowptr.
+static int bk_csr_plan_pairs(bk_handle* h, bk_csr* A, cudaStream_t s) {
+  if (A->kernel != 2 || h->use_compress < 2) return BK_OK;
+  const long long nblk = (A->n + 255) / 256;
+  int* dstat = (int*)(h->counters + 8);
+  auto drop = [&]() {
+    if (A->pcodes) bk_pool_free(A->pcodes);
+    if (A->pdict) bk_pool_free(A->pdict);
+    if (A->pbptr) bk_pool_free(A->pbptr);
+    A->pcodes = nullptr;
+    A->pdict = nullptr;
+    A->pbptr = nullptr;
+  };
+  if (bk_pool_alloc((void**)&A->pbptr, sizeof(int) * (size_t)(nblk + 1), s) != cudaSuccess) {
+    cudaGetLastError();
+    return BK_OK;
+  }
+  bk_pair_block_bytes_kernel<<<h->num_sms * 8, 256, 0, s>>>(A->rowptr, A->n, nblk, (unsigned int*)A->pbptr);
+  int rc = bk_exclusive_scan_u32((unsigned int*)A->pbptr, nblk + 1, s);
+  if (rc != BK_OK) {
+    drop();
+    return rc;
+  }
+  unsigned int total = 0;
+  cudaMemcpyAsync(&total, A->pbptr + nblk, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return bk_fail(BK_ERR_CUDA, "csr registration (pair coding): %s", cudaGetErrorString(e));
+  // padding must stay modest (rows of similar length inside each chunk) and offsets must fit an int
+  if ((double)total > 1.5 * (double)A->nnz + 1152.0 * (double)nblk || total >= 0x7fffff00u || total == 0) {
+    drop();
+    return BK_OK;
+  }
+  if (bk_pool_alloc((void**)&A->pcodes, (size_t)total + 128, s) != cudaSuccess ||
+      bk_pool_alloc(&A->pdict, sizeof(bk_pair_entry) * 32 * (size_t)nblk, s) != cudaSuccess) {
+    cudaGetLastError();
+    drop();
+    return BK_OK;  // not enough memory for the coded copy
+  }
+  int host[2] = {0, 0};
+  cudaMemsetAsync(dstat, 0, 2 * sizeof(int), s);
+  cudaMemsetAsync(A->pcodes, BK_PAIR_ZERO, (size_t)total + 128, s);
+  long long want = (nblk + 7) / 8;
+  int grid = (int)(want < (long long)h->num_sms * 8 ? want : (long long)h->num_sms * 8);
+  if (grid < 1) grid = 1;
+  if (A->dtype == BK_F64)
+    bk_build_pair_dict_kernel<double><<<grid, 256, 0, s>>>(A->rowptr, A->col, (const double*)A->val, A->n, nblk,
+                                                          A->pbptr, (bk_pair_entry*)A->pdict, A->pcodes, dstat + 1);
+  else
+    bk_build_pair_dict_kernel<float><<<grid, 256, 0, s>>>(A->rowptr, A->col, (const float*)A->val, A->n, nblk,
+                                                         A->pbptr, (bk_pair_entry*)A->pdict, A->pcodes, dstat + 1);
+  bk_block_span_kernel<<<h->num_sms * 4, 256, 0, s>>>(A->pbptr, nblk, nblk, 1, 128, dstat);
+  cudaMemcpyAsync(host, dstat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+  e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return bk_fail(BK_ERR_CUDA, "csr registration (pair coding): %s", cudaGetErrorString(e));
+  const int cap = (host[0] + 127) & ~127;
+  const size_t stage = (size_t)cap + BK_PAIR_DICT_BYTES;
+  if (host[1] != 0 || cap <= 0 || 2 * stage > 110 * 1024) {  // a block with > 31 distinct pairs, or too wide
+    drop();
+    return BK_OK;
+  }
+  A->pair_cap = cap;
+  A->kernel = 5;
+  return BK_OK;
+}
+
 // Decide whether the TMA row-stream kernel (bk_spmv_tma.cuh) can serve this matrix, size its pipeline and
 // build the 4-entry tail buffers.  Falls back silently to kernel 0 when a requirement is not met.
 static int bk_csr_plan_tma(bk_handle* h, bk_csr* A, cudaStream_t s) {
@@ -454,6 +626,7 @@ static int bk_csr_plan_tma(bk_handle* h, bk_csr* A, cudaStream_t s) {
   A->tma_cap = cap;
   A->tma_stages = stages;
   A->kernel = 2;
+  BK_TRY(bk_csr_plan_pairs(h, A, s));
   return bk_csr_plan_compress(h, A, s);
 }
 
@@ -568,6 +741,9 @@ extern "C" int bk_csr_destroy(bk_csr* A) {
   if (A->dict) bk_pool_free(A->dict);
   if (A->tail_val16) bk_pool_free(A->tail_val16);
   if (A->tail_code16) bk_pool_free(A->tail_code16);
+  if (A->pcodes) bk_pool_free(A->pcodes);
+  if (A->pdict) bk_pool_free(A->pdict);
+  if (A->pbptr) bk_pool_free(A->pbptr);
   free(A);
   return BK_OK;
 }

@@ -94,7 +94,8 @@ struct bk_csr {
   void* own_rowptr;   // non-null when the library owns (converted / copied) arrays
   void* own_col;
   void* own_val;
-  int kernel;         // 0 row-stream (LDG staged), 1 sub-warp vector, 2 row-stream with TMA-staged tiles, 3 = 2 + 8-bit column codes
+  int kernel;         // 0 row-stream (LDG staged), 1 sub-warp vector, 2 row-stream with TMA-staged tiles, 3 = 2 + 8-bit column
+                      // codes, 4 long rows split into virtual rows, 5 = 2 with 8-bit (offset, value) pair codes
   int lanes_per_row;
   int cap;            // row-stream: shared-memory products per warp
   int tma_cap;        // TMA row-stream: entries per pipeline stage (multiple of 4)
@@ -107,6 +108,12 @@ struct bk_csr {
   void* tail_val16;          // last nnz%16 entries zero-padded to 16 (own)
   unsigned char* tail_code16;
   int cmp_cap;               // entries per stage for the compressed variant
+  // pair-coded stream (kernel 5, bk_spmv_pair.cuh): 8-bit codes into per-block dictionaries of (column - row, value)
+  // pairs, stored SELL-32-4; the SpMV reads neither val, col nor rowptr
+  unsigned char* pcodes;     // code stream, own
+  void* pdict;               // nblk * 32 bk_pair_entry (16 B each), own
+  int* pbptr;                // [n/256 + 1] byte offset of every 256-row block span in pcodes, own
+  int pair_cap;              // code bytes per pipeline stage
   int max_row_nnz;
   double mean_row_nnz;
   bk_csr* transpose;  // cached, owned
@@ -137,13 +144,14 @@ struct bk_handle {
   int grid_mult_vec;   // CTAs/SM of elementwise kernels
   int grid_mult_spmv;  // CTAs/SM of SpMV kernels
   int tma_ctas;        // CTAs/SM of the TMA row-stream SpMV (2..4)
+  int pair_ctas;       // CTAs/SM of the pair-coded SpMV (2..6)
   int tma_stages;      // 0 = fill shared memory, else cap on the pipeline depth
   int use_tma;         // allow the TMA row-stream kernel
   int prefetch_x;      // kernel 3: L2 bulk prefetch of the forward-diagonal x ranges
   int persistent;      // CG: run small systems in ONE cooperative persistent kernel (grid barriers instead of launches)
   int persistent_max_n;
   int use_split;       // split very long rows into virtual rows (skewed matrices)
-  int use_compress;    // allow the 8-bit dictionary-coded column stream (kernel 3)
+  int use_compress;    // 0 off | 1 8-bit dictionary-coded column stream (kernel 3) | 2 also try (offset, value) pair codes (kernel 5)
   int dist_p2p;        // multi-GPU: use the peer-memory path (halo push + one-shot all-reduce) when it is connected
   int loop_mode;
   int chunk;

@@ -224,6 +224,7 @@ bk_spmv_vector_kernel(const bk_spmv_args a, const bk_scratch sc, Epi epi) {
 }
 
 #include "bk_spmv_tma.cuh"
+#include "bk_spmv_pair.cuh"
 
 // Second half of the long-row path: y[r] = (b[r] -) sum of the partial sums of r's virtual rows, added in order
 // (deterministic), fused with the requested dots and the solver's scalar epilogue.
@@ -314,7 +315,42 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
       return bk_launch_spmv_split<T, MODE, DOTS, Epi>(h, A, a, sc, epi, s);
     }
   }
-  if ((A->kernel == 2 || A->kernel == 3) && XMODE == 0) {
+  if (A->kernel == 5 && XMODE == 0) {
+    if constexpr (XMODE == 0) {
+      // pair-coded SELL stream: stages are tiny (~2 KB for a 7-point stencil), so occupancy is set by registers
+      const size_t stage_bytes = (size_t)A->pair_cap + BK_PAIR_DICT_BYTES;
+      int ctas = h->pair_ctas < 2 ? 2 : (h->pair_ctas > 6 ? 6 : h->pair_ctas);
+      int stages = 0;
+      for (; ctas >= 2; --ctas) {
+        stages = (int)(((size_t)224 * 1024 / ctas - 2048) / stage_bytes);
+        if (stages >= 2) break;
+      }
+      if (stages > BK_TMA_MAX_STAGES) stages = BK_TMA_MAX_STAGES;
+      if (h->tma_stages >= 2 && h->tma_stages < stages) stages = h->tma_stages;
+      const size_t sm = (size_t)stages * stage_bytes;
+      bk_pair_plan plan;
+      plan.bptr = A->pbptr;
+      plan.codes = A->pcodes;
+      plan.dict = (const bk_pair_entry*)A->pdict;
+      plan.cap = A->pair_cap;
+      plan.stages = stages;
+      int g = h->num_sms * ctas;
+      if (g > BK_MAXB) g = BK_MAXB;
+      g = bk_grid_rows(g, A->n, BK_TMA_RPB);
+      auto launch = [&](auto k) -> int {
+        BK_TRY(bk_ensure_dyn_smem((const void*)k, sm));
+        k<<<g, BK_TMA_THREADS, sm, s>>>(a, plan, sc, epi);
+        return BK_OK;
+      };
+      switch (ctas) {
+        case 2: BK_TRY(launch(bk_spmv_pair_kernel<T, MODE, DOTS, 2, Epi>)); break;
+        case 3: BK_TRY(launch(bk_spmv_pair_kernel<T, MODE, DOTS, 3, Epi>)); break;
+        case 4: BK_TRY(launch(bk_spmv_pair_kernel<T, MODE, DOTS, 4, Epi>)); break;
+        case 5: BK_TRY(launch(bk_spmv_pair_kernel<T, MODE, DOTS, 5, Epi>)); break;
+        default: BK_TRY(launch(bk_spmv_pair_kernel<T, MODE, DOTS, 6, Epi>)); break;
+      }
+    }
+  } else if ((A->kernel == 2 || A->kernel == 3) && XMODE == 0) {
     if constexpr (XMODE == 0) {
       // CTAs per SM (2..4) trade pipeline depth for consumer warps; stages fill the per-CTA share of shared memory
       int ctas = h->tma_ctas < 2 ? 2 : (h->tma_ctas > 4 ? 4 : h->tma_ctas);
@@ -362,7 +398,7 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
         BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 4, 0, Epi>));
       }
     }
-  } else if (A->kernel == 0 || A->kernel == 2 || A->kernel == 3) {
+  } else if (A->kernel == 0 || A->kernel == 2 || A->kernel == 3 || A->kernel == 5) {
     const int grid = bk_grid_rows(bk_grid_spmv(h), A->n, BK_BLOCK);
     if (A->cap <= 256) {
       auto k = bk_spmv_stream_kernel<T, 256, MODE, DOTS, XMODE, Epi>;

@@ -103,7 +103,7 @@ def test_spmv_matches_cpu(name, make, idx):
 def test_spmv_kernel_selection():
     from pytorch_sparse_solver import _native
     m = _native.register_matrix(build_matrix(dict(matrix="poisson3d", n=12), device="cuda"))
-    assert m.info()["kernel"] in (0, 2, 3) and m.info()["max_row_nnz"] == 7
+    assert m.info()["kernel"] in (0, 2, 3, 5) and m.info()["max_row_nnz"] == 7
     m2 = _native.register_matrix(_random_csr(600, 200, 4).cuda())
     assert m2.info()["kernel"] == 1
 
@@ -131,7 +131,7 @@ def test_spmv_tma_and_ldg_row_stream_agree(name, make):
         _native.clear_cache()
     assert k0 in (0, 1, 4)
     if k0 == 0 and name != "rand_mean20":
-        assert k1 in (2, 3), "short-row matrices should take the TMA row-stream kernel"
+        assert k1 in (2, 3, 5), "short-row matrices should take the TMA row-stream kernel"
     scale = float(y0.abs().max()) + 1e-300
     assert float((y0 - y1).abs().max()) <= 1e-13 * scale
     assert abs(float(d1) - float(torch.dot(x, y0))) <= 1e-11 * float(x.abs() @ y0.abs() + 1e-300)
@@ -159,12 +159,32 @@ def test_spmv_dictionary_coded_columns_bitwise(gen, dtype):
         assert m3.info()["kernel"] == 3, "stencil matrices have <= 32 distinct offsets per block"
         t3 = m3.transpose()
         yt = t3.spmv(x)
+        h.set_option("use_compress", 2)
+        _native.clear_cache()
+        m5 = _native.register_matrix(A, dtype)
+        y5, d5 = m5.spmv_dot(x, x)
+        assert m5.info()["kernel"] == 5, "constant-coefficient stencils have <= 31 (offset, value) pairs per block"
+        yt5 = m5.transpose().spmv(x)
     finally:
-        h.set_option("use_compress", 1)
+        h.set_option("use_compress", 2)
         _native.clear_cache()
     assert torch.equal(y2, y3) and float(d2) == float(d3)
+    assert torch.equal(y2, y5) and float(d2) == float(d5), "kernel 5 (pair codes, no value stream) must be bit-identical"
     ref = torch.matmul(A.cpu().to_dense().T.double(), x.cpu().double())
     assert rel_diff(yt, ref) <= (1e-13 if dtype == torch.float64 else 1e-5)
+    assert torch.equal(yt, yt5)
+
+
+def test_spmv_pair_codes_fall_back_on_varying_values():
+    """Stencil sparsity with all-different values: too many (offset, value) pairs -> column codes only (kernel 3)."""
+    from pytorch_sparse_solver import _native
+    A = build_matrix(dict(matrix="poisson3d", n=12), device="cuda")
+    vals = torch.randn(A.values().numel(), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(8))
+    B = torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), vals, size=A.shape)
+    m = _native.register_matrix(B)
+    assert m.info()["kernel"] == 3
+    x = torch.randn(A.shape[0], dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(9))
+    assert rel_diff(m.spmv(x), torch.matmul(B.cpu().to_dense(), x.cpu())) <= 1e-13
 
 
 def test_spmv_dictionary_falls_back_on_unstructured():
@@ -321,7 +341,7 @@ def test_solvers_bitwise_deterministic(ma, manifest, name):
     assert torch.equal(xs[0], xs[1]) and torch.equal(xs[0], xs[2])
 
 
-@pytest.mark.parametrize("opts", [dict(persistent=0), dict(persistent=0, fuse_xpay=1), dict(persistent=0, fuse_xpay=0), dict(persistent=0, snake=0), dict(persistent=0, fuse_xpay=1, snake=0), dict(persistent=0, chunk=2), dict(persistent=0, use_tma=0), dict(persistent=0, use_compress=0),
+@pytest.mark.parametrize("opts", [dict(persistent=0), dict(persistent=0, fuse_xpay=1), dict(persistent=0, fuse_xpay=0), dict(persistent=0, snake=0), dict(persistent=0, fuse_xpay=1, snake=0), dict(persistent=0, chunk=2), dict(persistent=0, use_tma=0), dict(persistent=0, use_compress=0), dict(persistent=0, use_compress=1),
                                   dict(persistent=0, grid_mult_spmv=2, grid_mult_vec=2), dict(persistent=1)])
 def test_cg_kernel_variants(ma, manifest, opts):
     from pytorch_sparse_solver import _native

@@ -91,17 +91,27 @@ def main():
         h.set_option("prefetch_x", pf)
         ms = time_gpu(lambda: m.spmv_dot(x, x), reps=10)
         emit(what="bk_spmv_dot_prefetch", prefetch_x=pf, kernel=m.info()["kernel"], gbs_algorithmic=bytes_spmv / ms / 1e6, ms=ms)
-    for cmp_ in (0, 1):
+    for cmp_ in (0, 1, 2):
         h.set_option("use_compress", cmp_)
         _native.clear_cache()
         mm = _native.register_matrix(A)
-        for ctas in (3, 4):
+        for ctas in (2, 3, 4):
             h.set_option("tma_ctas", ctas)
             ms = time_gpu(lambda: mm.spmv_dot(x, x), reps=10)
             emit(what="bk_spmv_dot_compress", kernel=mm.info()["kernel"], use_compress=cmp_, tma_ctas=ctas,
                  gbs_algorithmic=bytes_spmv / ms / 1e6, ms=ms)
+        if mm.info()["kernel"] == 5:
+            for ctas in (3, 4, 5, 6):
+                h.set_option("pair_ctas", ctas)
+                for st in (0, 4):
+                    h.set_option("tma_stages", st)
+                    ms = time_gpu(lambda: mm.spmv_dot(x, x), reps=10)
+                    emit(what="bk_spmv_dot_pair", kernel=5, pair_ctas=ctas, tma_stages=st,
+                         gbs_algorithmic=bytes_spmv / ms / 1e6, ms=ms)
+            h.set_option("pair_ctas", 4)
+            h.set_option("tma_stages", 0)
     h.set_option("tma_ctas", 4)
-    h.set_option("use_compress", 1)
+    h.set_option("use_compress", 2)
     _native.clear_cache()
     m = _native.register_matrix(A)
     for gm in (() if m.info()["kernel"] == 2 else (2, 3, 4, 6, 8)):
