@@ -3,12 +3,12 @@
 //
 // Per iteration (recurrences and operation order exactly the reference's, :843-853):
 //   K1  Ap = A p            fused with p.Ap ; epilogue: alpha = gamma / p.Ap
-//   K2  x += alpha p ; r -= alpha Ap ; fused with r.r ; epilogue: beta = gamma'/gamma, k += 1,
+//   K2  r -= alpha Ap ; fused with r.r ; epilogue: beta = gamma'/gamma, k += 1,
 //       stop test `k >= maxiter or gamma' <= atol2` (:841) for the next iteration
-//   K3  p = r + beta p
+//   K3  x += alpha p ; p = r + beta p      (x rides along with the p-update: both read p_k; 8n instead of 9n)
 // With option fuse_xpay K3 disappears: K1 gathers r[c] + beta p_old[c] on the fly (bitwise the
 // same value K3 would have stored) and writes the new p for its own rows (double-buffered p).
-// Algorithmic HBM bytes per iteration: nnz*(8+4) + (n+1)*4 + 11*n*8  (SURVEY §8d).
+// Algorithmic HBM bytes per iteration (the reference-equivalent plan): nnz*(8+4) + (n+1)*4 + 11*n*8  (SURVEY §8d).
 #include "bk_internal.cuh"
 #include "bk_loop.cuh"
 #include "bk_spmv.cuh"
@@ -251,7 +251,7 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
     BK_TRY((bk_launch_spmv<0, 1, 0>(h, A, a, bk_slot(h, 0), epi, s)));
     pcur = v.p[0];
   }
-  {
+  if (fuse) {
     bk_op_cg_update<T> op;
     op.p = pcur;
     op.ap = v.ap;
@@ -260,14 +260,24 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
     op.st = st;
     op.snake = h->snake;
     BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
-  }
-  if (!fuse) {
-    bk_op_xpay<T> op;
-    op.r = v.r;
-    op.p = v.p[0];
-    op.st = st;
-    op.snake = h->snake;
-    BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), s));
+  } else {
+    {
+      bk_op_cg_r<T> op;
+      op.ap = v.ap;
+      op.r = v.r;
+      op.st = st;
+      op.snake = h->snake;
+      BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
+    }
+    {
+      bk_op_cg_xp<T> op;
+      op.x = v.x;
+      op.p = v.p[0];
+      op.r = v.r;
+      op.st = st;
+      op.snake = h->snake;
+      BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), s));
+    }
   }
   return BK_OK;
 }
@@ -417,19 +427,18 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
   auto enqueue_iter = [&](cudaStream_t cs) -> int {
     BK_TRY((sys.matvec<T, 0, 1>(p, ap, p, nullptr, 1, bk_epi_cg_pAp{st}, cs)));
     {
-      bk_op_cg_update<T> op;
-      op.p = p;
+      bk_op_cg_r<T> op;
       op.ap = ap;
-      op.x = x;
       op.r = r;
       op.st = st;
       op.snake = 0;
       BK_TRY(sys.ew<T>(op, true, 1, cs));
     }
     {
-      bk_op_xpay<T> op;
-      op.r = r;
+      bk_op_cg_xp<T> op;
+      op.x = x;
       op.p = p;
+      op.r = r;
       op.st = st;
       op.snake = 0;
       BK_TRY(sys.ew<T>(op, true, 2, cs));

@@ -48,6 +48,7 @@ struct bk_dev_state {
   long long maxiter;
   long long matvecs;
   int done;           // 1 => every guarded kernel is an exact no-op
+  int just_done;      // CG: `done` was set by THIS iteration's r-update, whose x/p-update kernel must still run once
   int status;         // enum bk_status
   int exit_early;     // BiCGStab: s.s < atol2 (:920)
   int parity;         // flips every iteration (sweep direction for the "snake" option)

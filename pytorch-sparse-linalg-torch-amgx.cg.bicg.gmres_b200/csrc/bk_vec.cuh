@@ -286,6 +286,115 @@ struct bk_op_xpay {
   __device__ void epilogue(const double*) const {}
 };
 
+// The same CG iteration cut differently (large systems): K2 touches only r, K3 updates x together with p — both read
+// p_k anyway, so x costs one vector pass less (8n instead of 9n per iteration).  Bitwise the same x, r, p.
+//   K2  r -= alpha Ap ; gamma' = r.r ; epilogue as above                       (:847, :849-851)
+//   K3  x += alpha p ; p = r + beta p                                          (:846, :852)
+// K3 must also run in the iteration whose K2 set `done` (x is not final before): K2's epilogue raises `just_done`,
+// and a K2 that finds `done` already set (every later, skipped iteration) lowers it again.
+template <typename T>
+struct bk_op_cg_r {
+  static constexpr int R = 1;
+  struct Ctx {
+    T alpha;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> ap, r;
+  };
+  const T* ap;
+  T* r;
+  bk_dev_state* st;
+  int snake;
+  __device__ bool skip() const {
+    if (st->done == 0) return false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->just_done = 0;
+    return true;
+  }
+  __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.alpha = static_cast<T>(st->alpha);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.ap = bk_ld<T, W>(ap + i);
+    in.r = bk_ld<T, W>(r + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&acc)[1]) const {
+    bk_vec<T, W> ro;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      ro.v[j] = bk_sub(in.r.v[j], bk_mul(c.alpha, in.ap.v[j]));
+      acc[0] += (double)ro.v[j] * (double)ro.v[j];
+    }
+    bk_st<T, W>(r + i, ro);
+  }
+  __device__ void epilogue(const double* s) const {
+    const double gamma_new = s[0];
+    st->beta = gamma_new / st->gamma;
+    st->gamma = gamma_new;
+    const long long k = st->k + 1;
+    st->k = k;
+    st->parity ^= 1;
+    if (k >= st->maxiter) {
+      st->done = 1;
+      st->just_done = 1;
+      st->status = BK_ST_MAXITER;
+    }
+    if (gamma_new <= st->atol2) {
+      st->done = 1;
+      st->just_done = 1;
+      st->status = BK_ST_CONVERGED;
+    }
+  }
+};
+
+template <typename T>
+struct bk_op_cg_xp {
+  static constexpr int R = 0;
+  struct Ctx {
+    T alpha, beta;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> x, p, r;
+  };
+  T* x;
+  T* p;
+  const T* r;
+  const bk_dev_state* st;
+  int snake;
+  __device__ bool skip() const { return st->done != 0 && st->just_done == 0; }
+  __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.alpha = static_cast<T>(st->alpha);
+    c.beta = static_cast<T>(st->beta);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.x = bk_ld<T, W>(x + i);
+    in.p = bk_ld<T, W>(p + i);
+    in.r = bk_ld<T, W>(r + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
+    bk_vec<T, W> xo, po;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      xo.v[j] = bk_add(in.x.v[j], bk_mul(c.alpha, in.p.v[j]));
+      po.v[j] = bk_add(in.r.v[j], bk_mul(c.beta, in.p.v[j]));
+    }
+    bk_st<T, W>(x + i, xo);
+    bk_st<T, W>(p + i, po);
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
 // ---- BiCGStab ----------------------------------------------------------------------------------
 // p = r + beta (p - omega q)                               (_bicgstab_solve :906-907)
 template <typename T>
