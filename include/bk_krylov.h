@@ -169,6 +169,14 @@ int bk_cg(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, dou
           int64_t maxiter, bk_result* result, void* stream);
 int bk_bicgstab(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, double tol,
                 double atol, int64_t maxiter, bk_result* result, void* stream);
+/* Jacobi-preconditioned CG: _cg_solve with M = (r -> r / diag), :820-853 — z = M r, gamma = r.z, the stop test on
+ * rs = r.r (:838), p = z + beta p — and _isolve's final check on ||M (b - A x)|| (:1008).  `diag`: device vector of
+ * A's dtype (bk_csr_diagonal extracts it).  What the reference does through a user-supplied Python callable
+ * `M = lambda r: r / d`, kept on the device.  Same result fields as bk_cg. */
+int bk_cg_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b, void* x, int has_x0, double tol,
+                 double atol, int64_t maxiter, bk_result* result, void* stream);
+/* out[r] = A[r][r] (0 when the row stores no diagonal entry); out: device vector of A's dtype */
+int bk_csr_diagonal(bk_handle* h, const bk_csr* A, void* out, void* stream);
 /* bk_gmres replaces gmres :641-784, _gmres_solve_with_method :788-803, _gmres_batched :431-493,
  * _gmres_incremental :557-638, _kth_arnoldi_iteration :331-388, _iterative_classical_gram_schmidt
  * :284-328, _givens_rotation :508-518, _safe_normalize :217-273.

@@ -1,6 +1,6 @@
 """CPU oracle for Module A's Krylov path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-A plain restatement (torch-CPU ops, single-tensor `b`, no preconditioner) of the reference algorithms in
+A plain restatement (torch-CPU ops, single-tensor `b`; a preconditioner only for CG) of the reference algorithms in
 src/pytorch_sparse_solver/module_a/torch_sparse_linalg.py.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / `--impl reference` leg may import this file; the product package never does.
 
@@ -62,24 +62,25 @@ def _safe_normalize(x: torch.Tensor, thresh=None) -> Tuple[torch.Tensor, torch.T
 
 
 # --------------------------------------------------------------------------------------------------
-def _cg_solve(A, b, x0, maxiter, tol, atol):                   # :806-856
+def _cg_solve(A, b, x0, maxiter, tol, atol, M=None):           # :806-856
     bs = _vdot(b, b)
     atol2 = torch.maximum(torch.square(torch.tensor(tol)) * bs, torch.square(torch.tensor(atol)))   # :815-817
     r = b - A(x0)                                              # :820
-    p = r                                                      # :821 (M = identity)
-    gamma = _vdot(r, r).to(r.dtype)                            # :826
+    p = z = r if M is None else M(r)                           # :821
+    gamma = _vdot(r, z).to(r.dtype)                            # :826
     x, k = x0, 0
     while True:
-        rs = gamma                                             # :835-836
+        rs = gamma if M is None else _vdot(r, r)               # :835-838
         if k >= maxiter or rs <= atol2:                        # :841
             break
         Ap = A(p)                                              # :844
         alpha = gamma / _vdot(p, Ap).to(r.dtype)               # :845
         x = x + alpha * p                                      # :846
         r = r - alpha * Ap                                     # :847
-        gamma_new = _vdot(r, r).to(r.dtype)                    # :849-850
+        z = r if M is None else M(r)                           # :848
+        gamma_new = _vdot(r, z).to(r.dtype)                    # :849-850
         beta = gamma_new / gamma                               # :851
-        p = r + beta * p                                       # :852
+        p = z + beta * p                                       # :852
         gamma = gamma_new
         k += 1
     return x, k
@@ -135,7 +136,7 @@ def _bicgstab_solve(A, b, x0, maxiter, tol, atol):             # :859-964
     return x, (k if k >= 0 else iters), k
 
 
-def _isolve(kind: str, A_t: torch.Tensor, b: torch.Tensor, x0, tol, atol, maxiter):   # :967-1016
+def _isolve(kind: str, A_t: torch.Tensor, b: torch.Tensor, x0, tol, atol, maxiter, M=None):   # :967-1016
     if x0 is None:
         x0 = torch.zeros_like(b)
     b = b.to(torch.float64)
@@ -147,11 +148,11 @@ def _isolve(kind: str, A_t: torch.Tensor, b: torch.Tensor, x0, tol, atol, maxite
     A = _CountingMatvec(A_t)
     status = 0
     if kind == 'cg':
-        x, iters = _cg_solve(A, b, x0, maxiter, tol, atol)
+        x, iters = _cg_solve(A, b, x0, maxiter, tol, atol, M)
     else:
         x, iters, status = _bicgstab_solve(A, b, x0, maxiter, tol, atol)
     matvecs = A.calls
-    final_residual = _norm(b - A(x))                           # :1008
+    final_residual = _norm(b - A(x)) if M is None else _norm(M(b - A(x)))   # :1008
     b_norm = _norm(b)
     atol_tensor = torch.maximum(torch.tensor(tol) * b_norm, torch.tensor(atol))   # :1010-1011
     failed = bool(torch.isnan(_norm(x))) or bool(final_residual > atol_tensor)
@@ -161,9 +162,11 @@ def _isolve(kind: str, A_t: torch.Tensor, b: torch.Tensor, x0, tol, atol, maxite
     return x, info, stats
 
 
-def cg(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None, *, tol=1e-5, atol=0.0, maxiter=None):
-    """reference cg (:1019-1088) without the autograd wrapper.  Returns (x, info, stats)."""
-    return _isolve('cg', A, b, x0, tol, atol, maxiter)
+def cg(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None, *, tol=1e-5, atol=0.0, maxiter=None,
+       M=None):
+    """reference cg (:1019-1088) without the autograd wrapper.  Returns (x, info, stats).  M: optional preconditioner
+    callable (the fixtures use Jacobi, `lambda r: r / d`)."""
+    return _isolve('cg', A, b, x0, tol, atol, maxiter, M)
 
 
 def bicgstab(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None, *, tol=1e-5, atol=0.0,

@@ -73,17 +73,22 @@ def main():
         x, info, stats = getattr(orc, kind)(A, b, x0, **kw)
         return x, info, stats
 
-    def pin(name, kind, A, b, x0=None, store_vectors=True, gen=None, **kw):
+    def pin(name, kind, A, b, x0=None, store_vectors=True, gen=None, jacobi=False, **kw):
         t0 = time.time()
-        xr, inf_r, mv_r = run_ref(kind, A, b, x0, **kw)
-        xo, inf_o, st = run_orc(kind, A, b, x0, **kw)
+        if jacobi:  # M = diag(A)^-1 written the way users of the reference write it
+            d = problems.csr_diagonal(A)
+            kw_run = dict(kw, M=lambda r: r / d)
+        else:
+            kw_run = kw
+        xr, inf_r, mv_r = run_ref(kind, A, b, x0, **kw_run)
+        xo, inf_o, st = run_orc(kind, A, b, x0, **kw_run)
         # reference matvecs include its final residual check (1), ours are counted before it
         assert torch.equal(xr, xo), f"{name}: oracle x differs from reference (max {float((xr - xo).abs().max()):.3e})"
         assert inf_r == inf_o, f"{name}: info {inf_r} vs {inf_o}"
         assert mv_r == st["matvecs"] + 1, f"{name}: matvecs {mv_r} vs {st['matvecs']}+1"
         entry = dict(kind=kind, n=int(b.numel()), info=inf_r, matvecs_ref=mv_r, iterations=st["iterations"],
                      final_residual=st["final_residual"], b_norm=st["b_norm"], gen=gen or {},
-                     kwargs={k: v for k, v in kw.items()}, x_norm=float(torch.linalg.norm(xr)),
+                     kwargs={k: v for k, v in kw.items()}, jacobi=bool(jacobi), x_norm=float(torch.linalg.norm(xr)),
                      x_sum=float(xr.sum()), seconds=round(time.time() - t0, 2))
         arrays = {}
         if store_vectors:
@@ -133,6 +138,18 @@ def main():
     A = problems.poisson3d_csr(64)
     pin("cg_p3d64_ones_digest", "cg", A, torch.ones(A.shape[0], dtype=torch.float64), store_vectors=False,
         gen=dict(matrix="poisson3d", n=64), tol=1e-8)
+
+    # Jacobi-preconditioned CG (M = lambda r: r / diag(A)) on a badly scaled SPD system
+    A = problems.scaled_poisson3d_csr(12)
+    b, _ = problems.manufactured_rhs(A, 2)
+    gsp = dict(matrix="scaled_poisson3d", n=12, seed=7)
+    # (without M this system needs 8747 iterations at tol 1e-10; with Jacobi 53)
+    pin("cg_sp3d12_jacobi", "cg", A, b, gen=gsp, jacobi=True, tol=1e-10)
+    pin("cg_sp3d12_jacobi_fixed7", "cg", A, b, gen=gsp, jacobi=True, tol=0.0, atol=0.0, maxiter=7)
+    x0 = torch.randn(A.shape[0], dtype=torch.float64, generator=torch.Generator().manual_seed(11))
+    pin("cg_sp3d12_jacobi_x0", "cg", A, b, x0, gen=gsp, jacobi=True, tol=1e-9, atol=1e-14)
+    pin("cg_p3d16_jacobi", "cg", problems.poisson3d_csr(16), problems.manufactured_rhs(problems.poisson3d_csr(16), 0)[0],
+        gen=dict(matrix="poisson3d", n=16), jacobi=True, tol=1e-10)
 
     # ---- BiCGStab --------------------------------------------------------------------------------
     A = problems.convdiff3d_csr(16)

@@ -388,6 +388,153 @@ extern "C" int bk_cg(bk_handle* h, const bk_csr* A, const void* b, void* x, int 
   return bk_cg_t<float>(h, A, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
 }
 
+// ---- Jacobi-preconditioned CG (a built-in M so that preconditioning need not leave the device) ------
+struct bk_epi_pcg_bs {  // bs = b.b ; atol2 (:815-817)
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const {
+    st->bs = s[0];
+    st->atol2 = fmax(st->tolsq32 * s[0], st->atolsq32);
+  }
+};
+struct bk_epi_ignore {
+  __device__ __forceinline__ void operator()(const double*) const {}
+};
+
+template <typename T>
+static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, void* x_user, int has_x0, double tol,
+                    double atol, int64_t maxiter, bk_result* res, cudaStream_t s) {
+  const long long n = A->n;
+  const size_t npad = ((size_t)n + 63) & ~(size_t)63;
+  BK_TRY(bk_ws_reserve(h, (size_t)4 * npad * sizeof(T)));
+  T* x = (T*)h->ws;
+  T* r = x + npad;
+  T* p = r + npad;
+  T* ap = p + npad;
+  bk_dev_state* st = h->st;
+  const size_t vbytes = (size_t)n * sizeof(T);
+  const bk_sys_local sys{h, A};
+
+  bk_dev_state init;
+  memset(&init, 0, sizeof(init));
+  init.maxiter = maxiter < 0 ? 10 * n : maxiter;
+  init.status = BK_ST_MAXITER;
+  bk_state_fill_tol(&init, tol, atol);
+  bk_state_set_kernel<<<1, 1, 0, s>>>(st, init);
+  BK_KERNEL_CHECK();
+
+  BK_TRY((sys.dot<T>(b, b, bk_epi_pcg_bs{st}, 1, s)));
+  if (has_x0) {
+    BK_CUDA(cudaMemcpyAsync(x, x_user, vbytes, cudaMemcpyDeviceToDevice, s));
+    BK_TRY((sys.matvec<T, 1, 2>(x, r, nullptr, b, 0, bk_epi_ignore{}, s)));  // r0 = b - A x0 (:820)
+  } else {
+    BK_CUDA(cudaMemsetAsync(x, 0, vbytes, s));
+    BK_CUDA(cudaMemcpyAsync(r, b, vbytes, cudaMemcpyDeviceToDevice, s));
+  }
+  {
+    bk_op_pcg_init<T> op;
+    op.r = r;
+    op.d = d;
+    op.p = p;
+    op.st = st;
+    BK_TRY(sys.ew<T>(op, bk_aligned16(d), 1, s));
+  }
+  const bool al = bk_aligned16(d);
+  auto enqueue_iter = [&](cudaStream_t cs) -> int {
+    BK_TRY((sys.matvec<T, 0, 1>(p, ap, p, nullptr, 1, bk_epi_cg_pAp{st}, cs)));
+    {
+      bk_op_pcg_r<T> op;
+      op.ap = ap;
+      op.r = r;
+      op.d = d;
+      op.st = st;
+      BK_TRY(sys.ew<T>(op, al, 1, cs));
+    }
+    {
+      bk_op_pcg_xp<T> op;
+      op.x = x;
+      op.p = p;
+      op.r = r;
+      op.d = d;
+      op.st = st;
+      BK_TRY(sys.ew<T>(op, al, 2, cs));
+    }
+    return BK_OK;
+  };
+  const double bytes_iter = sys.matrix_bytes() + 13.0 * n * sizeof(T);
+  const int chunk = bk_pick_chunk(h, bytes_iter, 3);
+  const bool use_graph = h->loop_mode != BK_LOOP_STREAM;
+  uint64_t key[6] = {5 /*jacobi cg*/, A->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
+                     (uint64_t)A->dtype | ((uint64_t)chunk << 16) | ((uint64_t)al << 8),
+                     (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
+  // the diagonal's address is baked into the captured graph: make it part of the key
+  key[1] ^= (uint64_t)(uintptr_t)d * 0x9e3779b97f4a7c15ull;
+  auto enqueue_chunk = [&](cudaStream_t cs) -> int {
+    for (int it = 0; it < chunk; ++it) BK_TRY(enqueue_iter(cs));
+    return BK_OK;
+  };
+  int64_t chunks = 0;
+  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
+
+  // final check of _isolve: || M (b - A x) || against max(tol ||b||, atol) (:1008-1013)
+  BK_TRY((sys.matvec<T, 1, 2>(x, ap, nullptr, b, 0, bk_epi_ignore{}, s)));
+  {
+    bk_op_scaled_sq<T, bk_epi_final_r> op;
+    op.t = ap;
+    op.d = d;
+    op.epi = bk_epi_final_r{st};
+    BK_TRY(sys.ew<T>(op, al, 1, s));
+  }
+  BK_TRY((sys.dot<T>(x, x, bk_epi_final_x{st}, 1, s)));
+  BK_CUDA(cudaMemcpyAsync(x_user, x, vbytes, cudaMemcpyDeviceToDevice, s));
+  BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
+  BK_CUDA(cudaStreamSynchronize(s));
+  const bk_dev_state* fin = &h->st_host[3];
+  bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
+  res->rr_last = fin->rs;
+  res->kernel_launches = chunks * chunk * 3 + 4 + (has_x0 ? 1 : 0) + 3;
+  return BK_OK;
+}
+
+extern "C" int bk_cg_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b, void* x, int has_x0,
+                            double tol, double atol, int64_t maxiter, bk_result* result, void* stream) {
+  BK_TRY(bk_solver_args_check("bk_cg_jacobi", h, A, b, x, result));
+  if (!diag && A->n > 0) return bk_fail(BK_ERR_ARG, "bk_cg_jacobi: null diagonal");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (A->n == 0) return BK_OK;
+  if (A->dtype == BK_F64)
+    return bk_pcg_t<double>(h, A, (const double*)diag, b, x, has_x0, tol, atol, maxiter, result,
+                            (cudaStream_t)stream);
+  return bk_pcg_t<float>(h, A, (const float*)diag, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+}
+
+// diag[r] = A[r][r] (sum of the stored entries with col == r; 0 when the row has none)
+template <typename T>
+__global__ void bk_csr_diag_kernel(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                   const T* __restrict__ val, long long n, T* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    T dsum = T(0);
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k)
+      if (col[k] == (int)r) dsum += val[k];
+    out[r] = dsum;
+  }
+}
+
+extern "C" int bk_csr_diagonal(bk_handle* h, const bk_csr* A, void* out, void* stream) {
+  if (!h || !A || (!out && A->n > 0)) return bk_fail(BK_ERR_ARG, "bk_csr_diagonal: null argument");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (A->n == 0) return BK_OK;
+  const int g = bk_grid_rows(h->num_sms * 8, A->n, 256);
+  if (A->dtype == BK_F64)
+    bk_csr_diag_kernel<double><<<g, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, (const double*)A->val, A->n,
+                                                                    (double*)out);
+  else
+    bk_csr_diag_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, (const float*)A->val, A->n,
+                                                                   (float*)out);
+  BK_KERNEL_CHECK();
+  return BK_OK;
+}
+
 // ---- row-partitioned CG --------------------------------------------------------------------------
 // The 3-kernel iteration above on the distributed system: K1's halo exchange overlaps the local-block SpMV, p.Ap and
 // r.r become global sums (peer path: inside the epilogues of the boundary-row kernel and of K2; NCCL path:

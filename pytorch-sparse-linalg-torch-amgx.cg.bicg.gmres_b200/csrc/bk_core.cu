@@ -524,6 +524,9 @@ bk_build_pair_dict_kernel(const int* __restrict__ rowptr, const int* __restrict_
 // Try the pair-coded stream (kernel 5); on success one SpMV reads neither val, col nor rowptr.
 static int bk_csr_plan_pairs(bk_handle* h, bk_csr* A, cudaStream_t s) {
   if (A->kernel != 2 || h->use_compress < 2) return BK_OK;
+  // virtual-row views (kernel 4) number their rows beyond the length of x: the padding entries' x[row] would be out
+  // of bounds there
+  if (A->is_view) return BK_OK;
   const long long nblk = (A->n + 255) / 256;
   int* dstat = (int*)(h->counters + 8);
   auto drop = [&]() {

@@ -395,6 +395,192 @@ struct bk_op_cg_xp {
   __device__ void epilogue(const double*) const {}
 };
 
+// ---- Jacobi-preconditioned CG (M = diag(A)^-1, applied as r / d like the reference's `M = lambda r: r / d`) ------
+// _cg_solve with M (:820-853): z = M r ; gamma = r.z ; the stop test uses rs = r.r (:838) ; p = z + beta p.
+// z is never stored: K2 forms it on the fly for r.z, K3 again for the p-update (reading d once more costs one
+// vector pass; storing and re-reading z would cost two).
+template <typename T>
+struct bk_op_pcg_init {  // p0 = z0 = r0 / d ; sums: [0] r0.z0  [1] r0.r0    (:821-826)
+  static constexpr int R = 2;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> r, d;
+  };
+  const T* r;
+  const T* d;
+  T* p;
+  bk_dev_state* st;
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.r = bk_ld<T, W>(r + i);
+    in.d = bk_ld<T, W>(d + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx&, double (&acc)[2]) const {
+    bk_vec<T, W> z;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      z.v[j] = in.r.v[j] / in.d.v[j];
+      acc[0] += (double)in.r.v[j] * (double)z.v[j];
+      acc[1] += (double)in.r.v[j] * (double)in.r.v[j];
+    }
+    bk_st<T, W>(p + i, z);
+  }
+  __device__ void epilogue(const double* s) const {  // first stop test (:841) — atol2 was set by the b.b reduction
+    st->gamma = s[0];
+    st->rs = s[1];
+    if (st->maxiter <= 0) {
+      st->done = 1;
+      st->status = BK_ST_MAXITER;
+    }
+    if (s[1] <= st->atol2) {
+      st->done = 1;
+      st->status = BK_ST_CONVERGED;
+    }
+  }
+};
+
+template <typename T>
+struct bk_op_pcg_r {  // r -= alpha Ap ; z = r / d ; sums: [0] r.z  [1] r.r    (:847-850, :838)
+  static constexpr int R = 2;
+  struct Ctx {
+    T alpha;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> ap, r, d;
+  };
+  const T* ap;
+  T* r;
+  const T* d;
+  bk_dev_state* st;
+  __device__ bool skip() const {
+    if (st->done == 0) return false;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->just_done = 0;
+    return true;
+  }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.alpha = static_cast<T>(st->alpha);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.ap = bk_ld<T, W>(ap + i);
+    in.r = bk_ld<T, W>(r + i);
+    in.d = bk_ld<T, W>(d + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&acc)[2]) const {
+    bk_vec<T, W> ro;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      ro.v[j] = bk_sub(in.r.v[j], bk_mul(c.alpha, in.ap.v[j]));
+      const T z = ro.v[j] / in.d.v[j];
+      acc[0] += (double)ro.v[j] * (double)z;
+      acc[1] += (double)ro.v[j] * (double)ro.v[j];
+    }
+    bk_st<T, W>(r + i, ro);
+  }
+  __device__ void epilogue(const double* s) const {
+    const double gamma_new = s[0];
+    st->beta = gamma_new / st->gamma;
+    st->gamma = gamma_new;
+    st->rs = s[1];
+    const long long k = st->k + 1;
+    st->k = k;
+    if (k >= st->maxiter) {
+      st->done = 1;
+      st->just_done = 1;
+      st->status = BK_ST_MAXITER;
+    }
+    if (s[1] <= st->atol2) {
+      st->done = 1;
+      st->just_done = 1;
+      st->status = BK_ST_CONVERGED;
+    }
+  }
+};
+
+template <typename T>
+struct bk_op_pcg_xp {  // x += alpha p ; p = r / d + beta p    (:846, :852)
+  static constexpr int R = 0;
+  struct Ctx {
+    T alpha, beta;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> x, p, r, d;
+  };
+  T* x;
+  T* p;
+  const T* r;
+  const T* d;
+  const bk_dev_state* st;
+  __device__ bool skip() const { return st->done != 0 && st->just_done == 0; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.alpha = static_cast<T>(st->alpha);
+    c.beta = static_cast<T>(st->beta);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.x = bk_ld<T, W>(x + i);
+    in.p = bk_ld<T, W>(p + i);
+    in.r = bk_ld<T, W>(r + i);
+    in.d = bk_ld<T, W>(d + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
+    bk_vec<T, W> xo, po;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      xo.v[j] = bk_add(in.x.v[j], bk_mul(c.alpha, in.p.v[j]));
+      po.v[j] = bk_add(in.r.v[j] / in.d.v[j], bk_mul(c.beta, in.p.v[j]));
+    }
+    bk_st<T, W>(x + i, xo);
+    bk_st<T, W>(p + i, po);
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
+template <typename T, typename Epi>
+struct bk_op_scaled_sq {  // sum (t / d)^2 — the final ||M (b - A x)||^2 of _isolve (:1008)
+  static constexpr int R = 1;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> t, d;
+  };
+  const T* t;
+  const T* d;
+  Epi epi;
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.t = bk_ld<T, W>(t + i);
+    in.d = bk_ld<T, W>(d + i);
+  }
+  template <int W>
+  __device__ void apply(long long, const In<W>& in, const Ctx&, double (&acc)[1]) const {
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const T z = in.t.v[j] / in.d.v[j];
+      acc[0] += (double)z * (double)z;
+    }
+  }
+  __device__ void epilogue(const double* s) const { epi(s); }
+};
+
 // ---- BiCGStab ----------------------------------------------------------------------------------
 // p = r + beta (p - omega q)                               (_bicgstab_solve :906-907)
 template <typename T>

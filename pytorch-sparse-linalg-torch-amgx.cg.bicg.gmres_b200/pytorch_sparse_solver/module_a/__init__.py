@@ -5,12 +5,14 @@ from .krylov import (
     cg_differentiable, bicgstab_differentiable, gmres_differentiable,
     LinearSolveFunction,
 )
+from .preconditioners import JacobiPreconditioner
 from .torch_tree_util import tree_leaves, tree_map, tree_flatten, tree_unflatten, Partial
 
 __all__ = [
     'cg', 'bicgstab', 'gmres',
     'cg_differentiable', 'bicgstab_differentiable', 'gmres_differentiable',
     'LinearSolveFunction',
+    'JacobiPreconditioner',   # addition: built-in M that keeps cg() on the device
     'tree_leaves', 'tree_map', 'tree_flatten', 'tree_unflatten', 'Partial',
 ]
 

@@ -28,6 +28,7 @@ from typing import Any, Callable, Optional, Tuple, Union
 import torch
 
 from .. import _native
+from .preconditioners import JacobiPreconditioner
 from .torch_tree_util import tree_leaves
 
 __all__ = [
@@ -73,9 +74,11 @@ def _check_x0(b, x0):
             raise ValueError(f'arrays in x0 and b must have matching shapes: {xl.shape} vs {bl.shape}')
 
 
-def _route(A, b, x0, M) -> str:
+def _route(A, b, x0, M, native_M: bool = False) -> str:
+    """native_M: the solver has a device implementation for a built-in preconditioner object (cg + Jacobi)."""
     kind = _check_operator(A)
-    if kind == "callable" or M is not None or not isinstance(b, torch.Tensor):
+    builtin = native_M and isinstance(M, JacobiPreconditioner) and kind == "tensor" and A.is_cuda
+    if kind == "callable" or (M is not None and not builtin) or not isinstance(b, torch.Tensor):
         return "generic"
     if b.ndim != 1 or b.shape[0] != A.shape[0]:
         raise ValueError(f"b must be a vector of length {A.shape[0]}, got shape {tuple(b.shape)}")
@@ -124,11 +127,13 @@ def _gmres_effective_tolerances(tol: float, atol: float, size: int, device_type:
 # --------------------------------------------------------------------------------------------------
 def _solve_core(name: str, A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor], tol: float, atol: float,
                 maxiter: Optional[int], restart: int = 20, solve_method: str = 'batched',
-                transpose: bool = False) -> Tuple[torch.Tensor, int]:
+                transpose: bool = False, precond=None) -> Tuple[torch.Tensor, int]:
     """Run one solver on (A or A^T).  Returns (x, info) with x of the work dtype on b's device."""
     global last_result
     route = "native" if A.is_cuda else "host"
     wdt = _work_dtype(A, b)
+    if precond is not None and route != "native":
+        raise _native.NativeLibraryError("built-in preconditioners run on the native CUDA route only")
     if name == "gmres":
         if solve_method == 'incremental':
             method = _native.BK_GMRES_INCREMENTAL
@@ -144,7 +149,9 @@ def _solve_core(name: str, A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.
             mat = _native.register_matrix(A, wdt)
             if transpose:
                 mat = mat.transpose()
-            if name == "cg":
+            if name == "cg" and precond is not None:   # diag(A^T) == diag(A): the adjoint solve reuses M (:1079-1084)
+                x, res = mat.cg_jacobi(precond.diagonal(wdt, bw.device), bw, x0w, tol, atol, maxiter)
+            elif name == "cg":
                 x, res = mat.cg(bw, x0w, tol, atol, maxiter)
             elif name == "bicgstab":
                 x, res = mat.bicgstab(bw, x0w, tol, atol, maxiter)
@@ -178,25 +185,25 @@ class _ImplicitAdjoint(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, A, b, x, name, x0, tol, atol, restart, maxiter, solve_method):
+    def forward(ctx, A, b, x, name, x0, tol, atol, restart, maxiter, solve_method, precond=None):
         ctx.A = A
         ctx.x = x.detach()
-        ctx.meta = (name, x0, tol, atol, restart, maxiter, solve_method)
+        ctx.meta = (name, x0, tol, atol, restart, maxiter, solve_method, precond)
         return x.clone()
 
     @staticmethod
     def backward(ctx, grad_output):
-        name, x0, tol, atol, restart, maxiter, solve_method = ctx.meta
+        name, x0, tol, atol, restart, maxiter, solve_method, precond = ctx.meta
         grad_b = grad_A = None
         want_A = GRAD_WRT_A and ctx.needs_input_grad[0]
         if ctx.needs_input_grad[1] or want_A:
             g, _ = _solve_core(name, ctx.A, grad_output.contiguous(), x0, tol, atol, maxiter, restart, solve_method,
-                               transpose=True)
+                               transpose=True, precond=precond)
             if ctx.needs_input_grad[1]:
                 grad_b = g.to(grad_output.dtype)
             if want_A:
                 grad_A = _grad_wrt_matrix(ctx.A, g, ctx.x)
-        return (grad_A, grad_b) + (None,) * 8
+        return (grad_A, grad_b) + (None,) * 9
 
 
 def _grad_wrt_matrix(A: torch.Tensor, g: torch.Tensor, x: torch.Tensor) -> Optional[torch.Tensor]:
@@ -216,9 +223,9 @@ def _grad_wrt_matrix(A: torch.Tensor, g: torch.Tensor, x: torch.Tensor) -> Optio
         return torch.sparse_coo_tensor(A._indices(), vals, A.shape).coalesce()
 
 
-def _finish(name, A, b, x, info, x0, tol, atol, restart, maxiter, solve_method):
+def _finish(name, A, b, x, info, x0, tol, atol, restart, maxiter, solve_method, precond=None):
     if _use_implicit_diff(A, b):
-        x = _ImplicitAdjoint.apply(A, b, x, name, x0, tol, atol, restart, maxiter, solve_method)
+        x = _ImplicitAdjoint.apply(A, b, x, name, x0, tol, atol, restart, maxiter, solve_method, precond)
     return x, info
 
 
@@ -231,14 +238,14 @@ def cg(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any] =
     """Conjugate gradient for hermitian positive definite A.  Same contract as reference cg (:1019-1088):
     returns (x, info), x fp64 (fp32 when A and b are both fp32), info 0 if ||b - A x|| <= max(tol*||b||, atol)
     else -1; gradients w.r.t. b by implicit differentiation with a second (transposed) solve."""
-    route = _route(A, b, x0, M)
+    route = _route(A, b, x0, M, native_M=True)
     if route == "generic":
         from .generic import generic_cg
         return generic_cg(A, b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M)
     if x0 is not None:
         _check_x0(b, x0)
-    x, info = _solve_core("cg", A, b, x0, tol, atol, maxiter)
-    return _finish("cg", A, b, x, info, x0, tol, atol, 20, maxiter, 'batched')
+    x, info = _solve_core("cg", A, b, x0, tol, atol, maxiter, precond=M)
+    return _finish("cg", A, b, x, info, x0, tol, atol, 20, maxiter, 'batched', precond=M)
 
 
 def bicgstab(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any] = None, *, tol: float = 1e-5,

@@ -66,6 +66,30 @@ def poisson3d_csr(n: int, **kw) -> torch.Tensor:
     return stencil3d_csr(n, **kw)
 
 
+def scaled_poisson3d_csr(n: int, seed: int = 7, spread: float = 3.0, **kw) -> torch.Tensor:
+    """S A S with A = P3D-n and S = diag(10^(spread * u)), u ~ U(-0.5, 0.5) (CPU generator, seeded): SPD, same
+    sparsity, strongly varying diagonal — the textbook case for a Jacobi preconditioner."""
+    A = stencil3d_csr(n, **kw)
+    N = A.shape[0]
+    u = torch.rand(N, dtype=torch.float64, generator=torch.Generator().manual_seed(seed)) - 0.5
+    sc = torch.pow(torch.tensor(10.0, dtype=torch.float64), spread * u).to(A.device)
+    crow, col = A.crow_indices(), A.col_indices()
+    rows = torch.repeat_interleave(torch.arange(N, device=A.device), crow[1:] - crow[:-1])
+    vals = (A.values().double() * sc[rows] * sc[col.long()]).to(A.values().dtype)
+    return torch.sparse_csr_tensor(crow, col, vals, size=(N, N))
+
+
+def csr_diagonal(A: torch.Tensor) -> torch.Tensor:
+    """diag(A) of a CSR tensor as a dense vector (set-up helper for tests / fixtures)."""
+    N = A.shape[0]
+    crow, col = A.crow_indices(), A.col_indices()
+    rows = torch.repeat_interleave(torch.arange(N, device=A.device), crow[1:] - crow[:-1])
+    d = torch.zeros(N, dtype=A.values().dtype, device=A.device)
+    m = rows == col
+    d.index_add_(0, rows[m], A.values()[m])
+    return d
+
+
 def convdiff3d_csr(n: int, gamma=(1.0, 0.5, 0.25), **kw) -> torch.Tensor:
     """CD3D-n: first-order upwind convection-diffusion, non-symmetric M-matrix."""
     g = gamma

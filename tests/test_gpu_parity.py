@@ -279,6 +279,8 @@ def _solve_case(ma, name, manifest, idx=torch.int64, **override):
     x0 = data["x0"].cuda() if "x0" in data else None
     kw = dict(entry["kwargs"])
     kw.update(override)
+    if entry.get("jacobi") and "M" not in kw:
+        kw["M"] = ma.JacobiPreconditioner(A)     # built-in M: stays on the native path (bk_cg_jacobi)
     x, info = getattr(ma, entry["kind"])(A, b.cuda(), x0, **kw)
     return entry, data, x, info
 
@@ -725,3 +727,59 @@ def test_c_abi_argument_validation_on_gpu():
     assert lib.bk_gmres(h.ptr, m.ptr, b.data_ptr(), x.data_ptr(), 0, 1e-8, 0.0, 1000, -1, 0, C.byref(res), s) == -4  # > 256
     assert lib.bk_gmres(h.ptr, m.ptr, b.data_ptr(), x.data_ptr(), 0, 1e-8, 0.0, 10, -1, 5, C.byref(res), s) == -1   # method
     assert lib.bk_spmv(h.ptr, m.ptr, b.data_ptr(), b.data_ptr(), s) == -1                                        # aliasing
+
+
+# --------------------------------------------------------------------------------------------------
+# built-in Jacobi preconditioner: device PCG vs the reference run with M = lambda r: r / d
+# --------------------------------------------------------------------------------------------------
+def test_jacobi_pcg_routes_and_autograd(ma, manifest):
+    """cg(M=JacobiPreconditioner) stays native; any other M and any other solver take the generic route with the
+    same numbers; the adjoint solve reuses M (reference :1079-1084)."""
+    from pytorch_sparse_solver import problems
+    from pytorch_sparse_solver.module_a import krylov
+    entry = manifest["cases"]["cg_sp3d12_jacobi"]
+    data = load_case("cg_sp3d12_jacobi")
+    A = build_matrix(entry["gen"], device="cuda")
+    b = data["b"].cuda()
+    M = ma.JacobiPreconditioner(A)
+    d = problems.csr_diagonal(A)
+    assert torch.equal(M.d, d), "bk_csr_diagonal"
+    x, info = ma.cg(A, b, tol=1e-10, M=M)
+    assert krylov.last_result["route"] == "native" and info == 0
+    assert abs(krylov.last_result["iterations"] - entry["iterations"]) <= 2
+    assert rel_diff(x, data["x"]) <= FP64_TOL
+    xg, infog = ma.cg(A, b, tol=1e-10, M=lambda r: r / d)            # user lambda: generic route
+    assert infog == 0 and rel_diff(xg, data["x"]) <= FP64_TOL
+    xb, infob = ma.bicgstab(A, b, tol=1e-10, M=M)                    # other solvers: M is just a callable
+    assert infob == 0 and rel_diff(xb, data["x"]) <= 1e-5   # ill-conditioned system: x follows the residual loosely
+    # dense and COO inputs build the same preconditioner
+    assert torch.equal(ma.JacobiPreconditioner(A.to_dense()).d, d)
+    assert torch.equal(ma.JacobiPreconditioner(A.to_sparse_coo()).d, d)
+    # gradient w.r.t. b through the preconditioned adjoint solve == A^-T (2 x)
+    b1 = b.clone().requires_grad_(True)
+    x1, _ = ma.cg(A, b1, tol=1e-12, M=M)
+    (x1 ** 2).sum().backward()
+    Ad = A.to_dense()
+    g_exact = torch.linalg.solve(Ad.T, 2.0 * torch.linalg.solve(Ad, b))
+    assert rel_diff(b1.grad, g_exact) <= 1e-8
+    with pytest.raises(ValueError):
+        ma.JacobiPreconditioner(torch.zeros(3, 3, device="cuda"))
+
+
+def test_jacobi_pcg_edge_cases(ma):
+    from pytorch_sparse_solver.module_a import krylov
+    A = build_matrix(dict(matrix="scaled_poisson3d", n=6), device="cuda")
+    M = ma.JacobiPreconditioner(A)
+    z = torch.zeros(A.shape[0], dtype=torch.float64, device="cuda")
+    x, info = ma.cg(A, z, M=M)
+    assert info == 0 and float(x.abs().max()) == 0.0 and krylov.last_result["iterations"] == 0
+    b = torch.ones(A.shape[0], dtype=torch.float64, device="cuda")
+    x5, info5 = ma.cg(A, b, tol=0.0, atol=0.0, maxiter=5, M=M)
+    assert info5 == -1 and krylov.last_result["iterations"] == 5
+    x5b, _ = ma.cg(A, b, tol=0.0, atol=0.0, maxiter=5, M=M)
+    assert torch.equal(x5, x5b)
+    # fp32 native path
+    A32 = torch.sparse_csr_tensor(A.crow_indices(), A.col_indices(), A.values().float(), size=A.shape)
+    x32, info32 = ma.cg(A32, b.float(), tol=1e-5, M=ma.JacobiPreconditioner(A32))
+    x64, _ = ma.cg(A, b, tol=1e-10, M=M)
+    assert info32 == 0 and x32.dtype == torch.float32 and rel_diff(x32, x64) <= 1e-4

@@ -35,7 +35,12 @@ def test_oracle_matches_reference_golden(name, manifest):
         else:
             b = torch.ones(n, dtype=torch.float64)
     x0 = data.get("x0")
-    x, info, stats = getattr(orc, entry["kind"])(A, b, x0, **entry["kwargs"])
+    kw = dict(entry["kwargs"])
+    if entry.get("jacobi"):
+        from pytorch_sparse_solver import problems
+        d = problems.csr_diagonal(A)
+        kw["M"] = lambda r: r / d
+    x, info, stats = getattr(orc, entry["kind"])(A, b, x0, **kw)
     assert info == entry["info"]
     assert stats["matvecs"] + 1 == entry["matvecs_ref"]
     assert stats["iterations"] == entry["iterations"]
