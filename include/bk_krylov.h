@@ -106,6 +106,7 @@ int bk_destroy(bk_handle* h);
  *   loop_mode      0 auto (= graph) | 1 plain stream launches | 2 CUDA graph of `chunk` flag-guarded iterations
  *   chunk          iterations per graph / poll (0 = sized for ~2 ms of GPU work)
  *   use_tma        1: short-row matrices use the TMA-staged row-stream SpMV (kernel 2/3), 0: LDG-staged (kernel 0)
+ *   dist_fuse_push 1: multi-GPU CG on the peer path folds the halo push into the p-update kernel when the partition allows it
  *   use_split      1: matrices with a short mean row but a few very long rows are run on a virtual-row view (kernel 4)
  *   use_compress   0: off | 1: stream column indices as 8-bit dictionary codes when the matrix allows it (kernel 3)
  *                  | 2 (default): first try 8-bit codes of (column - row, value) pairs (kernel 5), then kernel 3

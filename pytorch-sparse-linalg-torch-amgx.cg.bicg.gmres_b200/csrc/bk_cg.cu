@@ -570,9 +570,13 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
   }
   BK_TRY((sys.dot<T>(b, b, bk_epi_cg_init{st, has_x0}, 1, s)));
   BK_CUDA(cudaMemcpyAsync(p, r, vbytes, cudaMemcpyDeviceToDevice, s));
+  // peer path on slab-like partitions: K3 itself pushes the new p into the neighbours (no push kernel in the loop);
+  // p0 goes out here, guarded so that a solve that ends before its first iteration pushes nothing
+  const bool fuse_push = sys.can_fuse_push() && h->dist_fuse_push;
+  if (fuse_push) BK_TRY(sys.halo_begin<T>(p, 1, true, s));
 
   auto enqueue_iter = [&](cudaStream_t cs) -> int {
-    BK_TRY((sys.matvec<T, 0, 1>(p, ap, p, nullptr, 1, bk_epi_cg_pAp{st}, cs)));
+    BK_TRY((sys.matvec<T, 0, 1>(p, ap, p, nullptr, 1, bk_epi_cg_pAp{st}, cs, fuse_push)));
     {
       bk_op_cg_r<T> op;
       op.ap = ap;
@@ -581,7 +585,9 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
       op.snake = 0;
       BK_TRY(sys.ew<T>(op, true, 1, cs));
     }
-    {
+    if (fuse_push) {
+      BK_TRY(sys.cg_xp_push<T>(x, p, r, cs));
+    } else {
       bk_op_cg_xp<T> op;
       op.x = x;
       op.p = p;
@@ -596,7 +602,7 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
   const int chunk = bk_pick_chunk(h, bytes_iter, 8);
   const bool use_graph = h->loop_mode != BK_LOOP_STREAM;  // NCCL calls are captured into the iteration graph too
   uint64_t key[6] = {4 /*dist cg*/, sys.uid(), (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
-                     (uint64_t)sys.dtype() | ((uint64_t)chunk << 16),
+                     (uint64_t)sys.dtype() | ((uint64_t)fuse_push << 8) | ((uint64_t)chunk << 16),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   auto enqueue_chunk = [&](cudaStream_t cs) -> int {
     for (int it = 0; it < chunk; ++it) BK_TRY(enqueue_iter(cs));
@@ -614,7 +620,7 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->gamma;
-  res->kernel_launches = chunks * chunk * (sys.p2p ? 5 : 7) + 12;
+  res->kernel_launches = chunks * chunk * (sys.p2p ? (fuse_push ? 4 : 5) : 7) + 12;
   return sys.check_comm(fin, "bk_dist_cg");
 }
 

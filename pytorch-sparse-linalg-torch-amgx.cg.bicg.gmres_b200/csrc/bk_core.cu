@@ -68,6 +68,7 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->grid_mult_spmv = (int)bk_env_int("BK_GRID_MULT_SPMV", 4);
   h->tma_ctas = (int)bk_env_int("BK_TMA_CTAS", 4);
   h->pair_ctas = (int)bk_env_int("BK_PAIR_CTAS", 4);
+  h->dist_fuse_push = (int)bk_env_int("BK_DIST_FUSE_PUSH", 1);
   h->tma_stages = (int)bk_env_int("BK_TMA_STAGES", 0);
   h->use_tma = (int)bk_env_int("BK_SPMV_TMA", 1);
   h->dist_p2p = (int)bk_env_int("BK_DIST_P2P", 1);
@@ -154,6 +155,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "grid_mult")) return &h->grid_mult_spmv;
   if (!strcmp(key, "tma_ctas")) return &h->tma_ctas;
   if (!strcmp(key, "pair_ctas")) return &h->pair_ctas;
+  if (!strcmp(key, "dist_fuse_push")) return &h->dist_fuse_push;
   if (!strcmp(key, "tma_stages")) return &h->tma_stages;
   if (!strcmp(key, "use_tma")) return &h->use_tma;
   if (!strcmp(key, "dist_p2p")) return &h->dist_p2p;

@@ -225,6 +225,32 @@ extern "C" int bk_dist_p2p_connect(bk_dist* D, const void* handles, const int64_
     BK_CUDA(cudaMemcpy(D->d_remote_flag, rf, sizeof(void*) * np, cudaMemcpyHostToDevice));
     BK_CUDA(cudaMemcpy(D->d_peer_ranks, D->peer_ranks, sizeof(int) * np, cudaMemcpyHostToDevice));
   }
+  // fused push: possible when every neighbour's send list is one ascending contiguous index range
+  D->push_nranges = -1;
+  if (np <= BK_PUSH_MAXR && D->send_total > 0) {
+    int* idx_h = (int*)malloc(sizeof(int) * (size_t)D->send_total);
+    if (idx_h && cudaMemcpy(idx_h, D->send_idx, sizeof(int) * (size_t)D->send_total, cudaMemcpyDeviceToHost) ==
+                     cudaSuccess) {
+      bool ok = true;
+      int nr = 0;
+      for (int i = 0; i < np && ok; ++i) {
+        const long long c = D->send_counts[i];
+        if (c == 0) continue;
+        const int* seg_i = idx_h + seg[i];
+        for (long long k = 1; k < c && ok; ++k) ok = (seg_i[k] == seg_i[0] + (int)k);
+        D->push_lo[nr] = seg_i[0];
+        D->push_hi[nr] = seg_i[0] + c;
+        D->push_dst[nr] = rg[i];
+        ++nr;
+      }
+      if (ok) D->push_nranges = nr;
+    } else {
+      cudaGetLastError();
+    }
+    free(idx_h);
+  } else if (D->send_total == 0 && np <= BK_PUSH_MAXR) {
+    D->push_nranges = 0;
+  }
   D->p2p.P = D->nranks;
   D->p2p_enabled = 1;
   bk_graphs_invalidate(D->h);

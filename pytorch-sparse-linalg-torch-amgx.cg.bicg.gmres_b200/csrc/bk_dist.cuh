@@ -41,6 +41,7 @@ enum { BK_NCCL_SUM = 0, BK_NCCL_F32 = 7, BK_NCCL_F64 = 8 };
                                 g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");              \
   } while (0)
 
+#define BK_PUSH_MAXR 4
 #define BK_DIST_RED_DOUBLES 16  // [0..3] sums being all-reduced  [4] CG local partial  [8..9] local-block partials
 
 struct bk_dist {
@@ -70,6 +71,12 @@ struct bk_dist {
   void** d_remote_ghost;               // device [npeers]: where my entries land in each peer's ghost vector
   unsigned long long** d_remote_flag;  // device [npeers]: my arrival flag inside each peer's window
   int* d_peer_ranks;                   // device [npeers]
+  // fused push (peer path): when every neighbour's boundary entries form ONE contiguous index range (slab
+  // partitions), the kernel that PRODUCES a vector can store those entries straight into the neighbours' ghost
+  // vectors while it streams — no separate push kernel.  push_nranges < 0: pattern not contiguous, not available.
+  int push_nranges;
+  long long push_lo[BK_PUSH_MAXR], push_hi[BK_PUSH_MAXR];
+  void* push_dst[BK_PUSH_MAXR];
   double* red;                         // BK_DIST_RED_DOUBLES doubles
   bk_nccl_comm comm;
   cudaStream_t comm_stream;
@@ -207,6 +214,74 @@ bk_ghost_rows_kernel(const bk_ghost_args<T> ga, const bk_scratch sc, const doubl
   });
 }
 
+// CG's K3 (x += alpha p ; p = r + beta p, bk_op_cg_xp) with the halo push of the NEW p folded in: elements inside a
+// neighbour's range are also stored into that neighbour's ghost vector over NVLink while the kernel streams; the last
+// CTA publishes the arrival flags.  In the iteration that ended the solve (`done` just set) only x is still needed:
+// nothing is pushed, so pushes and halo waits stay paired on every rank.
+template <typename T>
+struct bk_push_ranges {
+  int nr;
+  long long lo[BK_PUSH_MAXR], hi[BK_PUSH_MAXR];
+  T* dst[BK_PUSH_MAXR];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(BK_BLOCK, 3)
+bk_cg_xp_push_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__ r, const long long n,
+                     const bk_dev_state* st, const bk_push_ranges<T> pr,
+                     unsigned long long* const* __restrict__ remote_flag, const int npeers, unsigned int* counters) {
+  const int done = st->done;
+  if (done != 0 && st->just_done == 0) return;
+  const bool push = (done == 0);
+  __shared__ int s_last;
+  const T alpha = static_cast<T>(st->alpha), beta = static_cast<T>(st->beta);
+  constexpr int W = bk_native_w<T>::value;
+  const long long npack = n / W;
+  const long long stride = (long long)gridDim.x * BK_BLOCK;
+  auto one = [&](long long i, T xv, T pv, T rv, T& xo, T& po) {
+    xo = bk_add(xv, bk_mul(alpha, pv));
+    po = bk_add(rv, bk_mul(beta, pv));
+    if (push) {
+#pragma unroll
+      for (int q = 0; q < BK_PUSH_MAXR; ++q)
+        if (q < pr.nr && i >= pr.lo[q] && i < pr.hi[q]) pr.dst[q][i - pr.lo[q]] = po;
+    }
+  };
+  for (long long k = (long long)blockIdx.x * BK_BLOCK + threadIdx.x; k < npack; k += stride) {
+    const long long i = k * W;
+    const bk_vec<T, W> xv = bk_ld<T, W>(x + i), pv = bk_ld<T, W>(p + i), rv = bk_ld<T, W>(r + i);
+    bk_vec<T, W> xo, po;
+#pragma unroll
+    for (int j = 0; j < W; ++j) one(i + j, xv.v[j], pv.v[j], rv.v[j], xo.v[j], po.v[j]);
+    bk_st<T, W>(x + i, xo);
+    bk_st<T, W>(p + i, po);
+  }
+  {
+    const long long t = npack * W + (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
+    if (t < n) {
+      T xo, po;
+      one(t, x[t], p[t], r[t], xo, po);
+      x[t] = xo;
+      p[t] = po;
+    }
+  }
+  if (!push) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(&counters[3], gridDim.x - 1);
+    s_last = (t == gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    const unsigned int seq = counters[1] + 1u;
+    if (threadIdx.x < npeers) bk_st_release_sys_u64(remote_flag[threadIdx.x], (unsigned long long)seq);
+    __syncthreads();
+    if (threadIdx.x == 0) counters[1] = seq;
+  }
+}
+
 // ---- the multi-GPU "system" ----------------------------------------------------------------------------------
 struct bk_sys_dist {
   static constexpr bool kDist = true;
@@ -316,8 +391,10 @@ struct bk_sys_dist {
     return ghost_rows<T, 0, 0>(y, nullptr, 0, false, bk_epi_none(), cs);
   }
 
+  // halo_pushed: the kernel that produced x already stored the boundary entries into the neighbours (fused push)
   template <typename T, int MODE, int DOTS, typename Epi>
-  int matvec(const void* x, void* y, const void* w, const void* b, int guard, Epi epi, cudaStream_t cs) const {
+  int matvec(const void* x, void* y, const void* w, const void* b, int guard, Epi epi, cudaStream_t cs,
+             bool halo_pushed = false) const {
     static_assert(DOTS != 0, "distributed solver matvecs always carry a reduction");
     static_assert(MODE == 0 || DOTS == 2, "residual matvecs carry ||y||^2 only");
     // A residual's norm is tiny next to the pieces it is assembled from, so correcting the local block's ||y||^2
@@ -325,7 +402,7 @@ struct bk_sys_dist {
     constexpr int KD = (MODE == 1) ? 0 : DOTS;
     constexpr int R = bk_ndots<KD>::value;
     bk_dev_state* st = h->st;
-    BK_TRY(halo_begin<T>(x, guard, p2p, cs));
+    if (!halo_pushed) BK_TRY(halo_begin<T>(x, guard, p2p, cs));
     {  // local block (overlaps the exchange)
       bk_spmv_args a = bk_spmv_base(D->Aloc, st);
       a.x = x;
@@ -382,6 +459,24 @@ struct bk_sys_dist {
     op.y = (const T*)b;
     op.epi = epi;
     return ew<T>(op, bk_aligned16(a) && bk_aligned16(b), slot, cs);
+  }
+
+  bool can_fuse_push() const { return p2p && D->npeers > 0 && D->push_nranges >= 0; }
+  template <typename T>
+  int cg_xp_push(T* x, T* p, const T* r, cudaStream_t cs) const {
+    bk_push_ranges<T> pr;
+    pr.nr = D->push_nranges;
+    for (int q = 0; q < BK_PUSH_MAXR; ++q) {
+      pr.lo[q] = q < pr.nr ? D->push_lo[q] : 0;
+      pr.hi[q] = q < pr.nr ? D->push_hi[q] : 0;
+      pr.dst[q] = q < pr.nr ? (T*)D->push_dst[q] : nullptr;
+    }
+    constexpr int NW = bk_native_w<T>::value;
+    const int grid = bk_grid_vec_n(h, n(), 2 * NW);
+    bk_cg_xp_push_kernel<T><<<grid, BK_BLOCK, 0, cs>>>(x, p, r, n(), h->st, pr, D->d_remote_flag, D->npeers,
+                                                      D->p2p.counters);
+    BK_KERNEL_CHECK();
+    return BK_OK;
   }
 
   int check_comm(const bk_dev_state* fin, const char* who) const {

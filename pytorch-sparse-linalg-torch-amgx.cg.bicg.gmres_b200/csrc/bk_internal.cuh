@@ -146,6 +146,7 @@ struct bk_handle {
   int grid_mult_spmv;  // CTAs/SM of SpMV kernels
   int tma_ctas;        // CTAs/SM of the TMA row-stream SpMV (2..4)
   int pair_ctas;       // CTAs/SM of the pair-coded SpMV (2..6)
+  int dist_fuse_push;  // multi-GPU CG, peer path: fold the halo push into the kernel that produces p (1)
   int tma_stages;      // 0 = fill shared memory, else cap on the pipeline depth
   int use_tma;         // allow the TMA row-stream kernel
   int prefetch_x;      // kernel 3: L2 bulk prefetch of the forward-diagonal x ranges

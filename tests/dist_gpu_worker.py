@@ -53,6 +53,21 @@ def main():
         assert torch.equal(x, x2), "dist cg must be bitwise reproducible"
     D.handle.set_option("loop_mode", 0)
     D.handle.set_option("dist_p2p", 1)
+    if D.p2p:   # halo push folded into the p-update kernel (default) vs the separate push kernel: same bits
+        xs = {}
+        for fuse in (1, 0, 1):
+            D.handle.set_option("dist_fuse_push", fuse)
+            xs[fuse], rf = D.cg(bg[sl].contiguous(), None, 1e-8, 0.0, None)
+            assert rf["info"] == 0 and rf["iterations"] == r["iterations"], (fuse, rf, r)
+        assert torch.equal(xs[0], xs[1]), "fused and separate halo push must give identical results"
+        D.handle.set_option("dist_fuse_push", 1)
+        # solves that end before / at the first iteration must leave the push/wait counters paired
+        xz, rz = D.cg(torch.zeros_like(bg[sl]), None, 1e-8, 0.0, None)
+        assert rz["info"] == 0 and rz["iterations"] == 0 and float(xz.abs().max()) == 0.0
+        x1, r1 = D.cg(bg[sl].contiguous(), None, 0.0, 0.0, 1)
+        assert r1["iterations"] == 1
+        xa, ra = D.cg(bg[sl].contiguous(), None, 1e-8, 0.0, None)
+        assert torch.equal(xa, xs[1]), "state after short solves"
     # fixed window + warm start
     x0 = xg * 0.01
     x_ref, r_ref = m.cg(bg, x0, 0.0, 0.0, 7)
