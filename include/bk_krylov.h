@@ -130,6 +130,17 @@ int bk_device_info(bk_handle* h, int32_t* num_sms, int64_t* l2_bytes, int64_t* m
 int bk_csr_create(bk_handle* h, int64_t n, int64_t nnz, const void* rowptr, const void* col,
                   int idx_bits, const void* val, int dtype, int copy, void* stream, bk_csr** out);
 int bk_csr_destroy(bk_csr* A);
+/* Other layouts -> the library's CSR, on the device, with the library owning all arrays (the
+ * reference's tests and LDC example pass DENSE matrices to _normalize_matvec, torch_sparse_linalg.py:176-208).
+ * bk_csr_from_dense: row-major n x n device matrix, row stride `ld` elements; entries != 0 are kept, columns ascending
+ *   (the structure of torch's A.to_sparse_csr()).  Two passes over the matrix: count, ordered compaction.
+ * bk_csr_from_coo: device triplets (rows, cols: int32 or int64 per idx_bits; vals), any order, duplicates allowed:
+ *   stably sorted by (row, col) and equal positions summed in input order (torch's coalesce()).
+ * in_dtype: dtype of the given values; dtype: dtype of the registered matrix (fp32 inputs may be widened). */
+int bk_csr_from_dense(bk_handle* h, int64_t n, const void* dense, int64_t ld, int in_dtype, int dtype, void* stream,
+                      bk_csr** out);
+int bk_csr_from_coo(bk_handle* h, int64_t n, int64_t nnz, const void* rows, const void* cols, int idx_bits,
+                    const void* val, int in_dtype, int dtype, void* stream, bk_csr** out);
 int bk_csr_get_info(const bk_csr* A, bk_csr_info* out);
 /* Cached transpose (CSC of A == CSR of A^T) built on the device by a stable LSD radix
  * sort on the column index — deterministic.  Replaces `A_matrix.T` in

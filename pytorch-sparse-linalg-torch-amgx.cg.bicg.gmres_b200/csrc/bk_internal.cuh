@@ -203,6 +203,10 @@ void bk_state_fill_tol(bk_dev_state* v, double tol, double atol);
 void bk_fill_result_isolve(const bk_dev_state* st, bk_result* res, int64_t matvecs);
 void bk_convert_i64_i32(bk_handle* h, const void* in, void* out, long long n, cudaStream_t s);
 int bk_exclusive_scan_u32(unsigned int* data, long long n, cudaStream_t s);
+int bk_sort_pairs_i32(bk_handle* h, int* k0, int* k1, int* v0, int* v1, long long n, int bits, cudaStream_t s,
+                      int** ks, int** vs);
+void bk_lower_bound_i32(bk_handle* h, const int* keys, long long count, long long n, int* out, cudaStream_t s);
+void bk_iota_i32(bk_handle* h, int* out, long long n, cudaStream_t s);
 #define BK_SPLIT_LEN 256
 int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s);
 int bk_solver_args_check(const char* who, bk_handle* h, const bk_csr* A, const void* b, void* x, bk_result* res);

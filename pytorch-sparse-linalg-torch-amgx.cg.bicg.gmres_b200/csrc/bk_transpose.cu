@@ -217,6 +217,51 @@ __global__ void bk_gather_transposed_kernel(const int* __restrict__ perm, const 
   }
 }
 
+// Stable LSD radix sort of (key, payload) int32 pairs on keys in [0, 2^bits).  Ping-pongs between the caller's two
+// buffer pairs; *ks / *vs point at the sorted keys / payloads on return (one of the two pairs).  Asynchronous on `s`.
+int bk_sort_pairs_i32(bk_handle* h, int* k0, int* k1, int* v0, int* v1, long long n, int bits, cudaStream_t s,
+                      int** ks, int** vs) {
+  *ks = k0;
+  *vs = v0;
+  if (n <= 0) return BK_OK;
+  const int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+  const long long hist_n = 256LL * ntiles;
+  const long long nchunks = (hist_n + SC_CHUNK - 1) / SC_CHUNK;
+  unsigned int *hist = nullptr, *sums = nullptr;
+  if (bk_pool_alloc((void**)&hist, sizeof(unsigned int) * (size_t)hist_n, s) != cudaSuccess ||
+      bk_pool_alloc((void**)&sums, sizeof(unsigned int) * (size_t)(nchunks + 1), s) != cudaSuccess) {
+    cudaGetLastError();
+    if (hist) bk_pool_free(hist);
+    return bk_fail(BK_ERR_ALLOC, "radix sort scratch allocation failed");
+  }
+  int *ki = k0, *ko = k1, *vi = v0, *vo = v1;
+  for (int shift = 0; shift < bits; shift += 8) {
+    bk_rs_hist_kernel<<<ntiles, BK_BLOCK, 0, s>>>(ki, n, shift, ntiles, hist);
+    bk_scan_sums_kernel<<<(unsigned)nchunks, BK_BLOCK, 0, s>>>(hist, hist_n, sums);
+    bk_scan_serial_kernel<<<1, BK_BLOCK, 0, s>>>(sums, nchunks);
+    bk_scan_apply_kernel<<<(unsigned)nchunks, BK_BLOCK, 0, s>>>(hist, hist_n, sums);
+    bk_rs_scatter_kernel<<<ntiles, BK_BLOCK, 0, s>>>(ki, vi, ko, vo, n, shift, ntiles, hist);
+    int* t = ki; ki = ko; ko = t;
+    t = vi; vi = vo; vo = t;
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(hist, s);
+  cudaFreeAsync(sums, s);
+  if (e != cudaSuccess) return bk_fail(BK_ERR_CUDA, "radix sort: %s", cudaGetErrorString(e));
+  *ks = ki;
+  *vs = vi;
+  return BK_OK;
+}
+
+// out[c] = first position in the ascending `keys` with key >= c, c = 0..n   (row pointers from sorted row ids)
+void bk_lower_bound_i32(bk_handle* h, const int* keys, long long count, long long n, int* out, cudaStream_t s) {
+  bk_lower_bound_kernel<<<h->num_sms * 8, 256, 0, s>>>(keys, count, n, out);
+}
+
+void bk_iota_i32(bk_handle* h, int* out, long long n, cudaStream_t s) {
+  bk_iota_kernel<<<h->num_sms * 8, 256, 0, s>>>(out, n);
+}
+
 int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s);  // bk_core.cu
 
 extern "C" int bk_csr_transpose(bk_handle* h, bk_csr* A, void* stream, bk_csr** out) {
@@ -238,17 +283,11 @@ extern "C" int bk_csr_transpose(bk_handle* h, bk_csr* A, void* stream, bk_csr** 
   const size_t vs = bk_dtype_size(A->dtype);
   const size_t nn = (size_t)(nnz > 0 ? nnz : 1);
   int *k0 = nullptr, *k1 = nullptr, *v0 = nullptr, *v1 = nullptr;
-  unsigned int *hist = nullptr, *sums = nullptr;
-  const int ntiles = (int)((nnz + RS_TILE - 1) / RS_TILE);
-  const long long hist_n = 256LL * (ntiles > 0 ? ntiles : 1);
-  const long long nchunks = (hist_n + SC_CHUNK - 1) / SC_CHUNK;
   auto cleanup = [&]() {
     if (k0) bk_pool_free(k0);
     if (k1) bk_pool_free(k1);
     if (v0) bk_pool_free(v0);
     if (v1) bk_pool_free(v1);
-    if (hist) bk_pool_free(hist);
-    if (sums) bk_pool_free(sums);
   };
   bool ok = bk_pool_alloc(&Tm->own_rowptr, sizeof(int) * (size_t)(n + 1), s) == cudaSuccess &&
             bk_pool_alloc(&Tm->own_col, sizeof(int) * nn, s) == cudaSuccess &&
@@ -256,9 +295,7 @@ extern "C" int bk_csr_transpose(bk_handle* h, bk_csr* A, void* stream, bk_csr** 
             bk_pool_alloc((void**)&k0, sizeof(int) * nn, s) == cudaSuccess &&
             bk_pool_alloc((void**)&k1, sizeof(int) * nn, s) == cudaSuccess &&
             bk_pool_alloc((void**)&v0, sizeof(int) * nn, s) == cudaSuccess &&
-            bk_pool_alloc((void**)&v1, sizeof(int) * nn, s) == cudaSuccess &&
-            bk_pool_alloc((void**)&hist, sizeof(unsigned int) * (size_t)hist_n, s) == cudaSuccess &&
-            bk_pool_alloc((void**)&sums, sizeof(unsigned int) * (size_t)(nchunks + 1), s) == cudaSuccess;
+            bk_pool_alloc((void**)&v1, sizeof(int) * nn, s) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
     cleanup();
@@ -271,15 +308,13 @@ extern "C" int bk_csr_transpose(bk_handle* h, bk_csr* A, void* stream, bk_csr** 
     bk_iota_kernel<<<g, 256, 0, s>>>(v0, nnz);
     int bits = 1;
     while ((1LL << bits) < n) ++bits;
-    int *ki = k0, *ko = k1, *vi = v0, *vo = v1;
-    for (int shift = 0; shift < bits; shift += 8) {
-      bk_rs_hist_kernel<<<ntiles, BK_BLOCK, 0, s>>>(ki, nnz, shift, ntiles, hist);
-      bk_scan_sums_kernel<<<(unsigned)nchunks, BK_BLOCK, 0, s>>>(hist, hist_n, sums);
-      bk_scan_serial_kernel<<<1, BK_BLOCK, 0, s>>>(sums, nchunks);
-      bk_scan_apply_kernel<<<(unsigned)nchunks, BK_BLOCK, 0, s>>>(hist, hist_n, sums);
-      bk_rs_scatter_kernel<<<ntiles, BK_BLOCK, 0, s>>>(ki, vi, ko, vo, nnz, shift, ntiles, hist);
-      int* t = ki; ki = ko; ko = t;
-      t = vi; vi = vo; vo = t;
+    int *ki = nullptr, *vi = nullptr;
+    int src = bk_sort_pairs_i32(h, k0, k1, v0, v1, nnz, bits, s, &ki, &vi);
+    if (src != BK_OK) {
+      cudaStreamSynchronize(s);
+      cleanup();
+      bk_csr_destroy(Tm);
+      return src;
     }
     // ki: sorted columns (= rows of A^T), vi: original positions
     bk_lower_bound_kernel<<<g, 256, 0, s>>>(ki, nnz, n, (int*)Tm->own_rowptr);

@@ -97,6 +97,9 @@ _SIGNATURES = {
     "bk_dist_spmv": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "bk_dist_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64,
                              C.POINTER(bk_result), _VP]),
+    "bk_csr_from_dense": (C.c_int, [_VP, C.c_int64, _VP, C.c_int64, C.c_int, C.c_int, _VP, C.POINTER(_VP)]),
+    "bk_csr_from_coo": (C.c_int, [_VP, C.c_int64, C.c_int64, _VP, _VP, C.c_int, _VP, C.c_int, C.c_int, _VP,
+                                  C.POINTER(_VP)]),
     "bk_cg_jacobi": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64,
                                C.POINTER(bk_result), _VP]),
     "bk_csr_diagonal": (C.c_int, [_VP, _VP, _VP, _VP]),
@@ -431,6 +434,44 @@ def _csr_components(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.
     return A.crow_indices(), A.col_indices(), A.values()
 
 
+def _ingest_native(A: torch.Tensor, dtype: torch.dtype) -> Optional[CsrMatrix]:
+    """dense / COO CUDA tensors -> CsrMatrix through the library's own conversion kernels (bk_csr_from_dense /
+    bk_csr_from_coo).  Returns None for layouts / dtypes those entry points do not take (handled via torch)."""
+    if A.layout not in (torch.strided, torch.sparse_coo) or A.dtype not in (torch.float64, torch.float32):
+        return None
+    if os.environ.get("BK_NATIVE_INGEST", "1") == "0":
+        return None
+    h = Handle.get(A.device)
+    n = int(A.shape[0])
+    p = _VP()
+    with torch.no_grad(), torch.cuda.device(A.device):
+        s = _stream_ptr(A.device)
+        if A.layout == torch.strided:
+            D = A.detach()
+            if D.stride(1) != 1 and n > 1:
+                D = D.contiguous()
+            ld = int(D.stride(0)) if n > 1 else max(n, 1)
+            if ld < n:
+                D, ld = D.contiguous(), n
+            _check(h.lib.bk_csr_from_dense(h.ptr, n, D.data_ptr(), ld, _dtype_code(D.dtype), _dtype_code(dtype), s,
+                                           C.byref(p)), "bk_csr_from_dense")
+            keep = (D,)
+        else:
+            idx = A.detach()._indices()
+            val = A.detach()._values().contiguous()
+            rows, cols = idx[0].contiguous(), idx[1].contiguous()
+            _check(h.lib.bk_csr_from_coo(h.ptr, n, int(val.numel()), rows.data_ptr(), cols.data_ptr(),
+                                         64 if rows.dtype == torch.int64 else 32, val.data_ptr(),
+                                         _dtype_code(val.dtype), _dtype_code(dtype), s, C.byref(p)), "bk_csr_from_coo")
+            keep = (rows, cols, val)
+        torch.cuda.current_stream(A.device).synchronize()
+    m = CsrMatrix._wrap(h, p, n, 0, dtype, A.device, keep)
+    m._owned = True
+    m._finalizer = weakref.finalize(m, CsrMatrix._destroy, h.lib, p)
+    m.nnz = int(m.info()["nnz"])
+    return m
+
+
 def register_matrix(A: torch.Tensor, dtype: torch.dtype = torch.float64) -> CsrMatrix:
     """Register a 2-D CUDA tensor with the library (cached per storage + version)."""
     if not A.is_cuda:
@@ -449,11 +490,13 @@ def register_matrix(A: torch.Tensor, dtype: torch.dtype = torch.float64) -> CsrM
     if hit is not None:
         _CACHE.move_to_end(key)
         return hit
-    with torch.no_grad():
-        crow, col, val = _csr_components(A.detach())
-        if val.dtype != dtype:
-            val = val.to(dtype)
-    m = CsrMatrix(Handle.get(A.device), crow, col, val, A.shape[0])
+    m = _ingest_native(A, dtype)
+    if m is None:
+        with torch.no_grad():
+            crow, col, val = _csr_components(A.detach())
+            if val.dtype != dtype:
+                val = val.to(dtype)
+        m = CsrMatrix(Handle.get(A.device), crow, col, val, A.shape[0])
     m._keep = m._keep + (A,)  # keep the source alive so the data_ptr key stays unique
     _CACHE[key] = m
     while len(_CACHE) > _CACHE_MAX:

@@ -783,3 +783,67 @@ def test_jacobi_pcg_edge_cases(ma):
     x32, info32 = ma.cg(A32, b.float(), tol=1e-5, M=ma.JacobiPreconditioner(A32))
     x64, _ = ma.cg(A, b, tol=1e-10, M=M)
     assert info32 == 0 and x32.dtype == torch.float32 and rel_diff(x32, x64) <= 1e-4
+
+
+# --------------------------------------------------------------------------------------------------
+# dense / COO ingestion by the library's own kernels against torch's conversions
+# --------------------------------------------------------------------------------------------------
+def _csr_triplet(m):
+    crow, col, val = m.arrays()
+    return crow.cpu().long(), col.cpu().long(), val.cpu()
+
+
+@pytest.mark.parametrize("n,density,dtype", [(1, 1.0, torch.float64), (37, 0.3, torch.float64), (300, 0.02, torch.float64),
+                                              (257, 1.0, torch.float32), (1000, 0.004, torch.float64)])
+def test_dense_ingestion_matches_torch(n, density, dtype):
+    from pytorch_sparse_solver import _native
+    g = torch.Generator().manual_seed(n)
+    D = torch.randn(n, n, dtype=dtype, generator=g)
+    D[torch.rand(n, n, generator=g) > density] = 0.0
+    if n > 30:
+        D[5, :] = 0.0                                   # an empty row
+    ref = D.to_sparse_csr()
+    _native.clear_cache()
+    m = _native.register_matrix(D.cuda(), dtype)
+    crow, col, val = _csr_triplet(m)
+    assert torch.equal(crow, ref.crow_indices()) and torch.equal(col, ref.col_indices())
+    assert torch.equal(val, ref.values())
+    # a non-contiguous view (transposed) and an fp32 matrix registered as fp64
+    mt = _native.register_matrix(D.cuda().t(), torch.float64)
+    rt = D.t().contiguous().double().to_sparse_csr()
+    crow, col, val = _csr_triplet(mt)
+    assert torch.equal(crow, rt.crow_indices()) and torch.equal(col, rt.col_indices()) and torch.equal(val, rt.values())
+    x = torch.randn(n, dtype=dtype, generator=g)
+    assert rel_diff(m.spmv(x.cuda()), D.double() @ x.double()) <= (1e-13 if dtype == torch.float64 else 1e-5)
+
+
+@pytest.mark.parametrize("n,nnz,dups", [(1, 1, False), (50, 400, True), (3000, 20000, True), (70000, 300000, False)])
+def test_coo_ingestion_matches_torch(n, nnz, dups):
+    from pytorch_sparse_solver import _native
+    g = torch.Generator().manual_seed(nnz)
+    rows = torch.randint(0, n, (nnz,), generator=g)
+    cols = torch.randint(0, n, (nnz,), generator=g)
+    if dups:                                            # force repeated positions, some cancelling exactly
+        rows[nnz // 2:] = rows[:nnz - nnz // 2]
+        cols[nnz // 2:] = cols[:nnz - nnz // 2]
+    vals = torch.randn(nnz, dtype=torch.float64, generator=g)
+    if dups:
+        vals[nnz // 2] = -vals[0]
+    C = torch.sparse_coo_tensor(torch.stack([rows, cols]), vals, (n, n))
+    ref = C.coalesce().to_sparse_csr()
+    _native.clear_cache()
+    m = _native.register_matrix(C.cuda())
+    crow, col, val = _csr_triplet(m)
+    assert torch.equal(crow, ref.crow_indices()) and torch.equal(col, ref.col_indices())
+    assert rel_diff(val, ref.values()) <= 1e-15 and m.nnz == ref.values().numel()
+    x = torch.randn(n, dtype=torch.float64, generator=g)
+    assert rel_diff(m.spmv(x.cuda()), torch.sparse.mm(C.coalesce(), x[:, None])[:, 0]) <= 1e-12
+    # bad index -> error, not a crash
+    badC = torch.sparse_coo_tensor(torch.tensor([[0], [0]]), torch.ones(1, dtype=torch.float64), (1, 1)).cuda()
+    bad_idx = badC._indices().clone()
+    h = _native.Handle.get(torch.device("cuda"))
+    p = _native._VP()
+    bad_idx[0, 0] = 7
+    rc = h.lib.bk_csr_from_coo(h.ptr, 1, 1, bad_idx[0].contiguous().data_ptr(), bad_idx[1].contiguous().data_ptr(), 64,
+                               badC._values().data_ptr(), _native.BK_F64, _native.BK_F64, None, _native.C.byref(p))
+    assert rc == -1
