@@ -308,7 +308,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    if world > 1 or args.gpus > 1 or args.strong:
+    if world > 1 or args.gpus > 1 or args.strong or os.environ.get("BK_BENCH_FORCE_DIST"):  # env: 1-rank run of the multi-GPU path
         if "RANK" not in os.environ:
             raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
         run_dist(args, rank, world)

@@ -582,7 +582,7 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
       op.ap = ap;
       op.r = r;
       op.st = st;
-      op.snake = 0;
+      op.snake = sys.snake ? 1 : 0;
       BK_TRY(sys.ew<T>(op, true, 1, cs));
     }
     if (fuse_push) {
@@ -593,7 +593,7 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
       op.p = p;
       op.r = r;
       op.st = st;
-      op.snake = 0;
+      op.snake = sys.snake ? 1 : 0;
       BK_TRY(sys.ew<T>(op, true, 2, cs));
     }
     return BK_OK;
@@ -602,7 +602,7 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
   const int chunk = bk_pick_chunk(h, bytes_iter, 8);
   const bool use_graph = h->loop_mode != BK_LOOP_STREAM;  // NCCL calls are captured into the iteration graph too
   uint64_t key[6] = {4 /*dist cg*/, sys.uid(), (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
-                     (uint64_t)sys.dtype() | ((uint64_t)fuse_push << 8) | ((uint64_t)chunk << 16),
+                     (uint64_t)sys.dtype() | ((uint64_t)fuse_push << 8) | ((uint64_t)sys.snake << 9) | ((uint64_t)chunk << 16),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   auto enqueue_chunk = [&](cudaStream_t cs) -> int {
     for (int it = 0; it < chunk; ++it) BK_TRY(enqueue_iter(cs));
@@ -630,7 +630,7 @@ extern "C" int bk_dist_cg(bk_handle* h, bk_dist* D, const void* b_local, void* x
   if (D->n_local > 0 && (!b_local || !x_local)) return bk_fail(BK_ERR_ARG, "bk_dist_cg: null vector");
   memset(result, 0, sizeof(*result));
   BK_CUDA(cudaSetDevice(h->device));
-  const bk_sys_dist sys{h, D, D->p2p_enabled && h->dist_p2p, n_global};
+  const bk_sys_dist sys{h, D, D->p2p_enabled && h->dist_p2p, n_global, h->snake != 0};
   if (D->dtype == BK_F64)
     return bk_dist_cg_t<double>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
   return bk_dist_cg_t<float>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);

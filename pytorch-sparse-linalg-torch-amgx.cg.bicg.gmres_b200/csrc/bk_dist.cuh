@@ -229,10 +229,12 @@ template <typename T>
 __global__ void __launch_bounds__(BK_BLOCK, 3)
 bk_cg_xp_push_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__ r, const long long n,
                      const bk_dev_state* st, const bk_push_ranges<T> pr,
-                     unsigned long long* const* __restrict__ remote_flag, const int npeers, unsigned int* counters) {
+                     unsigned long long* const* __restrict__ remote_flag, const int npeers, unsigned int* counters,
+                     const int snake) {
   const int done = st->done;
   if (done != 0 && st->just_done == 0) return;
   const bool push = (done == 0);
+  const bool rev = snake && ((st->parity & 1) == 0);  // same rule as bk_op_cg_xp::reverse()
   __shared__ int s_last;
   const T alpha = static_cast<T>(st->alpha), beta = static_cast<T>(st->beta);
   constexpr int W = bk_native_w<T>::value;
@@ -248,7 +250,7 @@ bk_cg_xp_push_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__
     }
   };
   for (long long k = (long long)blockIdx.x * BK_BLOCK + threadIdx.x; k < npack; k += stride) {
-    const long long i = k * W;
+    const long long i = (rev ? (npack - 1 - k) : k) * W;
     const bk_vec<T, W> xv = bk_ld<T, W>(x + i), pv = bk_ld<T, W>(p + i), rv = bk_ld<T, W>(r + i);
     bk_vec<T, W> xo, po;
 #pragma unroll
@@ -289,6 +291,7 @@ struct bk_sys_dist {
   bk_dist* D;
   bool p2p;
   int64_t n_glob;
+  bool snake = false;  // CG: alternate the sweep direction of consecutive kernels (st->parity) for L2 reuse
 
   long long n() const { return D->n_local; }
   long long n_global() const { return n_glob; }
@@ -355,7 +358,7 @@ struct bk_sys_dist {
     if (!peer && D->npeers > 0) BK_CUDA(cudaStreamWaitEvent(cs, D->ev_halo, 0));
     int g = (int)((D->n_brows + BK_BLOCK - 1) / BK_BLOCK);
     if (g < 1) g = 1;
-    if (g > h->num_sms * 4) g = h->num_sms * 4;
+    if (g > h->num_sms * 8) g = h->num_sms * 8;  // one or two rows per thread: the kernel is a chain of dependent loads
     bk_ghost_args<T> ga;
     ga.brow_ids = D->brow_ids;
     ga.rowptr = D->gh_rowptr;
@@ -410,6 +413,7 @@ struct bk_sys_dist {
       a.w = w;
       a.b = b;
       a.guard = guard;
+      a.use_parity = snake ? 1 : 0;
       if constexpr (KD != 0) {
         bk_epi_store_n<R> store{D->red + 8};
         BK_TRY((bk_launch_spmv_t<T, MODE, KD, 0>(h, D->Aloc, a, bk_slot(h, 0), store, cs)));
@@ -474,7 +478,7 @@ struct bk_sys_dist {
     constexpr int NW = bk_native_w<T>::value;
     const int grid = bk_grid_vec_n(h, n(), 2 * NW);
     bk_cg_xp_push_kernel<T><<<grid, BK_BLOCK, 0, cs>>>(x, p, r, n(), h->st, pr, D->d_remote_flag, D->npeers,
-                                                      D->p2p.counters);
+                                                      D->p2p.counters, snake ? 1 : 0);
     BK_KERNEL_CHECK();
     return BK_OK;
   }
