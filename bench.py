@@ -9,17 +9,20 @@ their device time (CUDA events), with the matrix and b already resident in HBM. 
 iteration) are far larger than L2, so no explicit L2 flush is needed between steps.
 
 Extra objects on the JSON line:
-  roofline      the dominant kernel (SpMV fused with p.Ap): algorithmic bytes per launch / its mean launch time,
-                timed live with CUDA events in a loop of back-to-back launches; peak = MEASURED_PEAKS.json hbm_gbs.
+  roofline      the dominant kernel (SpMV fused with p.Ap): ALGORITHMIC (CSR) bytes per launch / its mean launch time,
+                timed live with CUDA events in a loop of back-to-back launches; peak = MEASURED_PEAKS.json hbm_gbs;
+                traffic = DRAM bytes per launch from the committed ncu capture (the coded SpMV kernels move far fewer
+                bytes than the CSR count, so frac can exceed 1).
   iteration     the whole CG iteration: algorithmic bytes per iteration * value, vs the same peak.
   e2e           the same solve through the host-buffer C-ABI entry (bk_solve_host): pinned HOST CSR arrays and b are
                 copied H2D, solved, x copied D2H, all inside the timed region.
   cpu_baseline  the oracle port of the reference (torch CPU, all host threads) on a bounded fixed-iteration window
                 of the same system.
 With --impl reference the oracle port itself is the thing timed (rank 0 only).
-For N > 1 (torchrun, one rank per GPU) the matrix is row-partitioned into N slabs of n^3 rows each (weak scaling:
-an N*n x n x n grid), halos exchanged over NCCL; value = N * global iterations/s, i.e. "n^3-row CG iterations
-per second" summed over ranks.
+For N > 1 (torchrun, one rank per GPU) the matrix is row-partitioned into N slabs of n^3 rows each (weak scaling;
+BASELINE configs[4] geometry: 2n x 2n planes, n/4 planes per GPU, so N = 8 is exactly the (2n)^3 system), halos and
+the dot-product all-reduces go through CUDA-IPC peer memory over NVLink (NCCL with BK_DIST_P2P=0); value = N * global
+iterations/s, i.e. "n^3-row CG iterations per second" summed over ranks.  --strong splits the SAME (2n)^3 system.
 """
 import argparse
 import json

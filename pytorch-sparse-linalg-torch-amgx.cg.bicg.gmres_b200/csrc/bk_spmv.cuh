@@ -2,23 +2,25 @@
 // the Krylov recurrences.  Replaces torch.matmul(CSR, v) (reference torch_sparse_linalg.py:191)
 // + the torch.vdot that consumes its result (:845 p.Ap, :910 rhat.q, :926-930 t.s/t.t).
 //
-// Two kernels, chosen per matrix from its row-length statistics (bk_csr_create):
+// Kernels, chosen per matrix at registration (bk_csr_finish_plan, bk_core.cu) from its row-length statistics and
+// from what its entries allow:
 //
-//  * row-stream (short rows, mean <= 32 nnz: stencils, FEM/FVM):  a warp owns 32 consecutive
-//    rows.  Their nnz range [rowptr[r0], rowptr[r0+32]) is ONE contiguous span of val/col, so the
-//    warp reads it fully coalesced with streaming (evict-first) loads, multiplies by the gathered
-//    x[col] (served by L1/L2: for a stencil the gathers are 7 contiguous runs) and parks the
-//    products in its private shared-memory strip; then lane l adds the products of row r0+l in
-//    CSR order.  No block barrier, only __syncwarp; rows longer than the strip are handled by
-//    sweeping the strip over the span.  HBM sees each matrix byte exactly once.
-//
-//  * sub-warp vector (long rows: dense-ish matrices the reference tests use): LPR lanes per row,
+//  * row-stream (short rows, mean <= 32 nnz: stencils, FEM/FVM):  a warp owns 32 consecutive rows.  Three stagings:
+//      - kernel 5, bk_spmv_pair.cuh: one byte per entry — a code of the entry's (column - row, value) pair, sliced-ELL
+//        stream, TMA-staged; for constant-coefficient stencils (every BASELINE config)
+//      - kernels 2 / 3, bk_spmv_tma.cuh: val/col (or val + 8-bit column codes) spans staged by 1-D TMA bulk copies
+//      - kernel 0, below: LDG-staged — the span [rowptr[r0], rowptr[r0+32]) of val/col is read fully coalesced with
+//        streaming loads, multiplied by the gathered x[col] and parked in the warp's shared-memory strip; lane l
+//        then adds the products of row r0+l in CSR order.  Serves misaligned arrays, rows too wide for a TMA stage
+//        and the small-system CG variant that forms p = r + beta p inside the gather.
+//  * sub-warp vector (kernel 1; long rows: the dense-ish matrices the reference tests use): LPR lanes per row,
 //    strided coalesced reads along the row, fixed shuffle tree.
+//  * kernel 4: matrices with a short mean row but a few very long rows run any of the above on a virtual-row view
+//    (rows cut at BK_SPLIT_LEN entries) followed by an ordered per-row reduction.
 //
-// Both are persistent (grid = SMs x k, blocked-cyclic over row blocks so the whole chip sweeps
-// one contiguous window of the matrix, which keeps the x-gather window L2 resident) and end in
-// bk_grid_reduce, whose last CTA runs the solver's scalar epilogue.  Summation order is fixed
-// => bitwise reproducible fp64.
+// All are persistent (grid = SMs x k, blocked-cyclic over row blocks so the whole chip sweeps one contiguous window
+// of the matrix, which keeps the x-gather window L2 resident) and end in bk_grid_reduce, whose last CTA runs the
+// solver's scalar epilogue.  Summation order is fixed => bitwise reproducible fp64; all stagings give the same bits.
 #pragma once
 
 #include "bk_internal.cuh"

@@ -188,6 +188,7 @@ struct bk_op_axpby {
 // ---- CG --------------------------------------------------------------------------------------
 // x += alpha p ; r -= alpha Ap ; gamma' = r.r          (_cg_solve :846-850)
 // epilogue: beta = gamma'/gamma, gamma = gamma', k += 1, stop test of :841 for the NEXT iteration.
+// (used by the small-system variant whose SpMV forms p = r + beta p on the fly; large systems use the cut below)
 template <typename T>
 struct bk_op_cg_update {
   static constexpr int R = 1;
@@ -246,44 +247,6 @@ struct bk_op_cg_update {
       st->status = BK_ST_CONVERGED;
     }
   }
-};
-
-// p = r + beta p                                           (_cg_solve :852)
-template <typename T>
-struct bk_op_xpay {
-  static constexpr int R = 0;
-  struct Ctx {
-    T beta;
-  };
-  template <int W>
-  struct In {
-    bk_vec<T, W> r, p;
-  };
-  const T* r;
-  T* p;
-  const bk_dev_state* st;
-  int snake;
-  __device__ bool skip() const { return st->done != 0; }
-  // parity was flipped by the update kernel's epilogue; sweep the same way as this iteration's SpMV
-  __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
-  __device__ Ctx prepare() const {
-    Ctx c;
-    c.beta = static_cast<T>(st->beta);
-    return c;
-  }
-  template <int W>
-  __device__ void load(long long i, In<W>& in) const {
-    in.r = bk_ld<T, W>(r + i);
-    in.p = bk_ld<T, W>(p + i);
-  }
-  template <int W>
-  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
-    bk_vec<T, W> o;
-#pragma unroll
-    for (int j = 0; j < W; ++j) o.v[j] = bk_add(in.r.v[j], bk_mul(c.beta, in.p.v[j]));
-    bk_st<T, W>(p + i, o);
-  }
-  __device__ void epilogue(const double*) const {}
 };
 
 // The same CG iteration cut differently (large systems): K2 touches only r, K3 updates x together with p — both read
