@@ -29,7 +29,7 @@ def t(fn, reps=3):
     return (time.perf_counter() - t0) / reps * 1e3
 
 
-for cmp_ in (1, 0):
+for cmp_ in (2, 1, 0):
     h.set_option("use_compress", cmp_)
 
     def reg():
@@ -42,9 +42,10 @@ val_h = A.values().cpu().pin_memory()
 b_h = b.cpu().pin_memory()
 nbytes = sum(x.numel() * x.element_size() for x in (crow_h, col_h, val_h, b_h))
 print(f"H2D of {nbytes/1e9:.2f} GB: {t(lambda: [x.to(dev, non_blocking=True) for x in (crow_h, col_h, val_h, b_h)]):8.2f} ms")
-for cmp_ in (1, 0):
+for cmp_ in (2, 1, 0):
     h.set_option("use_compress", cmp_)
     ms = t(lambda: _native.solve_host(_native.METHOD_CG, crow_h, col_h, val_h, b_h, None, 1e-8, 0.0, None))
+    _native.clear_cache()
     m = _native.register_matrix(A)
     ms_dev = t(lambda: m.cg(b, None, 1e-8, 0.0, None))
     print(f"use_compress={cmp_}: solve_host {ms:8.2f} ms ; device-resident solve {ms_dev:8.2f} ms")
