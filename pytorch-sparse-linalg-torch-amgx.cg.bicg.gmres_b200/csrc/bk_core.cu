@@ -113,6 +113,8 @@ extern "C" int bk_destroy(bk_handle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   bk_graphs_invalidate(h);
+  // h->dist_comm (NCCL) is deliberately not destroyed here: handles die at interpreter exit, when peers may already
+  // be gone, and ncclCommDestroy may then block; the driver reclaims it with the process
   if (h->partials) cudaFree(h->partials);
   if (h->counters) cudaFree(h->counters);
   if (h->st) cudaFree(h->st);

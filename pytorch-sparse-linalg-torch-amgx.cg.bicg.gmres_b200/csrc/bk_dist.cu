@@ -54,6 +54,11 @@ extern "C" int bk_dist_unique_id(void* id128) {
   return BK_OK;
 }
 
+void bk_dist_release_comm(bk_handle* h) {
+  if (h && h->dist_comm && g_nccl.CommDestroy) g_nccl.CommDestroy((bk_nccl_comm)h->dist_comm);
+  if (h) h->dist_comm = nullptr;
+}
+
 extern "C" int bk_dist_destroy(bk_dist* D) {
   if (!D) return BK_OK;
   if (D->h) {
@@ -61,7 +66,7 @@ extern "C" int bk_dist_destroy(bk_dist* D) {
     cudaDeviceSynchronize();
     bk_graphs_invalidate(D->h);
   }
-  if (D->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(D->comm);
+  // D->comm belongs to the handle (shared by all matrices of this rank set): see bk_dist_release_comm
   if (D->Aloc) bk_csr_destroy(D->Aloc);
   for (int q = 0; q < BK_P2P_MAXP; ++q)
     if (D->peer_mapped[q]) cudaIpcCloseMemHandle(D->peer_mapped[q]);
@@ -152,14 +157,22 @@ extern "C" int bk_dist_create(bk_handle* h, const void* id128, int rank, int nra
     bk_dist_destroy(D);
     return bk_fail(BK_ERR_CUDA, "bk_dist_create: %s", cudaGetErrorString(e));
   }
-  bk_nccl_id id;
-  memcpy(&id, id128, 128);
-  int nr = g_nccl.CommInitRank(&D->comm, nranks, id, rank);
-  if (nr != 0) {
-    const char* msg = g_nccl.GetErrorString(nr);
-    D->comm = nullptr;
-    bk_dist_destroy(D);
-    return bk_fail(BK_ERR_NCCL, "ncclCommInitRank failed: %s", msg);
+  if (h->dist_comm && h->dist_comm_rank == rank && h->dist_comm_nranks == nranks) {
+    D->comm = (bk_nccl_comm)h->dist_comm;  // every rank takes this branch together (same registration sequence)
+  } else {
+    bk_dist_release_comm(h);
+    bk_nccl_id id;
+    memcpy(&id, id128, 128);
+    int nr = g_nccl.CommInitRank(&D->comm, nranks, id, rank);
+    if (nr != 0) {
+      const char* msg = g_nccl.GetErrorString(nr);
+      D->comm = nullptr;
+      bk_dist_destroy(D);
+      return bk_fail(BK_ERR_NCCL, "ncclCommInitRank failed: %s", msg);
+    }
+    h->dist_comm = D->comm;
+    h->dist_comm_rank = rank;
+    h->dist_comm_nranks = nranks;
   }
   *out = D;
   return BK_OK;

@@ -182,6 +182,10 @@ struct bk_handle {
   void* stage;              // bk_solve_host: cached device staging area
   size_t stage_bytes;
   uint64_t next_uid;
+  // multi-GPU: the NCCL communicator is created once per handle and shared by every row-partitioned matrix
+  // registered with the same (rank, nranks) — ncclCommInitRank costs 0.1-1 s (bk_dist.cu)
+  void* dist_comm;
+  int dist_comm_rank, dist_comm_nranks;
 };
 
 static inline bk_scratch bk_slot(bk_handle* h, int slot) {
@@ -199,6 +203,7 @@ cudaError_t bk_pool_alloc(void** p, size_t bytes, cudaStream_t s);
 void bk_pool_free(void* p);
 int bk_ws_reserve(bk_handle* h, size_t bytes);  // grows h->ws (invalidates cached graphs)
 void bk_graphs_invalidate(bk_handle* h);
+void bk_dist_release_comm(bk_handle* h);  // bk_dist.cu
 void bk_state_fill_tol(bk_dev_state* v, double tol, double atol);
 void bk_fill_result_isolve(const bk_dev_state* st, bk_result* res, int64_t matvecs);
 void bk_convert_i64_i32(bk_handle* h, const void* in, void* out, long long n, cudaStream_t s);

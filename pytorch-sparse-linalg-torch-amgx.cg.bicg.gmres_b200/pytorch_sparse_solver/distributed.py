@@ -323,7 +323,8 @@ def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSample
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e = {"value": world * re_["iterations"] / float(dt), "unit": unit, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": rows * 8, "ms_per_step": 1e3 * float(dt), "steps": 1,
-           "note": "includes partition set-up and NCCL communicator creation"}
+           "note": "includes partition set-up, halo-plan exchange and IPC window mapping (the NCCL communicator of "
+                   "the process is reused)"}
     D2.close()
     if rank != 0:
         return None
