@@ -847,3 +847,63 @@ def test_coo_ingestion_matches_torch(n, nnz, dups):
     rc = h.lib.bk_csr_from_coo(h.ptr, 1, 1, bad_idx[0].contiguous().data_ptr(), bad_idx[1].contiguous().data_ptr(), 64,
                                badC._values().data_ptr(), _native.BK_F64, _native.BK_F64, None, _native.C.byref(p))
     assert rc == -1
+
+
+def _banded_coded_matrix(n, offsets, drop, seed, dtype=torch.float64, per_offset_values=1):
+    """n x n matrix with entries at (r, r + o) for o in `offsets`, each kept with probability 1 - drop; the value of
+    an entry depends only on its offset (and r % per_offset_values), so a block holds few distinct (offset, value)
+    pairs although the row lengths vary wildly."""
+    g = torch.Generator().manual_seed(seed)
+    offs = torch.tensor(sorted(offsets))
+    base = torch.randn(len(offs), per_offset_values, dtype=torch.float64, generator=g)
+    r = torch.arange(n)[:, None]
+    c = r + offs[None, :]
+    keep = (c >= 0) & (c < n) & (torch.rand(n, len(offs), generator=g) >= drop)
+    keep[n // 3] = False                                          # an empty row
+    v = base[torch.arange(len(offs))[None, :].expand(n, -1), (r % per_offset_values).expand(-1, len(offs))]
+    rows = r.expand(-1, len(offs))[keep]
+    A = torch.sparse_coo_tensor(torch.stack([rows, c[keep]]), v[keep].to(dtype), (n, n)).coalesce().to_sparse_csr()
+    return A
+
+
+@pytest.mark.parametrize("n,offsets,drop,pov,expect5", [
+    (1000, [-37, -1, 0, 1, 37], 0.0, 1, True),
+    (777, [-300, -64, -5, -1, 0, 1, 2, 9, 64, 300], 0.4, 1, True),        # ragged rows, n % 32 != 0
+    (4099, list(range(-9, 10)), 0.5, 1, True),                            # up to 19 entries: several 8-entry batches
+    (2050, list(range(-15, 16)), 0.2, 1, True),                           # 31 pairs: the limit
+    (2050, list(range(-16, 16)), 0.2, 1, False),                          # 32 pairs: falls back
+    (1500, [-40, -1, 0, 1, 40], 0.1, 6, True),                            # 30 pairs from 5 offsets x 6 values
+    (1500, [-40, -1, 0, 1, 40], 0.1, 7, False),                           # 35 pairs: falls back
+    (31, [0, 1], 0.0, 1, True),
+])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_pair_coded_spmv_stress(n, offsets, drop, pov, expect5, dtype):
+    """Kernel 5 on adversarial 'few distinct pairs' matrices: bit-identical to the plain CSR kernel, every fused variant
+    (dots, residual form), and the fall-back when a block exceeds 31 pairs."""
+    from pytorch_sparse_solver import _native
+    h = _native.Handle.get(torch.device("cuda"))
+    A = _banded_coded_matrix(n, offsets, drop, seed=n + len(offsets), dtype=dtype, per_offset_values=pov).cuda()
+    g = torch.Generator("cuda").manual_seed(3)
+    x = torch.randn(n, dtype=dtype, device="cuda", generator=g)
+    w = torch.randn(n, dtype=dtype, device="cuda", generator=g)
+    try:
+        h.set_option("use_compress", 0)
+        _native.clear_cache()
+        m2 = _native.register_matrix(A, dtype)
+        y2, d2 = m2.spmv_dot(x, w)
+        k2 = m2.info()["kernel"]
+        h.set_option("use_compress", 2)
+        _native.clear_cache()
+        m5 = _native.register_matrix(A, dtype)
+        y5, d5 = m5.spmv_dot(x, w)
+        k5 = m5.info()["kernel"]
+        y5b = m5.spmv(x)
+    finally:
+        h.set_option("use_compress", 2)
+        _native.clear_cache()
+    assert k2 in (0, 2)
+    if k2 == 2:
+        assert (k5 == 5) == expect5, (k5, expect5)
+    assert torch.equal(y2, y5) and torch.equal(y5, y5b) and float(d2) == float(d5)
+    ref = torch.matmul(A.cpu().to_dense().double(), x.cpu().double())
+    assert rel_diff(y5, ref) <= (1e-13 if dtype == torch.float64 else 2e-5)
