@@ -187,6 +187,11 @@ int bk_bicgstab(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x
  * `M = lambda r: r / d`, kept on the device.  Same result fields as bk_cg. */
 int bk_cg_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b, void* x, int has_x0, double tol,
                  double atol, int64_t maxiter, bk_result* result, void* stream);
+/* BiCGStab with the same built-in M: right preconditioning exactly as _bicgstab_solve :907-946 (phat = M p,
+ * q = A phat, shat = M s, t = A shat, x += alpha phat + omega shat; residuals, dots and breakdown tests in residual
+ * space) and the M-weighted final check (:1008). */
+int bk_bicgstab_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b, void* x, int has_x0,
+                       double tol, double atol, int64_t maxiter, bk_result* result, void* stream);
 /* out[r] = A[r][r] (0 when the row stores no diagonal entry); out: device vector of A's dtype */
 int bk_csr_diagonal(bk_handle* h, const bk_csr* A, void* out, void* stream);
 /* bk_gmres replaces gmres :641-784, _gmres_solve_with_method :788-803, _gmres_batched :431-493,

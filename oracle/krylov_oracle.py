@@ -1,6 +1,6 @@
 """CPU oracle for Module A's Krylov path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-A plain restatement (torch-CPU ops, single-tensor `b`; a preconditioner only for CG) of the reference algorithms in
+A plain restatement (torch-CPU ops, single-tensor `b`; a preconditioner for CG / BiCGStab) of the reference algorithms in
 src/pytorch_sparse_solver/module_a/torch_sparse_linalg.py.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / `--impl reference` leg may import this file; the product package never does.
 
@@ -86,7 +86,7 @@ def _cg_solve(A, b, x0, maxiter, tol, atol, M=None):           # :806-856
     return x, k
 
 
-def _bicgstab_solve(A, b, x0, maxiter, tol, atol):             # :859-964
+def _bicgstab_solve(A, b, x0, maxiter, tol, atol, M=None):     # :859-964
     bs = _vdot(b, b)
     atol2 = torch.maximum(torch.square(torch.tensor(tol)) * bs, torch.square(torch.tensor(atol)))   # :870-872
     r0 = b - A(x0)                                             # :875
@@ -108,14 +108,16 @@ def _bicgstab_solve(A, b, x0, maxiter, tol, atol):             # :859-964
             break
         beta = rho_new / rho * alpha / omega                   # :906
         p_ = r + beta * (p - omega * q)                        # :907
-        q_ = A(p_)                                             # :909
+        phat = p_ if M is None else M(p_)                      # :908
+        q_ = A(phat)                                           # :909
         alpha_new = rho_new / _vdot(rhat, q_)                  # :910
         if torch.abs(alpha_new) < eps:                         # :913
             k = -11
             break
         s = r - alpha_new * q_                                 # :917
         exit_early = _vdot(s, s) < atol2                       # :920
-        t = A(s)                                               # :923
+        shat = s if M is None else M(s)                        # :922
+        t = A(shat)                                            # :923
         t_norm_sq = _vdot(t, t)
         if torch.abs(t_norm_sq) < eps:                         # :927
             omega_new = torch.tensor(0.0, dtype=dtype)
@@ -124,8 +126,8 @@ def _bicgstab_solve(A, b, x0, maxiter, tol, atol):             # :859-964
         if torch.abs(omega_new) < eps and not exit_early:      # :934
             k = -11
             break
-        x_early = x + alpha_new * p_                           # :942
-        x_full = x + (alpha_new * p_ + omega_new * s)          # :943
+        x_early = x + alpha_new * phat                         # :942
+        x_full = x + (alpha_new * phat + omega_new * shat)     # :943
         x = torch.where(exit_early, x_early, x_full)
         r = torch.where(exit_early, s, s - omega_new * t)      # :948-950
         p, q, rho, alpha, omega = p_, q_, rho_new, alpha_new, omega_new
@@ -150,7 +152,7 @@ def _isolve(kind: str, A_t: torch.Tensor, b: torch.Tensor, x0, tol, atol, maxite
     if kind == 'cg':
         x, iters = _cg_solve(A, b, x0, maxiter, tol, atol, M)
     else:
-        x, iters, status = _bicgstab_solve(A, b, x0, maxiter, tol, atol)
+        x, iters, status = _bicgstab_solve(A, b, x0, maxiter, tol, atol, M)
     matvecs = A.calls
     final_residual = _norm(b - A(x)) if M is None else _norm(M(b - A(x)))   # :1008
     b_norm = _norm(b)
@@ -170,9 +172,9 @@ def cg(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None, *, t
 
 
 def bicgstab(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None, *, tol=1e-5, atol=0.0,
-             maxiter=None):
+             maxiter=None, M=None):
     """reference bicgstab (:1091-1158) without the autograd wrapper."""
-    return _isolve('bicgstab', A, b, x0, tol, atol, maxiter)
+    return _isolve('bicgstab', A, b, x0, tol, atol, maxiter, M)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -166,6 +166,15 @@ def main():
     pin("bicgstab_cd3d64_rand_digest", "bicgstab", A, b, store_vectors=False, gen=dict(matrix="convdiff3d", n=64),
         tol=1e-10)
 
+    # Jacobi-preconditioned BiCGStab on a badly scaled non-symmetric system (S A S, A = upwind convection-diffusion)
+    A = problems.scaled_convdiff3d_csr(12)
+    b, _ = problems.manufactured_rhs(A, 4)
+    gsc = dict(matrix="scaled_convdiff3d", n=12, seed=7)
+    pin("bicgstab_scd3d12_jacobi", "bicgstab", A, b, gen=gsc, jacobi=True, tol=1e-10)
+    pin("bicgstab_scd3d12_jacobi_fixed5", "bicgstab", A, b, gen=gsc, jacobi=True, tol=0.0, atol=0.0, maxiter=5)
+    x0 = torch.randn(A.shape[0], dtype=torch.float64, generator=torch.Generator().manual_seed(12))
+    pin("bicgstab_scd3d12_jacobi_x0", "bicgstab", A, b, x0, gen=gsc, jacobi=True, tol=1e-9)
+
     # ---- GMRES -----------------------------------------------------------------------------------
     A = problems.convdiff3d_csr(12)
     b, _ = problems.manufactured_rhs(A, 0)

@@ -102,12 +102,25 @@ struct bk_epi_final_x2 {
 template <typename T>
 struct bk_bicg_vecs {
   T *x, *r, *rhat, *p, *q, *s, *t;
+  T *phat, *shat;  // Jacobi: the preconditioned copies the SpMVs gather from
+  const T* d;      // Jacobi: diag(A); nullptr = unpreconditioned
 };
 
 template <typename T, typename Sys>
 static int bk_bicg_enqueue_iter(const Sys& sys, const bk_bicg_vecs<T>& v, cudaStream_t s) {
   bk_dev_state* st = sys.h->st;
-  {
+  const bool pc = v.d != nullptr;
+  const bool al = !pc || bk_aligned16(v.d);
+  if (pc) {
+    bk_op_bicg_p_pc<T> op;
+    op.r = v.r;
+    op.p = v.p;
+    op.q = v.q;
+    op.st = st;
+    op.d = v.d;
+    op.phat = v.phat;
+    BK_TRY(sys.template ew<T>(op, al, 2, s));
+  } else {
     bk_op_bicg_p<T> op;
     op.r = v.r;
     op.p = v.p;
@@ -115,8 +128,17 @@ static int bk_bicg_enqueue_iter(const Sys& sys, const bk_bicg_vecs<T>& v, cudaSt
     op.st = st;
     BK_TRY(sys.template ew<T>(op, true, 2, s));
   }
-  BK_TRY((sys.template matvec<T, 0, 1>(v.p, v.q, v.rhat, nullptr, 1, bk_epi_bicg_alpha<T>{st}, s)));
-  {
+  BK_TRY((sys.template matvec<T, 0, 1>(pc ? v.phat : v.p, v.q, v.rhat, nullptr, 1, bk_epi_bicg_alpha<T>{st}, s)));
+  if (pc) {
+    bk_op_bicg_s_pc<T> op;
+    op.r = v.r;
+    op.q = v.q;
+    op.s = v.s;
+    op.st = st;
+    op.d = v.d;
+    op.shat = v.shat;
+    BK_TRY(sys.template ew<T>(op, al, 1, s));
+  } else {
     bk_op_bicg_s<T> op;
     op.r = v.r;
     op.q = v.q;
@@ -124,8 +146,20 @@ static int bk_bicg_enqueue_iter(const Sys& sys, const bk_bicg_vecs<T>& v, cudaSt
     op.st = st;
     BK_TRY(sys.template ew<T>(op, true, 1, s));
   }
-  BK_TRY((sys.template matvec<T, 0, 3>(v.s, v.t, v.s, nullptr, 3, bk_epi_bicg_omega<T>{st}, s)));
-  {
+  // t = A shat ; the dots are t.s and t.t with the UNpreconditioned s (:926-930)
+  BK_TRY((sys.template matvec<T, 0, 3>(pc ? v.shat : v.s, v.t, v.s, nullptr, 3, bk_epi_bicg_omega<T>{st}, s)));
+  if (pc) {
+    bk_op_bicg_xr_pc<T> op;
+    op.x = v.x;
+    op.p = v.phat;
+    op.s = v.s;
+    op.t = v.t;
+    op.rhat = v.rhat;
+    op.r = v.r;
+    op.st = st;
+    op.shat = v.shat;
+    BK_TRY(sys.template ew<T>(op, true, 1, s));
+  } else {
     bk_op_bicg_xr<T> op;
     op.x = v.x;
     op.p = v.p;
@@ -141,11 +175,11 @@ static int bk_bicg_enqueue_iter(const Sys& sys, const bk_bicg_vecs<T>& v, cudaSt
 
 template <typename T, typename Sys>
 static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0, double tol, double atol,
-                         int64_t maxiter, bk_result* res, cudaStream_t s) {
+                         int64_t maxiter, bk_result* res, cudaStream_t s, const T* diag = nullptr) {
   bk_handle* h = sys.h;
   const long long n = sys.n();
   const size_t npad = ((size_t)n + 63) & ~(size_t)63;
-  BK_TRY(bk_ws_reserve(h, (size_t)7 * npad * sizeof(T)));
+  BK_TRY(bk_ws_reserve(h, (size_t)(diag ? 9 : 7) * npad * sizeof(T)));
   bk_bicg_vecs<T> v;
   v.x = (T*)h->ws;
   v.r = v.x + npad;
@@ -154,6 +188,9 @@ static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0
   v.q = v.p + npad;
   v.s = v.q + npad;
   v.t = v.s + npad;
+  v.phat = v.t + npad;
+  v.shat = v.phat + npad;
+  v.d = diag;
   bk_dev_state* st = h->st;
   const size_t vbytes = (size_t)n * sizeof(T);
 
@@ -179,12 +216,13 @@ static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0
   BK_CUDA(cudaMemcpyAsync(v.p, v.r, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(v.q, v.r, vbytes, cudaMemcpyDeviceToDevice, s));
 
-  const double bytes_iter = 2.0 * sys.matrix_bytes() + 19.0 * n * sizeof(T);
+  const double bytes_iter = 2.0 * sys.matrix_bytes() + (diag ? 25.0 : 19.0) * n * sizeof(T);
   const int chunk = bk_pick_chunk(h, bytes_iter, 5);
   const bool use_graph = h->loop_mode != BK_LOOP_STREAM;
   uint64_t key[6] = {2 /*bicgstab*/, sys.uid(), (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
                      (uint64_t)sys.dtype() | ((uint64_t)chunk << 16),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
+  if (diag) key[1] ^= (uint64_t)(uintptr_t)diag * 0x9e3779b97f4a7c15ull;  // its address is baked into the graph
   auto enqueue_chunk = [&](cudaStream_t cs) -> int {
     for (int it = 0; it < chunk; ++it) BK_TRY((bk_bicg_enqueue_iter<T, Sys>(sys, v, cs)));
     return BK_OK;
@@ -193,6 +231,13 @@ static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0
   BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
 
   BK_TRY((sys.template matvec<T, 1, 2>(v.x, v.t, nullptr, b, 0, bk_epi_final_r2{st}, s)));
+  if (diag) {  // _isolve checks || M (b - A x) || (:1008)
+    bk_op_scaled_sq<T, bk_epi_final_r2> op;
+    op.t = v.t;
+    op.d = diag;
+    op.epi = bk_epi_final_r2{st};
+    BK_TRY(sys.template ew<T>(op, bk_aligned16(diag), 1, s));
+  }
   BK_TRY((sys.template dot<T>(v.x, v.x, bk_epi_final_x2{st}, 1, s)));
   BK_CUDA(cudaMemcpyAsync(x_user, v.x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
@@ -213,6 +258,22 @@ extern "C" int bk_bicgstab(bk_handle* h, const bk_csr* A, const void* b, void* x
   if (A->dtype == BK_F64)
     return bk_bicgstab_t<double>(sys, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
   return bk_bicgstab_t<float>(sys, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+}
+
+/* BiCGStab with the built-in Jacobi preconditioner (right preconditioning, _bicgstab_solve :907-946 with
+ * M = (v -> v / diag)); see bk_cg_jacobi. */
+extern "C" int bk_bicgstab_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b, void* x, int has_x0,
+                                  double tol, double atol, int64_t maxiter, bk_result* result, void* stream) {
+  BK_TRY(bk_solver_args_check("bk_bicgstab_jacobi", h, A, b, x, result));
+  if (!diag && A->n > 0) return bk_fail(BK_ERR_ARG, "bk_bicgstab_jacobi: null diagonal");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (A->n == 0) return BK_OK;
+  const bk_sys_local sys{h, A};
+  if (A->dtype == BK_F64)
+    return bk_bicgstab_t<double>(sys, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream,
+                                 (const double*)diag);
+  return bk_bicgstab_t<float>(sys, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream,
+                              (const float*)diag);
 }
 
 // Row-partitioned BiCGStab: same driver, every reduction made global ("BiCGStab: 3 allreduce points").

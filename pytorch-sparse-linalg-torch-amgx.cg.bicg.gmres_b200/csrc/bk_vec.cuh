@@ -720,6 +720,108 @@ struct bk_op_bicg_xr {
   }
 };
 
+// ---- Jacobi-preconditioned BiCGStab (right preconditioning as in _bicgstab_solve :907-946: phat = M p, q = A phat,
+// shat = M s, t = A shat, x += alpha phat + omega shat; r, s, t and all dots stay in residual space) -------------
+// The three element-wise kernels additionally read d and write the preconditioned copy the next SpMV gathers from.
+template <typename T>
+struct bk_op_bicg_p_pc : bk_op_bicg_p<T> {
+  using Base = bk_op_bicg_p<T>;
+  using Ctx = typename Base::Ctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> r, p, q, d;
+  };
+  const T* d;
+  T* phat;
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.r = bk_ld<T, W>(this->r + i);
+    in.p = bk_ld<T, W>(this->p + i);
+    in.q = bk_ld<T, W>(this->q + i);
+    in.d = bk_ld<T, W>(d + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
+    bk_vec<T, W> o, oh;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      o.v[j] = bk_add(in.r.v[j], bk_mul(c.beta, bk_sub(in.p.v[j], bk_mul(c.omega, in.q.v[j]))));
+      oh.v[j] = o.v[j] / in.d.v[j];
+    }
+    bk_st<T, W>(this->p + i, o);
+    bk_st<T, W>(phat + i, oh);
+  }
+};
+
+template <typename T>
+struct bk_op_bicg_s_pc : bk_op_bicg_s<T> {
+  using Base = bk_op_bicg_s<T>;
+  using Ctx = typename Base::Ctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> r, q, d;
+  };
+  const T* d;
+  T* shat;
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.r = bk_ld<T, W>(this->r + i);
+    in.q = bk_ld<T, W>(this->q + i);
+    in.d = bk_ld<T, W>(d + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&acc)[1]) const {
+    bk_vec<T, W> o, oh;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      o.v[j] = bk_sub(in.r.v[j], bk_mul(c.alpha, in.q.v[j]));
+      oh.v[j] = o.v[j] / in.d.v[j];
+      acc[0] += (double)o.v[j] * (double)o.v[j];
+    }
+    bk_st<T, W>(this->s + i, o);
+    bk_st<T, W>(shat + i, oh);
+  }
+};
+
+template <typename T>
+struct bk_op_bicg_xr_pc : bk_op_bicg_xr<T> {  // base fields p / s hold phat / s; shat is extra
+  using Base = bk_op_bicg_xr<T>;
+  using Ctx = typename Base::Ctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> x, ph, sh, s, t, rh;
+  };
+  const T* shat;
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.x = bk_ld<T, W>(this->x + i);
+    in.ph = bk_ld<T, W>(this->p + i);
+    in.sh = bk_ld<T, W>(shat + i);
+    in.s = bk_ld<T, W>(this->s + i);
+    in.t = bk_ld<T, W>(this->t + i);
+    in.rh = bk_ld<T, W>(this->rhat + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&acc)[2]) const {
+    bk_vec<T, W> xo, ro;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const T ap = bk_mul(c.alpha, in.ph.v[j]);
+      if (c.early) {
+        xo.v[j] = bk_add(in.x.v[j], ap);
+        ro.v[j] = in.s.v[j];
+      } else {
+        xo.v[j] = bk_add(in.x.v[j], bk_add(ap, bk_mul(c.omega, in.sh.v[j])));
+        ro.v[j] = bk_sub(in.s.v[j], bk_mul(c.omega, in.t.v[j]));
+      }
+      acc[0] += (double)ro.v[j] * (double)ro.v[j];
+      acc[1] += (double)in.rh.v[j] * (double)ro.v[j];
+    }
+    bk_st<T, W>(this->x + i, xo);
+    bk_st<T, W>(this->r + i, ro);
+  }
+};
+
 // ---- GMRES -------------------------------------------------------------------------------------
 // v = use ? w / norm : 0                                  (_safe_normalize :266-272)
 template <typename T>

@@ -102,6 +102,8 @@ _SIGNATURES = {
                                   C.POINTER(_VP)]),
     "bk_cg_jacobi": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64,
                                C.POINTER(bk_result), _VP]),
+    "bk_bicgstab_jacobi": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64,
+                                     C.POINTER(bk_result), _VP]),
     "bk_csr_diagonal": (C.c_int, [_VP, _VP, _VP, _VP]),
     "bk_dist_bicgstab": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64,
                                    C.POINTER(bk_result), _VP]),
@@ -361,8 +363,7 @@ class CsrMatrix:
                                                    _stream_ptr(self.device)), "bk_csr_diagonal")
         return out
 
-    def cg_jacobi(self, diag: torch.Tensor, b, x0, tol, atol, maxiter):
-        """CG preconditioned with M = (r -> r / diag), all on the device (bk_cg_jacobi)."""
+    def _solve_jacobi(self, fn_name: str, diag: torch.Tensor, b, x0, tol, atol, maxiter):
         d = self._vec(diag)
         b = self._vec(b)
         if x0 is None:
@@ -371,15 +372,20 @@ class CsrMatrix:
             x, has_x0 = self._vec(x0).clone(), 1
         res = bk_result()
         with torch.cuda.device(self.device):
-            rc = self.handle.lib.bk_cg_jacobi(self.handle.ptr, self.ptr, d.data_ptr(), b.data_ptr(), x.data_ptr(),
-                                              has_x0, float(tol), float(atol), -1 if maxiter is None else int(maxiter),
-                                              C.byref(res), _stream_ptr(self.device))
-        _check(rc, "bk_cg_jacobi")
+            rc = getattr(self.handle.lib, fn_name)(self.handle.ptr, self.ptr, d.data_ptr(), b.data_ptr(), x.data_ptr(),
+                                                   has_x0, float(tol), float(atol),
+                                                   -1 if maxiter is None else int(maxiter), C.byref(res),
+                                                   _stream_ptr(self.device))
+        _check(rc, fn_name)
         return x, res.as_dict()
 
-    def gmres(self, b, x0, tol_eff, atol_eff, restart, maxiter, method):
-        return self._solve("gmres", b, x0, float(tol_eff), float(atol_eff), int(restart),
-                           -1 if maxiter is None else int(maxiter), int(method))
+    def cg_jacobi(self, diag: torch.Tensor, b, x0, tol, atol, maxiter):
+        """CG preconditioned with M = (r -> r / diag), all on the device (bk_cg_jacobi)."""
+        return self._solve_jacobi("bk_cg_jacobi", diag, b, x0, tol, atol, maxiter)
+
+    def bicgstab_jacobi(self, diag: torch.Tensor, b, x0, tol, atol, maxiter):
+        """BiCGStab right-preconditioned with M = (v -> v / diag), all on the device (bk_bicgstab_jacobi)."""
+        return self._solve_jacobi("bk_bicgstab_jacobi", diag, b, x0, tol, atol, maxiter)
 
 
 # ---- building-block vector ops (deterministic reductions) ------------------------------------------

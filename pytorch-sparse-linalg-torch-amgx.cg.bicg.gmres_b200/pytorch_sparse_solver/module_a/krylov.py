@@ -153,6 +153,8 @@ def _solve_core(name: str, A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.
                 x, res = mat.cg_jacobi(precond.diagonal(wdt, bw.device), bw, x0w, tol, atol, maxiter)
             elif name == "cg":
                 x, res = mat.cg(bw, x0w, tol, atol, maxiter)
+            elif name == "bicgstab" and precond is not None:
+                x, res = mat.bicgstab_jacobi(precond.diagonal(wdt, bw.device), bw, x0w, tol, atol, maxiter)
             elif name == "bicgstab":
                 x, res = mat.bicgstab(bw, x0w, tol, atol, maxiter)
             else:
@@ -252,14 +254,14 @@ def bicgstab(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[
              atol: float = 0.0, maxiter: Optional[int] = None, M: Optional[Callable[[Any], Any]] = None
              ) -> Tuple[Any, Optional[int]]:
     """Bi-conjugate gradient stabilised for general A.  Same contract as reference bicgstab (:1091-1158)."""
-    route = _route(A, b, x0, M)
+    route = _route(A, b, x0, M, native_M=True)
     if route == "generic":
         from .generic import generic_bicgstab
         return generic_bicgstab(A, b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M)
     if x0 is not None:
         _check_x0(b, x0)
-    x, info = _solve_core("bicgstab", A, b, x0, tol, atol, maxiter)
-    return _finish("bicgstab", A, b, x, info, x0, tol, atol, 20, maxiter, 'batched')
+    x, info = _solve_core("bicgstab", A, b, x0, tol, atol, maxiter, precond=M)
+    return _finish("bicgstab", A, b, x, info, x0, tol, atol, 20, maxiter, 'batched', precond=M)
 
 
 def gmres(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any] = None, *, tol: float = 1e-5,

@@ -66,10 +66,18 @@ def poisson3d_csr(n: int, **kw) -> torch.Tensor:
     return stencil3d_csr(n, **kw)
 
 
+def scaled_convdiff3d_csr(n: int, seed: int = 7, spread: float = 3.0, **kw) -> torch.Tensor:
+    """S A S with A = CD3D-n (non-symmetric) and the same diagonal scaling as scaled_poisson3d_csr."""
+    return _diag_scaled(convdiff3d_csr(n, **kw), seed, spread)
+
+
 def scaled_poisson3d_csr(n: int, seed: int = 7, spread: float = 3.0, **kw) -> torch.Tensor:
     """S A S with A = P3D-n and S = diag(10^(spread * u)), u ~ U(-0.5, 0.5) (CPU generator, seeded): SPD, same
     sparsity, strongly varying diagonal — the textbook case for a Jacobi preconditioner."""
-    A = stencil3d_csr(n, **kw)
+    return _diag_scaled(stencil3d_csr(n, **kw), seed, spread)
+
+
+def _diag_scaled(A: torch.Tensor, seed: int, spread: float) -> torch.Tensor:
     N = A.shape[0]
     u = torch.rand(N, dtype=torch.float64, generator=torch.Generator().manual_seed(seed)) - 0.5
     sc = torch.pow(torch.tensor(10.0, dtype=torch.float64), spread * u).to(A.device)

@@ -53,6 +53,8 @@ def build_matrix(gen, device="cpu", index_dtype=torch.int64):
         return problems.poisson3d_csr(gen["n"], device=device, index_dtype=index_dtype)
     if kind == "convdiff3d":
         return problems.convdiff3d_csr(gen["n"], device=device, index_dtype=index_dtype)
+    if kind == "scaled_convdiff3d":
+        return problems.scaled_convdiff3d_csr(gen["n"], seed=gen.get("seed", 7), device=device, index_dtype=index_dtype)
     if kind == "scaled_poisson3d":
         return problems.scaled_poisson3d_csr(gen["n"], seed=gen.get("seed", 7), device=device, index_dtype=index_dtype)
     if kind == "ldc":
