@@ -192,6 +192,12 @@ int bk_cg_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b,
  * space) and the M-weighted final check (:1008). */
 int bk_bicgstab_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b, void* x, int has_x0,
                        double tol, double atol, int64_t maxiter, bk_result* result, void* stream);
+/* GMRES with the same built-in M applied from the left, as the reference does with a callable M: v = M(A v) in every
+ * Arnoldi step (:351), r = M(b - A x) at every restart (:491, :636, :791), ptol from ||M b|| (:750-753), final check on
+ * ||M(b - A x)|| (:766).  Arguments as bk_gmres. */
+int bk_gmres_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b, void* x, int has_x0,
+                    double tol_eff, double atol_eff, int restart, int64_t maxiter, int method, bk_result* result,
+                    void* stream);
 /* out[r] = A[r][r] (0 when the row stores no diagonal entry); out: device vector of A's dtype */
 int bk_csr_diagonal(bk_handle* h, const bk_csr* A, void* out, void* stream);
 /* bk_gmres replaces gmres :641-784, _gmres_solve_with_method :788-803, _gmres_batched :431-493,

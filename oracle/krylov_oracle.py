@@ -1,6 +1,6 @@
 """CPU oracle for Module A's Krylov path — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-A plain restatement (torch-CPU ops, single-tensor `b`; a preconditioner for CG / BiCGStab) of the reference algorithms in
+A plain restatement (torch-CPU ops, single-tensor `b`, optional preconditioner callable) of the reference algorithms in
 src/pytorch_sparse_solver/module_a/torch_sparse_linalg.py.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / `--impl reference` leg may import this file; the product package never does.
 
@@ -178,9 +178,11 @@ def bicgstab(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None
 
 
 # --------------------------------------------------------------------------------------------------
-def _kth_arnoldi_iteration(k, A, V, H):                        # :331-388
+def _kth_arnoldi_iteration(k, A, V, H, M=None):                # :331-388
     eps = torch.finfo(V.dtype).eps
     v = A(V[..., k])                                           # :349-351
+    if M is not None:
+        v = M(v)                                               # :351  v = M(A(v))
     _, v_norm_0 = _safe_normalize(v)                           # :352
     # one classical Gram-Schmidt pass over ALL columns (:284-328; the second pass can never run)
     h = torch.einsum("...n,...->n", V, v)                      # :279
@@ -219,24 +221,24 @@ def _givens_rotation(a, b):                                    # :508-518
     return cs, sn
 
 
-def _gmres_batched(A, b, x0, unit_residual, residual_norm, ptol, restart):     # :431-493
+def _gmres_batched(A, b, x0, unit_residual, residual_norm, ptol, restart, M=None):     # :431-493
     dtype = b.dtype
     V = torch.cat([unit_residual.unsqueeze(-1), torch.zeros(unit_residual.shape + (restart,), dtype=dtype)], dim=-1)
     H = torch.zeros(restart + 1, restart, dtype=dtype)
     k, breakdown = 0, False
     while k < restart and not breakdown:                       # :463
-        V, H, breakdown = _kth_arnoldi_iteration(k, A, V, H)
+        V, H, breakdown = _kth_arnoldi_iteration(k, A, V, H, M)
         k += 1
     beta_vec = torch.zeros(restart + 1, dtype=dtype)
     beta_vec[0] = residual_norm.to(dtype)
     y = _lstsq(H[:k + 1, :k], beta_vec[:k + 1]) if k > 0 else torch.zeros(0, dtype=dtype)   # :475-484
     x = x0 + torch.matmul(V[..., :k], y)                       # :488-490
-    residual = b - A(x)                                        # :491
+    residual = b - A(x) if M is None else M(b - A(x))          # :491
     unit_residual, residual_norm = _safe_normalize(residual)
     return x, unit_residual, residual_norm
 
 
-def _gmres_incremental(A, b, x0, unit_residual, residual_norm, ptol, restart):  # :557-638
+def _gmres_incremental(A, b, x0, unit_residual, residual_norm, ptol, restart, M=None):  # :557-638
     dtype = b.dtype
     V = torch.cat([unit_residual.unsqueeze(-1), torch.zeros(unit_residual.shape + (restart,), dtype=dtype)], dim=-1)
     H = torch.zeros(restart + 1, restart, dtype=dtype)
@@ -246,7 +248,7 @@ def _gmres_incremental(A, b, x0, unit_residual, residual_norm, ptol, restart):  
     beta_vec[0] = residual_norm.to(dtype)
     k, err = 0, residual_norm
     while k < restart and err > ptol:                          # :591
-        V, H, breakdown = _kth_arnoldi_iteration(k, A, V, H)
+        V, H, breakdown = _kth_arnoldi_iteration(k, A, V, H, M)
         H_col = H[:k + 2, k].clone()
         for i in range(k):                                     # :599-603
             cs, sn = givens[i, 0], givens[i, 1]
@@ -271,7 +273,7 @@ def _gmres_incremental(A, b, x0, unit_residual, residual_norm, ptol, restart):  
     else:
         dx = torch.zeros_like(x0)
     x = x0 + dx
-    residual = b - A(x)                                        # :636
+    residual = b - A(x) if M is None else M(b - A(x))          # :636
     unit_residual, residual_norm = _safe_normalize(residual)
     return x, unit_residual, residual_norm
 
@@ -292,7 +294,7 @@ def gmres_tolerances(tol: float, atol: float, size: int, b_norm: torch.Tensor, d
 
 
 def gmres(A_t: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None, *, tol=1e-5, atol=0.0, restart=20,
-          maxiter=None, solve_method='batched', device_type='cpu'):
+          maxiter=None, solve_method='batched', device_type='cpu', M=None):
     """reference gmres (:641-784) + _gmres_solve_with_method (:788-803) without the autograd wrapper."""
     if x0 is None:
         x0 = torch.zeros_like(b)
@@ -306,20 +308,22 @@ def gmres(A_t: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] = None,
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         atol_tensor, ptol = gmres_tolerances(tol, atol, b.numel(), b_norm, device_type)
+    if M is not None:                                          # :750-753  ptol uses ||M b||
+        ptol = _norm(M(b)) * torch.minimum(torch.tensor(1.0), atol_tensor / b_norm)
     if solve_method == 'incremental':
         cycle = _gmres_incremental
     elif solve_method == 'batched':
         cycle = _gmres_batched
     else:
         raise ValueError(f"Unsupported solve_method: {solve_method}")
-    residual = b - A(x0)                                       # :791
+    residual = b - A(x0) if M is None else M(b - A(x0))        # :791
     unit_residual, residual_norm = _safe_normalize(residual)
     k, x = 0, x0
     while k < maxiter and residual_norm > atol_tensor:         # :798
-        x, unit_residual, residual_norm = cycle(A, b, x, unit_residual, residual_norm, ptol, restart)
+        x, unit_residual, residual_norm = cycle(A, b, x, unit_residual, residual_norm, ptol, restart, M)
         k += 1
     matvecs = A.calls
-    final_residual = _norm(b - A(x))                           # :766
+    final_residual = _norm(b - A(x)) if M is None else _norm(M(b - A(x)))   # :766
     failed = bool(torch.isnan(_norm(x))) or bool(final_residual > atol_tensor * 10)   # :769-770
     info = -1 if failed else 0
     stats = dict(iterations=int(k), matvecs=int(matvecs), final_residual=float(final_residual),

@@ -188,6 +188,16 @@ def main():
     pin("gmres_zero_rhs", "gmres", A, torch.zeros(A.shape[0], dtype=torch.float64), gen=dict(matrix="convdiff3d", n=12),
         tol=1e-8, restart=10)
 
+    # Jacobi (left-)preconditioned GMRES on the badly scaled non-symmetric system
+    A = problems.scaled_convdiff3d_csr(12)
+    b, _ = problems.manufactured_rhs(A, 4)
+    gsc = dict(matrix="scaled_convdiff3d", n=12, seed=7)
+    for sm in ("batched", "incremental"):
+        pin(f"gmres_scd3d12_jacobi_{sm}", "gmres", A, b, gen=gsc, jacobi=True, tol=1e-9, restart=20, solve_method=sm)
+    pin("gmres_scd3d12_jacobi_2cycles", "gmres", A, b, gen=gsc, jacobi=True, tol=0.0, atol=0.0, restart=8, maxiter=2)
+    x0 = torch.randn(A.shape[0], dtype=torch.float64, generator=torch.Generator().manual_seed(13))
+    pin("gmres_scd3d12_jacobi_x0", "gmres", A, b, x0, gen=gsc, jacobi=True, tol=1e-9, restart=15)
+
     # LDC pressure systems: matrix from our vectorised builder must equal the reference driver's, RHS sequence is
     # produced by the reference driver itself (ldc_solver_common.py:185-201)
     sys.path.insert(0, "/root/reference/FVM_example/LDC_by_torchsp")

@@ -105,6 +105,21 @@ struct bk_epi_gm_vnorm0 {  // _, v_norm_0 = safe_normalize(A v_j)   (:352)
   }
 };
 
+struct bk_epi_gm_ignore {
+  __device__ __forceinline__ void operator()(const double*) const {}
+};
+struct bk_epi_gm_ptol {  // Jacobi: ptol = ||M b|| * min(1, atol / ||b||)   (:750-753); s[0] = ||M b||^2
+  bk_dev_state* st;
+  __device__ __forceinline__ void operator()(const double* s) const {
+    st->g_ptol = sqrt(fmax(s[0], 0.0)) * fmin(1.0, st->g_atol / st->g_bnorm);
+  }
+};
+template <typename T>
+struct bk_epi_gm_resid0 {  // Jacobi, x0 = 0: r0 = M b (no matvec to count)
+  bk_dev_state* st;
+  bk_gm_small sm;
+  __device__ __forceinline__ void operator()(const double* s) const { bk_gm_after_residual<T>(st, sm, s[0], 1); }
+};
 struct bk_epi_gm_xx {
   bk_dev_state* st;
   __device__ __forceinline__ void operator()(const double* s) const { st->xx = s[0]; }
@@ -375,7 +390,8 @@ __global__ void bk_gm_solve_kernel(bk_dev_state* st, const bk_gm_small sm) {
 
 template <typename T, typename Sys>
 static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, double tol_eff, double atol_eff,
-                      int restart, int64_t maxiter, int method, bk_result* res, cudaStream_t s) {
+                      int restart, int64_t maxiter, int method, bk_result* res, cudaStream_t s,
+                      const T* diag = nullptr) {
   bk_handle* h = sys.h;
   const long long n = sys.n();
   const int m = restart;
@@ -456,21 +472,51 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
   BK_CUDA(cudaMemcpyAsync(bw, b, vbytes, cudaMemcpyDeviceToDevice, s));
   b = bw;
   BK_TRY((sys.template dot<T>(b, b, bk_epi_gm_tol{st}, 1, s)));
+  const bool dal = diag && bk_aligned16(diag);
+  // left Jacobi preconditioning (diag != nullptr): every A-product is followed by an in-place division by d that also
+  // carries the norm the unpreconditioned path fuses into the SpMV
+  auto scale_sq = [&](T* vec, auto epi, int guard, cudaStream_t cs) -> int {
+    bk_op_scale_sq<T, decltype(epi)> op;
+    op.w = vec;
+    op.d = diag;
+    op.epi = epi;
+    op.st = st;
+    op.guard = guard;
+    return sys.template ew<T>(op, dal, 1, cs);
+  };
+  if (diag) {
+    BK_CUDA(cudaMemcpyAsync(w, b, vbytes, cudaMemcpyDeviceToDevice, s));
+    BK_TRY(scale_sq(w, bk_epi_gm_ptol{st}, 0, s));  // w = M b (also r0 when x0 = 0)
+  }
   if (has_x0) {
     BK_CUDA(cudaMemcpyAsync(x, x_user, vbytes, cudaMemcpyDeviceToDevice, s));
-    BK_TRY((sys.template matvec<T, 1, 2>(x, w, nullptr, b, 0, bk_epi_gm_resid<T>{st, sm, 1}, s)));
+    if (diag) {
+      BK_TRY((sys.template matvec<T, 1, 2>(x, w, nullptr, b, 0, bk_epi_gm_ignore{}, s)));
+      BK_TRY(scale_sq(w, bk_epi_gm_resid<T>{st, sm, 1}, 0, s));
+    } else {
+      BK_TRY((sys.template matvec<T, 1, 2>(x, w, nullptr, b, 0, bk_epi_gm_resid<T>{st, sm, 1}, s)));
+    }
   } else {
     BK_CUDA(cudaMemsetAsync(x, 0, vbytes, s));
-    BK_CUDA(cudaMemcpyAsync(w, b, vbytes, cudaMemcpyDeviceToDevice, s));
-    bk_gm_resid_from_bs_kernel<T><<<1, 1, 0, s>>>(st, sm);
-    BK_KERNEL_CHECK();
+    if (diag) {  // w already holds M b; its norm is ||M b|| = sqrt of what the ptol pass summed: recompute cheaply
+      BK_TRY((sys.template dot<T>(w, w, bk_epi_gm_resid0<T>{st, sm}, 1, s)));
+    } else {
+      BK_CUDA(cudaMemcpyAsync(w, b, vbytes, cudaMemcpyDeviceToDevice, s));
+      bk_gm_resid_from_bs_kernel<T><<<1, 1, 0, s>>>(st, sm);
+      BK_KERNEL_CHECK();
+    }
   }
   BK_TRY(normalize(w, V, 0, s));
 
   // ---- one restart cycle ------------------------------------------------------------------------
   auto enqueue_cycle = [&](cudaStream_t cs) -> int {
     for (int j = 0; j < m; ++j) {
-      BK_TRY((sys.template matvec<T, 0, 2>(V + (size_t)j * npad, w, nullptr, nullptr, 2, bk_epi_gm_vnorm0<T>{st}, cs)));
+      if (diag) {
+        BK_TRY((sys.template matvec<T, 0, 2>(V + (size_t)j * npad, w, nullptr, nullptr, 2, bk_epi_gm_ignore{}, cs)));
+        BK_TRY(scale_sq(w, bk_epi_gm_vnorm0<T>{st}, 2, cs));
+      } else {
+        BK_TRY((sys.template matvec<T, 0, 2>(V + (size_t)j * npad, w, nullptr, nullptr, 2, bk_epi_gm_vnorm0<T>{st}, cs)));
+      }
       bk_multidot_kernel<T, NW><<<grid, BK_BLOCK, 0, cs>>>(V, npad, j + 1, w, n, h->gm_partials, h->counters + 4, st,
                                                             sm.hcol, gs);
       BK_KERNEL_CHECK();
@@ -488,7 +534,12 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
     BK_KERNEL_CHECK();
     bk_multiaxpy_kernel<T, NW, 1><<<grid, BK_BLOCK, 0, cs>>>(V, npad, 0, x, n, bk_slot(h, 1), st, sm, 0, gs);
     BK_KERNEL_CHECK();
-    BK_TRY((sys.template matvec<T, 1, 2>(x, w, nullptr, b, 1, bk_epi_gm_resid<T>{st, sm, 0}, cs)));
+    if (diag) {
+      BK_TRY((sys.template matvec<T, 1, 2>(x, w, nullptr, b, 1, bk_epi_gm_ignore{}, cs)));
+      BK_TRY(scale_sq(w, bk_epi_gm_resid<T>{st, sm, 0}, 1, cs));
+    } else {
+      BK_TRY((sys.template matvec<T, 1, 2>(x, w, nullptr, b, 1, bk_epi_gm_resid<T>{st, sm, 0}, cs)));
+    }
     BK_TRY(normalize(w, V, 1, cs));
     return BK_OK;
   };
@@ -496,6 +547,7 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
   uint64_t key[6] = {3 /*gmres*/, sys.uid(), (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
                      (uint64_t)sys.dtype() | ((uint64_t)m << 8) | ((uint64_t)method << 24),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
+  if (diag) key[1] ^= (uint64_t)(uintptr_t)diag * 0x9e3779b97f4a7c15ull;  // its address is baked into the graph
   int64_t chunks = 0;
   BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_cycle, &chunks));
 
@@ -539,6 +591,25 @@ extern "C" int bk_gmres(bk_handle* h, const bk_csr* A, const void* b, void* x, i
                               (cudaStream_t)stream);
   return bk_gmres_t<float>(sys, b, x, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
                            (cudaStream_t)stream);
+}
+
+/* GMRES with the built-in Jacobi preconditioner applied from the left exactly as the reference does with a callable M:
+ * v = M(A v) in every Arnoldi step (:351), r = M(b - A x) at every restart (:491/:636/:791), ptol from ||M b|| (:750),
+ * final check on ||M(b - A x)|| (:766). */
+extern "C" int bk_gmres_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b, void* x, int has_x0,
+                               double tol_eff, double atol_eff, int restart, int64_t maxiter, int method,
+                               bk_result* result, void* stream) {
+  BK_TRY(bk_solver_args_check("bk_gmres_jacobi", h, A, b, x, result));
+  BK_TRY(bk_gmres_args_check("bk_gmres_jacobi", restart, method));
+  if (!diag && A->n > 0) return bk_fail(BK_ERR_ARG, "bk_gmres_jacobi: null diagonal");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (A->n == 0) return BK_OK;
+  const bk_sys_local sys{h, A};
+  if (A->dtype == BK_F64)
+    return bk_gmres_t<double>(sys, b, x, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
+                              (cudaStream_t)stream, (const double*)diag);
+  return bk_gmres_t<float>(sys, b, x, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
+                           (cudaStream_t)stream, (const float*)diag);
 }
 
 // Row-partitioned GMRES: the basis is partitioned like every vector; V^T w is one all-reduce of j+1 doubles and the

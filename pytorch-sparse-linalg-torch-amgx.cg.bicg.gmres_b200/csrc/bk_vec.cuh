@@ -720,6 +720,46 @@ struct bk_op_bicg_xr {
   }
 };
 
+// w = w / d in place, sum w^2 -> epi   (left Jacobi preconditioning of GMRES: v = M(A v) :351, r = M(b - A x) :491)
+template <typename T, typename Epi>
+struct bk_op_scale_sq {
+  static constexpr int R = 1;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> w, d;
+  };
+  T* w;
+  const T* d;
+  Epi epi;
+  const bk_dev_state* st;
+  int guard;  // 0 none | 1 st->done | 2 st->done || st->g_cycle_over
+  __device__ bool skip() const {
+    if (guard == 0) return false;
+    if (st->done) return true;
+    if (guard == 2 && st->g_cycle_over) return true;
+    return false;
+  }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.w = bk_ld<T, W>(w + i);
+    in.d = bk_ld<T, W>(d + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx&, double (&acc)[1]) const {
+    bk_vec<T, W> o;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      o.v[j] = in.w.v[j] / in.d.v[j];
+      acc[0] += (double)o.v[j] * (double)o.v[j];
+    }
+    bk_st<T, W>(w + i, o);
+  }
+  __device__ void epilogue(const double* s) const { epi(s); }
+};
+
 // ---- Jacobi-preconditioned BiCGStab (right preconditioning as in _bicgstab_solve :907-946: phat = M p, q = A phat,
 // shat = M s, t = A shat, x += alpha phat + omega shat; r, s, t and all dots stay in residual space) -------------
 // The three element-wise kernels additionally read d and write the preconditioned copy the next SpMV gathers from.

@@ -104,6 +104,8 @@ _SIGNATURES = {
                                C.POINTER(bk_result), _VP]),
     "bk_bicgstab_jacobi": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64,
                                      C.POINTER(bk_result), _VP]),
+    "bk_gmres_jacobi": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int64,
+                                  C.c_int, C.POINTER(bk_result), _VP]),
     "bk_csr_diagonal": (C.c_int, [_VP, _VP, _VP, _VP]),
     "bk_dist_bicgstab": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64,
                                    C.POINTER(bk_result), _VP]),
@@ -355,6 +357,10 @@ class CsrMatrix:
     def bicgstab(self, b, x0, tol, atol, maxiter):
         return self._solve("bicgstab", b, x0, float(tol), float(atol), -1 if maxiter is None else int(maxiter))
 
+    def gmres(self, b, x0, tol_eff, atol_eff, restart, maxiter, method):
+        return self._solve("gmres", b, x0, float(tol_eff), float(atol_eff), int(restart),
+                           -1 if maxiter is None else int(maxiter), int(method))
+
     def diagonal(self) -> torch.Tensor:
         """diag(A) as a device vector of the matrix dtype (bk_csr_diagonal)."""
         out = torch.empty(self.n, dtype=self.dtype, device=self.device)
@@ -382,6 +388,23 @@ class CsrMatrix:
     def cg_jacobi(self, diag: torch.Tensor, b, x0, tol, atol, maxiter):
         """CG preconditioned with M = (r -> r / diag), all on the device (bk_cg_jacobi)."""
         return self._solve_jacobi("bk_cg_jacobi", diag, b, x0, tol, atol, maxiter)
+
+    def gmres_jacobi(self, diag: torch.Tensor, b, x0, tol_eff, atol_eff, restart, maxiter, method):
+        """GMRES left-preconditioned with M = (v -> v / diag), all on the device (bk_gmres_jacobi)."""
+        d = self._vec(diag)
+        b = self._vec(b)
+        if x0 is None:
+            x, has_x0 = torch.empty_like(b), 0
+        else:
+            x, has_x0 = self._vec(x0).clone(), 1
+        res = bk_result()
+        with torch.cuda.device(self.device):
+            rc = self.handle.lib.bk_gmres_jacobi(self.handle.ptr, self.ptr, d.data_ptr(), b.data_ptr(), x.data_ptr(),
+                                                 has_x0, float(tol_eff), float(atol_eff), int(restart),
+                                                 -1 if maxiter is None else int(maxiter), int(method), C.byref(res),
+                                                 _stream_ptr(self.device))
+        _check(rc, "bk_gmres_jacobi")
+        return x, res.as_dict()
 
     def bicgstab_jacobi(self, diag: torch.Tensor, b, x0, tol, atol, maxiter):
         """BiCGStab right-preconditioned with M = (v -> v / diag), all on the device (bk_bicgstab_jacobi)."""

@@ -75,7 +75,7 @@ def _check_x0(b, x0):
 
 
 def _route(A, b, x0, M, native_M: bool = False) -> str:
-    """native_M: the solver has a device implementation for a built-in preconditioner object (cg + Jacobi)."""
+    """native_M: the solver has a device implementation for a built-in preconditioner object (Jacobi)."""
     kind = _check_operator(A)
     builtin = native_M and isinstance(M, JacobiPreconditioner) and kind == "tensor" and A.is_cuda
     if kind == "callable" or (M is not None and not builtin) or not isinstance(b, torch.Tensor):
@@ -159,7 +159,11 @@ def _solve_core(name: str, A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.
                 x, res = mat.bicgstab(bw, x0w, tol, atol, maxiter)
             else:
                 tol_eff, atol_eff = _gmres_effective_tolerances(tol, atol, n, 'cuda')
-                x, res = mat.gmres(bw, x0w, tol_eff, atol_eff, restart, maxiter, method)
+                if precond is not None:
+                    x, res = mat.gmres_jacobi(precond.diagonal(wdt, bw.device), bw, x0w, tol_eff, atol_eff, restart,
+                                              maxiter, method)
+                else:
+                    x, res = mat.gmres(bw, x0w, tol_eff, atol_eff, restart, maxiter, method)
         else:
             Ad = A.detach()
             if transpose:
@@ -272,7 +276,7 @@ def gmres(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any
     early exit inside a cycle); info 0 iff ||b - A x|| <= 10*atol_eff and x is finite."""
     if solve_method not in ('batched', 'incremental'):
         raise ValueError(f"Unsupported solve_method: {solve_method}")
-    route = _route(A, b, x0, M)
+    route = _route(A, b, x0, M, native_M=True)
     if route == "generic":
         from .generic import generic_gmres
         return generic_gmres(A, b, x0, tol=tol, atol=atol, restart=restart, maxiter=maxiter, M=M,
@@ -281,8 +285,8 @@ def gmres(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any
         _check_x0(b, x0)
     if restart < 1:
         raise ValueError("restart must be >= 1")
-    x, info = _solve_core("gmres", A, b, x0, tol, atol, maxiter, restart, solve_method)
-    return _finish("gmres", A, b, x, info, x0, tol, atol, restart, maxiter, solve_method)
+    x, info = _solve_core("gmres", A, b, x0, tol, atol, maxiter, restart, solve_method, precond=M)
+    return _finish("gmres", A, b, x, info, x0, tol, atol, restart, maxiter, solve_method, precond=M)
 
 
 class LinearSolveFunction(torch.autograd.Function):

@@ -2,10 +2,10 @@
 
 The reference takes `M` as an arbitrary Python callable (torch_sparse_linalg.py:821, :849), which forces every
 application through the interpreter.  `JacobiPreconditioner(A)` is such a callable — `M(r) = r / diag(A)`, exactly
-what users of the reference write as `M = lambda r: r / d` — that `cg()` and `bicgstab()` additionally recognise: for
-a CUDA matrix the whole preconditioned iteration then stays on the device (`bk_cg_jacobi`, `bk_bicgstab_jacobi`), with
-results identical to passing the lambda to the reference (golden fixtures `*_jacobi*`).  Used with GMRES, with a
-callable `A`, or on CPU tensors it behaves like any other callable `M`.
+what users of the reference write as `M = lambda r: r / d` — that `cg()`, `bicgstab()` and `gmres()` additionally
+recognise: for a CUDA matrix the whole preconditioned iteration then stays on the device (`bk_cg_jacobi`,
+`bk_bicgstab_jacobi`, `bk_gmres_jacobi`), with results identical to passing the lambda to the reference (golden
+fixtures `*_jacobi*`).  With a callable `A` or on CPU tensors it behaves like any other callable `M`.
 """
 from __future__ import annotations
 

@@ -753,8 +753,11 @@ def test_jacobi_pcg_routes_and_autograd(ma, manifest):
     xb, infob = ma.bicgstab(A, b, tol=1e-10, M=M)                    # BiCGStab has a device path for it too
     assert krylov.last_result["route"] == "native"
     assert infob == 0 and rel_diff(xb, data["x"]) <= 1e-5   # ill-conditioned system: x follows the residual loosely
-    xg2, infog2 = ma.gmres(A, b, tol=1e-10, restart=30, M=M)         # GMRES: M is just a callable (generic route)
+    xg2, infog2 = ma.gmres(A, b, tol=1e-10, restart=30, M=M)         # and GMRES (left preconditioning)
+    assert krylov.last_result["route"] == "native"
     assert infog2 == 0 and rel_diff(xg2, data["x"]) <= 1e-5
+    xg3, infog3 = ma.gmres(A, b, tol=1e-10, restart=30, M=lambda r: r / d)   # user lambda: generic route, same answer
+    assert infog3 == 0 and rel_diff(xg3, xg2) <= 1e-8
     # dense and COO inputs build the same preconditioner
     assert torch.equal(ma.JacobiPreconditioner(A.to_dense()).d, d)
     assert torch.equal(ma.JacobiPreconditioner(A.to_sparse_coo()).d, d)

@@ -162,3 +162,14 @@ def test_c_abi_error_paths_without_gpu():
     assert lib.bk_solve_host(None, 0, 4, 4, None, None, 32, None, 0, None, None, 0, 1e-5, 0.0, -1, 20, 0, C.byref(res)) == -1
     assert lib.bk_dist_p2p_export(None, None) == -1
     assert lib.bk_csr_destroy(None) == 0 and lib.bk_destroy(None) == 0 and lib.bk_dist_destroy(None) == 0
+
+
+def test_matrix_wrapper_exposes_every_solver_entry():
+    """krylov.py reaches the C solvers through these CsrMatrix methods: a missing one would only show up on a GPU."""
+    from pytorch_sparse_solver import _native
+    for name in ("spmv", "spmv_dot", "cg", "bicgstab", "gmres", "cg_jacobi", "bicgstab_jacobi", "gmres_jacobi",
+                 "diagonal", "transpose", "arrays", "grad_pattern", "info"):
+        assert callable(getattr(_native.CsrMatrix, name, None)), name
+    for sym in ("bk_cg", "bk_bicgstab", "bk_gmres", "bk_cg_jacobi", "bk_bicgstab_jacobi", "bk_gmres_jacobi",
+                "bk_csr_from_dense", "bk_csr_from_coo", "bk_dist_cg", "bk_dist_bicgstab", "bk_dist_gmres"):
+        assert sym in _native._SIGNATURES, sym
