@@ -20,7 +20,8 @@
 //
 // All are persistent (grid = SMs x k, blocked-cyclic over row blocks so the whole chip sweeps one contiguous window
 // of the matrix, which keeps the x-gather window L2 resident) and end in bk_grid_reduce, whose last CTA runs the
-// solver's scalar epilogue.  Summation order is fixed => bitwise reproducible fp64; all stagings give the same bits.
+// solver's scalar epilogue.  Summation order is fixed => bitwise reproducible fp64; kernels 2, 3 and 5 (fma chains in
+// CSR order) give identical bits, kernel 0 (rounded products, then adds) agrees with them to the last bit or two.
 #pragma once
 
 #include "bk_internal.cuh"

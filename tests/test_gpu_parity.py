@@ -913,3 +913,46 @@ def test_pair_coded_spmv_stress(n, offsets, drop, pov, expect5, dtype):
     assert torch.equal(y2, y5) and torch.equal(y5, y5b) and float(d2) == float(d5)
     ref = torch.matmul(A.cpu().to_dense().double(), x.cpu().double())
     assert rel_diff(y5, ref) <= (1e-13 if dtype == torch.float64 else 2e-5)
+
+
+@pytest.mark.parametrize("kind", ["poisson3d", "convdiff3d"])
+def test_full_size_spmv_all_stagings_bitwise(kind):
+    """BASELINE's full size (256^3, 117 M entries): the pair-coded stream (kernel 5), the coded-column stream (3), the
+    TMA-staged CSR stream (2) must produce the same bits; the LDG-staged kernel (0) agrees to rounding."""
+    from pytorch_sparse_solver import _native
+    h = _native.Handle.get(torch.device("cuda"))
+    A = build_matrix(dict(matrix=kind, n=256), device="cuda")
+    N = A.shape[0]
+    g = torch.Generator("cuda").manual_seed(11)
+    x = torch.randn(N, dtype=torch.float64, device="cuda", generator=g)
+    w = torch.randn(N, dtype=torch.float64, device="cuda", generator=g)
+    outs = {}
+    saved = {k: h.get_option(k) for k in ("use_tma", "use_compress")}
+    try:
+        for label, opts, want in (("k5", dict(use_tma=1, use_compress=2), 5), ("k3", dict(use_tma=1, use_compress=1), 3),
+                                  ("k2", dict(use_tma=1, use_compress=0), 2), ("k0", dict(use_tma=0, use_compress=0), 0)):
+            for k, v in opts.items():
+                h.set_option(k, v)
+            _native.clear_cache()
+            m = _native.register_matrix(A)
+            assert m.info()["kernel"] == want, (label, m.info()["kernel"])
+            y, d = m.spmv_dot(x, w)
+            outs[label] = (y.clone(), float(d))
+            del m
+    finally:
+        for k, v in saved.items():
+            h.set_option(k, v)
+        _native.clear_cache()
+    for label in ("k3", "k2"):
+        assert torch.equal(outs["k5"][0], outs[label][0]), label
+    # kernel 0 parks rounded products in shared memory and adds them (mul + add), the TMA kernels use fma chains
+    assert rel_diff(outs["k0"][0], outs["k5"][0]) <= 1e-15
+    # the dot is reduced over a kernel-specific grid, so it may differ in the last bits between stagings
+    scale = float(w.abs() @ outs["k5"][0].abs())
+    for label in ("k3", "k2", "k0"):
+        assert abs(outs["k5"][1] - outs[label][1]) <= 1e-13 * scale, (label, outs["k5"][1], outs[label][1])
+    # a size-independent property: row sums of the Poisson matrix are 0 away from the boundary => A * ones is
+    # non-zero only on boundary rows; for both matrices A*(2x) == 2*(A x) exactly (scaling by 2 is exact)
+    _native.clear_cache()
+    m = _native.register_matrix(A)
+    assert torch.equal(m.spmv(2.0 * x), 2.0 * outs["k5"][0])
