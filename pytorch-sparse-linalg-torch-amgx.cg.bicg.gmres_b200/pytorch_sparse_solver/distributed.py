@@ -259,7 +259,6 @@ class DistMatrix:
 def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSampler):
     """N slabs of n^3 rows each: a (N*n) x n x n Poisson grid, slab q on rank q.  value = N * global iterations/s
     (n^3-row CG iterations per second summed over ranks)."""
-    import json
     import time
     import torch.distributed as dist
     from . import problems

@@ -14,7 +14,7 @@ from typing import Any, Callable, List, Optional, Tuple
 import torch
 
 from .. import _native
-from .torch_tree_util import tree_flatten, tree_leaves, tree_map, tree_unflatten
+from .torch_tree_util import tree_flatten, tree_leaves, tree_unflatten
 
 _EPS = torch.finfo(torch.float64).eps
 

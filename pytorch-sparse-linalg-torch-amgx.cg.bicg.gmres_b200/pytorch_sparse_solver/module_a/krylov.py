@@ -22,7 +22,6 @@ Routes:
 """
 from __future__ import annotations
 
-import math
 from typing import Any, Callable, Optional, Tuple, Union
 
 import torch

@@ -2,7 +2,6 @@
 argument validation mirrors the reference's exceptions, tolerance helpers mirror the reference's roundings,
 pytree helpers, problem generators.  No compute call is made (there is no GPU here)."""
 import re
-from pathlib import Path
 
 import pytest
 import torch
