@@ -114,11 +114,21 @@ class SparseSolver:
         x, info = module[method](A, b, **solve_kwargs)
         res = dict(krylov.last_result)
         iterations = None
-        if res.get("route") in ("native", "host"):
+        if res.get("route") in ("native", "host") and M is None:
             # ||b - A x|| / ||b|| from the library's own final true-residual pass (reference recomputes it
             # with torch.mv, solver.py:362-368 — same quantity, no cuSPARSE on our path)
             bn = res["b_norm"]
             residual = res["final_residual"] / bn if bn != 0.0 else float('nan')
+            iterations = int(res["iterations"])
+        elif res.get("route") == "native":
+            # built-in preconditioner: the library's final check is on ||M (b - A x)|| (as the reference's, :1008),
+            # the router reports the UNpreconditioned relative residual (solver.py:362-368) — one more SpMV of ours
+            from . import _native
+            with torch.no_grad():
+                xw = x.detach()
+                r = b.detach().to(xw.dtype) - _native.register_matrix(A, xw.dtype).spmv(xw.contiguous())
+                bn = float(_native.nrm2(b.detach().to(xw.dtype).contiguous()))
+                residual = float(_native.nrm2(r)) / bn if bn != 0.0 else float('nan')
             iterations = int(res["iterations"])
         else:
             with torch.no_grad():

@@ -770,6 +770,12 @@ def test_jacobi_pcg_routes_and_autograd(ma, manifest):
     assert rel_diff(b1.grad, g_exact) <= 1e-8
     with pytest.raises(ValueError):
         ma.JacobiPreconditioner(torch.zeros(3, 3, device="cuda"))
+    # through the router: SolverResult.residual stays the UNpreconditioned ||b - A x|| / ||b|| (solver.py:362-368)
+    import pytorch_sparse_solver as pss
+    xr, resr = pss.SparseSolver().solve(A, b, method='cg', backend='module_a', tol=1e-10, M=M)
+    true_rel = float(torch.linalg.norm(b - torch.mv(Ad, xr)) / torch.linalg.norm(b))
+    assert resr.converged and resr.iterations == krylov.last_result["iterations"]
+    assert abs(resr.residual - true_rel) <= 1e-3 * true_rel + 1e-16
 
 
 def test_jacobi_pcg_edge_cases(ma):
