@@ -172,3 +172,43 @@ def test_matrix_wrapper_exposes_every_solver_entry():
     for sym in ("bk_cg", "bk_bicgstab", "bk_gmres", "bk_cg_jacobi", "bk_bicgstab_jacobi", "bk_gmres_jacobi",
                 "bk_csr_from_dense", "bk_csr_from_coo", "bk_dist_cg", "bk_dist_bicgstab", "bk_dist_gmres"):
         assert sym in _native._SIGNATURES, sym
+
+
+def test_problem_generators_scaled_systems():
+    """The badly scaled fixtures: same sparsity as their parents, S A S values, symmetric iff the parent is."""
+    from pytorch_sparse_solver import problems
+    P = problems.poisson3d_csr(5)
+    S = problems.scaled_poisson3d_csr(5)
+    C = problems.scaled_convdiff3d_csr(5)
+    assert torch.equal(P.crow_indices(), S.crow_indices()) and torch.equal(P.col_indices(), S.col_indices())
+    Sd, Cd = S.to_dense(), C.to_dense()
+    assert torch.allclose(Sd, Sd.T, rtol=0, atol=0), "S A S of a symmetric A is symmetric bit for bit"
+    assert not torch.allclose(Cd, Cd.T)
+    assert torch.equal(problems.csr_diagonal(S), torch.diagonal(Sd))
+    assert torch.equal(problems.csr_diagonal(C), torch.diagonal(Cd))
+    assert float(torch.linalg.eigvalsh(Sd).min()) > 0.0, "still positive definite"
+    d = torch.diagonal(Sd)
+    assert float(d.max() / d.min()) > 100.0, "strongly varying diagonal (what Jacobi is for)"
+
+
+def test_oracle_preconditioned_solvers_agree_with_dense_solve():
+    """Oracle with M = r / d (the form pinned against the reference) on a small badly scaled system."""
+    from oracle import krylov_oracle as orc
+    from pytorch_sparse_solver import problems
+    A = problems.scaled_convdiff3d_csr(5)
+    d = problems.csr_diagonal(A)
+    xt = torch.randn(A.shape[0], dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    b = torch.mv(A.to_dense(), xt)
+    M = lambda r: r / d  # noqa: E731
+    for kind, kw in (("bicgstab", dict(tol=1e-12)), ("gmres", dict(tol=1e-12, restart=20))):
+        x, info, st = getattr(orc, kind)(A, b, None, M=M, **kw)
+        x0, info0, st0 = getattr(orc, kind)(A, b, None, **kw)
+        assert info == 0 and float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt)) <= 1e-8
+        assert st["matvecs"] < st0["matvecs"], (kind, st["matvecs"], st0["matvecs"])
+    S = problems.scaled_poisson3d_csr(5)
+    ds = problems.csr_diagonal(S)
+    bs = torch.mv(S.to_dense(), xt)
+    x, info, st = orc.cg(S, bs, None, tol=1e-12, M=lambda r: r / ds)
+    x0, info0, st0 = orc.cg(S, bs, None, tol=1e-12)
+    assert info == 0 and st["iterations"] < st0["iterations"]
+    assert float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt)) <= 1e-8
