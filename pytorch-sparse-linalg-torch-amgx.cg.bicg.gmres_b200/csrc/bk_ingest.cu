@@ -131,11 +131,15 @@ __global__ void bk_coo_gather_kernel(const int* __restrict__ src, const int* __r
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = src[perm[i]];
 }
 
-__global__ void bk_coo_range_check_kernel(const int* __restrict__ rows, const int* __restrict__ cols, long long nnz,
-                                          int n, int* __restrict__ bad) {
+// on the ORIGINAL index arrays (before any narrowing to int32, which would hide indices >= 2^32)
+template <typename I>
+__global__ void bk_coo_range_check_kernel(const I* __restrict__ rows, const I* __restrict__ cols, long long nnz,
+                                          long long n, int* __restrict__ bad) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride)
-    if ((unsigned)rows[i] >= (unsigned)n || (unsigned)cols[i] >= (unsigned)n) *bad = 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+    const long long r = (long long)rows[i], c = (long long)cols[i];
+    if (r < 0 || r >= n || c < 0 || c >= n) *bad = 1;
+  }
 }
 
 __device__ __forceinline__ bool bk_coo_is_head(const int* srow, const int* scol, long long i) {
@@ -226,15 +230,17 @@ extern "C" int bk_csr_from_coo(bk_handle* h, int64_t n, int64_t nnz, const void*
       return fail(bk_fail(BK_ERR_ALLOC, "bk_csr_from_coo: allocation failed"));
     }
   } else {
+    int* bad = (int*)(h->counters + 8);
+    cudaMemsetAsync(bad, 0, sizeof(int), s);
     if (idx_bits == 64) {
+      bk_coo_range_check_kernel<long long><<<g, 256, 0, s>>>((const long long*)rows, (const long long*)cols, nnz, n, bad);
       bk_convert_i64_i32(h, rows, r32, nnz, s);
       bk_convert_i64_i32(h, cols, c32, nnz, s);
       rows32 = r32;
       cols32 = c32;
+    } else {
+      bk_coo_range_check_kernel<int><<<g, 256, 0, s>>>(rows32, cols32, nnz, n, bad);
     }
-    int* bad = (int*)(h->counters + 8);
-    cudaMemsetAsync(bad, 0, sizeof(int), s);
-    bk_coo_range_check_kernel<<<g, 256, 0, s>>>(rows32, cols32, nnz, (int)n, bad);
     int bits = 1;
     while ((1LL << bits) < n) ++bits;
     // stable sort by column, then by row: (row, col) order with ties in input order

@@ -855,7 +855,7 @@ def test_coo_ingestion_matches_torch(n, nnz, dups):
     bad_idx = badC._indices().clone()
     h = _native.Handle.get(torch.device("cuda"))
     p = _native._VP()
-    bad_idx[0, 0] = 7
+    bad_idx[0, 0] = (1 << 32)            # would alias index 0 if it were narrowed to int32 before the check
     rc = h.lib.bk_csr_from_coo(h.ptr, 1, 1, bad_idx[0].contiguous().data_ptr(), bad_idx[1].contiguous().data_ptr(), 64,
                                badC._values().data_ptr(), _native.BK_F64, _native.BK_F64, None, _native.C.byref(p))
     assert rc == -1
