@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BK_VERSION 100 /* 0.1.0 */
+#define BK_VERSION 200 /* 0.2.0 */
 
 typedef struct bk_handle bk_handle; /* per-device context: scratch, workspaces, graph cache */
 typedef struct bk_csr bk_csr;       /* a registered CSR matrix + its kernel plan */
@@ -80,6 +80,10 @@ typedef struct bk_result {
   double b_norm;         /* || b ||_2 */
   double x_norm;         /* || x ||_2 (NaN check of the reference) */
   double rr_last;        /* last recurrence value: CG gamma = r.r, BiCGStab r.r, GMRES residual norm */
+  int32_t loop_mode_used;/* how the iteration loop actually ran: 1 plain stream launches, 2 CUDA graph of chunks,
+                            3 one persistent cooperative kernel (a failed graph capture shows up here as 1) */
+  int32_t reserved0;
+  double device_ms;      /* device time of the whole call (CUDA events on `stream`: set-up, loop, final check) */
 } bk_result;
 
 typedef struct bk_csr_info {
@@ -88,11 +92,15 @@ typedef struct bk_csr_info {
   int32_t kernel;       /* 0 row-stream (LDG-staged) | 1 sub-warp vector | 2 row-stream, TMA-staged tiles, int32 columns |
                            3 = 2 with 8-bit dictionary-coded columns | 4 long rows split into virtual rows (skewed
                            matrices) + ordered per-row reduction | 5 = 2 with 8-bit codes of (column - row, value)
-                           PAIRS and no value stream (constant-coefficient stencils; lossless, bit-identical) */
+                           PAIRS and no value stream (constant-coefficient stencils; lossless, bit-identical) |
+                           6 = one presence BITMASK per row over its 32-row chunk's pattern of (column - row, value)
+                           pairs; the pattern lives in registers (stencils with <= 8 pairs per chunk; bit-identical) */
   int32_t lanes_per_row;/* for kernel 1 */
   int32_t max_row_nnz;
   double mean_row_nnz;
-  int64_t bytes_matrix; /* bytes one SpMV must read for the matrix: nnz*(sizeof val + 4) + (n+1)*4 */
+  int64_t bytes_matrix; /* ALGORITHMIC bytes one SpMV reads for the matrix: nnz*(sizeof val + 4) + (n+1)*4 (CSR, int32) */
+  int64_t bytes_stream; /* ACTUAL matrix-side bytes the selected kernel streams per SpMV (coded streams, dictionaries,
+                           headers, row pointers ... counted at registration; equals bytes_matrix for kernels 0/1/2) */
 } bk_csr_info;
 
 /* ---- library / handle ------------------------------------------------------------ */
@@ -151,6 +159,11 @@ int bk_csr_transpose(bk_handle* h, bk_csr* A, void* stream, bk_csr** out);
  * entries of A on its sparsity pattern, given g = A^-T dL/dx (the adjoint solve) and the solution x.
  * No reference counterpart in Module A (it returns None for A, :1248); SURVEY §8f-3. */
 int bk_csr_grad_pattern(bk_handle* h, const bk_csr* A, const void* g, const void* x, void* out_vals, void* stream);
+/* 64-bit position-dependent checksum of `nbytes` of device memory (nbytes % 4 == 0), written to *out_host after a
+ * stream synchronisation.  Integer arithmetic only => deterministic.  The Python front end uses it to validate a cached
+ * registration of a BORROWED value array: torch gives no reliable way to notice that a user updated `vals` in place
+ * (the wrapper's version counter does not move), and a stale pair dictionary would silently solve the wrong system. */
+int bk_checksum(bk_handle* h, const void* data, int64_t nbytes, void* stream, uint64_t* out_host);
 /* Export the arrays of a registered matrix (int32 rowptr/col): device pointers, borrowed. */
 int bk_csr_arrays(const bk_csr* A, const void** rowptr, const void** col, const void** val);
 
@@ -167,6 +180,13 @@ int bk_nrm2(bk_handle* h, int64_t n, int dtype, const void* x, double* out, void
 /* z = a x + b y  (z may alias x or y)             (_add/_sub/_mul :165-173) */
 int bk_axpby(bk_handle* h, int64_t n, int dtype, double a, const void* x, double b, const void* y,
              void* z, void* stream);
+/* z = (sa * *a_dev) x + (sb * *b_dev) y with the scalars read from DEVICE memory (fp64; a null pointer stands for 1):
+ * the callable-A route keeps alpha / beta of _cg_solve (:845, :851) on the device, one host sync per iteration
+ * (the stop test, as in the reference :841) instead of one per dot product. */
+int bk_axpby_dev(bk_handle* h, int64_t n, int dtype, double sa, const double* a_dev, const void* x, double sb,
+                 const double* b_dev, const void* y, void* z, void* stream);
+/* z = x / d — true division, the reference's `y / norm` (_safe_normalize :266-272) */
+int bk_div_scalar(bk_handle* h, int64_t n, int dtype, const void* x, double d, void* z, void* stream);
 
 /* ---- solvers ------------------------------------------------------------------------
  * b: device vector (read only).  x: device vector, in = initial guess when has_x0 != 0
@@ -212,8 +232,10 @@ int bk_gmres(bk_handle* h, const bk_csr* A, const void* b, void* x, int has_x0, 
 
 /* ---- host-buffer entry (end-to-end path: H2D copies + solve + D2H inside) -----------
  * All pointers are HOST memory (pinned or pageable).  idx_bits 32/64.  method: 0 cg, 1 bicgstab,
- * 2 gmres (restart/gmres_method used only then; tol/atol are the raw Python floats and the
- * GMRES CUDA-device constants of :737-741 are applied inside).  x_inout: x0 in (if has_x0) / x out. */
+ * 2 gmres (restart/gmres_method used only then).  tol/atol: for cg/bicgstab the caller's Python floats; for gmres
+ * they are forwarded unchanged to bk_gmres, i.e. they must be tol_eff / atol_eff as documented there (the caller
+ * applies the reference's device-dependent constants of :737-748; the Python front end does, with the 'cpu'
+ * constants because the tensors it was given live on the CPU).  x_inout: x0 in (if has_x0) / x out. */
 int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, const void* rowptr, const void* col,
                   int idx_bits, const void* val, int dtype, const void* b, void* x_inout, int has_x0,
                   double tol, double atol, int64_t maxiter, int restart, int gmres_method,

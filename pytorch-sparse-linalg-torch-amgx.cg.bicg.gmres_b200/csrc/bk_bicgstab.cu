@@ -193,6 +193,7 @@ static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0
   v.d = diag;
   bk_dev_state* st = h->st;
   const size_t vbytes = (size_t)n * sizeof(T);
+  bk_call_begin(h, s, "bk_bicgstab");
 
   bk_dev_state init;
   memset(&init, 0, sizeof(init));
@@ -228,7 +229,9 @@ static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0
     return BK_OK;
   };
   int64_t chunks = 0;
+  bk_call_mark(h, "loop");
   BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
+  bk_call_mark(h, "final");
 
   BK_TRY((sys.template matvec<T, 1, 2>(v.x, v.t, nullptr, b, 0, bk_epi_final_r2{st}, s)));
   if (diag) {  // _isolve checks || M (b - A x) || (:1008)
@@ -241,11 +244,13 @@ static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0
   BK_TRY((sys.template dot<T>(v.x, v.x, bk_epi_final_x2{st}, 1, s)));
   BK_CUDA(cudaMemcpyAsync(x_user, v.x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
+  bk_call_stop(h, s);
   BK_CUDA(cudaStreamSynchronize(s));
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, 2 * fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->rs;
   res->kernel_launches = chunks * chunk * 5 + 2 + (has_x0 ? 1 : 0) + 2;
+  bk_call_finish(h, res);
   return sys.check_comm(fin, "bicgstab");
 }
 

@@ -300,6 +300,7 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   v.ap = v.p[1] + npad;
   bk_dev_state* st = h->st;
   const size_t vbytes = (size_t)n * sizeof(T);
+  bk_call_begin(h, s, "bk_cg");
 
   bk_dev_state init;
   memset(&init, 0, sizeof(init));
@@ -344,13 +345,16 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   };
   int64_t chunks = 0;
   bool persistent = false;
+  bk_call_mark(h, "loop");
   BK_TRY(bk_cg_try_persistent<T>(h, A, v.x, v.r, v.p[0], v.p[1], v.ap, s, &persistent));
+  if (persistent) h->last_loop_mode = 3;
   if (!persistent) {
     if (persist_ok)  // cooperative launch unavailable after all: the unfused loop expects p = r0
       BK_CUDA(cudaMemcpyAsync(v.p[0], v.r, vbytes, cudaMemcpyDeviceToDevice, s));
     BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
   }
 
+  bk_call_mark(h, "final");
   {  // final true residual  ||b - A x||  and  ||x||   (_isolve :1008-1013)
     bk_spmv_args a = bk_spmv_base(A, st);
     a.x = v.x;
@@ -363,11 +367,13 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   }
   BK_CUDA(cudaMemcpyAsync(x_user, v.x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
+  bk_call_stop(h, s);
   BK_CUDA(cudaStreamSynchronize(s));
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->gamma;
   res->kernel_launches = (persistent ? 1 : chunks * chunk * (fuse ? 2 : 3)) + 2 /*state, b.b*/ + (has_x0 ? 1 : 0) + 2 /*final*/;
+  bk_call_finish(h, res);
   return BK_OK;
 }
 
@@ -413,6 +419,7 @@ static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, vo
   bk_dev_state* st = h->st;
   const size_t vbytes = (size_t)n * sizeof(T);
   const bk_sys_local sys{h, A};
+  bk_call_begin(h, s, "bk_cg_jacobi");
 
   bk_dev_state init;
   memset(&init, 0, sizeof(init));
@@ -473,7 +480,9 @@ static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, vo
     return BK_OK;
   };
   int64_t chunks = 0;
+  bk_call_mark(h, "loop");
   BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
+  bk_call_mark(h, "final");
 
   // final check of _isolve: || M (b - A x) || against max(tol ||b||, atol) (:1008-1013)
   BK_TRY((sys.matvec<T, 1, 2>(x, ap, nullptr, b, 0, bk_epi_ignore{}, s)));
@@ -487,11 +496,13 @@ static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, vo
   BK_TRY((sys.dot<T>(x, x, bk_epi_final_x{st}, 1, s)));
   BK_CUDA(cudaMemcpyAsync(x_user, x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
+  bk_call_stop(h, s);
   BK_CUDA(cudaStreamSynchronize(s));
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->rs;
   res->kernel_launches = chunks * chunk * 3 + 4 + (has_x0 ? 1 : 0) + 3;
+  bk_call_finish(h, res);
   return BK_OK;
 }
 
@@ -552,6 +563,7 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
   T* ap = p + npad;
   bk_dev_state* st = h->st;
   const size_t vbytes = (size_t)n * sizeof(T);
+  bk_call_begin(h, s, "bk_dist_cg");
 
   bk_dev_state init;
   memset(&init, 0, sizeof(init));
@@ -609,18 +621,22 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
     return BK_OK;
   };
   int64_t chunks = 0;
+  bk_call_mark(h, "loop");
   BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
+  bk_call_mark(h, "final");
 
   // final true residual and ||x|| (global)
   BK_TRY((sys.matvec<T, 1, 2>(x, ap, nullptr, b, 0, bk_epi_final_r{st}, s)));
   BK_TRY((sys.dot<T>(x, x, bk_epi_final_x{st}, 1, s)));
   BK_CUDA(cudaMemcpyAsync(x_user, x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
+  bk_call_stop(h, s);
   BK_CUDA(cudaStreamSynchronize(s));
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->gamma;
   res->kernel_launches = chunks * chunk * (sys.p2p ? (fuse_push ? 4 : 5) : 7) + 12;
+  bk_call_finish(h, res);
   return sys.check_comm(fin, "bk_dist_cg");
 }
 

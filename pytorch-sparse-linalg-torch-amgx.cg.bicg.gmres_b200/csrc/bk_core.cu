@@ -2,11 +2,45 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "bk_internal.cuh"
 #include "bk_spmv.cuh"
 #include "bk_vec.cuh"
 
 thread_local char bk_err_buf[512] = {0};
+
+// ---- per-call bracket: NVTX ranges (BK_NVTX=1 / option nvtx) and device time of the call (bk_result.device_ms) -----
+// the reference has no profiler hooks; these are ours.  nvtx3 is header-only and binds to the
+// profiler's injection library lazily, so there is nothing to link and the calls are no-ops outside a profiler.
+void bk_call_begin(bk_handle* h, cudaStream_t s, const char* name) {
+  h->last_loop_mode = 0;
+  if (h->nvtx) {
+    nvtxRangePushA(name);
+    nvtxRangePushA("setup");
+  }
+  cudaEventRecord(h->ev_t0, s);
+}
+void bk_call_mark(bk_handle* h, const char* phase) {
+  if (h->nvtx) {
+    nvtxRangePop();
+    nvtxRangePushA(phase);
+  }
+}
+void bk_call_stop(bk_handle* h, cudaStream_t s) { cudaEventRecord(h->ev_t1, s); }
+void bk_call_finish(bk_handle* h, bk_result* res) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1) != cudaSuccess) {
+    cudaGetLastError();
+    ms = 0.f;
+  }
+  res->device_ms = (double)ms;
+  res->loop_mode_used = h->last_loop_mode;
+  if (h->nvtx) {
+    nvtxRangePop();
+    nvtxRangePop();
+  }
+}
 
 int bk_fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -68,11 +102,14 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->grid_mult_spmv = (int)bk_env_int("BK_GRID_MULT_SPMV", 4);
   h->tma_ctas = (int)bk_env_int("BK_TMA_CTAS", 4);
   h->pair_ctas = (int)bk_env_int("BK_PAIR_CTAS", 4);
+  h->mask_ctas = (int)bk_env_int("BK_MASK_CTAS", 4);
+  h->mask_group = (int)bk_env_int("BK_MASK_GROUP", 8);
+  h->nvtx = (int)bk_env_int("BK_NVTX", 0);
   h->dist_fuse_push = (int)bk_env_int("BK_DIST_FUSE_PUSH", 1);
   h->tma_stages = (int)bk_env_int("BK_TMA_STAGES", 0);
   h->use_tma = (int)bk_env_int("BK_SPMV_TMA", 1);
   h->dist_p2p = (int)bk_env_int("BK_DIST_P2P", 1);
-  h->use_compress = (int)bk_env_int("BK_SPMV_COMPRESS", 2);
+  h->use_compress = (int)bk_env_int("BK_SPMV_COMPRESS", 3);
   h->use_split = (int)bk_env_int("BK_SPMV_SPLIT", 1);
   h->persistent = (int)bk_env_int("BK_PERSISTENT", 1);
   h->persistent_max_n = (int)bk_env_int("BK_PERSISTENT_MAX_N", 200000);
@@ -90,6 +127,9 @@ extern "C" int bk_create(int device, bk_handle** out) {
   if (e == cudaSuccess) e = cudaMemset(h->st, 0, sizeof(bk_dev_state));
   if (e == cudaSuccess) e = cudaMallocHost(&h->st_host, sizeof(bk_dev_state) * 4);
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev[i], cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t1);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->cksum, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
@@ -125,6 +165,9 @@ extern "C" int bk_destroy(bk_handle* h) {
   if (h->gm_partials) cudaFree(h->gm_partials);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->cksum) cudaFree(h->cksum);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->io_stream) cudaStreamDestroy(h->io_stream);
   free(h);
@@ -157,6 +200,9 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "grid_mult")) return &h->grid_mult_spmv;
   if (!strcmp(key, "tma_ctas")) return &h->tma_ctas;
   if (!strcmp(key, "pair_ctas")) return &h->pair_ctas;
+  if (!strcmp(key, "mask_ctas")) return &h->mask_ctas;
+  if (!strcmp(key, "mask_group")) return &h->mask_group;
+  if (!strcmp(key, "nvtx")) return &h->nvtx;
   if (!strcmp(key, "dist_fuse_push")) return &h->dist_fuse_push;
   if (!strcmp(key, "tma_stages")) return &h->tma_stages;
   if (!strcmp(key, "use_tma")) return &h->use_tma;
@@ -214,7 +260,8 @@ void bk_convert_i64_i32(bk_handle* h, const void* in, void* out, long long n, cu
 
 // max row length + validity (monotone rowptr, columns in range) in one pass over rowptr/col
 __global__ void bk_csr_stats_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, long long n,
-                                    long long nnz, int* __restrict__ out /* [0] max len, [1] bad flag */) {
+                                    long long n_cols, long long nnz,
+                                    int* __restrict__ out /* [0] max len, [1] bad flag */) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int mx = 0;
@@ -226,7 +273,7 @@ __global__ void bk_csr_stats_kernel(const int* __restrict__ rowptr, const int* _
   }
   for (long long i = tid; i < nnz; i += stride) {
     const int c = col[i];
-    if (c < 0 || c >= n) bad = 1;
+    if (c < 0 || c >= n_cols) bad = 1;
   }
   for (int o = 16; o > 0; o >>= 1) {
     mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -419,6 +466,7 @@ static int bk_csr_plan_compress(bk_handle* h, bk_csr* A, cudaStream_t s) {
   }
   A->cmp_cap = cap;
   A->kernel = 3;
+  A->bytes_stream = A->nnz * (int64_t)(vs + 1) + nblk * 128 + (A->n + 1) * 4;
   return BK_OK;
 }
 
@@ -592,7 +640,346 @@ static int bk_csr_plan_pairs(bk_handle* h, bk_csr* A, cudaStream_t s) {
   }
   A->pair_cap = cap;
   A->kernel = 5;
+  A->bytes_stream = (int64_t)total + nblk * (int64_t)BK_PAIR_DICT_BYTES + (nblk + 1) * 4;
   return BK_OK;
+}
+
+// ---- row bitmasks over per-chunk patterns of (column - row, value) pairs (kernel 6, bk_spmv_mask.cuh) -------------
+// One warp per 32-row chunk: (1) collect the chunk's distinct pairs (lane i keeps pair i; leader broadcast + ballot as
+// in the pair-dictionary builder above); (2) rank them by (global offset, value bits, ...) -> the sorted PATTERN;
+// (3) every lane ORs the ranks of its row's entries into its mask and checks that they ascend, i.e. that the pattern
+// order is the CSR order of every row (the SpMV then reproduces the CSR FMA chain bit for bit).
+// Row-partitioned matrices (n_cols > n): columns >= n index the ghost vector; `ghost_gid` gives their global ids and
+// `row_begin` the global id of row 0, so that pairs are ordered by GLOBAL offset like the rows of the global matrix.
+struct bk_mask_key {
+  long long goff;          // global column - global row (sort key)
+  unsigned long long vb;   // value bits
+  int off;                 // load offset: index into x (or the ghost vector) minus the local row
+  int gh;                  // 1: ghost entry
+};
+__device__ __forceinline__ bool bk_mask_less(const bk_mask_key& a, const bk_mask_key& b) {
+  if (a.goff != b.goff) return a.goff < b.goff;
+  if (a.vb != b.vb) return a.vb < b.vb;
+  if (a.gh != b.gh) return a.gh < b.gh;
+  return a.off < b.off;
+}
+__device__ __forceinline__ bool bk_mask_same(const bk_mask_key& a, const bk_mask_key& b) {
+  return a.goff == b.goff && a.vb == b.vb && a.gh == b.gh && a.off == b.off;
+}
+__device__ __forceinline__ bk_mask_key bk_mask_shfl(const bk_mask_key& k, int src) {
+  bk_mask_key r;
+  r.goff = __shfl_sync(0xffffffffu, k.goff, src);
+  r.vb = __shfl_sync(0xffffffffu, k.vb, src);
+  r.off = __shfl_sync(0xffffffffu, k.off, src);
+  r.gh = __shfl_sync(0xffffffffu, k.gh, src);
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bk_mask_build_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, const T* __restrict__ val,
+                     long long n, long long nchunks, const long long* __restrict__ ghost_gid, long long row_begin,
+                     bk_pair_entry* __restrict__ cpat, unsigned char* __restrict__ masks, int* __restrict__ pids,
+                     int* __restrict__ fail) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * 8;
+  for (long long ch = warp0; ch < nchunks; ch += nwarps) {
+    if (*(volatile int*)fail) return;  // another chunk already disqualified the matrix
+    const long long r = ch * 32 + lane;
+    int s = 0, e = 0;
+    if (r < n) {
+      s = rowptr[r];
+      e = rowptr[r + 1];
+    }
+    const int len = e - s;
+    int maxlen = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    bool bad = maxlen > BK_MASK_L;
+    bk_mask_key tab;  // lane i < count holds pattern entry i (unsorted)
+    tab.goff = 0;
+    tab.vb = 0ull;
+    tab.off = 0;
+    tab.gh = 0;
+    int count = 0;
+    int codes[BK_MASK_L];
+    int any_ghost = 0;
+#pragma unroll
+    for (int k = 0; k < BK_MASK_L; ++k) {
+      codes[k] = 0;
+      if (k < maxlen && !bad) {  // warp-uniform
+        const bool active = k < len;
+        bk_mask_key me;
+        me.goff = 0;
+        me.vb = 0ull;
+        me.off = 0;
+        me.gh = 0;
+        if (active) {
+          const int c = col[s + k];
+          if ((long long)c >= n) {  // ghost column of a row-partitioned matrix
+            me.gh = 1;
+            me.off = (int)((long long)c - n - r);
+            me.goff = ghost_gid[c - n] - (row_begin + r);
+          } else {
+            me.off = (int)((long long)c - r);
+            me.goff = (long long)c - r;
+          }
+          if (sizeof(T) == 8) me.vb = (unsigned long long)__double_as_longlong((double)val[s + k]);
+          else me.vb = (unsigned long long)__float_as_uint((float)val[s + k]);
+        }
+        any_ghost |= me.gh;
+        unsigned int remaining = __ballot_sync(0xffffffffu, active);
+        while (remaining) {
+          const int leader = __ffs(remaining) - 1;
+          const bk_mask_key lk = bk_mask_shfl(me, leader);
+          const bool same = active && bk_mask_same(me, lk);
+          const unsigned int grp = __ballot_sync(0xffffffffu, same);
+          const unsigned int hit = __ballot_sync(0xffffffffu, lane < count && bk_mask_same(tab, lk));
+          int idx;
+          if (hit) {
+            idx = __ffs(hit) - 1;
+          } else if (count >= BK_MASK_L) {
+            bad = true;
+            idx = 0;
+          } else {
+            idx = count;
+            if (lane == count) tab = lk;
+            ++count;
+          }
+          if (same) codes[k] = idx;
+          remaining &= ~grp;
+        }
+      }
+    }
+    // rank of every table entry in the sorted pattern
+    int rank = 0;
+    for (int j = 0; j < count; ++j) {
+      const bk_mask_key kj = bk_mask_shfl(tab, j);
+      if (lane < count && bk_mask_less(kj, tab)) ++rank;
+    }
+    unsigned int mask = 0u;
+    int prev = -1;
+    bool disorder = false;
+#pragma unroll
+    for (int k = 0; k < BK_MASK_L; ++k) {
+      const int rk = __shfl_sync(0xffffffffu, rank, codes[k]);
+      if (k < len) {
+        if (rk <= prev) disorder = true;  // columns not ascending / repeated inside the row
+        prev = rk;
+        mask |= 1u << rk;
+      }
+    }
+    if (__any_sync(0xffffffffu, disorder)) bad = true;
+    any_ghost = __any_sync(0xffffffffu, any_ghost != 0) ? 1 : 0;
+    if (bad) {
+      if (lane == 0) *fail = 1;
+      return;
+    }
+    masks[ch * 32 + lane] = (unsigned char)((r < n) ? mask : 0u);
+    bk_pair_entry ent;
+    ent.val = 0ull;
+    ent.off = 0;
+    ent.pad = 0;
+    if (lane < count) {
+      ent.val = tab.vb;
+      ent.off = tab.off;
+      ent.pad = tab.gh ? BK_MASK_GHOST : 0;
+      cpat[ch * BK_MASK_L + rank] = ent;
+    } else if (lane < BK_MASK_L) {
+      cpat[ch * BK_MASK_L + lane] = ent;  // lanes count..7 fill the unused tail (ranks cover 0..count-1)
+    }
+    if (lane == 0) pids[ch] = any_ghost ? BK_MASK_PID_GHOST : 0;
+  }
+}
+
+__device__ __forceinline__ unsigned long long bk_mix64(unsigned long long x) {
+  x ^= x >> 30;
+  x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27;
+  x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+// De-duplicate the chunk patterns into an open-addressing table keyed by a 64-bit hash of the 128 pattern bytes; the
+// chunk that claims a slot stores its pattern there.  bk_mask_verify_kernel (next launch) compares every chunk's pattern
+// with the stored one, so a hash collision disqualifies the matrix instead of corrupting it.
+__global__ void bk_mask_insert_kernel(const bk_pair_entry* __restrict__ cpat, long long nchunks,
+                                      unsigned long long* __restrict__ keys, bk_pair_entry* __restrict__ ptab,
+                                      int* __restrict__ pids, int* __restrict__ stat /* [0] fail [1] patterns */) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride) {
+    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(cpat + ch * BK_MASK_L);
+    ulonglong2 q[BK_MASK_L];
+    unsigned long long hsh = 0x9e3779b97f4a7c15ull;
+#pragma unroll
+    for (int e = 0; e < BK_MASK_L; ++e) {
+      q[e] = src[e];
+      hsh = bk_mix64(hsh ^ q[e].x) + 0x632be59bd9b4e019ull;
+      hsh = bk_mix64(hsh ^ q[e].y);
+    }
+    if (hsh == 0ull) hsh = 1ull;
+    int slot = (int)(hsh & (BK_MASK_HT - 1));
+    bool found = false;
+    for (int probe = 0; probe < BK_MASK_HT; ++probe) {
+      const unsigned long long old = atomicCAS(&keys[slot], 0ull, hsh);
+      if (old == 0ull) {
+        atomicAdd(&stat[1], 1);
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(ptab + (size_t)slot * BK_MASK_L);
+#pragma unroll
+        for (int e = 0; e < BK_MASK_L; ++e) dst[e] = q[e];
+        found = true;
+        break;
+      }
+      if (old == hsh) {
+        found = true;
+        break;
+      }
+      slot = (slot + 1) & (BK_MASK_HT - 1);
+    }
+    if (!found) stat[0] = 2;
+    pids[ch] |= slot;
+  }
+}
+
+__global__ void bk_mask_verify_kernel(const bk_pair_entry* __restrict__ cpat, long long nchunks,
+                                      const bk_pair_entry* __restrict__ ptab, const int* __restrict__ pids,
+                                      int* __restrict__ stat) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride) {
+    const ulonglong2* a = reinterpret_cast<const ulonglong2*>(cpat + ch * BK_MASK_L);
+    const ulonglong2* b =
+        reinterpret_cast<const ulonglong2*>(ptab + (size_t)(pids[ch] & (BK_MASK_PID_GHOST - 1)) * BK_MASK_L);
+    bool same = true;
+#pragma unroll
+    for (int e = 0; e < BK_MASK_L; ++e) {
+      const ulonglong2 x = a[e], y = b[e];
+      same = same && x.x == y.x && x.y == y.y;
+    }
+    if (!same) stat[0] = 3;
+  }
+}
+
+// flags[ch] = 1 for chunks with ghost entries -> (after an exclusive scan) their compact list
+__global__ void bk_mask_flag_kernel(const int* __restrict__ pids, long long nchunks, unsigned int* __restrict__ flags) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch <= nchunks; ch += stride)
+    flags[ch] = (ch < nchunks && (pids[ch] & BK_MASK_PID_GHOST)) ? 1u : 0u;
+}
+__global__ void bk_mask_compact_kernel(const int* __restrict__ pids, long long nchunks,
+                                       const unsigned int* __restrict__ pos, int* __restrict__ out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long ch = (long long)blockIdx.x * blockDim.x + threadIdx.x; ch < nchunks; ch += stride)
+    if (pids[ch] & BK_MASK_PID_GHOST) out[pos[ch]] = (int)ch;
+}
+
+// Try the row-bitmask plan (kernel 6).  ghost_gid / row_begin: see bk_mask_build_kernel (nullptr / 0 on one GPU).
+int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long long row_begin, cudaStream_t s) {
+  if (h->use_compress < 3 || A->is_view || A->n == 0 || A->nnz == 0 || A->max_row_nnz > BK_MASK_L) return BK_OK;
+  const long long nchunks = (A->n + 31) / 32;
+  bk_pair_entry* cpat = nullptr;
+  unsigned long long* keys = nullptr;
+  int* dstat = (int*)(h->counters + 8);
+  auto drop = [&]() {
+    if (A->mmasks) bk_pool_free(A->mmasks);
+    if (A->mpids) bk_pool_free(A->mpids);
+    if (A->mptab) bk_pool_free(A->mptab);
+    if (A->mdeferred) bk_pool_free(A->mdeferred);
+    A->mmasks = nullptr;
+    A->mpids = nullptr;
+    A->mptab = nullptr;
+    A->mdeferred = nullptr;
+    A->n_mdeferred = 0;
+  };
+  auto done = [&](int rc) {
+    if (cpat) bk_pool_free(cpat);
+    if (keys) bk_pool_free(keys);
+    return rc;
+  };
+  if (bk_pool_alloc((void**)&cpat, sizeof(bk_pair_entry) * BK_MASK_L * (size_t)nchunks, s) != cudaSuccess ||
+      bk_pool_alloc((void**)&keys, sizeof(unsigned long long) * BK_MASK_HT, s) != cudaSuccess ||
+      bk_pool_alloc((void**)&A->mmasks, (size_t)nchunks * 32, s) != cudaSuccess ||
+      bk_pool_alloc((void**)&A->mpids, sizeof(int) * (size_t)nchunks, s) != cudaSuccess ||
+      bk_pool_alloc(&A->mptab, sizeof(bk_pair_entry) * BK_MASK_L * BK_MASK_HT, s) != cudaSuccess) {
+    cudaGetLastError();
+    drop();
+    return done(BK_OK);  // not enough memory for the coded copy: other plans follow
+  }
+  int host[2] = {0, 0};
+  cudaMemsetAsync(dstat, 0, 2 * sizeof(int), s);
+  cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * BK_MASK_HT, s);
+  cudaMemsetAsync(A->mptab, 0, sizeof(bk_pair_entry) * BK_MASK_L * BK_MASK_HT, s);
+  long long want = (nchunks + 7) / 8;
+  int grid = (int)(want < (long long)h->num_sms * 8 ? want : (long long)h->num_sms * 8);
+  if (grid < 1) grid = 1;
+  if (A->dtype == BK_F64)
+    bk_mask_build_kernel<double><<<grid, 256, 0, s>>>(A->rowptr, A->col, (const double*)A->val, A->n, nchunks, ghost_gid,
+                                                     row_begin, cpat, A->mmasks, A->mpids, dstat);
+  else
+    bk_mask_build_kernel<float><<<grid, 256, 0, s>>>(A->rowptr, A->col, (const float*)A->val, A->n, nchunks, ghost_gid,
+                                                    row_begin, cpat, A->mmasks, A->mpids, dstat);
+  cudaMemcpyAsync(host, dstat, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    drop();
+    return done(bk_fail(BK_ERR_CUDA, "csr registration (row bitmasks): %s", cudaGetErrorString(e)));
+  }
+  if (host[0] != 0) {  // some chunk has > 8 distinct pairs, or rows with unsorted / repeated columns
+    drop();
+    return done(BK_OK);
+  }
+  want = (nchunks + 255) / 256;
+  grid = (int)(want < (long long)h->num_sms * 8 ? want : (long long)h->num_sms * 8);
+  if (grid < 1) grid = 1;
+  bk_mask_insert_kernel<<<grid, 256, 0, s>>>(cpat, nchunks, keys, (bk_pair_entry*)A->mptab, A->mpids, dstat);
+  bk_mask_verify_kernel<<<grid, 256, 0, s>>>(cpat, nchunks, (const bk_pair_entry*)A->mptab, A->mpids, dstat);
+  cudaMemcpyAsync(host, dstat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+  e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    drop();
+    return done(bk_fail(BK_ERR_CUDA, "csr registration (pattern table): %s", cudaGetErrorString(e)));
+  }
+  if (host[0] != 0 || host[1] > BK_MASK_HT / 2) {  // table overflow / hash collision: not a pattern matrix
+    drop();
+    return done(BK_OK);
+  }
+  A->mask_patterns = host[1];
+  if (A->n_cols > A->n) {  // row partition: compact list of the chunks that gather from the ghost vector
+    unsigned int* flags = nullptr;
+    if (bk_pool_alloc((void**)&flags, sizeof(unsigned int) * (size_t)(nchunks + 1), s) != cudaSuccess) {
+      cudaGetLastError();
+      drop();
+      return done(BK_OK);
+    }
+    bk_mask_flag_kernel<<<grid, 256, 0, s>>>(A->mpids, nchunks, flags);
+    int rc = bk_exclusive_scan_u32(flags, nchunks + 1, s);
+    unsigned int total = 0;
+    if (rc == BK_OK) {
+      cudaMemcpyAsync(&total, flags + nchunks, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+      if (cudaStreamSynchronize(s) != cudaSuccess) rc = bk_fail(BK_ERR_CUDA, "csr registration (deferred chunks)");
+    }
+    if (rc == BK_OK && total > 0) {
+      if (bk_pool_alloc((void**)&A->mdeferred, sizeof(int) * (size_t)total, s) != cudaSuccess) {
+        cudaGetLastError();
+        rc = bk_fail(BK_ERR_ALLOC, "csr registration (deferred chunks): allocation failed");
+      } else {
+        bk_mask_compact_kernel<<<grid, 256, 0, s>>>(A->mpids, nchunks, flags, A->mdeferred);
+        if (cudaStreamSynchronize(s) != cudaSuccess) rc = bk_fail(BK_ERR_CUDA, "csr registration (deferred chunks)");
+      }
+    }
+    bk_pool_free(flags);
+    if (rc != BK_OK) {
+      drop();
+      return done(rc);
+    }
+    A->n_mdeferred = (int)total;
+  }
+  A->kernel = 6;
+  A->bytes_stream = nchunks * 32 + nchunks * 4 + (int64_t)A->mask_patterns * BK_MASK_L * (int64_t)sizeof(bk_pair_entry);
+  return done(BK_OK);
 }
 
 // Decide whether the TMA row-stream kernel (bk_spmv_tma.cuh) can serve this matrix, size its pipeline and
@@ -640,11 +1027,12 @@ static int bk_csr_plan_tma(bk_handle* h, bk_csr* A, cudaStream_t s) {
 // statistics + validation + kernel plan (one sync at registration time; never on the per-iteration path)
 int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s) {
   const int64_t n = A->n, nnz = A->nnz;
+  if (A->n_cols < n) A->n_cols = n;
   int* dstat = (int*)(h->counters + 8);
   int hstat[2] = {0, 0};
   int ends[2] = {0, 0};
   cudaMemsetAsync(dstat, 0, 2 * sizeof(int), s);
-  if (n > 0) bk_csr_stats_kernel<<<h->num_sms * 8, 256, 0, s>>>(A->rowptr, A->col, n, nnz, dstat);
+  if (n > 0) bk_csr_stats_kernel<<<h->num_sms * 8, 256, 0, s>>>(A->rowptr, A->col, n, A->n_cols, nnz, dstat);
   cudaMemcpyAsync(hstat, dstat, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(&ends[0], A->rowptr, sizeof(int), cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(&ends[1], A->rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, s);
@@ -656,8 +1044,14 @@ int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s) {
                    (long long)nnz, hstat[1]);
   A->max_row_nnz = hstat[0];
   bk_csr_plan(h, A);
+  A->bytes_stream = nnz * (int64_t)(bk_dtype_size(A->dtype) + 4) + (n + 1) * 4;
   BK_TRY(bk_csr_plan_split(h, A, s));
-  if (A->split) return BK_OK;  // the virtual-row view carries the kernel plan
+  if (A->split) {  // the virtual-row view carries the kernel plan
+    A->bytes_stream = A->split->bytes_stream + (n + 1) * 4 + 2 * A->split->n * (int64_t)bk_dtype_size(A->dtype);
+    return BK_OK;
+  }
+  if (A->kernel == 0 && A->n_cols == A->n) BK_TRY(bk_csr_plan_mask(h, A, nullptr, 0, s));
+  if (A->kernel == 6) return BK_OK;
   return bk_csr_plan_tma(h, A, s);
 }
 
@@ -751,6 +1145,10 @@ extern "C" int bk_csr_destroy(bk_csr* A) {
   if (A->pcodes) bk_pool_free(A->pcodes);
   if (A->pdict) bk_pool_free(A->pdict);
   if (A->pbptr) bk_pool_free(A->pbptr);
+  if (A->mmasks) bk_pool_free(A->mmasks);
+  if (A->mpids) bk_pool_free(A->mpids);
+  if (A->mptab) bk_pool_free(A->mptab);
+  if (A->mdeferred) bk_pool_free(A->mdeferred);
   free(A);
   return BK_OK;
 }
@@ -765,6 +1163,7 @@ extern "C" int bk_csr_get_info(const bk_csr* A, bk_csr_info* out) {
   out->max_row_nnz = A->max_row_nnz;
   out->mean_row_nnz = A->mean_row_nnz;
   out->bytes_matrix = A->nnz * (int64_t)(bk_dtype_size(A->dtype) + 4) + (A->n + 1) * 4;
+  out->bytes_stream = A->bytes_stream;
   return BK_OK;
 }
 
@@ -861,6 +1260,48 @@ extern "C" int bk_axpby(bk_handle* h, int64_t n, int dtype, double a, const void
   return bk_fail(BK_ERR_ARG, "bk_axpby: bad dtype %d", dtype);
 }
 
+template <typename T>
+static int bk_axpby_dev_t(bk_handle* h, int64_t n, double sa, const double* pa, const void* x, double sb,
+                          const double* pb, const void* y, void* z, cudaStream_t s) {
+  bk_op_axpby_dev<T> op;
+  op.x = (const T*)x;
+  op.y = (const T*)y;
+  op.z = (T*)z;
+  op.pa = pa;
+  op.pb = pb;
+  op.sa = sa;
+  op.sb = sb;
+  return bk_launch_ew<T>(h, op, n, bk_aligned16(x) && bk_aligned16(y) && bk_aligned16(z), bk_slot(h, 0), s);
+}
+
+extern "C" int bk_axpby_dev(bk_handle* h, int64_t n, int dtype, double sa, const double* a_dev, const void* x,
+                            double sb, const double* b_dev, const void* y, void* z, void* stream) {
+  if (!h || (n > 0 && (!x || !y || !z))) return bk_fail(BK_ERR_ARG, "bk_axpby_dev: null argument");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (n == 0) return BK_OK;
+  if (dtype == BK_F64) return bk_axpby_dev_t<double>(h, n, sa, a_dev, x, sb, b_dev, y, z, (cudaStream_t)stream);
+  if (dtype == BK_F32) return bk_axpby_dev_t<float>(h, n, sa, a_dev, x, sb, b_dev, y, z, (cudaStream_t)stream);
+  return bk_fail(BK_ERR_ARG, "bk_axpby_dev: bad dtype %d", dtype);
+}
+
+template <typename T>
+static int bk_div_t(bk_handle* h, int64_t n, const void* x, double d, void* z, cudaStream_t s) {
+  bk_op_div<T> op;
+  op.x = (const T*)x;
+  op.z = (T*)z;
+  op.d = (T)d;
+  return bk_launch_ew<T>(h, op, n, bk_aligned16(x) && bk_aligned16(z), bk_slot(h, 0), s);
+}
+
+extern "C" int bk_div_scalar(bk_handle* h, int64_t n, int dtype, const void* x, double d, void* z, void* stream) {
+  if (!h || (n > 0 && (!x || !z))) return bk_fail(BK_ERR_ARG, "bk_div_scalar: null argument");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (n == 0) return BK_OK;
+  if (dtype == BK_F64) return bk_div_t<double>(h, n, x, d, z, (cudaStream_t)stream);
+  if (dtype == BK_F32) return bk_div_t<float>(h, n, x, d, z, (cudaStream_t)stream);
+  return bk_fail(BK_ERR_ARG, "bk_div_scalar: bad dtype %d", dtype);
+}
+
 // ---- gradient with respect to the stored entries of A -----------------------------------------
 // For A x = b and a loss L(x):  dL/dA_ij = -(A^-T dL/dx)_i x_j = -g_i x_j, evaluated on the sparsity pattern only
 // (an SDDMM-shaped kernel).  The reference returns no gradient for A (torch_sparse_linalg.py:1248); its Modules B/C
@@ -891,5 +1332,37 @@ extern "C" int bk_csr_grad_pattern(bk_handle* h, const bk_csr* A, const void* g,
     bk_grad_pattern_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(A->rowptr, A->col, (const float*)g,
                                                                            (const float*)x, (float*)out_vals, A->n);
   BK_KERNEL_CHECK();
+  return BK_OK;
+}
+
+// ---- checksum of a device array (cache validation of borrowed value arrays; see include/bk_krylov.h) ---------------
+__global__ void bk_checksum_kernel(const unsigned int* __restrict__ p, long long nwords, unsigned long long* out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned long long acc = 0ull;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride)
+    acc += bk_mix64(((unsigned long long)p[i] << 32) ^ (unsigned long long)i ^ 0x9e3779b97f4a7c15ull);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc != 0ull) atomicAdd(out, acc);  // integer sum: order-independent
+}
+
+extern "C" int bk_checksum(bk_handle* h, const void* data, int64_t nbytes, void* stream, uint64_t* out_host) {
+  if (!h || !out_host || nbytes < 0 || (nbytes > 0 && !data)) return bk_fail(BK_ERR_ARG, "bk_checksum: bad argument");
+  if (nbytes % 4 != 0 || (((uintptr_t)data) & 3u) != 0)
+    return bk_fail(BK_ERR_ARG, "bk_checksum: data and size must be 4-byte aligned");
+  BK_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  BK_CUDA(cudaMemsetAsync(h->cksum, 0, sizeof(unsigned long long), s));
+  const long long nwords = nbytes / 4;
+  if (nwords > 0) {
+    long long want = (nwords + 256 * 8 - 1) / (256 * 8);
+    int grid = (int)(want < (long long)h->num_sms * 8 ? want : (long long)h->num_sms * 8);
+    bk_checksum_kernel<<<grid, 256, 0, s>>>((const unsigned int*)data, nwords, h->cksum);
+    BK_KERNEL_CHECK();
+  }
+  unsigned long long v = 0;
+  BK_CUDA(cudaMemcpyAsync(&v, h->cksum, sizeof(v), cudaMemcpyDeviceToHost, s));
+  BK_CUDA(cudaStreamSynchronize(s));
+  *out_host = (uint64_t)(v ^ (unsigned long long)nbytes);
   return BK_OK;
 }

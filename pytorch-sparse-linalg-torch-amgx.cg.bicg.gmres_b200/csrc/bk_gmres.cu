@@ -405,6 +405,7 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
   const size_t vbytes = (size_t)n * sizeof(T);
   constexpr int NW = bk_native_w<T>::value;
   const bk_gsum gs = sys.gsum();
+  bk_call_begin(h, s, "bk_gmres");
 
   // small dense arrays
   const size_t small_doubles = (size_t)(m + 1) * m + 2 * (size_t)m + 2 * (size_t)(m + 1) + m + 16;
@@ -549,14 +550,18 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   if (diag) key[1] ^= (uint64_t)(uintptr_t)diag * 0x9e3779b97f4a7c15ull;  // its address is baked into the graph
   int64_t chunks = 0;
+  bk_call_mark(h, "loop");
   BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_cycle, &chunks));
+  bk_call_mark(h, "final");
 
   // ---- final check (:766-773): the last residual pass already holds ||b - A x||; add ||x|| --------
   BK_TRY((sys.template dot<T>(x, x, bk_epi_gm_xx{st}, 1, s)));
   BK_CUDA(cudaMemcpyAsync(x_user, x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
+  bk_call_stop(h, s);
   BK_CUDA(cudaStreamSynchronize(s));
   const bk_dev_state* fin = &h->st_host[3];
+  bk_call_finish(h, res);
   res->iterations = fin->k;
   res->matvecs = fin->matvecs;
   res->kernel_launches = chunks * (4 * (int64_t)m + 4) + 5;

@@ -11,7 +11,8 @@
 // ---- dense ---------------------------------------------------------------------------------------------------
 template <typename TI>
 __global__ void __launch_bounds__(256)
-bk_dense_count_kernel(const TI* __restrict__ a, long long n, long long ld, unsigned int* __restrict__ cnt) {
+bk_dense_count_kernel(const TI* __restrict__ a, long long n, long long ld, unsigned int* __restrict__ cnt,
+                      unsigned long long* __restrict__ total /* 64-bit count: the 32-bit scan below could wrap */) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -21,7 +22,10 @@ bk_dense_count_kernel(const TI* __restrict__ a, long long n, long long ld, unsig
     for (long long j = lane; j < n; j += 32) c += (row[j] != TI(0)) ? 1u : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) cnt[r] = c;
+    if (lane == 0) {
+      cnt[r] = c;
+      if (c) atomicAdd(total, (unsigned long long)c);
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) cnt[n] = 0u;
 }
@@ -84,10 +88,20 @@ extern "C" int bk_csr_from_dense(bk_handle* h, int64_t n, const void* dense, int
     return fail(bk_fail(BK_ERR_ALLOC, "bk_csr_from_dense: allocation failed"));
   }
   const int g = h->num_sms * 8;
+  cudaMemsetAsync(h->cksum, 0, sizeof(unsigned long long), s);
   if (in_dtype == BK_F64)
-    bk_dense_count_kernel<double><<<g, 256, 0, s>>>((const double*)dense, n, ld, (unsigned int*)A->own_rowptr);
+    bk_dense_count_kernel<double><<<g, 256, 0, s>>>((const double*)dense, n, ld, (unsigned int*)A->own_rowptr, h->cksum);
   else
-    bk_dense_count_kernel<float><<<g, 256, 0, s>>>((const float*)dense, n, ld, (unsigned int*)A->own_rowptr);
+    bk_dense_count_kernel<float><<<g, 256, 0, s>>>((const float*)dense, n, ld, (unsigned int*)A->own_rowptr, h->cksum);
+  {  // the row-pointer scan is 32-bit: reject matrices with >= 2^31 non-zeros on the 64-bit total BEFORE trusting it
+    unsigned long long total = 0;
+    cudaMemcpyAsync(&total, h->cksum, sizeof(total), cudaMemcpyDeviceToHost, s);
+    cudaError_t e0 = cudaStreamSynchronize(s);
+    if (e0 == cudaSuccess) e0 = cudaGetLastError();
+    if (e0 != cudaSuccess) return fail(bk_fail(BK_ERR_CUDA, "bk_csr_from_dense: %s", cudaGetErrorString(e0)));
+    if (total >= 2147483647ull)
+      return fail(bk_fail(BK_ERR_UNSUPPORTED, "bk_csr_from_dense: nnz must be < 2^31 (matrix has %llu non-zeros)", total));
+  }
   int rc = bk_exclusive_scan_u32((unsigned int*)A->own_rowptr, n + 1, s);
   if (rc != BK_OK) return fail(rc);
   unsigned int nnz_u = 0;

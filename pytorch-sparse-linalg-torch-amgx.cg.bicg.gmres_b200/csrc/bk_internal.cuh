@@ -115,6 +115,16 @@ struct bk_csr {
   void* pdict;               // nblk * 32 bk_pair_entry (16 B each), own
   int* pbptr;                // [n/256 + 1] byte offset of every 256-row block span in pcodes, own
   int pair_cap;              // code bytes per pipeline stage
+  // row-bitmask stream (kernel 6, bk_spmv_mask.cuh): one presence byte per row over its 32-row chunk's pattern of
+  // (column - row, value) pairs, one pattern-table slot per chunk
+  unsigned char* mmasks;     // [nchunks * 32], own
+  int* mpids;                // [nchunks], own
+  void* mptab;               // BK_MASK_HT * 8 bk_pair_entry, own
+  int* mdeferred;            // multi-GPU: chunks with ghost entries (processed after the halo arrived), own
+  int n_mdeferred;
+  int mask_patterns;         // distinct patterns in the table
+  int64_t n_cols;            // columns (== n except for the extended local+ghost matrix of a row partition)
+  int64_t bytes_stream;      // actual matrix-side bytes the selected kernel reads per SpMV (bk_csr_info)
   int max_row_nnz;
   double mean_row_nnz;
   bk_csr* transpose;  // cached, owned
@@ -146,6 +156,10 @@ struct bk_handle {
   int grid_mult_spmv;  // CTAs/SM of SpMV kernels
   int tma_ctas;        // CTAs/SM of the TMA row-stream SpMV (2..4)
   int pair_ctas;       // CTAs/SM of the pair-coded SpMV (2..6)
+  int mask_ctas;       // CTAs/SM of the row-bitmask SpMV (kernel 6; 2..6)
+  int mask_group;      // kernel 6: consecutive 256-row blocks dealt to a CTA at a time
+  int nvtx;            // emit NVTX ranges around the phases of every solve (BK_NVTX=1)
+  int last_loop_mode;  // how the last iteration loop actually ran (bk_result.loop_mode_used)
   int dist_fuse_push;  // multi-GPU CG, peer path: fold the halo push into the kernel that produces p (1)
   int tma_stages;      // 0 = fill shared memory, else cap on the pipeline depth
   int use_tma;         // allow the TMA row-stream kernel
@@ -175,6 +189,8 @@ struct bk_handle {
   size_t gm_partials_bytes;
   // poll events
   cudaEvent_t ev[4];
+  cudaEvent_t ev_t0, ev_t1;  // device time of a solve (bk_result.device_ms)
+  unsigned long long* cksum; // device scratch of bk_checksum
   // graph cache
   bk_graph_entry graphs[8];
   cudaStream_t cap_stream;
@@ -205,6 +221,12 @@ int bk_ws_reserve(bk_handle* h, size_t bytes);  // grows h->ws (invalidates cach
 void bk_graphs_invalidate(bk_handle* h);
 void bk_dist_release_comm(bk_handle* h);  // bk_dist.cu
 void bk_state_fill_tol(bk_dev_state* v, double tol, double atol);
+// bracket of every solver entry: NVTX range + start event | stop event (enqueue before the final stream sync) |
+// after the sync: device_ms, loop_mode_used, NVTX pop
+void bk_call_begin(bk_handle* h, cudaStream_t s, const char* name);
+void bk_call_mark(bk_handle* h, const char* phase);  // NVTX only: closes the previous phase range, opens `phase`
+void bk_call_stop(bk_handle* h, cudaStream_t s);
+void bk_call_finish(bk_handle* h, bk_result* res);
 void bk_fill_result_isolve(const bk_dev_state* st, bk_result* res, int64_t matvecs);
 void bk_convert_i64_i32(bk_handle* h, const void* in, void* out, long long n, cudaStream_t s);
 int bk_exclusive_scan_u32(unsigned int* data, long long n, cudaStream_t s);
@@ -214,6 +236,7 @@ void bk_lower_bound_i32(bk_handle* h, const int* keys, long long count, long lon
 void bk_iota_i32(bk_handle* h, int* out, long long n, cudaStream_t s);
 #define BK_SPLIT_LEN 256
 int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s);
+int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long long row_begin, cudaStream_t s);
 int bk_solver_args_check(const char* who, bk_handle* h, const bk_csr* A, const void* b, void* x, bk_result* res);
 
 static inline int bk_grid_vec(const bk_handle* h) {

@@ -80,6 +80,7 @@ static int bk_run_loop(bk_handle* h, cudaStream_t s, bool use_graph, const uint6
       exec = nullptr;
     }
   }
+  h->last_loop_mode = exec ? BK_LOOP_GRAPH : BK_LOOP_STREAM;
   int slot = 0, prev = 0;
   bool pending = false;
   int64_t chunks = 0;
@@ -106,9 +107,12 @@ static int bk_run_loop(bk_handle* h, cudaStream_t s, bool use_graph, const uint6
 
 static inline int bk_pick_chunk(const bk_handle* h, double bytes_per_iter, int kernels_per_iter) {
   if (h->chunk > 0) return (h->chunk + 1) & ~1;
-  // aim at ~2 ms of GPU work per chunk (>> the ~20 us poll latency), assuming ~5 TB/s and ~3 us per launch
+  // aim at ~2 ms of GPU work per chunk (>> the ~20 us poll latency), assuming ~5 TB/s and ~3 us per launch; launch-bound
+  // (small) systems get ~0.3 ms chunks: the loop overshoots by up to two chunks of guarded no-op launches, which cost
+  // nothing next to a 300 us iteration but as much as a real iteration when that takes 10 us
   const double t_iter = bytes_per_iter / 5.0e12 + kernels_per_iter * 3.0e-6;
-  int c = (int)(2.0e-3 / t_iter);
+  const double target = (t_iter < 40.0e-6) ? 0.3e-3 : 2.0e-3;
+  int c = (int)(target / t_iter);
   if (c < 2) c = 2;
   if (c > 64) c = 64;
   return (c + 1) & ~1;

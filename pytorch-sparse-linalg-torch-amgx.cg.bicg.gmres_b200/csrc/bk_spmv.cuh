@@ -228,6 +228,7 @@ bk_spmv_vector_kernel(const bk_spmv_args a, const bk_scratch sc, Epi epi) {
 
 #include "bk_spmv_tma.cuh"
 #include "bk_spmv_pair.cuh"
+#include "bk_spmv_mask.cuh"
 
 // Second half of the long-row path: y[r] = (b[r] -) sum of the partial sums of r's virtual rows, added in order
 // (deterministic), fused with the requested dots and the solver's scalar epilogue.
@@ -318,7 +319,28 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
       return bk_launch_spmv_split<T, MODE, DOTS, Epi>(h, A, a, sc, epi, s);
     }
   }
-  if (A->kernel == 5 && XMODE == 0) {
+  if (A->kernel == 6 && XMODE == 0) {
+    if constexpr (XMODE == 0) {
+      // row-bitmask stream (bk_spmv_mask.cuh): no shared memory, occupancy set by registers
+      bk_mask_plan plan;
+      memset(&plan, 0, sizeof(plan));
+      plan.masks = A->mmasks;
+      plan.pids = A->mpids;
+      plan.ptab = (const bk_pair_entry*)A->mptab;
+      plan.group = h->mask_group < 1 ? 1 : (h->mask_group > 64 ? 64 : h->mask_group);
+      int ctas = h->mask_ctas < 2 ? 2 : (h->mask_ctas > 6 ? 6 : h->mask_ctas);
+      int g = h->num_sms * ctas;
+      if (g > BK_MAXB) g = BK_MAXB;
+      g = bk_grid_rows(g, A->n, BK_BLOCK * plan.group);
+      switch (ctas) {
+        case 2: bk_spmv_mask_kernel<T, MODE, DOTS, false, 2, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
+        case 3: bk_spmv_mask_kernel<T, MODE, DOTS, false, 3, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
+        case 4: bk_spmv_mask_kernel<T, MODE, DOTS, false, 4, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
+        case 5: bk_spmv_mask_kernel<T, MODE, DOTS, false, 5, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
+        default: bk_spmv_mask_kernel<T, MODE, DOTS, false, 6, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
+      }
+    }
+  } else if (A->kernel == 5 && XMODE == 0) {
     if constexpr (XMODE == 0) {
       // pair-coded SELL stream: stages are tiny (~2 KB for a 7-point stencil), so occupancy is set by registers
       const size_t stage_bytes = (size_t)A->pair_cap + BK_PAIR_DICT_BYTES;
@@ -401,7 +423,7 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
         BK_TRY(launch(bk_spmv_tma_kernel<T, MODE, DOTS, 4, 0, Epi>));
       }
     }
-  } else if (A->kernel == 0 || A->kernel == 2 || A->kernel == 3 || A->kernel == 5) {
+  } else if (A->kernel == 0 || A->kernel == 2 || A->kernel == 3 || A->kernel == 5 || A->kernel == 6) {
     const int grid = bk_grid_rows(bk_grid_spmv(h), A->n, BK_BLOCK);
     if (A->cap <= 256) {
       auto k = bk_spmv_stream_kernel<T, 256, MODE, DOTS, XMODE, Epi>;

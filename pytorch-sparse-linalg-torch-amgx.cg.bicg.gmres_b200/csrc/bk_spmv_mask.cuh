@@ -1,0 +1,211 @@
+// bk_spmv_mask.cuh — kernel 6: SpMV for matrices whose 32-row chunks each hold at most 8 distinct
+// (column - row, value) PAIRS (constant-coefficient stencils: Poisson, upwind convection-diffusion, the LDC pressure
+// matrix ...), the successor of the pair-coded kernel 5 for that class.
+//
+// ncu on kernel 5 (profiles/r01_ncu_full_final_cg.txt) showed it bound by the L1/LSU data pipe (72 %) and by issue
+// slots (59 %), not by HBM (41 %): every entry cost a 16-byte dictionary fetch from shared memory PER LANE (4 LSU
+// wavefronts — the return path moves 128 B per cycle whether or not the 32 lanes read the same address), a gather
+// (2-3 wavefronts) and ~18 instructions.  Kernel 6 removes the per-entry matrix traffic from the SM altogether:
+//   * registration (bk_csr_plan_mask, bk_core.cu) sorts every chunk's distinct pairs by (offset, value) into a PATTERN
+//     of <= 8 entries, de-duplicates the patterns of the whole matrix in a small table (a 7-point stencil has a dozen),
+//     and stores per row ONE BYTE: the bitmask of pattern entries the row actually has; per chunk the pattern id.
+//     Matrix stream: 1.125 B per ROW instead of 12 B per ENTRY (P3D-256: 19 MB instead of 1.40 GB per SpMV);
+//   * a warp owns a 32-row chunk, lane <-> row; the pattern {value, offset} x 8 lives in REGISTERS and is reloaded only
+//     when the chunk's pattern id differs from the previous chunk's (warp-uniform branch, a few times per 256 blocks);
+//   * per entry the warp issues one predicated, fully coalesced gather (lanes of a stencil diagonal read 32 consecutive
+//     elements) and one FMA — ~4 instructions; absent entries load nothing and contribute fma(v, 0, sum) = sum;
+//   * row blocks are dealt to CTAs in groups of consecutive blocks, so neighbouring grid lines are gathered from L1
+//     while the chip as a whole still sweeps one window of the vectors (L2 reuse between consecutive kernels);
+//   * the row sum is the same FMA chain in CSR order as kernels 2 / 3 / 5 => bit-identical results (tested).
+// Requirements (else registration falls through to kernel 5 / 3 / 2): columns ascending within every row, <= 8 entries
+// per row, <= 8 distinct pairs per 32-row chunk, <= BK_MASK_HT/2 distinct patterns in the matrix.
+//
+// Multi-GPU (bk_dist.cuh): a pattern entry can be flagged GHOST — its gather then reads the halo vector instead of x,
+// which folds the boundary rows of a row-partitioned matrix into this kernel (no separate ghost-row kernel).
+#pragma once
+
+#include "bk_internal.cuh"
+#include "bk_p2p.cuh"
+
+#define BK_MASK_L 8          // pattern entries per chunk (mask bits per row)
+#define BK_MASK_HT 4096      // slots of the pattern table (open addressing; at most half may fill)
+#define BK_MASK_GHOST 1      // bk_pair_entry.pad flag: gather from the ghost vector
+
+struct bk_mask_plan {
+  const unsigned char* masks;  // [nchunks * 32] presence bits of every row over its chunk's pattern
+  const int* pids;             // [nchunks] pattern table slot of every chunk (bit 30: chunk has ghost entries)
+  const bk_pair_entry* ptab;   // [BK_MASK_HT][BK_MASK_L]
+  const void* xg;              // ghost vector (multi-GPU) or nullptr
+  const int* deferred;         // chunks with ghost entries, processed after the halo has arrived (multi-GPU)
+  int n_deferred;
+  int group;                   // consecutive 256-row blocks dealt to a CTA at a time
+  // halo arrival (peer-memory path): flags[peer] == want  (nullptr: no wait, e.g. NCCL path orders by stream)
+  const unsigned long long* flags;
+  const int* flag_peers;
+  int n_flag_peers;
+  unsigned int* halo_seq;      // counters[2] of the peer context: halos consumed so far (want = *halo_seq + 1)
+  unsigned int* err_flag;      // counters[4]
+};
+
+#define BK_MASK_PID_GHOST (1 << 30)
+
+template <typename T>
+struct bk_mask_pat {
+  T val[BK_MASK_L];
+  int off[BK_MASK_L];
+  unsigned int ghost;  // bit e: entry e gathers from the ghost vector
+};
+
+template <typename T>
+__device__ __forceinline__ void bk_mask_load_pattern(const bk_pair_entry* __restrict__ ptab, int slot, bk_mask_pat<T>& p) {
+  const uint4* src = reinterpret_cast<const uint4*>(ptab + (size_t)slot * BK_MASK_L);
+  p.ghost = 0u;
+#pragma unroll
+  for (int e = 0; e < BK_MASK_L; ++e) {
+    const uint4 q = __ldg(src + e);  // same address in every lane: one sector
+    if constexpr (sizeof(T) == 8) p.val[e] = __hiloint2double((int)q.y, (int)q.x);
+    else p.val[e] = __uint_as_float(q.x);
+    p.off[e] = (int)q.z;
+    p.ghost |= (q.w & BK_MASK_GHOST) ? (1u << e) : 0u;
+  }
+}
+
+// one 32-row chunk: y[row] = sum_e [mask bit e] val_e * x[row + off_e]   (+ fused residual / dots)
+template <typename T, int MODE, int DOTS, bool GHOST>
+__device__ __forceinline__ void bk_mask_chunk(const bk_spmv_args& a, const bk_mask_pat<T>& p, const T* __restrict__ x,
+                                              const T* __restrict__ xg, const int row, const unsigned int m,
+                                              const int n32, double* acc) {
+  T xv[BK_MASK_L];
+#pragma unroll
+  for (int e = 0; e < BK_MASK_L; ++e) {
+    xv[e] = T(0);
+    if (m & (1u << e)) {
+      if (GHOST && (p.ghost & (1u << e))) xv[e] = __ldcg(xg + (row + p.off[e]));
+      else xv[e] = __ldg(x + (row + p.off[e]));
+    }
+  }
+  T sum = T(0);
+#pragma unroll
+  for (int e = 0; e < BK_MASK_L; ++e) sum = fma(p.val[e], xv[e], sum);
+  if (row < n32) {
+    T out = sum;
+    if constexpr (MODE == 1) out = bk_sub(__ldg(static_cast<const T*>(a.b) + row), sum);
+    static_cast<T*>(a.y)[row] = out;
+    if constexpr ((DOTS & 1) != 0)
+      acc[0] += static_cast<double>(__ldg(static_cast<const T*>(a.w) + row)) * static_cast<double>(out);
+    if constexpr ((DOTS & 2) != 0) acc[DOTS & 1] += static_cast<double>(out) * static_cast<double>(out);
+  }
+}
+
+template <typename T, int MODE, int DOTS, bool GHOST, int MINB, typename Epi>
+__global__ void __launch_bounds__(BK_BLOCK, MINB)
+bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scratch sc, Epi epi) {
+  if (bk_spmv_skip(a)) return;
+  constexpr int R = bk_ndots<DOTS>::value;
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int n32 = (int)a.n;
+  const int nchunks = (n32 + 31) >> 5;
+  const int nblk = (n32 + 255) >> 8;
+  const int group = plan.group;
+  const int ngroups = (nblk + group - 1) / group;
+  int reverse = a.reverse;
+  if (a.use_parity) reverse ^= (a.st->parity & 1);
+  const T* __restrict__ x = static_cast<const T*>(a.x);
+  const T* __restrict__ xg = static_cast<const T*>(plan.xg);
+  const unsigned char* __restrict__ masks = plan.masks;
+  const int* __restrict__ pids = plan.pids;
+
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.0;
+
+  bk_mask_pat<T> pat;
+  int cur = -1;
+  // this warp's chunks: group g = blockIdx.x, blockIdx.x + gridDim.x, ... ; inside a group blocks ascend (descend when
+  // reversed), the warp takes chunk `wid` of each block
+  auto chunk_of = [&](int g, int j) -> int {
+    const int gg = reverse ? (ngroups - 1 - g) : g;
+    const int blk = gg * group + (reverse ? (group - 1 - j) : j);
+    return (blk < nblk) ? blk * 8 + wid : -1;
+  };
+  int g = (int)blockIdx.x, j = 0;
+  int ch = -1;
+  unsigned int m_next = 0;
+  int pid_next = 0;
+  auto advance = [&]() {  // next valid chunk of this warp (ch = -1 when exhausted) + prefetch of its mask / pattern id
+    ch = -1;
+    while (g < ngroups) {
+      const int c = chunk_of(g, j);
+      if (++j == group) {
+        j = 0;
+        g += (int)gridDim.x;
+      }
+      if (c >= 0 && c < nchunks) {
+        ch = c;
+        break;
+      }
+    }
+    if (ch >= 0) {
+      m_next = __ldg(masks + (size_t)ch * 32 + lane);
+      pid_next = __ldg(pids + ch);
+    }
+  };
+  advance();
+  while (ch >= 0) {
+    const int c0 = ch;
+    const unsigned int m = m_next;
+    const int pid = pid_next;
+    advance();  // the next chunk's mask / pattern id are in flight while this one is computed
+    if (GHOST && (pid & BK_MASK_PID_GHOST)) continue;  // boundary chunk: second phase
+    const int slot = pid & (BK_MASK_PID_GHOST - 1);
+    if (slot != cur) {
+      bk_mask_load_pattern<T>(plan.ptab, slot, pat);
+      cur = slot;
+    }
+    bk_mask_chunk<T, MODE, DOTS, false>(a, pat, x, xg, c0 * 32 + lane, m, n32, acc);
+  }
+  if constexpr (GHOST) {
+    // ---- second phase: chunks with ghost entries, after the neighbours' halos have landed ---------------------
+    if (plan.n_deferred > 0) {
+      bool ok = true;
+      if (plan.flags != nullptr) {
+        __shared__ int s_fail;
+        if (threadIdx.x == 0) s_fail = 0;
+        __syncthreads();
+        const unsigned int want = *plan.halo_seq + 1u;
+        if ((int)threadIdx.x < plan.n_flag_peers) {
+          const unsigned long long* flag = plan.flags + plan.flag_peers[threadIdx.x];
+          const long long t0 = clock64();
+          while ((unsigned int)bk_ld_acquire_sys_u64(flag) != want) {
+            if (clock64() - t0 > BK_P2P_TIMEOUT_CYCLES) {
+              s_fail = 1;
+              break;
+            }
+          }
+        }
+        __syncthreads();
+        if (s_fail) {
+          if (threadIdx.x == 0) *plan.err_flag = 1u;
+          ok = false;
+        }
+      }
+      if (ok) {
+        const int warps = (int)gridDim.x * BK_WARPS;
+        for (int i = (int)blockIdx.x * BK_WARPS + wid; i < plan.n_deferred; i += warps) {
+          const int c0 = __ldg(plan.deferred + i);
+          const unsigned int m = __ldg(masks + (size_t)c0 * 32 + lane);
+          const int slot = __ldg(pids + c0) & (BK_MASK_PID_GHOST - 1);
+          if (slot != cur) {
+            bk_mask_load_pattern<T>(plan.ptab, slot, pat);
+            cur = slot;
+          }
+          bk_mask_chunk<T, MODE, DOTS, true>(a, pat, x, xg, c0 * 32 + lane, m, n32, acc);
+        }
+      }
+    }
+  }
+  if constexpr (DOTS != 0) {
+    bk_grid_reduce<R, Epi, BK_WARPS>(acc, sc, epi);
+  }
+}

@@ -185,6 +185,76 @@ struct bk_op_axpby {
   __device__ void epilogue(const double*) const {}
 };
 
+// z = (*a) x + (*b) y with the scalars read from DEVICE memory (fp64; a null pointer means 1): lets the callable-A route
+// keep alpha / beta on the device instead of synchronising for every dot product (generic.py)
+template <typename T>
+struct bk_op_axpby_dev {
+  static constexpr int R = 0;
+  struct Ctx {
+    T ca, cb;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> a, b;
+  };
+  const T* x;
+  const T* y;
+  T* z;
+  const double* pa;
+  const double* pb;
+  double sa, sb;  // sign / constant factor applied to the loaded scalar (exact: +-1)
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.ca = static_cast<T>(pa ? sa * pa[0] : sa);
+    c.cb = static_cast<T>(pb ? sb * pb[0] : sb);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.a = bk_ld<T, W>(x + i);
+    in.b = bk_ld<T, W>(y + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
+    bk_vec<T, W> o;
+#pragma unroll
+    for (int j = 0; j < W; ++j) o.v[j] = bk_add(bk_mul(c.ca, in.a.v[j]), bk_mul(c.cb, in.b.v[j]));
+    bk_st<T, W>(z + i, o);
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
+// z = x / d  (true division, as the reference's `y / norm` in _safe_normalize :268)
+template <typename T>
+struct bk_op_div {
+  static constexpr int R = 0;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<T, W> a;
+  };
+  const T* x;
+  T* z;
+  T d;
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.a = bk_ld<T, W>(x + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx&, double (&)[1]) const {
+    bk_vec<T, W> o;
+#pragma unroll
+    for (int j = 0; j < W; ++j) o.v[j] = in.a.v[j] / d;
+    bk_st<T, W>(z + i, o);
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
 // ---- CG --------------------------------------------------------------------------------------
 // x += alpha p ; r -= alpha Ap ; gamma' = r.r          (_cg_solve :846-850)
 // epilogue: beta = gamma'/gamma, gamma = gamma', k += 1, stop test of :841 for the NEXT iteration.

@@ -39,6 +39,9 @@ class bk_result(C.Structure):
         ("b_norm", C.c_double),
         ("x_norm", C.c_double),
         ("rr_last", C.c_double),
+        ("loop_mode_used", C.c_int32),
+        ("reserved0", C.c_int32),
+        ("device_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -55,6 +58,7 @@ class bk_csr_info(C.Structure):
         ("max_row_nnz", C.c_int32),
         ("mean_row_nnz", C.c_double),
         ("bytes_matrix", C.c_int64),
+        ("bytes_stream", C.c_int64),
     ]
 
 
@@ -75,11 +79,14 @@ _SIGNATURES = {
     "bk_csr_transpose": (C.c_int, [_VP, _VP, _VP, C.POINTER(_VP)]),
     "bk_csr_grad_pattern": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
     "bk_csr_arrays": (C.c_int, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
+    "bk_checksum": (C.c_int, [_VP, _VP, C.c_int64, _VP, C.POINTER(C.c_uint64)]),
     "bk_spmv": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "bk_spmv_dot": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "bk_dot": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP, _VP, _VP]),
     "bk_nrm2": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, _VP, _VP]),
     "bk_axpby": (C.c_int, [_VP, C.c_int64, C.c_int, C.c_double, _VP, C.c_double, _VP, _VP, _VP]),
+    "bk_axpby_dev": (C.c_int, [_VP, C.c_int64, C.c_int, C.c_double, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP]),
+    "bk_div_scalar": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, C.c_double, _VP, _VP]),
     "bk_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(bk_result), _VP]),
     "bk_bicgstab": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(bk_result),
                               _VP]),
@@ -229,7 +236,9 @@ class CsrMatrix:
         self.nnz = int(val.numel())
         self.dtype = val.dtype
         self.device = val.device
-        self._keep = (crow, col, val)
+        # what the library BORROWS must stay alive: the values always, the index arrays only when they are int32
+        # (int64 indices are narrowed into a library-owned copy at registration)
+        self._keep = (val,) if crow.dtype == torch.int64 else (crow, col, val)
         p = _VP()
         with torch.cuda.device(self.device):
             _check(handle.lib.bk_csr_create(handle.ptr, self.n, self.nnz, crow.data_ptr(), col.data_ptr(),
@@ -444,9 +453,48 @@ def axpby(a: float, x: torch.Tensor, b: float, y: torch.Tensor, out: Optional[to
     return z
 
 
+def axpby_dev(sa: float, a: Optional[torch.Tensor], x: torch.Tensor, sb: float, b: Optional[torch.Tensor],
+              y: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """z = (sa * a) x + (sb * b) y with a, b 0-dim fp64 DEVICE tensors (None = 1): no host sync (bk_axpby_dev)."""
+    h = Handle.get(x.device)
+    x = x.contiguous()
+    y = y.contiguous()
+    z = torch.empty_like(x) if out is None else out
+    for t in (a, b):
+        if t is not None and (t.dtype != torch.float64 or not t.is_cuda):
+            raise ValueError("device scalars must be fp64 CUDA tensors")
+    with torch.cuda.device(x.device):
+        _check(h.lib.bk_axpby_dev(h.ptr, x.numel(), _dtype_code(x.dtype), float(sa), None if a is None else a.data_ptr(),
+                                  x.data_ptr(), float(sb), None if b is None else b.data_ptr(), y.data_ptr(),
+                                  z.data_ptr(), _stream_ptr(x.device)), "bk_axpby_dev")
+    return z
+
+
+def div_scalar(x: torch.Tensor, d: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """z = x / d (true division; bk_div_scalar)."""
+    h = Handle.get(x.device)
+    x = x.contiguous()
+    z = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        _check(h.lib.bk_div_scalar(h.ptr, x.numel(), _dtype_code(x.dtype), x.data_ptr(), float(d), z.data_ptr(),
+                                   _stream_ptr(x.device)), "bk_div_scalar")
+    return z
+
+
 # ---- matrix ingestion + cache ---------------------------------------------------------------------
-_CACHE: "OrderedDict[tuple, CsrMatrix]" = OrderedDict()
+# Registrations are cached per (layout, storage pointers, shape, dtypes, device).  torch offers no reliable way to
+# notice that a user changed `vals` in place (the version counter of a CSR / COO wrapper's value tensor does not move
+# when the tensor it was built from is written to, and `.data` writes never bump it), and the registration holds
+# value-dependent artefacts (the pattern / pair dictionaries of kernels 5 and 6, tail copies, the cached transpose,
+# dtype-converted copies).  A hit is therefore VALIDATED: the library checksums the arrays as they are now
+# (bk_checksum, one pass, ~0.3 ms for a 256^3 matrix) and a mismatch re-registers the matrix.  BK_CACHE_VALIDATE=0
+# turns the check off for callers who promise not to mutate registered matrices; `invalidate(A)` drops an entry.
+# Entries hold only what the library borrows (never the source tensor itself): when the source tensor has been
+# garbage-collected at most ONE such orphan is kept (the pattern `solve(torch.sparse_csr_tensor(...), b)` re-wraps the
+# same storages on every call), so a loop over distinct large systems does not pin their memory.
+_CACHE: "OrderedDict[tuple, dict]" = OrderedDict()
 _CACHE_MAX = 8
+_CACHE_MAX_ORPHANS = 1
 
 
 def _csr_components(A: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -484,7 +532,6 @@ def _ingest_native(A: torch.Tensor, dtype: torch.dtype) -> Optional[CsrMatrix]:
                 D, ld = D.contiguous(), n
             _check(h.lib.bk_csr_from_dense(h.ptr, n, D.data_ptr(), ld, _dtype_code(D.dtype), _dtype_code(dtype), s,
                                            C.byref(p)), "bk_csr_from_dense")
-            keep = (D,)
         else:
             idx = A.detach()._indices()
             val = A.detach()._values().contiguous()
@@ -492,33 +539,79 @@ def _ingest_native(A: torch.Tensor, dtype: torch.dtype) -> Optional[CsrMatrix]:
             _check(h.lib.bk_csr_from_coo(h.ptr, n, int(val.numel()), rows.data_ptr(), cols.data_ptr(),
                                          64 if rows.dtype == torch.int64 else 32, val.data_ptr(),
                                          _dtype_code(val.dtype), _dtype_code(dtype), s, C.byref(p)), "bk_csr_from_coo")
-            keep = (rows, cols, val)
         torch.cuda.current_stream(A.device).synchronize()
-    m = CsrMatrix._wrap(h, p, n, 0, dtype, A.device, keep)
+    m = CsrMatrix._wrap(h, p, n, 0, dtype, A.device, ())   # the library owns every array: nothing to keep alive
     m._owned = True
     m._finalizer = weakref.finalize(m, CsrMatrix._destroy, h.lib, p)
     m.nnz = int(m.info()["nnz"])
     return m
 
 
+def checksum(t: torch.Tensor) -> int:
+    """bk_checksum of a CUDA tensor's bytes (contiguous; 4-byte aligned size)."""
+    h = Handle.get(t.device)
+    t = t.contiguous()
+    out = C.c_uint64(0)
+    with torch.cuda.device(t.device):
+        _check(h.lib.bk_checksum(h.ptr, t.data_ptr(), t.numel() * t.element_size(), _stream_ptr(t.device),
+                                 C.byref(out)), "bk_checksum")
+    return int(out.value)
+
+
+def _key_and_parts(A: torch.Tensor, dtype: torch.dtype):
+    """Cache key + the tensors whose CONTENT defines the registration (checksummed on a hit)."""
+    if A.layout == torch.sparse_csr:
+        crow, col, v = A.crow_indices(), A.col_indices(), A.values()
+        key = ("csr", crow.data_ptr(), col.data_ptr(), v.data_ptr(), tuple(A.shape), v.numel(), crow.dtype, v.dtype,
+               dtype, A.device.index)
+        return key, (crow, col, v)
+    if A.layout == torch.sparse_coo:
+        idx, v = A._indices(), A._values()
+        key = ("coo", idx.data_ptr(), v.data_ptr(), tuple(A.shape), v.numel(), v.dtype, dtype, A.device.index,
+               A.is_coalesced())
+        return key, (idx, v)
+    key = ("dense", A.data_ptr(), tuple(A.shape), tuple(A.stride()), A.dtype, dtype, A.device.index)
+    return key, (A.detach(),)
+
+
+def _content_sum(parts) -> Optional[int]:
+    if os.environ.get("BK_CACHE_VALIDATE", "1") == "0":
+        return None
+    acc = 0
+    for i, t in enumerate(parts):
+        if t.numel() == 0:
+            continue
+        if t.element_size() % 4 != 0:      # exotic dtypes: view through a 4-byte-aligned copy
+            t = t.to(torch.float32)
+        acc ^= (checksum(t) * (2 * i + 1)) & 0xFFFFFFFFFFFFFFFF
+    return acc
+
+
+def _prune_cache():
+    orphans = [k for k, e in _CACHE.items() if e["src"]() is None]
+    for k in orphans[:max(0, len(orphans) - _CACHE_MAX_ORPHANS)]:
+        _CACHE.pop(k, None)
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)
+
+
 def register_matrix(A: torch.Tensor, dtype: torch.dtype = torch.float64) -> CsrMatrix:
-    """Register a 2-D CUDA tensor with the library (cached per storage + version)."""
+    """Register a 2-D CUDA tensor with the library (cached per storage, validated by content — see above)."""
     if not A.is_cuda:
         raise NativeLibraryError("register_matrix expects a CUDA tensor")
-    if A.layout == torch.sparse_csr:
-        v = A.values()
-        key = ("csr", A.crow_indices().data_ptr(), A.col_indices().data_ptr(), v.data_ptr(), v._version,
-               tuple(A.shape), v.dtype, dtype, A.device.index)
-    elif A.layout == torch.sparse_coo:
-        v = A._values()
-        key = ("coo", A._indices().data_ptr(), v.data_ptr(), v._version, tuple(A.shape), v.dtype, dtype,
-               A.device.index, A.is_coalesced())
-    else:
-        key = ("dense", A.data_ptr(), A._version, tuple(A.shape), tuple(A.stride()), A.dtype, dtype, A.device.index)
+    key, parts = _key_and_parts(A, dtype)
     hit = _CACHE.get(key)
+    csum = _content_sum(parts)
     if hit is not None:
-        _CACHE.move_to_end(key)
-        return hit
+        if csum is None or hit["sum"] is None or hit["sum"] == csum:
+            _CACHE.move_to_end(key)
+            if hit["src"]() is None:
+                try:
+                    hit["src"] = weakref.ref(A)
+                except TypeError:  # pragma: no cover
+                    pass
+            return hit["m"]
+        _CACHE.pop(key)            # same storage, different content: the user updated the matrix in place
     m = _ingest_native(A, dtype)
     if m is None:
         with torch.no_grad():
@@ -526,11 +619,23 @@ def register_matrix(A: torch.Tensor, dtype: torch.dtype = torch.float64) -> CsrM
             if val.dtype != dtype:
                 val = val.to(dtype)
         m = CsrMatrix(Handle.get(A.device), crow, col, val, A.shape[0])
-    m._keep = m._keep + (A,)  # keep the source alive so the data_ptr key stays unique
-    _CACHE[key] = m
-    while len(_CACHE) > _CACHE_MAX:
-        _CACHE.popitem(last=False)
+    try:
+        src = weakref.ref(A)
+    except TypeError:  # pragma: no cover
+        src = (lambda: None)
+    _CACHE[key] = {"m": m, "sum": csum, "src": src}
+    _prune_cache()
     return m
+
+
+def invalidate(A: Optional[torch.Tensor] = None):
+    """Drop the cached registration(s) of `A` (all dtypes), or of every matrix when A is None.  Only needed with
+    BK_CACHE_VALIDATE=0; with validation on, in-place updates of a registered matrix are detected by content."""
+    if A is None:
+        _CACHE.clear()
+        return
+    for dt in (torch.float64, torch.float32):
+        _CACHE.pop(_key_and_parts(A, dt)[0], None)
 
 
 def clear_cache():

@@ -255,6 +255,32 @@ class DistMatrix:
         return x, res.as_dict()
 
 
+    # ---- the reference API on a row-partitioned matrix ("API stays additive, e.g. a DistCSR wrapper
+    # passed as A"): module_a.cg / bicgstab / gmres(A=DistMatrix, b=this rank's slab) -> (x_local, info) -----------
+    def _module_a_solve(self, name: str, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, M=None, restart=20,
+                        solve_method='batched', _result=None):
+        from .module_a import krylov
+        if not isinstance(b, torch.Tensor) or b.ndim != 1 or b.shape[0] != self.split.n_local:
+            raise ValueError(f"b must be this rank's slab: a vector of length {self.split.n_local}")
+        if x0 is not None and tuple(x0.shape) != tuple(b.shape):
+            raise ValueError(f'arrays in x0 and b must have matching shapes: {x0.shape} vs {b.shape}')
+        if M is not None:
+            raise NotImplementedError("preconditioners on a DistMatrix: not wired yet")
+        with torch.no_grad():
+            bw = b.detach()
+            x0w = None if x0 is None else x0.detach()
+            if name == "cg":
+                x, res = self.cg(bw, x0w, tol, atol, maxiter)
+            elif name == "bicgstab":
+                x, res = self.bicgstab(bw, x0w, tol, atol, maxiter)
+            else:
+                if restart < 1:
+                    raise ValueError("restart must be >= 1")
+                x, res = self.gmres(bw, x0w, tol, atol, restart, maxiter, solve_method)
+        krylov._publish(dict(res, solver=name, route="dist"), _result)
+        return x, int(res["info"])
+
+
 # ---- weak-scaling benchmark used by bench.py --gpus N --------------------------------------------------------
 def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSampler):
     """N slabs of n^3 rows each: a (N*n) x n x n Poisson grid, slab q on rank q.  value = N * global iterations/s

@@ -1,10 +1,18 @@
 """Generic route of module_a: callable `A`, preconditioner `M`, pytree `b`.
 
 The reference's recurrences (torch_sparse_linalg.py: _cg_solve :806-856, _bicgstab_solve :859-964,
-_gmres_batched :431-493, _gmres_incremental :557-638, _kth_arnoldi_iteration :331-388) driven from Python — one
-host sync per iteration exactly like the reference — but every dot / norm / axpy on the vectors is done by the
-library's deterministic CUDA kernels (bk_dot / bk_axpby), never by a CPU loop.  The user's `A` / `M` callables are
-called as they are.  CPU pytrees are staged through the current CUDA device (callables are then fed CPU tensors).
+_gmres_batched :431-493, _gmres_incremental :557-638, _kth_arnoldi_iteration :331-388) driven from Python, but every
+dot / norm / axpy / division on the vectors is done by the library's deterministic CUDA kernels (bk_dot, bk_axpby,
+bk_axpby_dev, bk_div_scalar) and a matrix given as a TENSOR (A with a callable M, or M itself) is applied by the native
+SpMV of its registration — never by torch.matmul / cuSPARSE and never by a CPU loop.  The user's callables are called
+as they are.  CPU pytrees are staged through the current CUDA device (callables are then fed CPU tensors).
+
+Host synchronisations: CG keeps alpha / beta on the device (bk_axpby_dev reads them from device memory) and syncs
+once per iteration for the stop test — exactly the reference's one `bool()` per iteration (:841); BiCGStab syncs four
+times per iteration (reference: five, :895-936), GMRES three times per Arnoldi step (reference: at least three).
+
+`transpose=True` solves with A^T (tensor A only): the adjoint solve of the implicit-differentiation backward
+(reference :1237-1248), served by the cached device transpose.
 """
 from __future__ import annotations
 
@@ -44,23 +52,33 @@ class _Space:
             out = [t.cpu() for t in out]
         return tree_unflatten(self.treedef, out)
 
-    def wrap(self, fn: Optional[Callable]) -> Callable[[List[torch.Tensor]], List[torch.Tensor]]:
+    def wrap(self, fn: Optional[Callable], transpose: bool = False) -> Callable[[List[torch.Tensor]], List[torch.Tensor]]:
         """User callable pytree -> pytree  ==>  leaf-list -> leaf-list on the work device."""
         if fn is None:
             return lambda v: v
-        if isinstance(fn, torch.Tensor):  # a matrix given as preconditioner
-            mat = fn
+        if isinstance(fn, torch.Tensor):  # a matrix (A next to a callable M, or M given as a matrix): native SpMV
+            mat = fn.detach()
+            if mat.is_complex():
+                raise NotImplementedError("complex operators take the complex route (module_a/complex_route.py)")
+            if not mat.is_cuda:
+                mat = mat.to(self.device)
+            reg = _native.register_matrix(mat, torch.float64)
+            if transpose:
+                reg = reg.transpose()
 
             def mv(v):
-                flat = torch.cat(v)
-                m = mat.to(flat.device) if mat.device != flat.device else mat
-                y = torch.matmul(m.to(torch.float64), flat)
+                flat = v[0] if len(v) == 1 else torch.cat(v)
+                y = reg.spmv(flat)
+                if len(v) == 1:
+                    return [y]
                 outs, o = [], 0
                 for t in v:
                     outs.append(y[o:o + t.numel()].contiguous())
                     o += t.numel()
                 return outs
             return mv
+        if transpose:
+            raise ValueError("the transposed solve needs A as a tensor")
 
         def call(v):
             y = fn(self.to_tree(v))
@@ -68,28 +86,36 @@ class _Space:
         return call
 
 
-def _dot(x: List[torch.Tensor], y: List[torch.Tensor]) -> float:
+def _dotd(x: List[torch.Tensor], y: List[torch.Tensor]) -> torch.Tensor:
+    """x . y as a 0-dim fp64 DEVICE tensor (no host sync)."""
     acc = None
     for a, b in zip(x, y):
         d = _native.dot(a, b)
         acc = d if acc is None else acc + d
-    return float(acc)
+    return acc
+
+
+def _dot(x: List[torch.Tensor], y: List[torch.Tensor]) -> float:
+    return float(_dotd(x, y))
 
 
 def _dots(pairs) -> List[float]:
     """Several dots, one host sync."""
-    vals = []
-    for x, y in pairs:
-        acc = None
-        for a, b in zip(x, y):
-            d = _native.dot(a, b)
-            acc = d if acc is None else acc + d
-        vals.append(acc)
+    vals = [_dotd(x, y) for x, y in pairs]
     return [float(v) for v in torch.stack(vals).cpu()]
 
 
 def _axpby(a: float, x, b: float, y):
     return [_native.axpby(a, xi, b, yi) for xi, yi in zip(x, y)]
+
+
+def _axpby_dev(sa: float, a, x, sb: float, b, y):
+    """(sa * a) x + (sb * b) y with a, b 0-dim device tensors or None (= 1)."""
+    return [_native.axpby_dev(sa, a, xi, sb, b, yi) for xi, yi in zip(x, y)]
+
+
+def _div(x, d: float):
+    return [_native.div_scalar(t, d) for t in x]
 
 
 def _norm(x) -> float:
@@ -100,7 +126,7 @@ def _f32(v: float) -> float:
     return float(torch.tensor(v))  # the reference's torch.tensor(tol) is fp32 (:816)
 
 
-def _prepare(A, b, x0, M):
+def _prepare(A, b, x0, M, transpose: bool = False):
     sp = _Space(b)
     bv = sp.to_vec(b)
     if x0 is None:
@@ -113,7 +139,7 @@ def _prepare(A, b, x0, M):
             if bl.shape != xl.shape:
                 raise ValueError(f'arrays in x0 and b must have matching shapes: {xl.shape} vs {bl.shape}')
         xv = sp.to_vec(x0)
-    Aop = sp.wrap(A)
+    Aop = sp.wrap(A, transpose)
     Mop = sp.wrap(M)
     return sp, bv, xv, Aop, Mop
 
@@ -129,8 +155,8 @@ def _finish_isolve(sp, Aop, Mop, bv, xv, tol, atol, its, name):
     return sp.to_tree(xv), (-1 if failed else 0)
 
 
-def generic_cg(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, M=None):
-    sp, bv, x, Aop, Mop = _prepare(A, b, x0, M)
+def generic_cg(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, M=None, transpose=False):
+    sp, bv, x, Aop, Mop = _prepare(A, b, x0, M, transpose)
     maxiter = 10 * sp.size if maxiter is None else maxiter
     bs = _dot(bv, bv)
     t32, a32 = torch.tensor(tol), torch.tensor(atol)
@@ -138,27 +164,27 @@ def generic_cg(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, M=None):
     r = _axpby(1.0, bv, -1.0, Aop(x))
     z = Mop(r)
     p = z
-    gamma = _dot(r, z)
+    gamma = _dotd(r, z)                      # device scalar
     k = 0
     while True:
-        rs = gamma if M is None else _dot(r, r)
-        if k >= maxiter or rs <= atol2:
+        rs = gamma if M is None else _dotd(r, r)
+        if k >= maxiter or float(rs) <= atol2:   # the iteration's one host sync (reference :841)
             break
         Ap = Aop(p)
-        alpha = gamma / _dot(p, Ap)
-        x = _axpby(1.0, x, alpha, p)
-        r = _axpby(1.0, r, -alpha, Ap)
+        alpha = gamma / _dotd(p, Ap)             # 0-dim device tensors: IEEE fp64 division, as the reference's
+        x = _axpby_dev(1.0, None, x, 1.0, alpha, p)
+        r = _axpby_dev(1.0, None, r, -1.0, alpha, Ap)
         z = Mop(r)
-        gamma_new = _dot(r, z)
+        gamma_new = _dotd(r, z)
         beta = gamma_new / gamma
-        p = _axpby(1.0, z, beta, p)
+        p = _axpby_dev(1.0, None, z, 1.0, beta, p)
         gamma = gamma_new
         k += 1
     return _finish_isolve(sp, Aop, Mop, bv, x, tol, atol, k, "cg")
 
 
-def generic_bicgstab(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, M=None):
-    sp, bv, x, Aop, Mop = _prepare(A, b, x0, M)
+def generic_bicgstab(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, M=None, transpose=False):
+    sp, bv, x, Aop, Mop = _prepare(A, b, x0, M, transpose)
     maxiter = 10 * sp.size if maxiter is None else maxiter
     bs = _dot(bv, bv)
     atol2 = max(float(torch.square(torch.tensor(tol))) * bs, float(torch.square(torch.tensor(atol))))
@@ -210,7 +236,7 @@ def generic_bicgstab(A, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, M=None)
 def _safe_normalize(v, thresh: float = _EPS):
     n = _norm(v)
     if n > thresh:
-        return [t / n for t in v], n          # true division, as the reference's y / norm (:268)
+        return _div(v, n), n                 # true division, as the reference's y / norm (:268)
     return [torch.zeros_like(t) for t in v], 0.0
 
 
@@ -246,7 +272,7 @@ def _gmres_cycle(Aop, Mop, bv, x, v0, beta, ptol, restart, incremental):
         norm1 = _norm(w)
         use = norm1 > _EPS * vnorm0
         vnorm1 = norm1 if use else 0.0
-        V.append([t / norm1 for t in w] if use else [torch.zeros_like(t) for t in w])
+        V.append(_div(w, norm1) if use else [torch.zeros_like(t) for t in w])
         col = h + [vnorm1]
         for i in range(k):
             tmp = cs[i] * col[i] - sn[i] * col[i + 1]
@@ -277,9 +303,10 @@ def _gmres_cycle(Aop, Mop, bv, x, v0, beta, ptol, restart, incremental):
     return x, v0, beta
 
 
-def generic_gmres(A, b, x0=None, *, tol=1e-5, atol=0.0, restart=20, maxiter=None, M=None, solve_method='batched'):
+def generic_gmres(A, b, x0=None, *, tol=1e-5, atol=0.0, restart=20, maxiter=None, M=None, solve_method='batched',
+                  transpose=False):
     from . import krylov
-    sp, bv, x, Aop, Mop = _prepare(A, b, x0, M)
+    sp, bv, x, Aop, Mop = _prepare(A, b, x0, M, transpose)
     maxiter = 10 * sp.size if maxiter is None else maxiter
     bn = _norm(bv)
     dev = 'cpu' if sp.on_cpu else 'cuda'

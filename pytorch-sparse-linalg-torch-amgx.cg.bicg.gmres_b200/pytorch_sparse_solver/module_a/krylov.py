@@ -18,10 +18,18 @@ Routes:
              CPU solver, and raises if no CUDA device exists.
   * generic  callable A, preconditioner M or pytree b: the reference's recurrences driven from
              Python (one host sync per iteration, as in the reference) with every dot / axpy done
-             by the library's deterministic kernels (see generic.py).
+             by the library's deterministic kernels (see generic.py).  With a TENSOR A (and a callable
+             M) the implicit-differentiation backward is attached exactly as on the native route
+             (reference :1079-1086, :1145-1152, :775-782): the adjoint solve runs the same generic
+             solver on the cached device transpose with the same M.  A callable A cannot be
+             differentiated here (the reference lets autograd unroll its torch ops; our kernels are
+             not autograd ops): a warning says so once.
+  * dist     A is a distributed.DistMatrix (row-partitioned over the ranks of a process group), b this
+             rank's slab: bk_dist_cg / bk_dist_bicgstab / bk_dist_gmres (SURVEY §8e "API stays additive").
 """
 from __future__ import annotations
 
+import warnings
 from typing import Any, Callable, Optional, Tuple, Union
 
 import torch
@@ -44,9 +52,15 @@ GMRES_TOLERANCE_DEVICE: Optional[str] = None
 # Off by default because the reference returns None for A (:1248).
 GRAD_WRT_A: bool = False
 
-# Filled by every solve: the native bk_result of the most recent call (iterations, matvecs, ...).
-# The reference returns no iteration count (solver.py:373); this is strictly extra information.
+# Filled by every PUBLIC solve (cg / bicgstab / gmres / *_differentiable): the native bk_result of the most recent
+# call (iterations, matvecs, device_ms, loop_mode_used ...).  The reference returns no iteration count
+# (solver.py:373); this is strictly extra information.  Adjoint solves run inside backward() do not touch it, and
+# callers that must not depend on a module global (the router, re-entrant code) pass `_result={}` to the solver
+# functions and read the same dictionary from there.
 last_result: dict = {}
+
+# restarts above this run on the generic route (the native GMRES keeps its small dense arrays in shared memory)
+NATIVE_MAX_RESTART = 256
 
 
 # --------------------------------------------------------------------------------------------------
@@ -76,13 +90,15 @@ def _check_x0(b, x0):
 def _route(A, b, x0, M, native_M: bool = False) -> str:
     """native_M: the solver has a device implementation for a built-in preconditioner object (Jacobi)."""
     kind = _check_operator(A)
+    if kind == "tensor" and isinstance(b, torch.Tensor) and (A.is_complex() or b.is_complex()):
+        return "complex"
     builtin = native_M and isinstance(M, JacobiPreconditioner) and kind == "tensor" and A.is_cuda
     if kind == "callable" or (M is not None and not builtin) or not isinstance(b, torch.Tensor):
         return "generic"
     if b.ndim != 1 or b.shape[0] != A.shape[0]:
         raise ValueError(f"b must be a vector of length {A.shape[0]}, got shape {tuple(b.shape)}")
     if A.is_complex() or b.is_complex():
-        raise NotImplementedError("complex systems are outside this build's scope (real fp64/fp32 only)")
+        return "complex"
     if A.is_cuda != b.is_cuda:
         raise ValueError("A and b must live on the same device")
     return "native" if A.is_cuda else "host"
@@ -126,9 +142,8 @@ def _gmres_effective_tolerances(tol: float, atol: float, size: int, device_type:
 # --------------------------------------------------------------------------------------------------
 def _solve_core(name: str, A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor], tol: float, atol: float,
                 maxiter: Optional[int], restart: int = 20, solve_method: str = 'batched',
-                transpose: bool = False, precond=None) -> Tuple[torch.Tensor, int]:
-    """Run one solver on (A or A^T).  Returns (x, info) with x of the work dtype on b's device."""
-    global last_result
+                transpose: bool = False, precond=None) -> Tuple[torch.Tensor, int, dict]:
+    """Run one solver on (A or A^T).  Returns (x, info, result dict) with x of the work dtype on b's device."""
     route = "native" if A.is_cuda else "host"
     wdt = _work_dtype(A, b)
     if precond is not None and route != "native":
@@ -177,8 +192,15 @@ def _solve_core(name: str, A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.
             else:
                 code = _native.METHOD_CG if name == "cg" else _native.METHOD_BICGSTAB
                 x, res = _native.solve_host(code, crow, col, val, bw, x0w, tol, atol, maxiter)
-    last_result = dict(res, solver=name, route=route)
-    return x.reshape(b.shape), int(res["info"])
+    return x.reshape(b.shape), int(res["info"]), dict(res, solver=name, route=route)
+
+
+def _publish(res: dict, sink: Optional[dict]):
+    global last_result
+    last_result = res
+    if sink is not None:
+        sink.clear()
+        sink.update(res)
 
 
 class _ImplicitAdjoint(torch.autograd.Function):
@@ -202,8 +224,8 @@ class _ImplicitAdjoint(torch.autograd.Function):
         grad_b = grad_A = None
         want_A = GRAD_WRT_A and ctx.needs_input_grad[0]
         if ctx.needs_input_grad[1] or want_A:
-            g, _ = _solve_core(name, ctx.A, grad_output.contiguous(), x0, tol, atol, maxiter, restart, solve_method,
-                               transpose=True, precond=precond)
+            g, _, _ = _solve_core(name, ctx.A, grad_output.contiguous(), x0, tol, atol, maxiter, restart, solve_method,
+                                  transpose=True, precond=precond)
             if ctx.needs_input_grad[1]:
                 grad_b = g.to(grad_output.dtype)
             if want_A:
@@ -234,57 +256,140 @@ def _finish(name, A, b, x, info, x0, tol, atol, restart, maxiter, solve_method, 
     return x, info
 
 
+class _GenericAdjoint(torch.autograd.Function):
+    """The implicit-differentiation backward for the generic route with a TENSOR A and a callable M: the reference
+    attaches ImplicitAdjointFunction whenever A is a 2-D tensor, with or without M (:1079-1086 cg, :1145-1152 bicgstab,
+    :775-782 gmres), and its transpose_solve_fn re-uses M, x0 and the tolerances."""
+
+    @staticmethod
+    def forward(ctx, A, b, x, name, x0, tol, atol, restart, maxiter, solve_method, M):
+        ctx.A = A
+        ctx.meta = (name, x0, tol, atol, restart, maxiter, solve_method, M)
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        from . import generic
+        name, x0, tol, atol, restart, maxiter, solve_method, M = ctx.meta
+        grad_b = None
+        if ctx.needs_input_grad[1]:
+            global last_result
+            saved = last_result          # the adjoint solve must not overwrite the forward's record
+            try:
+                with torch.no_grad():
+                    g = grad_output.detach().contiguous()
+                    if name == "cg":
+                        gb, _ = generic.generic_cg(ctx.A, g, x0, tol=tol, atol=atol, maxiter=maxiter, M=M, transpose=True)
+                    elif name == "bicgstab":
+                        gb, _ = generic.generic_bicgstab(ctx.A, g, x0, tol=tol, atol=atol, maxiter=maxiter, M=M,
+                                                         transpose=True)
+                    else:
+                        gb, _ = generic.generic_gmres(ctx.A, g, x0, tol=tol, atol=atol, restart=restart,
+                                                      maxiter=maxiter, M=M, solve_method=solve_method, transpose=True)
+            finally:
+                last_result = saved
+            grad_b = gb.to(grad_output.dtype)
+        return (None, grad_b) + (None,) * 9
+
+
+_warned_callable_grad = False
+
+
+def _generic(name, A, b, x0, tol, atol, maxiter, M, restart=20, solve_method='batched', _result=None):
+    """Generic route + the autograd semantics of the reference for it."""
+    global _warned_callable_grad
+    from . import generic
+    fn = {"cg": generic.generic_cg, "bicgstab": generic.generic_bicgstab, "gmres": generic.generic_gmres}[name]
+    kw = dict(tol=tol, atol=atol, maxiter=maxiter, M=M)
+    if name == "gmres":
+        kw.update(restart=restart, solve_method=solve_method)
+    x, info = fn(A, b, x0, **kw)
+    _publish(dict(last_result), _result)
+    if _use_implicit_diff(A, b):
+        if A.is_complex() or b.is_complex():
+            return x, info
+        x = _GenericAdjoint.apply(A, b, x, name, x0, tol, atol, restart, maxiter, solve_method, M)
+    elif not _warned_callable_grad and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tree_leaves(b)):
+        _warned_callable_grad = True
+        warnings.warn("module_a: b requires grad but A is a callable — this build cannot differentiate through a "
+                      "callable operator (pass A as a tensor to get the implicit-differentiation backward)")
+    return x, info
+
+
+def _is_dist(A) -> bool:
+    return type(A).__name__ == "DistMatrix" and hasattr(A, "n_global")
+
+
 # --------------------------------------------------------------------------------------------------
 # public API
 # --------------------------------------------------------------------------------------------------
 def cg(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any] = None, *, tol: float = 1e-5,
-       atol: float = 0.0, maxiter: Optional[int] = None, M: Optional[Callable[[Any], Any]] = None
-       ) -> Tuple[Any, Optional[int]]:
+       atol: float = 0.0, maxiter: Optional[int] = None, M: Optional[Callable[[Any], Any]] = None,
+       _result: Optional[dict] = None) -> Tuple[Any, Optional[int]]:
     """Conjugate gradient for hermitian positive definite A.  Same contract as reference cg (:1019-1088):
     returns (x, info), x fp64 (fp32 when A and b are both fp32), info 0 if ||b - A x|| <= max(tol*||b||, atol)
     else -1; gradients w.r.t. b by implicit differentiation with a second (transposed) solve."""
+    if _is_dist(A):
+        return A._module_a_solve("cg", b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M, _result=_result)
     route = _route(A, b, x0, M, native_M=True)
+    if route == "complex":
+        from .complex_route import complex_solve
+        return complex_solve("cg", A, b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M, _result=_result)
     if route == "generic":
-        from .generic import generic_cg
-        return generic_cg(A, b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M)
+        return _generic("cg", A, b, x0, tol, atol, maxiter, M, _result=_result)
     if x0 is not None:
         _check_x0(b, x0)
-    x, info = _solve_core("cg", A, b, x0, tol, atol, maxiter, precond=M)
+    x, info, res = _solve_core("cg", A, b, x0, tol, atol, maxiter, precond=M)
+    _publish(res, _result)
     return _finish("cg", A, b, x, info, x0, tol, atol, 20, maxiter, 'batched', precond=M)
 
 
 def bicgstab(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any] = None, *, tol: float = 1e-5,
-             atol: float = 0.0, maxiter: Optional[int] = None, M: Optional[Callable[[Any], Any]] = None
-             ) -> Tuple[Any, Optional[int]]:
+             atol: float = 0.0, maxiter: Optional[int] = None, M: Optional[Callable[[Any], Any]] = None,
+             _result: Optional[dict] = None) -> Tuple[Any, Optional[int]]:
     """Bi-conjugate gradient stabilised for general A.  Same contract as reference bicgstab (:1091-1158)."""
+    if _is_dist(A):
+        return A._module_a_solve("bicgstab", b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M, _result=_result)
     route = _route(A, b, x0, M, native_M=True)
+    if route == "complex":
+        from .complex_route import complex_solve
+        return complex_solve("bicgstab", A, b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M, _result=_result)
     if route == "generic":
-        from .generic import generic_bicgstab
-        return generic_bicgstab(A, b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M)
+        return _generic("bicgstab", A, b, x0, tol, atol, maxiter, M, _result=_result)
     if x0 is not None:
         _check_x0(b, x0)
-    x, info = _solve_core("bicgstab", A, b, x0, tol, atol, maxiter, precond=M)
+    x, info, res = _solve_core("bicgstab", A, b, x0, tol, atol, maxiter, precond=M)
+    _publish(res, _result)
     return _finish("bicgstab", A, b, x, info, x0, tol, atol, 20, maxiter, 'batched', precond=M)
 
 
 def gmres(A: Union[torch.Tensor, Callable[[Any], Any]], b: Any, x0: Optional[Any] = None, *, tol: float = 1e-5,
           atol: float = 0.0, restart: int = 20, maxiter: Optional[int] = None,
-          M: Optional[Callable[[Any], Any]] = None, solve_method: str = 'batched') -> Tuple[Any, Optional[int]]:
+          M: Optional[Callable[[Any], Any]] = None, solve_method: str = 'batched',
+          _result: Optional[dict] = None) -> Tuple[Any, Optional[int]]:
     """Restarted GMRES.  Same contract as reference gmres (:641-784): `maxiter` counts restart cycles,
     solve_method 'batched' (default; always `restart` Arnoldi steps per cycle) or 'incremental' (Givens QR with
     early exit inside a cycle); info 0 iff ||b - A x|| <= 10*atol_eff and x is finite."""
     if solve_method not in ('batched', 'incremental'):
         raise ValueError(f"Unsupported solve_method: {solve_method}")
+    if _is_dist(A):
+        return A._module_a_solve("gmres", b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M, restart=restart,
+                                 solve_method=solve_method, _result=_result)
     route = _route(A, b, x0, M, native_M=True)
+    if route == "complex":
+        from .complex_route import complex_solve
+        return complex_solve("gmres", A, b, x0, tol=tol, atol=atol, maxiter=maxiter, M=M, restart=restart,
+                             solve_method=solve_method, _result=_result)
+    if route != "generic" and restart > NATIVE_MAX_RESTART:
+        route = "generic"         # the reference accepts any restart; very long cycles run Python-driven
     if route == "generic":
-        from .generic import generic_gmres
-        return generic_gmres(A, b, x0, tol=tol, atol=atol, restart=restart, maxiter=maxiter, M=M,
-                             solve_method=solve_method)
+        return _generic("gmres", A, b, x0, tol, atol, maxiter, M, restart, solve_method, _result=_result)
     if x0 is not None:
         _check_x0(b, x0)
     if restart < 1:
         raise ValueError("restart must be >= 1")
-    x, info = _solve_core("gmres", A, b, x0, tol, atol, maxiter, restart, solve_method, precond=M)
+    x, info, res = _solve_core("gmres", A, b, x0, tol, atol, maxiter, restart, solve_method, precond=M)
+    _publish(res, _result)
     return _finish("gmres", A, b, x, info, x0, tol, atol, restart, maxiter, solve_method, precond=M)
 
 
@@ -335,7 +440,11 @@ def _legacy(name, A, b, x0, tol, atol, maxiter, restart=20):
         else:
             (maxiter_,) = rest
             restart_ = 20
-        return _solve_core(name, A_use, rhs, x_init, tol_, atol_, maxiter_, restart_, 'batched', transpose=transpose)
+        x_, info_, res_ = _solve_core(name, A_use, rhs, x_init, tol_, atol_, maxiter_, restart_, 'batched',
+                                      transpose=transpose)
+        if not transpose:
+            _publish(res_, None)
+        return x_, info_
 
     solve_fn._bk_accepts_transposed = True
     args = (x0, tol, atol, restart, maxiter) if name == "gmres" else (x0, tol, atol, maxiter)

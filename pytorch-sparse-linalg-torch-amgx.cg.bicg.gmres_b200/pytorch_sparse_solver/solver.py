@@ -110,9 +110,8 @@ class SparseSolver:
             for k in ('restart', 'solve_method'):
                 if k in kwargs:
                     solve_kwargs[k] = kwargs[k]
-        from .module_a import krylov
-        x, info = module[method](A, b, **solve_kwargs)
-        res = dict(krylov.last_result)
+        res = {}
+        x, info = module[method](A, b, _result=res, **solve_kwargs)   # the solve's own record, not a module global
         iterations = None
         if res.get("route") in ("native", "host") and M is None:
             # ||b - A x|| / ||b|| from the library's own final true-residual pass (reference recomputes it

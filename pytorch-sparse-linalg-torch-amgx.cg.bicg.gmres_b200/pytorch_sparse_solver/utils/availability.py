@@ -6,9 +6,13 @@ from typing import Dict, List
 
 @lru_cache(maxsize=1)
 def check_module_a_available() -> bool:
+    """Module A here IS the CUDA library: available only when libbk_krylov.so is built and a CUDA device exists
+    (there is no CPU fallback to select)."""
     try:
+        import torch
         from .. import module_a  # noqa: F401
-        return True
+        from .. import _native
+        return _native.library_path().exists() and torch.cuda.is_available()
     except Exception:
         return False
 

@@ -18,14 +18,14 @@ def test_library_exports_every_header_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/bk_krylov.h but not exported"
     assert declared == set(_native._SIGNATURES), "ctypes signature table out of sync with the header"
-    assert lib.bk_version() == 100
+    assert lib.bk_version() == 200
 
 
 def test_library_result_struct_layout():
     from pytorch_sparse_solver import _native
     import ctypes
-    assert ctypes.sizeof(_native.bk_result) == 8 + 8 + 8 + 4 + 4 + 5 * 8
-    assert ctypes.sizeof(_native.bk_csr_info) == 8 + 8 + 4 * 4 + 8 + 8
+    assert ctypes.sizeof(_native.bk_result) == 8 + 8 + 8 + 4 + 4 + 5 * 8 + 4 + 4 + 8
+    assert ctypes.sizeof(_native.bk_csr_info) == 8 + 8 + 4 * 4 + 8 + 8 + 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -125,11 +125,17 @@ def test_generators_match_reference_conventions():
 
 def test_router_errors_and_availability():
     import pytorch_sparse_solver as pss
-    assert pss.get_available_backends() == {"module_a": True, "module_b": False, "module_c": False}
+    have = torch.cuda.is_available()   # module_a IS the CUDA library: no device -> not available (no CPU fallback)
+    assert pss.get_available_backends() == {"module_a": have, "module_b": False, "module_c": False}
     s = pss.SparseSolver()
-    assert s.available_backends == ["module_a"]
     A = torch.eye(3, dtype=torch.float64)
     b = torch.ones(3, dtype=torch.float64)
+    if not have:
+        assert s.available_backends == []
+        with pytest.raises(RuntimeError, match="No sparse solver backends"):
+            s.solve(A, b)
+        return
+    assert s.available_backends == ["module_a"]
     with pytest.raises(ValueError, match="not available"):
         s.solve(A, b, backend="module_c")
     with pytest.raises(ValueError):
