@@ -781,10 +781,11 @@ bk_mask_build_kernel(const int* __restrict__ rowptr, const int* __restrict__ col
     ent.val = 0ull;
     ent.off = 0;
     ent.pad = 0;
+    const int full = (1 << count) - 1;  // mask of a row that has every entry; kept in entry 0 (bk_mask_load_pattern)
     if (lane < count) {
       ent.val = tab.vb;
       ent.off = tab.off;
-      ent.pad = tab.gh ? BK_MASK_GHOST : 0;
+      ent.pad = (tab.gh ? BK_MASK_GHOST : 0) | (rank == 0 ? (full << BK_MASK_FULL_SHIFT) : 0);
       cpat[ch * BK_MASK_L + rank] = ent;
     } else if (lane < BK_MASK_L) {
       cpat[ch * BK_MASK_L + lane] = ent;  // lanes count..7 fill the unused tail (ranks cover 0..count-1)
@@ -878,6 +879,8 @@ __global__ void bk_mask_compact_kernel(const int* __restrict__ pids, long long n
 int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long long row_begin, cudaStream_t s) {
   if (h->use_compress < 3 || A->is_view || A->n == 0 || A->nnz == 0 || A->max_row_nnz > BK_MASK_L) return BK_OK;
   const long long nchunks = (A->n + 31) / 32;
+  const long long nblk8 = ((A->n + 255) / 256 + 32) * 8;  // chunks of whole 256-row blocks + 32 blocks of padding: the
+                                                          // kernel walks whole groups of up to 32 blocks without a tail test
   bk_pair_entry* cpat = nullptr;
   unsigned long long* keys = nullptr;
   int* dstat = (int*)(h->counters + 8);
@@ -899,8 +902,8 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
   };
   if (bk_pool_alloc((void**)&cpat, sizeof(bk_pair_entry) * BK_MASK_L * (size_t)nchunks, s) != cudaSuccess ||
       bk_pool_alloc((void**)&keys, sizeof(unsigned long long) * BK_MASK_HT, s) != cudaSuccess ||
-      bk_pool_alloc((void**)&A->mmasks, (size_t)nchunks * 32, s) != cudaSuccess ||
-      bk_pool_alloc((void**)&A->mpids, sizeof(int) * (size_t)nchunks, s) != cudaSuccess ||
+      bk_pool_alloc((void**)&A->mmasks, (size_t)nblk8 * 32, s) != cudaSuccess ||
+      bk_pool_alloc((void**)&A->mpids, sizeof(int) * (size_t)nblk8, s) != cudaSuccess ||
       bk_pool_alloc(&A->mptab, sizeof(bk_pair_entry) * BK_MASK_L * BK_MASK_HT, s) != cudaSuccess) {
     cudaGetLastError();
     drop();
@@ -910,6 +913,8 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
   cudaMemsetAsync(dstat, 0, 2 * sizeof(int), s);
   cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * BK_MASK_HT, s);
   cudaMemsetAsync(A->mptab, 0, sizeof(bk_pair_entry) * BK_MASK_L * BK_MASK_HT, s);
+  cudaMemsetAsync(A->mmasks, 0, (size_t)nblk8 * 32, s);
+  cudaMemsetAsync(A->mpids, 0, sizeof(int) * (size_t)nblk8, s);
   long long want = (nchunks + 7) / 8;
   int grid = (int)(want < (long long)h->num_sms * 8 ? want : (long long)h->num_sms * 8);
   if (grid < 1) grid = 1;

@@ -327,11 +327,15 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
       plan.masks = A->mmasks;
       plan.pids = A->mpids;
       plan.ptab = (const bk_pair_entry*)A->mptab;
-      plan.group = h->mask_group < 1 ? 1 : (h->mask_group > 64 ? 64 : h->mask_group);
+      {  // option mask_group = blocks per visit, rounded down to a power of two (the kernel shifts and masks)
+        int gs = 0;
+        while ((2 << gs) <= h->mask_group && gs < 5) ++gs;
+        plan.group = gs;
+      }
       int ctas = h->mask_ctas < 2 ? 2 : (h->mask_ctas > 6 ? 6 : h->mask_ctas);
       int g = h->num_sms * ctas;
       if (g > BK_MAXB) g = BK_MAXB;
-      g = bk_grid_rows(g, A->n, BK_BLOCK * plan.group);
+      g = bk_grid_rows(g, A->n, BK_BLOCK << plan.group);
       switch (ctas) {
         case 2: bk_spmv_mask_kernel<T, MODE, DOTS, false, 2, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
         case 3: bk_spmv_mask_kernel<T, MODE, DOTS, false, 3, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;

@@ -24,6 +24,8 @@
 // which folds the boundary rows of a row-partitioned matrix into this kernel (no separate ghost-row kernel).
 #pragma once
 
+#include <type_traits>
+
 #include "bk_internal.cuh"
 #include "bk_p2p.cuh"
 
@@ -38,7 +40,7 @@ struct bk_mask_plan {
   const void* xg;              // ghost vector (multi-GPU) or nullptr
   const int* deferred;         // chunks with ghost entries, processed after the halo has arrived (multi-GPU)
   int n_deferred;
-  int group;                   // consecutive 256-row blocks dealt to a CTA at a time
+  int group;                   // log2 of the consecutive 256-row blocks dealt to a CTA at a time (0..5)
   // halo arrival (peer-memory path): flags[peer] == want  (nullptr: no wait, e.g. NCCL path orders by stream)
   const unsigned long long* flags;
   const int* flag_peers;
@@ -49,11 +51,14 @@ struct bk_mask_plan {
 
 #define BK_MASK_PID_GHOST (1 << 30)
 
+#define BK_MASK_FULL_SHIFT 8  // bk_pair_entry.pad of a pattern's entry 0: bits 8..16 = mask of a row that has every entry
+
 template <typename T>
 struct bk_mask_pat {
   T val[BK_MASK_L];
   int off[BK_MASK_L];
   unsigned int ghost;  // bit e: entry e gathers from the ghost vector
+  unsigned int full;   // mask of a row that has every entry of the pattern (0xffffffff for an empty pattern)
 };
 
 template <typename T>
@@ -67,27 +72,78 @@ __device__ __forceinline__ void bk_mask_load_pattern(const bk_pair_entry* __rest
     else p.val[e] = __uint_as_float(q.x);
     p.off[e] = (int)q.z;
     p.ghost |= (q.w & BK_MASK_GHOST) ? (1u << e) : 0u;
+    if (e == 0) p.full = (q.w >> BK_MASK_FULL_SHIFT) & 0x1ffu;
   }
+  if (p.full == 0u) p.full = 0xffffffffu;
 }
 
-// one 32-row chunk: y[row] = sum_e [mask bit e] val_e * x[row + off_e]   (+ fused residual / dots)
-template <typename T, int MODE, int DOTS, bool GHOST>
-__device__ __forceinline__ void bk_mask_chunk(const bk_spmv_args& a, const bk_mask_pat<T>& p, const T* __restrict__ x,
-                                              const T* __restrict__ xg, const int row, const unsigned int m,
-                                              const int n32, double* acc) {
+// Gathers: the lane's row pointer lives in a register pair, so an address is ONE 64-bit multiply-add of the pattern
+// offset (ncu on the first version, whose addresses the compiler derived from `x[row + off]`: 145 instructions per
+// 32-row chunk, issue-bound at 116 us).  bk_ld_masked: bit ? base[off] : 0 (predicated load); bk_ld_plain: base[off].
+__device__ __forceinline__ double bk_ld_masked(const double* base, int off, unsigned int bit) {
+  double v;
+  asm("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %2, 0;\n\tmad.wide.s32 a, %3, 8, %1;\n\t"
+      "mov.f64 %0, 0d0000000000000000;\n\t@p ld.global.nc.f64 %0, [a];\n\t}"
+      : "=d"(v)
+      : "l"(base), "r"(bit), "r"(off));
+  return v;
+}
+__device__ __forceinline__ float bk_ld_masked(const float* base, int off, unsigned int bit) {
+  float v;
+  asm("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %2, 0;\n\tmad.wide.s32 a, %3, 4, %1;\n\t"
+      "mov.f32 %0, 0f00000000;\n\t@p ld.global.nc.f32 %0, [a];\n\t}"
+      : "=f"(v)
+      : "l"(base), "r"(bit), "r"(off));
+  return v;
+}
+__device__ __forceinline__ double bk_ld_masked_cg(const double* base, int off, unsigned int bit) {
+  double v;
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %2, 0;\n\tmad.wide.s32 a, %3, 8, %1;\n\t"
+               "mov.f64 %0, 0d0000000000000000;\n\t@p ld.global.cg.f64 %0, [a];\n\t}"
+               : "=d"(v)
+               : "l"(base), "r"(bit), "r"(off)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float bk_ld_masked_cg(const float* base, int off, unsigned int bit) {
+  float v;
+  asm volatile("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\tsetp.ne.u32 p, %2, 0;\n\tmad.wide.s32 a, %3, 4, %1;\n\t"
+               "mov.f32 %0, 0f00000000;\n\t@p ld.global.cg.f32 %0, [a];\n\t}"
+               : "=f"(v)
+               : "l"(base), "r"(bit), "r"(off)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ double bk_ld_plain(const double* base, int off) {
+  double v;
+  asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %2, 8, %1;\n\tld.global.nc.f64 %0, [a];\n\t}" : "=d"(v) : "l"(base), "r"(off));
+  return v;
+}
+__device__ __forceinline__ float bk_ld_plain(const float* base, int off) {
+  float v;
+  asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %2, 4, %1;\n\tld.global.nc.f32 %0, [a];\n\t}" : "=f"(v) : "l"(base), "r"(off));
+  return v;
+}
+
+// one 32-row chunk: y[row] = sum_e [mask bit e] val_e * x[row + off_e]   (+ fused residual / dots).
+// FAST: every row of the chunk has every entry of the pattern (warp-uniform test by the caller; ~3/4 of the chunks of
+// a stencil matrix): no predicates, no zero-fill, no bounds test (a row with a non-empty mask exists).
+template <typename T, int MODE, int DOTS, bool GHOST, bool FAST>
+__device__ __forceinline__ void bk_mask_chunk(const bk_spmv_args& a, const bk_mask_pat<T>& p, const T* x, const T* xg,
+                                              const int row, const unsigned int m, const int n32, double* acc) {
+  const T* xr = x + row;
+  const T* xgr = GHOST ? xg + row : nullptr;
   T xv[BK_MASK_L];
 #pragma unroll
   for (int e = 0; e < BK_MASK_L; ++e) {
-    xv[e] = T(0);
-    if (m & (1u << e)) {
-      if (GHOST && (p.ghost & (1u << e))) xv[e] = __ldcg(xg + (row + p.off[e]));
-      else xv[e] = __ldg(x + (row + p.off[e]));
-    }
+    if (GHOST && (p.ghost & (1u << e))) xv[e] = bk_ld_masked_cg(xgr, p.off[e], m & (1u << e));
+    else if (FAST) xv[e] = bk_ld_plain(xr, p.off[e]);  // entries past the pattern's length: value 0, offset 0
+    else xv[e] = bk_ld_masked(xr, p.off[e], m & (1u << e));
   }
   T sum = T(0);
 #pragma unroll
   for (int e = 0; e < BK_MASK_L; ++e) sum = fma(p.val[e], xv[e], sum);
-  if (row < n32) {
+  if (FAST || row < n32) {
     T out = sum;
     if constexpr (MODE == 1) out = bk_sub(__ldg(static_cast<const T*>(a.b) + row), sum);
     static_cast<T*>(a.y)[row] = out;
@@ -105,14 +161,14 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int n32 = (int)a.n;
-  const int nchunks = (n32 + 31) >> 5;
   const int nblk = (n32 + 255) >> 8;
-  const int group = plan.group;
-  const int ngroups = (nblk + group - 1) / group;
+  const int gshift = plan.group;  // log2 of the consecutive 256-row blocks a CTA takes per visit (0..5)
+  const int gmask = (1 << gshift) - 1;
+  const int ngroups = (nblk + gmask) >> gshift;
   int reverse = a.reverse;
   if (a.use_parity) reverse ^= (a.st->parity & 1);
-  const T* __restrict__ x = static_cast<const T*>(a.x);
-  const T* __restrict__ xg = static_cast<const T*>(plan.xg);
+  const T* x = static_cast<const T*>(a.x);
+  const T* xg = static_cast<const T*>(plan.xg);
   const unsigned char* __restrict__ masks = plan.masks;
   const int* __restrict__ pids = plan.pids;
 
@@ -122,48 +178,49 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
 
   bk_mask_pat<T> pat;
   int cur = -1;
-  // this warp's chunks: group g = blockIdx.x, blockIdx.x + gridDim.x, ... ; inside a group blocks ascend (descend when
-  // reversed), the warp takes chunk `wid` of each block
-  auto chunk_of = [&](int g, int j) -> int {
+  // Groups of 2^gshift consecutive blocks are dealt round-robin to the CTAs (the chip sweeps one window of the vectors;
+  // inside a group neighbouring grid lines are gathered from L1).  A warp takes chunk `wid` of every block of its
+  // groups: chunk t = 0 .. T-1 of its sequence.  `masks` / `pids` are padded to 32 whole blocks beyond the matrix (zero
+  // masks gather nothing), so the tail of the last group needs no test.
+  const int my_groups = (ngroups > (int)blockIdx.x) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int T_ = my_groups << gshift;
+  auto chunk_at = [&](int t) -> int {
+    const int g = (int)blockIdx.x + (t >> gshift) * (int)gridDim.x;
     const int gg = reverse ? (ngroups - 1 - g) : g;
-    const int blk = gg * group + (reverse ? (group - 1 - j) : j);
-    return (blk < nblk) ? blk * 8 + wid : -1;
+    return (((gg << gshift) + (t & gmask)) << 3) + wid;
   };
-  int g = (int)blockIdx.x, j = 0;
-  int ch = -1;
-  unsigned int m_next = 0;
-  int pid_next = 0;
-  auto advance = [&]() {  // next valid chunk of this warp (ch = -1 when exhausted) + prefetch of its mask / pattern id
-    ch = -1;
-    while (g < ngroups) {
-      const int c = chunk_of(g, j);
-      if (++j == group) {
-        j = 0;
-        g += (int)gridDim.x;
-      }
-      if (c >= 0 && c < nchunks) {
-        ch = c;
-        break;
-      }
-    }
-    if (ch >= 0) {
-      m_next = __ldg(masks + (size_t)ch * 32 + lane);
-      pid_next = __ldg(pids + ch);
-    }
-  };
-  advance();
-  while (ch >= 0) {
-    const int c0 = ch;
-    const unsigned int m = m_next;
-    const int pid = pid_next;
-    advance();  // the next chunk's mask / pattern id are in flight while this one is computed
-    if (GHOST && (pid & BK_MASK_PID_GHOST)) continue;  // boundary chunk: second phase
-    const int slot = pid & (BK_MASK_PID_GHOST - 1);
+  int t = 0;
+  int ch_next = 0, pid_next = 0;
+  unsigned int m_next = 0u;
+  if (T_ > 0) {
+    ch_next = chunk_at(0);
+    m_next = __ldg(masks + (size_t)ch_next * 32 + lane);
+    pid_next = __ldg(pids + ch_next);
+  }
+  while (t < T_) {
+    // a run of chunks with the same pattern: the pattern is (re)loaded here, outside the hot loop
+    const int slot = pid_next & (BK_MASK_PID_GHOST - 1);
     if (slot != cur) {
       bk_mask_load_pattern<T>(plan.ptab, slot, pat);
       cur = slot;
     }
-    bk_mask_chunk<T, MODE, DOTS, false>(a, pat, x, xg, c0 * 32 + lane, m, n32, acc);
+    do {
+      const int row = ch_next * 32 + lane;
+      const unsigned int m = m_next;
+      const bool ghost_chunk = GHOST && (pid_next & BK_MASK_PID_GHOST);
+      ++t;
+      if (t < T_) {  // the next chunk's mask / pattern id are in flight while this one is computed
+        ch_next = chunk_at(t);
+        m_next = __ldg(masks + (size_t)ch_next * 32 + lane);
+        pid_next = __ldg(pids + ch_next);
+      }
+      if (!ghost_chunk) {  // (chunks with ghost entries: second phase)
+        if (__all_sync(0xffffffffu, m == pat.full))
+          bk_mask_chunk<T, MODE, DOTS, false, true>(a, pat, x, xg, row, m, n32, acc);
+        else
+          bk_mask_chunk<T, MODE, DOTS, false, false>(a, pat, x, xg, row, m, n32, acc);
+      }
+    } while (t < T_ && (pid_next & (BK_MASK_PID_GHOST - 1)) == slot);
   }
   if constexpr (GHOST) {
     // ---- second phase: chunks with ghost entries, after the neighbours' halos have landed ---------------------
@@ -200,7 +257,7 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
             bk_mask_load_pattern<T>(plan.ptab, slot, pat);
             cur = slot;
           }
-          bk_mask_chunk<T, MODE, DOTS, true>(a, pat, x, xg, c0 * 32 + lane, m, n32, acc);
+          bk_mask_chunk<T, MODE, DOTS, true, false>(a, pat, x, xg, c0 * 32 + lane, m, n32, acc);
         }
       }
     }
