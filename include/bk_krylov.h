@@ -262,6 +262,16 @@ int bk_dist_create(bk_handle* h, const void* id128, int rank, int nranks, int64_
                    const int64_t* send_counts, const int64_t* recv_counts, const void* send_idx, int dtype,
                    void* stream, bk_dist** out);
 int bk_dist_destroy(bk_dist* D);
+/* Optional: the rows of this rank as ONE matrix over the extended vector [ local entries | ghost vector ] — CSR with
+ * n_local rows, columns < n_local + n_ghost (ghost entry g has column n_local + g), entries in the order of the GLOBAL
+ * matrix's rows.  When the row-bitmask plan (kernel 6) fits it, the peer-memory path runs ONE SpMV kernel per matvec:
+ * interior chunks first, the chunks that gather ghost entries last, after polling the neighbours' arrival flags — the
+ * separate boundary-row kernel and the correction of the dot partials disappear.  ghost_gid: device int64[n_ghost],
+ * global ids of the ghost entries; row_begin: global id of local row 0 (pattern entries are ordered by global offset,
+ * like the single-GPU matrix).  ext_val may be the array the local/ghost blocks were split from.  The arrays are only
+ * read during this call.  *folded = 1 when the plan was built (else the two-kernel path stays in use). */
+int bk_dist_set_extended(bk_dist* D, int64_t nnz_ext, const void* ext_rowptr, const void* ext_col, const void* ext_val,
+                         const void* ghost_gid, int64_t row_begin, void* stream, int32_t* folded);
 /* Peer-memory path (NVLink/NVSwitch, CUDA IPC).  Each rank exports the 64-byte IPC handle of its communication
  * window (all-reduce slots, halo flags, ghost vector); the caller gathers all handles and every rank maps them.
  * remote_ghost_offsets[i] = element offset inside halo peer i's ghost vector where this rank's entries land.
@@ -276,6 +286,16 @@ int bk_dist_spmv(bk_handle* h, bk_dist* D, const void* x_local, void* y_local, v
 /* distributed CG (same recurrences / stop test / info as bk_cg; n_global sets the default maxiter = 10 n) */
 int bk_dist_cg(bk_handle* h, bk_dist* D, const void* b_local, void* x_local, int has_x0, double tol,
                double atol, int64_t maxiter, int64_t n_global, bk_result* result, void* stream);
+/* the same three with the built-in Jacobi preconditioner (diag_local: this rank's slice of diag(A); the diagonal of a
+ * row partition is local).  Recurrences as bk_cg_jacobi / bk_bicgstab_jacobi / bk_gmres_jacobi. */
+int bk_dist_cg_jacobi(bk_handle* h, bk_dist* D, const void* diag_local, const void* b_local, void* x_local, int has_x0,
+                      double tol, double atol, int64_t maxiter, int64_t n_global, bk_result* result, void* stream);
+int bk_dist_bicgstab_jacobi(bk_handle* h, bk_dist* D, const void* diag_local, const void* b_local, void* x_local,
+                            int has_x0, double tol, double atol, int64_t maxiter, int64_t n_global, bk_result* result,
+                            void* stream);
+int bk_dist_gmres_jacobi(bk_handle* h, bk_dist* D, const void* diag_local, const void* b_local, void* x_local,
+                         int has_x0, double tol_eff, double atol_eff, int restart, int64_t maxiter, int method,
+                         int64_t n_global, bk_result* result, void* stream);
 /* distributed BiCGStab / GMRES: the single-GPU drivers (bk_bicgstab, bk_gmres — same recurrences, breakdown codes,
  * restart logic and info) run on the row-partitioned matrix; every dot product becomes a global sum (NCCL path:
  * ncclAllReduce + a one-thread scalar kernel; peer-memory path: all-reduced inside the reducing kernel's epilogue,

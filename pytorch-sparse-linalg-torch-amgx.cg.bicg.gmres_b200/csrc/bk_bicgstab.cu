@@ -293,3 +293,19 @@ extern "C" int bk_dist_bicgstab(bk_handle* h, bk_dist* D, const void* b_local, v
     return bk_bicgstab_t<double>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
   return bk_bicgstab_t<float>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
 }
+
+extern "C" int bk_dist_bicgstab_jacobi(bk_handle* h, bk_dist* D, const void* diag_local, const void* b_local,
+                                       void* x_local, int has_x0, double tol, double atol, int64_t maxiter,
+                                       int64_t n_global, bk_result* result, void* stream) {
+  if (!h || !D || !result) return bk_fail(BK_ERR_ARG, "bk_dist_bicgstab_jacobi: null handle/matrix/result");
+  if (D->n_local > 0 && (!b_local || !x_local || !diag_local))
+    return bk_fail(BK_ERR_ARG, "bk_dist_bicgstab_jacobi: null vector");
+  memset(result, 0, sizeof(*result));
+  BK_CUDA(cudaSetDevice(h->device));
+  const bk_sys_dist sys{h, D, D->p2p_enabled && h->dist_p2p, n_global};
+  if (D->dtype == BK_F64)
+    return bk_bicgstab_t<double>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream,
+                                 (const double*)diag_local);
+  return bk_bicgstab_t<float>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream,
+                              (const float*)diag_local);
+}

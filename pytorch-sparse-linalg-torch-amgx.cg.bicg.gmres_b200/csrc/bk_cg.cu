@@ -406,10 +406,11 @@ struct bk_epi_ignore {
   __device__ __forceinline__ void operator()(const double*) const {}
 };
 
-template <typename T>
-static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, void* x_user, int has_x0, double tol,
+template <typename T, typename Sys>
+static int bk_pcg_t(const Sys& sys, const T* d, const void* b, void* x_user, int has_x0, double tol,
                     double atol, int64_t maxiter, bk_result* res, cudaStream_t s) {
-  const long long n = A->n;
+  bk_handle* h = sys.h;
+  const long long n = sys.n();
   const size_t npad = ((size_t)n + 63) & ~(size_t)63;
   BK_TRY(bk_ws_reserve(h, (size_t)4 * npad * sizeof(T)));
   T* x = (T*)h->ws;
@@ -418,21 +419,20 @@ static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, vo
   T* ap = p + npad;
   bk_dev_state* st = h->st;
   const size_t vbytes = (size_t)n * sizeof(T);
-  const bk_sys_local sys{h, A};
   bk_call_begin(h, s, "bk_cg_jacobi");
 
   bk_dev_state init;
   memset(&init, 0, sizeof(init));
-  init.maxiter = maxiter < 0 ? 10 * n : maxiter;
+  init.maxiter = maxiter < 0 ? 10 * sys.n_global() : maxiter;
   init.status = BK_ST_MAXITER;
   bk_state_fill_tol(&init, tol, atol);
   bk_state_set_kernel<<<1, 1, 0, s>>>(st, init);
   BK_KERNEL_CHECK();
 
-  BK_TRY((sys.dot<T>(b, b, bk_epi_pcg_bs{st}, 1, s)));
+  BK_TRY((sys.template dot<T>(b, b, bk_epi_pcg_bs{st}, 1, s)));
   if (has_x0) {
     BK_CUDA(cudaMemcpyAsync(x, x_user, vbytes, cudaMemcpyDeviceToDevice, s));
-    BK_TRY((sys.matvec<T, 1, 2>(x, r, nullptr, b, 0, bk_epi_ignore{}, s)));  // r0 = b - A x0 (:820)
+    BK_TRY((sys.template matvec<T, 1, 2>(x, r, nullptr, b, 0, bk_epi_ignore{}, s)));  // r0 = b - A x0 (:820)
   } else {
     BK_CUDA(cudaMemsetAsync(x, 0, vbytes, s));
     BK_CUDA(cudaMemcpyAsync(r, b, vbytes, cudaMemcpyDeviceToDevice, s));
@@ -443,18 +443,18 @@ static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, vo
     op.d = d;
     op.p = p;
     op.st = st;
-    BK_TRY(sys.ew<T>(op, bk_aligned16(d), 1, s));
+    BK_TRY(sys.template ew<T>(op, bk_aligned16(d), 1, s));
   }
   const bool al = bk_aligned16(d);
   auto enqueue_iter = [&](cudaStream_t cs) -> int {
-    BK_TRY((sys.matvec<T, 0, 1>(p, ap, p, nullptr, 1, bk_epi_cg_pAp{st}, cs)));
+    BK_TRY((sys.template matvec<T, 0, 1>(p, ap, p, nullptr, 1, bk_epi_cg_pAp{st}, cs)));
     {
       bk_op_pcg_r<T> op;
       op.ap = ap;
       op.r = r;
       op.d = d;
       op.st = st;
-      BK_TRY(sys.ew<T>(op, al, 1, cs));
+      BK_TRY(sys.template ew<T>(op, al, 1, cs));
     }
     {
       bk_op_pcg_xp<T> op;
@@ -463,15 +463,15 @@ static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, vo
       op.r = r;
       op.d = d;
       op.st = st;
-      BK_TRY(sys.ew<T>(op, al, 2, cs));
+      BK_TRY(sys.template ew<T>(op, al, 2, cs));
     }
     return BK_OK;
   };
   const double bytes_iter = sys.matrix_bytes() + 13.0 * n * sizeof(T);
   const int chunk = bk_pick_chunk(h, bytes_iter, 3);
   const bool use_graph = h->loop_mode != BK_LOOP_STREAM;
-  uint64_t key[6] = {5 /*jacobi cg*/, A->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
-                     (uint64_t)A->dtype | ((uint64_t)chunk << 16) | ((uint64_t)al << 8),
+  uint64_t key[6] = {5 /*jacobi cg*/, sys.uid(), (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
+                     (uint64_t)sys.dtype() | ((uint64_t)chunk << 16) | ((uint64_t)al << 8),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   // the diagonal's address is baked into the captured graph: make it part of the key
   key[1] ^= (uint64_t)(uintptr_t)d * 0x9e3779b97f4a7c15ull;
@@ -485,15 +485,15 @@ static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, vo
   bk_call_mark(h, "final");
 
   // final check of _isolve: || M (b - A x) || against max(tol ||b||, atol) (:1008-1013)
-  BK_TRY((sys.matvec<T, 1, 2>(x, ap, nullptr, b, 0, bk_epi_ignore{}, s)));
+  BK_TRY((sys.template matvec<T, 1, 2>(x, ap, nullptr, b, 0, bk_epi_ignore{}, s)));
   {
     bk_op_scaled_sq<T, bk_epi_final_r> op;
     op.t = ap;
     op.d = d;
     op.epi = bk_epi_final_r{st};
-    BK_TRY(sys.ew<T>(op, al, 1, s));
+    BK_TRY(sys.template ew<T>(op, al, 1, s));
   }
-  BK_TRY((sys.dot<T>(x, x, bk_epi_final_x{st}, 1, s)));
+  BK_TRY((sys.template dot<T>(x, x, bk_epi_final_x{st}, 1, s)));
   BK_CUDA(cudaMemcpyAsync(x_user, x, vbytes, cudaMemcpyDeviceToDevice, s));
   BK_CUDA(cudaMemcpyAsync(&h->st_host[3], st, sizeof(bk_dev_state), cudaMemcpyDeviceToHost, s));
   bk_call_stop(h, s);
@@ -503,7 +503,7 @@ static int bk_pcg_t(bk_handle* h, const bk_csr* A, const T* d, const void* b, vo
   res->rr_last = fin->rs;
   res->kernel_launches = chunks * chunk * 3 + 4 + (has_x0 ? 1 : 0) + 3;
   bk_call_finish(h, res);
-  return BK_OK;
+  return sys.check_comm(fin, "cg_jacobi");
 }
 
 extern "C" int bk_cg_jacobi(bk_handle* h, const bk_csr* A, const void* diag, const void* b, void* x, int has_x0,
@@ -512,10 +512,10 @@ extern "C" int bk_cg_jacobi(bk_handle* h, const bk_csr* A, const void* diag, con
   if (!diag && A->n > 0) return bk_fail(BK_ERR_ARG, "bk_cg_jacobi: null diagonal");
   BK_CUDA(cudaSetDevice(h->device));
   if (A->n == 0) return BK_OK;
+  const bk_sys_local sys{h, A};
   if (A->dtype == BK_F64)
-    return bk_pcg_t<double>(h, A, (const double*)diag, b, x, has_x0, tol, atol, maxiter, result,
-                            (cudaStream_t)stream);
-  return bk_pcg_t<float>(h, A, (const float*)diag, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+    return bk_pcg_t<double>(sys, (const double*)diag, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+  return bk_pcg_t<float>(sys, (const float*)diag, b, x, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
 }
 
 // diag[r] = A[r][r] (sum of the stored entries with col == r; 0 when the row has none)
@@ -650,4 +650,19 @@ extern "C" int bk_dist_cg(bk_handle* h, bk_dist* D, const void* b_local, void* x
   if (D->dtype == BK_F64)
     return bk_dist_cg_t<double>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
   return bk_dist_cg_t<float>(sys, b_local, x_local, has_x0, tol, atol, maxiter, result, (cudaStream_t)stream);
+}
+
+extern "C" int bk_dist_cg_jacobi(bk_handle* h, bk_dist* D, const void* diag_local, const void* b_local, void* x_local,
+                                 int has_x0, double tol, double atol, int64_t maxiter, int64_t n_global,
+                                 bk_result* result, void* stream) {
+  if (!h || !D || !result) return bk_fail(BK_ERR_ARG, "bk_dist_cg_jacobi: null handle/matrix/result");
+  if (D->n_local > 0 && (!b_local || !x_local || !diag_local)) return bk_fail(BK_ERR_ARG, "bk_dist_cg_jacobi: null vector");
+  memset(result, 0, sizeof(*result));
+  BK_CUDA(cudaSetDevice(h->device));
+  const bk_sys_dist sys{h, D, D->p2p_enabled && h->dist_p2p, n_global, false};
+  if (D->dtype == BK_F64)
+    return bk_pcg_t<double>(sys, (const double*)diag_local, b_local, x_local, has_x0, tol, atol, maxiter, result,
+                            (cudaStream_t)stream);
+  return bk_pcg_t<float>(sys, (const float*)diag_local, b_local, x_local, has_x0, tol, atol, maxiter, result,
+                         (cudaStream_t)stream);
 }

@@ -104,8 +104,10 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->pair_ctas = (int)bk_env_int("BK_PAIR_CTAS", 4);
   h->mask_ctas = (int)bk_env_int("BK_MASK_CTAS", 4);
   h->mask_group = (int)bk_env_int("BK_MASK_GROUP", 8);
+  h->mask_prefetch = (int)bk_env_int("BK_MASK_PREFETCH", 1);
   h->nvtx = (int)bk_env_int("BK_NVTX", 0);
   h->dist_fuse_push = (int)bk_env_int("BK_DIST_FUSE_PUSH", 1);
+  h->dist_fold = (int)bk_env_int("BK_DIST_FOLD", 1);
   h->tma_stages = (int)bk_env_int("BK_TMA_STAGES", 0);
   h->use_tma = (int)bk_env_int("BK_SPMV_TMA", 1);
   h->dist_p2p = (int)bk_env_int("BK_DIST_P2P", 1);
@@ -202,8 +204,10 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "pair_ctas")) return &h->pair_ctas;
   if (!strcmp(key, "mask_ctas")) return &h->mask_ctas;
   if (!strcmp(key, "mask_group")) return &h->mask_group;
+  if (!strcmp(key, "mask_prefetch")) return &h->mask_prefetch;
   if (!strcmp(key, "nvtx")) return &h->nvtx;
   if (!strcmp(key, "dist_fuse_push")) return &h->dist_fuse_push;
+  if (!strcmp(key, "dist_fold")) return &h->dist_fold;
   if (!strcmp(key, "tma_stages")) return &h->tma_stages;
   if (!strcmp(key, "use_tma")) return &h->use_tma;
   if (!strcmp(key, "dist_p2p")) return &h->dist_p2p;
@@ -1055,7 +1059,11 @@ int bk_csr_finish_plan(bk_handle* h, bk_csr* A, cudaStream_t s) {
     A->bytes_stream = A->split->bytes_stream + (n + 1) * 4 + 2 * A->split->n * (int64_t)bk_dtype_size(A->dtype);
     return BK_OK;
   }
-  if (A->kernel == 0 && A->n_cols == A->n) BK_TRY(bk_csr_plan_mask(h, A, nullptr, 0, s));
+  if (A->n_cols != A->n) {  // extended [local | ghost] matrix of a row partition: the row-bitmask plan or nothing
+    if (A->kernel == 0) BK_TRY(bk_csr_plan_mask(h, A, A->reg_ghost_gid, A->reg_row_begin, s));
+    return BK_OK;
+  }
+  if (A->kernel == 0) BK_TRY(bk_csr_plan_mask(h, A, nullptr, 0, s));
   if (A->kernel == 6) return BK_OK;
   return bk_csr_plan_tma(h, A, s);
 }

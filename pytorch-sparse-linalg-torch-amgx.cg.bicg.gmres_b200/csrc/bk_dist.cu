@@ -68,6 +68,7 @@ extern "C" int bk_dist_destroy(bk_dist* D) {
   }
   // D->comm belongs to the handle (shared by all matrices of this rank set): see bk_dist_release_comm
   if (D->Aloc) bk_csr_destroy(D->Aloc);
+  if (D->Aext) bk_csr_destroy(D->Aext);
   for (int q = 0; q < BK_P2P_MAXP; ++q)
     if (D->peer_mapped[q]) cudaIpcCloseMemHandle(D->peer_mapped[q]);
   if (D->sendbuf) cudaFree(D->sendbuf);
@@ -175,6 +176,49 @@ extern "C" int bk_dist_create(bk_handle* h, const void* id128, int rank, int nra
     h->dist_comm_nranks = nranks;
   }
   *out = D;
+  return BK_OK;
+}
+
+extern "C" int bk_dist_set_extended(bk_dist* D, int64_t nnz_ext, const void* ext_rowptr, const void* ext_col,
+                                    const void* ext_val, const void* ghost_gid, int64_t row_begin, void* stream,
+                                    int32_t* folded) {
+  if (!D || !folded) return bk_fail(BK_ERR_ARG, "bk_dist_set_extended: null argument");
+  *folded = 0;
+  if (nnz_ext < 0 || !ext_rowptr || (nnz_ext > 0 && (!ext_col || !ext_val)) || (D->n_ghost > 0 && !ghost_gid))
+    return bk_fail(BK_ERR_ARG, "bk_dist_set_extended: null array");
+  bk_handle* h = D->h;
+  BK_CUDA(cudaSetDevice(h->device));
+  if (D->Aext) {
+    bk_csr_destroy(D->Aext);
+    D->Aext = nullptr;
+  }
+  if (D->n_local + D->n_ghost >= 2147483647LL || nnz_ext >= 2147483647LL) return BK_OK;  // two-kernel path stays
+  bk_csr* E = (bk_csr*)calloc(1, sizeof(bk_csr));
+  if (!E) return bk_fail(BK_ERR_ALLOC, "bk_dist_set_extended: host allocation failed");
+  E->h = h;
+  E->n = D->n_local;
+  E->n_cols = D->n_local + D->n_ghost;
+  E->nnz = nnz_ext;
+  E->dtype = D->dtype;
+  E->rowptr = (const int*)ext_rowptr;
+  E->col = (const int*)ext_col;
+  E->val = ext_val;
+  E->uid = h->next_uid++;
+  E->reg_ghost_gid = (const long long*)ghost_gid;
+  E->reg_row_begin = row_begin;
+  int rc = bk_csr_finish_plan(h, E, (cudaStream_t)stream);
+  // the plan (masks, pattern ids, pattern table) is self-contained: the CSR arrays are not referenced afterwards
+  E->rowptr = nullptr;
+  E->col = nullptr;
+  E->val = nullptr;
+  E->reg_ghost_gid = nullptr;
+  if (rc != BK_OK || E->kernel != 6) {
+    bk_csr_destroy(E);
+    return rc;
+  }
+  D->Aext = E;
+  *folded = 1;
+  bk_graphs_invalidate(h);
   return BK_OK;
 }
 

@@ -50,6 +50,7 @@ struct bk_dist {
   int64_t n_local, n_ghost, n_brows, nnz_gh;
   int dtype;
   bk_csr* Aloc;
+  bk_csr* Aext;  // [local | ghost] rows with a row-bitmask plan (kernel 6): one SpMV kernel per matvec on the peer path
   const int* brow_ids;
   const int* gh_rowptr;
   const int* gh_col;
@@ -284,6 +285,26 @@ bk_cg_xp_push_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__
   }
 }
 
+// Epilogue of the folded SpMV (bk_spmv_mask_kernel<GHOST>): the halo of this matvec is consumed, then the sums become
+// global and the solver's scalar step runs — what the boundary-row kernel's epilogue did on the two-kernel path.
+template <int R, typename Epi>
+struct bk_epi_fold {
+  Epi epi;
+  bk_gsum gs;
+  bk_dev_state* st;
+  int waited;
+  __device__ __forceinline__ void operator()(const double* s) const {
+    if (waited) gs.p2p.counters[2] += 1u;
+    if (gs.p2p.counters[4]) {
+      st->done = 1;
+      st->status = BK_ST_COMM_TIMEOUT;
+      return;
+    }
+    double g[R];
+    if (bk_gsum_finish<R>(gs, st, s, g)) epi(g);
+  }
+};
+
 // ---- the multi-GPU "system" ----------------------------------------------------------------------------------
 struct bk_sys_dist {
   static constexpr bool kDist = true;
@@ -402,9 +423,50 @@ struct bk_sys_dist {
     static_assert(MODE == 0 || DOTS == 2, "residual matvecs carry ||y||^2 only");
     // A residual's norm is tiny next to the pieces it is assembled from, so correcting the local block's ||y||^2
     // partial for the boundary rows would cancel catastrophically: reduce it in a pass of its own once y is complete.
+    bk_dev_state* st = h->st;
+    if (p2p && D->Aext != nullptr && h->dist_fold) {
+      // ---- folded: ONE kernel over [local | ghost]; boundary chunks last, after the arrival flags ----------------
+      if (!halo_pushed) BK_TRY(halo_begin<T>(x, guard, true, cs));
+      constexpr int RF = bk_ndots<DOTS>::value;
+      const bk_csr* E = D->Aext;
+      bk_spmv_args a = bk_spmv_base(E, st);
+      a.x = x;
+      a.y = y;
+      a.w = w;
+      a.b = b;
+      a.guard = guard;
+      a.use_parity = snake ? 1 : 0;
+      bk_mask_plan plan;
+      memset(&plan, 0, sizeof(plan));
+      plan.masks = E->mmasks;
+      plan.pids = E->mpids;
+      plan.ptab = (const bk_pair_entry*)E->mptab;
+      plan.xg = D->ghost;
+      plan.deferred = E->mdeferred;
+      plan.n_deferred = E->n_mdeferred;
+      {
+        int gs_ = 1;
+        while ((2 << gs_) <= h->mask_group && gs_ < 5) ++gs_;
+        plan.group = gs_;
+      }
+      plan.prefetch = (h->mask_prefetch && bk_aligned16(x)) ? 1 : 0;
+      if (D->npeers > 0) {
+        plan.flags = reinterpret_cast<const unsigned long long*>(D->p2p.win[D->p2p.rank] + BK_P2P_FLAG_OFF);
+        plan.flag_peers = D->d_peer_ranks;
+        plan.n_flag_peers = D->npeers;
+        plan.halo_seq = D->p2p.counters + 2;
+        plan.err_flag = D->p2p.counters + 4;
+      }
+      bk_epi_fold<RF, Epi> fe{epi, gsum(), st, D->npeers > 0 ? 1 : 0};
+      int g = h->num_sms * 4;
+      if (g > BK_MAXB) g = BK_MAXB;
+      g = bk_grid_rows(g, E->n, BK_BLOCK << plan.group);
+      bk_spmv_mask_kernel<T, MODE, DOTS, true, 4, bk_epi_fold<RF, Epi>><<<g, BK_BLOCK, 0, cs>>>(a, plan, bk_slot(h, 0), fe);
+      BK_KERNEL_CHECK();
+      return BK_OK;
+    }
     constexpr int KD = (MODE == 1) ? 0 : DOTS;
     constexpr int R = bk_ndots<KD>::value;
-    bk_dev_state* st = h->st;
     if (!halo_pushed) BK_TRY(halo_begin<T>(x, guard, p2p, cs));
     {  // local block (overlaps the exchange)
       bk_spmv_args a = bk_spmv_base(D->Aloc, st);

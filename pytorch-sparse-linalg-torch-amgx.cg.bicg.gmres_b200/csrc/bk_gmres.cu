@@ -260,6 +260,8 @@ __device__ __forceinline__ void bk_gm_dense_step(bk_dev_state* st, const bk_gm_s
   st->g_cycle_over = over ? 1 : 0;
 }
 
+#include "bk_gmres_persist.cuh"
+
 // ---- A3 (MODE 0): w -= sum_i h_i v_i, ||w||^2, then the step's small dense update
 // ---- C2 (MODE 1): x += sum_{i<kcur} y_i v_i
 template <typename T, int W, int MODE>
@@ -423,7 +425,7 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
     }
     h->gm_small_bytes = small_doubles * sizeof(double);
   }
-  const size_t part_bytes = (size_t)(m + 1) * BK_MAXB * sizeof(double);
+  const size_t part_bytes = (size_t)(m + 4) * BK_MAXB * sizeof(double);  // (+3 rows: the persistent kernel's norms)
   if (h->gm_partials_bytes < part_bytes) {
     bk_graphs_invalidate(h);
     if (h->gm_partials) {
@@ -551,7 +553,41 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
   if (diag) key[1] ^= (uint64_t)(uintptr_t)diag * 0x9e3779b97f4a7c15ull;  // its address is baked into the graph
   int64_t chunks = 0;
   bk_call_mark(h, "loop");
-  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_cycle, &chunks));
+  bool persistent = false;
+  if constexpr (!Sys::kDist) {
+    // launch-bound (L2-resident) systems: the whole solve in ONE cooperative kernel (bk_gmres_persist.cuh)
+    const bk_csr* A = sys.A;
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
+    if (h->persistent && coop && n <= (long long)h->persistent_max_n && A->rowptr && A->col) {
+      BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk_gmres_persistent_kernel<T>, BK_GP_BLOCK, 0));
+      const long long grid = (n + BK_GP_BLOCK - 1) / BK_GP_BLOCK;  // one row per thread
+      if (per_sm > 0 && grid <= (long long)per_sm * h->num_sms && grid <= BK_MAXB) {
+        bk_gp_args ga;
+        ga.rowptr = A->rowptr;
+        ga.col = A->col;
+        ga.val = A->val;
+        ga.diag = diag;
+        ga.n = n;
+        ga.V = V;
+        ga.ldv = npad;
+        ga.w = w;
+        ga.x = x;
+        ga.b = b;
+        ga.st = st;
+        ga.R = sm.R;
+        ga.y = sm.y;
+        ga.partials = h->gm_partials;
+        ga.m = m;
+        void* args[] = {(void*)&ga};
+        BK_CUDA(cudaLaunchCooperativeKernel((const void*)bk_gmres_persistent_kernel<T>, dim3((unsigned)grid),
+                                            dim3(BK_GP_BLOCK), args, 0, s));
+        persistent = true;
+        h->last_loop_mode = 3;
+      }
+    }
+  }
+  if (!persistent) BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_cycle, &chunks));
   bk_call_mark(h, "final");
 
   // ---- final check (:766-773): the last residual pass already holds ||b - A x||; add ||x|| --------
@@ -564,7 +600,7 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
   bk_call_finish(h, res);
   res->iterations = fin->k;
   res->matvecs = fin->matvecs;
-  res->kernel_launches = chunks * (4 * (int64_t)m + 4) + 5;
+  res->kernel_launches = (persistent ? 1 : chunks * (4 * (int64_t)m + 4)) + 5;
   res->status = fin->status;
   res->final_residual = sqrt(fmax(fin->rtrue2, 0.0));
   res->b_norm = fin->g_bnorm;
@@ -633,4 +669,21 @@ extern "C" int bk_dist_gmres(bk_handle* h, bk_dist* D, const void* b_local, void
                               (cudaStream_t)stream);
   return bk_gmres_t<float>(sys, b_local, x_local, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
                            (cudaStream_t)stream);
+}
+
+extern "C" int bk_dist_gmres_jacobi(bk_handle* h, bk_dist* D, const void* diag_local, const void* b_local, void* x_local,
+                                    int has_x0, double tol_eff, double atol_eff, int restart, int64_t maxiter,
+                                    int method, int64_t n_global, bk_result* result, void* stream) {
+  if (!h || !D || !result) return bk_fail(BK_ERR_ARG, "bk_dist_gmres_jacobi: null handle/matrix/result");
+  if (D->n_local > 0 && (!b_local || !x_local || !diag_local))
+    return bk_fail(BK_ERR_ARG, "bk_dist_gmres_jacobi: null vector");
+  BK_TRY(bk_gmres_args_check("bk_dist_gmres_jacobi", restart, method));
+  memset(result, 0, sizeof(*result));
+  BK_CUDA(cudaSetDevice(h->device));
+  const bk_sys_dist sys{h, D, D->p2p_enabled && h->dist_p2p, n_global};
+  if (D->dtype == BK_F64)
+    return bk_gmres_t<double>(sys, b_local, x_local, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
+                              (cudaStream_t)stream, (const double*)diag_local);
+  return bk_gmres_t<float>(sys, b_local, x_local, has_x0, tol_eff, atol_eff, restart, maxiter, method, result,
+                           (cudaStream_t)stream, (const float*)diag_local);
 }

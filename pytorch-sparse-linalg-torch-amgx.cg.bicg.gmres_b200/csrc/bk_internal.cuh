@@ -124,6 +124,8 @@ struct bk_csr {
   int n_mdeferred;
   int mask_patterns;         // distinct patterns in the table
   int64_t n_cols;            // columns (== n except for the extended local+ghost matrix of a row partition)
+  const long long* reg_ghost_gid;  // registration only (n_cols > n): global ids of the ghost columns
+  long long reg_row_begin;         // registration only: global id of row 0
   int64_t bytes_stream;      // actual matrix-side bytes the selected kernel reads per SpMV (bk_csr_info)
   int max_row_nnz;
   double mean_row_nnz;
@@ -158,9 +160,11 @@ struct bk_handle {
   int pair_ctas;       // CTAs/SM of the pair-coded SpMV (2..6)
   int mask_ctas;       // CTAs/SM of the row-bitmask SpMV (kernel 6; 2..6)
   int mask_group;      // kernel 6: consecutive 256-row blocks dealt to a CTA at a time
+  int mask_prefetch;   // kernel 6: L2 bulk prefetch of the x range of a CTA's next group
   int nvtx;            // emit NVTX ranges around the phases of every solve (BK_NVTX=1)
   int last_loop_mode;  // how the last iteration loop actually ran (bk_result.loop_mode_used)
   int dist_fuse_push;  // multi-GPU CG, peer path: fold the halo push into the kernel that produces p (1)
+  int dist_fold;       // multi-GPU, peer path: ONE SpMV kernel over [local | ghost] (kernel 6) instead of local + boundary rows
   int tma_stages;      // 0 = fill shared memory, else cap on the pipeline depth
   int use_tma;         // allow the TMA row-stream kernel
   int prefetch_x;      // kernel 3: L2 bulk prefetch of the forward-diagonal x ranges

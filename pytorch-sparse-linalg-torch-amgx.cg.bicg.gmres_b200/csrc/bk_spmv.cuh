@@ -328,10 +328,11 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
       plan.pids = A->mpids;
       plan.ptab = (const bk_pair_entry*)A->mptab;
       {  // option mask_group = blocks per visit, rounded down to a power of two (the kernel shifts and masks)
-        int gs = 0;
+        int gs = 1;  // (the kernel works on pairs of consecutive blocks)
         while ((2 << gs) <= h->mask_group && gs < 5) ++gs;
         plan.group = gs;
       }
+      plan.prefetch = (h->mask_prefetch && bk_aligned16(a.x)) ? 1 : 0;
       int ctas = h->mask_ctas < 2 ? 2 : (h->mask_ctas > 6 ? 6 : h->mask_ctas);
       int g = h->num_sms * ctas;
       if (g > BK_MAXB) g = BK_MAXB;

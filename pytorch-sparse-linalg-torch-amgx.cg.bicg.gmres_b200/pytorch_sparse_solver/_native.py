@@ -99,6 +99,13 @@ _SIGNATURES = {
                                  C.c_int64, _VP, _VP, _VP, C.c_int64, C.c_int, _VP, _VP, _VP, _VP, C.c_int, _VP,
                                  C.POINTER(_VP)]),
     "bk_dist_destroy": (C.c_int, [_VP]),
+    "bk_dist_set_extended": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP, C.c_int64, _VP, C.POINTER(C.c_int32)]),
+    "bk_dist_cg_jacobi": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.c_int64,
+                                    C.POINTER(bk_result), _VP]),
+    "bk_dist_bicgstab_jacobi": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64,
+                                          C.c_int64, C.POINTER(bk_result), _VP]),
+    "bk_dist_gmres_jacobi": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int64,
+                                       C.c_int, C.c_int64, C.POINTER(bk_result), _VP]),
     "bk_dist_p2p_export": (C.c_int, [_VP, _VP]),
     "bk_dist_p2p_connect": (C.c_int, [_VP, _VP, _VP]),
     "bk_dist_spmv": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),

@@ -37,6 +37,8 @@ class LocalSplit:
     gh_col: torch.Tensor       # int32, index into the ghost vector
     gh_val: torch.Tensor
     ghost_ids: torch.Tensor    # int64 [n_ghost] global ids of the ghost vector entries (ascending => grouped by owner)
+    ext_rowptr: torch.Tensor   # int32 [n_local+1]: the rows as ONE matrix over [local | ghost] (original entry order)
+    ext_col: torch.Tensor      # int32: local column, or n_local + ghost index
 
 
 def split_local_ghost(crow: torch.Tensor, col: torch.Tensor, val: torch.Tensor, row_begin: int,
@@ -69,8 +71,9 @@ def split_local_ghost(crow: torch.Tensor, col: torch.Tensor, val: torch.Tensor, 
         counts = torch.zeros(0, dtype=torch.int64, device=dev)
     gh_rowptr = torch.zeros(brow_ids.numel() + 1, dtype=torch.int64, device=dev)
     gh_rowptr[1:] = counts.cumsum(0)
+    ext_col = torch.where(is_loc, col - row_begin, n_local + torch.searchsorted(ghost_ids, col)).to(torch.int32)
     return LocalSplit(n_local, loc_rowptr.to(torch.int32), loc_col, loc_val, brow_ids.to(torch.int32),
-                      gh_rowptr.to(torch.int32), gh_col, gh_val, ghost_ids)
+                      gh_rowptr.to(torch.int32), gh_col, gh_val, ghost_ids, crow.to(torch.int32), ext_col)
 
 
 @dataclass
@@ -106,6 +109,43 @@ def build_halo_plan(ghost_ids: torch.Tensor, offsets: Sequence[int], rank: int, 
         recv_counts.append(int(needs[q].numel()) if q in needs else 0)
     send_idx = torch.cat(send_lists) if send_lists else torch.zeros(0, dtype=torch.int32)
     return HaloPlan(peers, send_counts, recv_counts, send_idx)
+
+
+def transpose_slab(crow: torch.Tensor, col: torch.Tensor, val: torch.Tensor, offsets: Sequence[int], rank: int,
+                   world: int, group=None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """This rank's slab of A^T (same row partition), as CSR arrays with GLOBAL columns, from this rank's slab of A:
+    every entry (r, c, v) goes to the owner of column c (torch.distributed all_to_all_single; set-up only), which
+    sorts what it receives by (c, r) — rows of A^T ascending, columns ascending inside a row.  Device-agnostic
+    (exercised with gloo on CPU by tests/test_dist_gloo.py)."""
+    import torch.distributed as dist
+    dev = col.device
+    off = torch.tensor(list(offsets), dtype=torch.int64, device=dev)
+    n_local = int(offsets[rank + 1] - offsets[rank])
+    n_global = int(offsets[-1])
+    lens = (crow[1:] - crow[:-1]).long()
+    grow = torch.repeat_interleave(torch.arange(n_local, device=dev), lens) + int(offsets[rank])
+    gcol = col.long()
+    owner = torch.bucketize(gcol, off[1:], right=True)
+    order = torch.argsort(owner, stable=True)
+    send_counts = torch.bincount(owner, minlength=world)
+    if world > 1:
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+
+        def exchange(t):
+            out = torch.empty(sum(rc), dtype=t.dtype, device=dev)
+            dist.all_to_all_single(out, t[order].contiguous(), rc, sc, group=group)
+            return out
+        t_row, t_col, t_val = exchange(gcol), exchange(grow), exchange(val)   # transposed: (col, row, val)
+    else:
+        t_row, t_col, t_val = gcol, grow, val
+    lrow = t_row - int(offsets[rank])
+    perm = torch.argsort(lrow * n_global + t_col, stable=True)
+    lrow, t_col, t_val = lrow[perm], t_col[perm].contiguous(), t_val[perm].contiguous()
+    tcrow = torch.zeros(n_local + 1, dtype=torch.int64, device=dev)
+    tcrow[1:] = torch.bincount(lrow, minlength=n_local).cumsum(0)
+    return tcrow, t_col, t_val
 
 
 class DistMatrix:
@@ -151,9 +191,27 @@ class DistMatrix:
                 _native._dtype_code(self.dtype), _native._stream_ptr(self.device), C.byref(p)), "bk_dist_create")
         self.ptr = p
         self.p2p = False
+        self.folded = False
+        self._group = group
+        self._src = (crow, col, val)      # the caller's slab (global columns): needed to build the transpose
+        self._transpose = None
+        self._diag = None
         import os
         if os.environ.get("BK_DIST_P2P", "1") != "0":
             self._connect_peer_memory(plan, group)
+        if self.p2p and os.environ.get("BK_DIST_FOLD", "1") != "0":
+            # the rows as one matrix over [local | ghost]: one SpMV kernel per matvec when the row-bitmask plan fits
+            folded = C.c_int32(0)
+            vals = val.contiguous()
+            gid = sp.ghost_ids.to(torch.int64).contiguous()
+            with torch.cuda.device(self.device):
+                _native._check(lib.bk_dist_set_extended(
+                    self.ptr, vals.numel(), sp.ext_rowptr.data_ptr(), sp.ext_col.data_ptr(), vals.data_ptr(),
+                    gid.data_ptr() if gid.numel() else None, int(offsets[rank]), _native._stream_ptr(self.device),
+                    C.byref(folded)), "bk_dist_set_extended")
+            self.folded = bool(folded.value)
+        sp.ext_col = None                 # only read during registration
+        sp.ext_rowptr = None
 
     def _connect_peer_memory(self, plan: HaloPlan, group=None):
         """Exchange CUDA-IPC handles of the communication windows and map every rank's window (NVLink peer memory)."""
@@ -189,9 +247,39 @@ class DistMatrix:
             self.handle.set_option("dist_p2p", 0)
 
     def close(self):
+        if getattr(self, "_transpose", None) is not None:
+            self._transpose.close()
+            self._transpose = None
         if getattr(self, "ptr", None) is not None:
             self.handle.lib.bk_dist_destroy(self.ptr)
             self.ptr = None
+
+    def local_info(self) -> dict:
+        return {"folded_single_kernel_spmv": self.folded, "p2p": self.p2p, "n_local": self.split.n_local,
+                "n_ghost": int(self.split.ghost_ids.numel()), "n_boundary_rows": int(self.split.brow_ids.numel())}
+
+    def diagonal(self) -> torch.Tensor:
+        """This rank's slice of diag(A) (the diagonal block of a row partition is local)."""
+        if self._diag is None:
+            sp = self.split
+            n = sp.n_local
+            rows = torch.repeat_interleave(torch.arange(n, device=self.device),
+                                           (sp.loc_rowptr[1:] - sp.loc_rowptr[:-1]).long())
+            m = rows == sp.loc_col.long()
+            d = torch.zeros(n, dtype=self.dtype, device=self.device)
+            d.index_add_(0, rows[m], sp.loc_val[m])
+            self._diag = d
+        return self._diag
+
+    def transpose(self) -> "DistMatrix":
+        """A^T with the same row partition (cached): every rank sends each peer the entries of its rows whose columns
+        that peer owns (torch.distributed all_to_all, set-up only); the owner sorts them by (row, col) into its slab
+        of A^T.  Used by the implicit-differentiation backward (reference :1237-1248 solves with A^T)."""
+        if self._transpose is not None:
+            return self._transpose
+        tcrow, t_col, t_val = transpose_slab(*self._src, self.offsets, self.rank, self.world, self._group)
+        self._transpose = DistMatrix(tcrow, t_col, t_val, self.offsets, self.rank, self.world, self._group)
+        return self._transpose
 
     def spmv(self, x_local: torch.Tensor) -> torch.Tensor:
         x = x_local.contiguous()
@@ -257,121 +345,79 @@ class DistMatrix:
 
     # ---- the reference API on a row-partitioned matrix ("API stays additive, e.g. a DistCSR wrapper
     # passed as A"): module_a.cg / bicgstab / gmres(A=DistMatrix, b=this rank's slab) -> (x_local, info) -----------
+    def _solve_local(self, name, bw, x0w, tol, atol, maxiter, restart, solve_method, diag):
+        from .module_a.krylov import _gmres_effective_tolerances
+        lib = self.handle.lib
+        b, x, has = self._vectors(bw, x0w)
+        res = _native.bk_result()
+        mi = -1 if maxiter is None else int(maxiter)
+        with torch.cuda.device(self.device):
+            s = _native._stream_ptr(self.device)
+            if name in ("cg", "bicgstab"):
+                if diag is None:
+                    fn = lib.bk_dist_cg if name == "cg" else lib.bk_dist_bicgstab
+                    rc = fn(self.handle.ptr, self.ptr, b.data_ptr(), x.data_ptr(), has, float(tol), float(atol), mi,
+                            self.n_global, C.byref(res), s)
+                else:
+                    fn = lib.bk_dist_cg_jacobi if name == "cg" else lib.bk_dist_bicgstab_jacobi
+                    rc = fn(self.handle.ptr, self.ptr, diag.data_ptr(), b.data_ptr(), x.data_ptr(), has, float(tol),
+                            float(atol), mi, self.n_global, C.byref(res), s)
+            else:
+                method = 1 if solve_method == 'incremental' else 0
+                rst = min(int(restart), self.n_global)
+                te, ae = _gmres_effective_tolerances(tol, atol, self.n_global, 'cuda')
+                if diag is None:
+                    rc = lib.bk_dist_gmres(self.handle.ptr, self.ptr, b.data_ptr(), x.data_ptr(), has, float(te),
+                                           float(ae), rst, mi, method, self.n_global, C.byref(res), s)
+                else:
+                    rc = lib.bk_dist_gmres_jacobi(self.handle.ptr, self.ptr, diag.data_ptr(), b.data_ptr(), x.data_ptr(),
+                                                  has, float(te), float(ae), rst, mi, method, self.n_global,
+                                                  C.byref(res), s)
+        _native._check(rc, f"bk_dist_{name}")
+        return x, res.as_dict()
+
+    # ---- the reference API on a row-partitioned matrix ("API stays additive, e.g. a DistCSR wrapper
+    # passed as A"): module_a.cg / bicgstab / gmres(A=DistMatrix, b=this rank's slab) -> (x_local, info), with the
+    # built-in Jacobi preconditioner (M = module_a.JacobiPreconditioner(D)) and the implicit-diff backward for b --------
     def _module_a_solve(self, name: str, b, x0=None, *, tol=1e-5, atol=0.0, maxiter=None, M=None, restart=20,
                         solve_method='batched', _result=None):
         from .module_a import krylov
+        from .module_a.preconditioners import JacobiPreconditioner
         if not isinstance(b, torch.Tensor) or b.ndim != 1 or b.shape[0] != self.split.n_local:
             raise ValueError(f"b must be this rank's slab: a vector of length {self.split.n_local}")
         if x0 is not None and tuple(x0.shape) != tuple(b.shape):
             raise ValueError(f'arrays in x0 and b must have matching shapes: {x0.shape} vs {b.shape}')
+        if name == "gmres" and restart < 1:
+            raise ValueError("restart must be >= 1")
+        diag = None
         if M is not None:
-            raise NotImplementedError("preconditioners on a DistMatrix: not wired yet")
+            if not isinstance(M, JacobiPreconditioner):
+                raise NotImplementedError("a DistMatrix takes the built-in JacobiPreconditioner (or M=None)")
+            diag = M.diagonal(self.dtype, self.device).contiguous()
         with torch.no_grad():
-            bw = b.detach()
-            x0w = None if x0 is None else x0.detach()
-            if name == "cg":
-                x, res = self.cg(bw, x0w, tol, atol, maxiter)
-            elif name == "bicgstab":
-                x, res = self.bicgstab(bw, x0w, tol, atol, maxiter)
-            else:
-                if restart < 1:
-                    raise ValueError("restart must be >= 1")
-                x, res = self.gmres(bw, x0w, tol, atol, restart, maxiter, solve_method)
+            x, res = self._solve_local(name, b.detach(), None if x0 is None else x0.detach(), tol, atol, maxiter,
+                                       restart, solve_method, diag)
         krylov._publish(dict(res, solver=name, route="dist"), _result)
+        if b.requires_grad:
+            x = _DistAdjoint.apply(b, x, self, name, x0, tol, atol, maxiter, restart, solve_method, diag)
         return x, int(res["info"])
 
 
-# ---- weak-scaling benchmark used by bench.py --gpus N --------------------------------------------------------
-def bench_weak_scaling(args, rank, world, local, metric, unit, peak, ClockSampler):
-    """N slabs of n^3 rows each: a (N*n) x n x n Poisson grid, slab q on rank q.  value = N * global iterations/s
-    (n^3-row CG iterations per second summed over ranks)."""
-    import time
-    import torch.distributed as dist
-    from . import problems
-    dev = torch.device("cuda", local)
-    n = args.n
-    rows = n ** 3
-    # BASELINE config 5 geometry: planes of (2n) x (2n), n/4 planes per GPU (n = 256: 64 planes of 512 x 512, so
-    # 8 GPUs hold exactly the 512^3 system and every halo is one 512^2 plane = 2 MiB); per-GPU rows stay n^3.
-    npl, ppg = 2 * n, max(n // 4, 1)
-    if ppg * npl * npl != rows:
-        npl, ppg = n, n
-    strong = bool(getattr(args, "strong", False))
-    if strong:  # BASELINE configs[4] as written: the SAME (2n)^3 system split over N GPUs (N must divide 2n)
-        ppg = npl // world
-        rows = ppg * npl * npl
-    offsets = [q * rows for q in range(world + 1)]
-    crow, col, val = problems.stencil3d_rows(npl, world * ppg, rank * ppg, (rank + 1) * ppg, device=dev)
-    nnz_local = val.numel()
-    D = DistMatrix(crow, col, val, offsets, rank, world)
-    del crow, col
-    b = torch.ones(rows, dtype=torch.float64, device=dev)
-    window = args.dist_window
-    for _ in range(max(args.warmup, 3)):
-        D.cg(b, None, 0.0, 0.0, min(window, 50))
-    torch.cuda.synchronize()
-    dist.barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    its = launches = 0
-    with ClockSampler(local) as clk:
-        torch.cuda.synchronize()
-        dist.barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            x, res = D.cg(b, None, 0.0, 0.0, window)
-            its += res["iterations"]
-            launches += res["kernel_launches"]
-        ev1.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms)
-    it_s = its / (ms * 1e-3)
-    value = it_s * (rows * world) / float(n ** 3)   # n^3-row CG iterations per second over all ranks
-    bytes_iter = problems.cg_bytes_per_iteration(rows, nnz_local)
-    # end to end: host slab -> device, registration, solve window, x back to host
-    crow_h, col_h, val_h = problems.stencil3d_rows(npl, world * ppg, rank * ppg, (rank + 1) * ppg)
-    crow_h, col_h, val_h, b_h = crow_h.pin_memory(), col_h.pin_memory(), val_h.pin_memory(), b.cpu().pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in (crow_h, col_h, val_h, b_h))
-    D.close()
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    D2 = DistMatrix(crow_h.to(dev, non_blocking=True), col_h.to(dev, non_blocking=True), val_h.to(dev, non_blocking=True),
-                    offsets, rank, world)
-    xe, re_ = D2.cg(b_h.to(dev, non_blocking=True), None, 0.0, 0.0, window)
-    xh = xe.cpu()
-    torch.cuda.synchronize()
-    dist.barrier()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * re_["iterations"] / float(dt), "unit": unit, "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": rows * 8, "ms_per_step": 1e3 * float(dt), "steps": 1,
-           "note": "includes partition set-up, halo-plan exchange and IPC window mapping (the NCCL communicator of "
-                   "the process is reused)"}
-    D2.close()
-    if rank != 0:
-        return None
-    pk, pk_kind = peak
-    return {
-        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "strong" if strong else "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"CG fp64, 7-pt Poisson {world * ppg}x{npl}x{npl} CSR row-partitioned over {world} GPUs "
-                               f"({n}^3 rows per GPU; 8 GPUs = BASELINE configs[4] 512^3), b=ones, fixed window of "
-                               f"{window} iterations per step",
-                   "comm": "peer-memory (CUDA IPC over NVLink): kernel halo push + one-shot all-reduce" if D.p2p
-                   else "NCCL send/recv + allreduce",
-                   "value_definition": f"{world} x global iterations/s = {n}^3-row CG iterations per second over all ranks",
-                   "global_iterations_per_second": it_s, "n_local": rows, "nnz_local": nnz_local,
-                   "halo_bytes_per_neighbour": npl * npl * 8, "peers_rank0": D.plan.peers,
-                   "l2_policy": "inputs exceed L2; no flush needed"},
-        "roofline": {"bound": "hbm", "kernel": "whole distributed CG iteration (per GPU)",
-                     "achieved": bytes_iter * it_s / 1e9, "peak": pk, "peak_kind": pk_kind, "unit": "GB/s",
-                     "frac": bytes_iter * it_s / 1e9 / pk, "traffic": None},
-        "iteration": {"bytes_per_iteration_per_gpu": bytes_iter, "us_per_iteration": 1e3 * ms / its,
-                      "frac_of_8tbs": bytes_iter * it_s / 8e12},
-        "e2e": e2e, "cpu_baseline": None, "gpu_launches": int(launches), "clocks": clk.summary(),
-    }
+class _DistAdjoint(torch.autograd.Function):
+    """grad_b = solve(A^T, grad_x) on the row-partitioned transpose (reference ImplicitAdjointFunction :1227-1248:
+    same x0 / tolerances, M re-used, no gradient for A)."""
+
+    @staticmethod
+    def forward(ctx, b, x, D, name, x0, tol, atol, maxiter, restart, solve_method, diag):
+        ctx.D = D
+        ctx.meta = (name, x0, tol, atol, maxiter, restart, solve_method, diag)
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        name, x0, tol, atol, maxiter, restart, solve_method, diag = ctx.meta
+        with torch.no_grad():
+            Dt = ctx.D.transpose()          # collective: every rank's backward reaches this point
+            g, _ = Dt._solve_local(name, grad_output.detach().contiguous(), None if x0 is None else x0.detach(), tol,
+                                   atol, maxiter, restart, solve_method, diag)
+        return (g.to(grad_output.dtype),) + (None,) * 10

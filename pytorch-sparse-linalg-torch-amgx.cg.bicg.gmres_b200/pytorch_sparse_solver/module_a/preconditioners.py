@@ -18,6 +18,13 @@ class JacobiPreconditioner:
     """M = diag(A)^-1, applied as r / d."""
 
     def __init__(self, A: torch.Tensor):
+        if type(A).__name__ == "DistMatrix" and hasattr(A, "diagonal"):   # row-partitioned: this rank's slice
+            d = A.diagonal()
+            if bool((d == 0).any()):
+                raise ValueError("JacobiPreconditioner: the matrix has a zero on its diagonal")
+            self.d = d
+            self.shape = (A.n_global, A.n_global)
+            return
         if not isinstance(A, torch.Tensor) or A.ndim != 2 or A.shape[0] != A.shape[1]:
             raise ValueError("JacobiPreconditioner needs a square 2-D tensor (dense, COO or CSR)")
         with torch.no_grad():

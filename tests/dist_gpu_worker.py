@@ -17,8 +17,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    from pytorch_sparse_solver import _native, problems
+    from pytorch_sparse_solver import _native, module_a, problems
     from pytorch_sparse_solver import distributed as bkd
+    from pytorch_sparse_solver.module_a import krylov
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     rows = n ** 3
     offsets = [q * rows for q in range(world + 1)]
@@ -40,19 +41,39 @@ def main():
     bg = torch.ones(world * rows, dtype=torch.float64, device=dev)
     x_ref, r_ref = m.cg(bg, None, 1e-8, 0.0, None)
     assert D.p2p or os.environ.get("BK_DIST_P2P") == "0", "peer-memory path should connect on an NVLink box"
-    for mode, p2p in ((1, 0), (2, 0), (1, 1), (2, 1)):   # plain launches / CUDA graph  x  NCCL / peer-memory path
+    if D.p2p and os.environ.get("BK_DIST_FOLD", "1") != "0":
+        assert D.folded, "a stencil slab must take the single-kernel (folded) SpMV on the peer path"
+    # plain launches / CUDA graph  x  NCCL / peer-memory path  x  folded single-kernel SpMV / local + boundary rows;
+    # every solve goes through the reference API: module_a.cg(A=DistMatrix, b=local slab)
+    for mode, p2p, fold in ((1, 0, 0), (2, 0, 0), (1, 1, 1), (2, 1, 1), (2, 1, 0)):
         if p2p and not D.p2p:
             continue
         D.handle.set_option("loop_mode", mode)
         D.handle.set_option("dist_p2p", p2p)
-        x, r = D.cg(bg[sl].contiguous(), None, 1e-8, 0.0, None)
-        assert r["info"] == r_ref["info"] == 0, (r, r_ref)
+        D.handle.set_option("dist_fold", fold)
+        x, info = module_a.cg(D, bg[sl].contiguous(), tol=1e-8)
+        r = dict(krylov.last_result)
+        assert info == r_ref["info"] == 0 and r["route"] == "dist", (r, r_ref)
         assert abs(r["iterations"] - r_ref["iterations"]) <= 2, (r["iterations"], r_ref["iterations"])
-        assert rel(x, x_ref[sl]) <= 1e-10, ("dist cg", mode, rel(x, x_ref[sl]))
-        x2, r2 = D.cg(bg[sl].contiguous(), None, 1e-8, 0.0, None)
+        assert rel(x, x_ref[sl]) <= 1e-10, ("dist cg", mode, p2p, fold, rel(x, x_ref[sl]))
+        x2, _ = module_a.cg(D, bg[sl].contiguous(), tol=1e-8)
         assert torch.equal(x, x2), "dist cg must be bitwise reproducible"
     D.handle.set_option("loop_mode", 0)
     D.handle.set_option("dist_p2p", 1)
+    D.handle.set_option("dist_fold", 1)
+    # implicit-diff backward through the row-partitioned transpose, against the single-GPU adjoint of the same system
+    b1 = bg[sl].clone().requires_grad_(True)
+    x1, _ = module_a.cg(D, b1, tol=1e-10)
+    (x1 ** 2).sum().backward()
+    bgr = bg.clone().requires_grad_(True)
+    xg1, _ = module_a.cg(A, bgr, tol=1e-10)
+    (xg1 ** 2).sum().backward()
+    assert rel(b1.grad, bgr.grad[sl]) <= 1e-8, ("dist grad_b", rel(b1.grad, bgr.grad[sl]))
+    # built-in Jacobi preconditioner on the partitioned matrix
+    Mj = module_a.JacobiPreconditioner(D)
+    xj, infoj = module_a.cg(D, bg[sl].contiguous(), tol=1e-10, M=Mj)
+    xjr, _ = module_a.cg(A, bg, tol=1e-10, M=module_a.JacobiPreconditioner(A))
+    assert infoj == 0 and rel(xj, xjr[sl]) <= 1e-9, ("dist jacobi cg", rel(xj, xjr[sl]))
     if D.p2p:   # halo push folded into the p-update kernel (default) vs the separate push kernel: same bits
         xs = {}
         for fuse in (1, 0, 1):
@@ -94,12 +115,13 @@ def main():
     xw_ref, rw_ref = mc.bicgstab(bc, x0c, 0.0, 0.0, 6)
     xgw_ref, rgw_ref = mc.gmres(bc, x0c, *_gmres_effective_tolerances(0.0, 0.0, Ng, 'cuda'), 12, 2,
                                 _native.BK_GMRES_BATCHED)
-    for mode, p2p in ((1, 0), (2, 0), (1, 1), (2, 1)):
+    for mode, p2p, fold in ((1, 0, 0), (2, 0, 0), (1, 1, 1), (2, 1, 1), (2, 1, 0)):
         if p2p and not Dc.p2p:
             continue
         Dc.handle.set_option("loop_mode", mode)
         Dc.handle.set_option("dist_p2p", p2p)
-        tag = ("mode", mode, "p2p", p2p)
+        Dc.handle.set_option("dist_fold", fold)
+        tag = ("mode", mode, "p2p", p2p, "fold", fold)
         x, r = Dc.bicgstab(bc[sl].contiguous(), None, 1e-10, 0.0, None)
         assert r["info"] == rb_ref["info"] == 0, (tag, r, rb_ref)
         assert abs(r["iterations"] - rb_ref["iterations"]) <= 2, (tag, r["iterations"], rb_ref["iterations"])
@@ -120,6 +142,20 @@ def main():
         assert r["iterations"] == 2 and rel(x, xgw_ref[sl]) <= 1e-11, ("gmres window", tag, rel(x, xgw_ref[sl]))
     Dc.handle.set_option("loop_mode", 0)
     Dc.handle.set_option("dist_p2p", 1)
+    Dc.handle.set_option("dist_fold", 1)
+    # reference API + Jacobi + backward on the non-symmetric system (BiCGStab, GMRES)
+    for kind, kw in (("bicgstab", dict(tol=1e-10)), ("gmres", dict(tol=1e-10, restart=30))):
+        b1 = bc[sl].clone().requires_grad_(True)
+        x1, i1 = getattr(module_a, kind)(Dc, b1, **kw)
+        (x1 ** 2).sum().backward()
+        bgr = bc.clone().requires_grad_(True)
+        xg1, ig = getattr(module_a, kind)(Ac, bgr, **kw)
+        (xg1 ** 2).sum().backward()
+        assert i1 == ig == 0 and rel(x1.detach(), xg1.detach()[sl]) <= 1e-9, (kind, rel(x1.detach(), xg1.detach()[sl]))
+        assert rel(b1.grad, bgr.grad[sl]) <= 1e-7, ("dist grad_b", kind, rel(b1.grad, bgr.grad[sl]))
+        xj, ij = getattr(module_a, kind)(Dc, bc[sl].contiguous(), M=module_a.JacobiPreconditioner(Dc), **kw)
+        xjr, _ = getattr(module_a, kind)(Ac, bc, M=module_a.JacobiPreconditioner(Ac), **kw)
+        assert ij == 0 and rel(xj, xjr[sl]) <= 1e-8, ("dist jacobi", kind, rel(xj, xjr[sl]))
     Dc.close()
     dist.barrier()
 
@@ -147,6 +183,7 @@ def main():
     dist.broadcast(bg2, 0)
     assert rel(D2.spmv(bg2[rb:re_].contiguous()), mg.spmv(bg2)[rb:re_]) <= 1e-14, "dist spmv (all-to-all)"
     xr2, rr2 = mg.cg(bg2, None, 1e-10, 0.0, None)
+    assert not D2.folded, "irregular couplings do not fit the row-bitmask plan: two-kernel path"
     for p2p in ((0, 1) if D2.p2p else (0,)):
         D2.handle.set_option("dist_p2p", p2p)
         x2, r2 = D2.cg(bg2[rb:re_].contiguous(), None, 1e-10, 0.0, None)

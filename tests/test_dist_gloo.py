@@ -92,6 +92,23 @@ def _worker(rank, world, port, kind):
         y, ghost = _emulated_dist_spmv(sp, plan, x[rb:re_].contiguous(), rank)
         assert torch.equal(ghost, x[sp.ghost_ids])
         assert float((y - y_ref).abs().max()) <= 1e-13 * float(y_ref.abs().max() + 1)
+        # the rows as ONE matrix over [local | ghost] (what bk_dist_set_extended registers): same product, and the
+        # entries keep the order of the global matrix's rows
+        assert sp.ext_col.dtype == torch.int32 and sp.ext_col.numel() == val[sl].numel()
+        A_ext = torch.sparse_csr_tensor(sp.ext_rowptr.long(), sp.ext_col.long(), val[sl],
+                                        size=(sp.n_local, sp.n_local + max(sp.ghost_ids.numel(), 1)))
+        x_ext = torch.cat([x[rb:re_], ghost if ghost.numel() else torch.zeros(1, dtype=x.dtype)])
+        assert float((torch.matmul(A_ext, x_ext) - y_ref).abs().max()) <= 1e-13 * float(y_ref.abs().max() + 1)
+        gid = torch.where(sp.ext_col.long() < sp.n_local, sp.ext_col.long() + rb,
+                          sp.ghost_ids[(sp.ext_col.long() - sp.n_local).clamp(min=0)])
+        assert torch.equal(gid, col[sl])
+        # the transposed slab (adjoint solves): exchange by column owner, against the global transpose
+        tcrow, tcol, tval = bkd.transpose_slab(lcrow, col[sl], val[sl], offsets, rank, world)
+        At = A.to_dense().T.contiguous().to_sparse_csr()
+        tc = At.crow_indices()
+        assert torch.equal(tcrow, tc[rb:re_ + 1] - tc[rb])
+        assert torch.equal(tcol, At.col_indices()[int(tc[rb]):int(tc[re_])])
+        assert torch.equal(tval, At.values()[int(tc[rb]):int(tc[re_])])
         dist.barrier()
     finally:
         dist.destroy_process_group()

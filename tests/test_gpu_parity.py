@@ -742,6 +742,35 @@ def test_result_reports_loop_mode_and_device_time(ma, manifest):
         assert _last()["loop_mode_used"] in (2, 3) and _last()["device_ms"] > 0.0
 
 
+@pytest.mark.parametrize("name", ["gmres_ldc100_step1_batched", "gmres_ldc32_step1_incremental", "gmres_cd3d12_x0",
+                                  "gmres_scd3d12_jacobi_incremental", "gmres_cd3d12_batched_2cycles", "gmres_zero_rhs"])
+def test_gmres_persistent_kernel_vs_multi_kernel(ma, manifest, name):
+    """Launch-bound systems run the whole GMRES solve in ONE cooperative kernel (bk_gmres_persist.cuh); it must agree
+    with the graph-launched multi-kernel path to rounding (sums are reduced over a different partition), take the same
+    number of cycles and matvecs, and be bitwise reproducible."""
+    from pytorch_sparse_solver import _native
+    h = _native.Handle.get(torch.device("cuda"))
+    entry, data, xp, infop = _solve_case(ma, name, manifest)
+    rp = dict(_last())
+    assert rp["loop_mode_used"] == 3 or rp["iterations"] == 0
+    _e, _d, xp2, _i = _solve_case(ma, name, manifest)
+    assert torch.equal(xp, xp2)
+    try:
+        h.set_option("persistent", 0)
+        _e, _d, xm, infom = _solve_case(ma, name, manifest)
+        rm = dict(_last())
+    finally:
+        h.set_option("persistent", 1)
+    assert rm["loop_mode_used"] == 2
+    assert infop == infom == entry["info"]
+    assert rp["iterations"] == rm["iterations"] == entry["iterations"]
+    assert abs(rp["matvecs"] - rm["matvecs"]) <= 1
+    if float(torch.linalg.norm(xm)) > 0:
+        assert rel_diff(xp, xm) <= (1e-9 if "ldc" in name else 1e-11)
+    else:
+        assert float(xp.abs().max()) == 0.0
+
+
 def test_gmres_restart_above_native_limit(ma, manifest):
     """The reference accepts any restart; above the native limit (256) the solve runs on the generic route."""
     entry = manifest["cases"]["gmres_cd3d12_batched"]

@@ -65,14 +65,19 @@ def main():
         emit(what="spmv", use_compress=uc, kernel=info["kernel"], bytes_stream=info["bytes_stream"], us_dot=1e3 * ms,
              us_plain=1e3 * ms0, actual_gbs=actual / ms / 1e6, algorithmic_gbs=bytes_alg / ms / 1e6)
         if info["kernel"] == 6 and not args.quick:
-            for ctas in (2, 3, 4, 5, 6):
-                for grp in (1, 2, 4, 8, 16, 32):
-                    h.set_option("mask_ctas", ctas)
-                    h.set_option("mask_group", grp)
-                    ms = time_gpu(lambda: m.spmv_dot(x, x), reps=10)
-                    emit(what="spmv_mask", mask_ctas=ctas, mask_group=grp, us_dot=1e3 * ms, actual_gbs=actual / ms / 1e6)
-            h.set_option("mask_ctas", 4)
-            h.set_option("mask_group", 8)
+            d_ctas, d_grp = h.get_option("mask_ctas"), h.get_option("mask_group")
+            for ctas in (2, 3, 4, 5):
+                for grp in (2, 4, 8, 16):
+                    for pf in (0, 1):
+                        h.set_option("mask_ctas", ctas)
+                        h.set_option("mask_group", grp)
+                        h.set_option("mask_prefetch", pf)
+                        ms = time_gpu(lambda: m.spmv_dot(x, x), reps=20)
+                        emit(what="spmv_mask", mask_ctas=ctas, mask_group=grp, mask_prefetch=pf, us_dot=1e3 * ms,
+                             actual_gbs=actual / ms / 1e6)
+            h.set_option("mask_prefetch", 1)
+            h.set_option("mask_ctas", d_ctas)
+            h.set_option("mask_group", d_grp)
         W = args.window
         ms = time_gpu(lambda: m.cg(b, None, 0.0, 0.0, W), reps=3, warm=1)
         emit(what="cg_window", use_compress=uc, kernel=info["kernel"], us_per_iter=1e3 * ms / W, it_s=W / ms * 1e3)
