@@ -115,6 +115,7 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->use_split = (int)bk_env_int("BK_SPMV_SPLIT", 1);
   h->persistent = (int)bk_env_int("BK_PERSISTENT", 1);
   h->persistent_max_n = (int)bk_env_int("BK_PERSISTENT_MAX_N", 200000);
+  h->persistent_cluster = (int)bk_env_int("BK_PERSISTENT_CLUSTER", 1);
   h->prefetch_x = (int)bk_env_int("BK_SPMV_PREFETCH_X", 0);  // measured: 5 % slower on P3D-256, kept as an experiment
   h->loop_mode = (int)bk_env_int("BK_LOOP_MODE", BK_LOOP_AUTO);
   h->chunk = (int)bk_env_int("BK_CHUNK", 0);
@@ -215,6 +216,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "use_split")) return &h->use_split;
   if (!strcmp(key, "persistent")) return &h->persistent;
   if (!strcmp(key, "persistent_max_n")) return &h->persistent_max_n;
+  if (!strcmp(key, "persistent_cluster")) return &h->persistent_cluster;
   if (!strcmp(key, "prefetch_x")) return &h->prefetch_x;
   if (!strcmp(key, "loop_mode")) return &h->loop_mode;
   if (!strcmp(key, "chunk")) return &h->chunk;

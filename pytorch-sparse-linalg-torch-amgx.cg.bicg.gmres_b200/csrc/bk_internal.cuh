@@ -170,6 +170,7 @@ struct bk_handle {
   int prefetch_x;      // kernel 3: L2 bulk prefetch of the forward-diagonal x ranges
   int persistent;      // CG: run small systems in ONE cooperative persistent kernel (grid barriers instead of launches)
   int persistent_max_n;
+  int persistent_cluster;  // persistent GMRES: run systems of <= 16384 rows as ONE thread-block cluster (hardware barrier)
   int use_split;       // split very long rows into virtual rows (skewed matrices)
   int use_compress;    // 0 off | 1 8-bit dictionary-coded column stream (kernel 3) | 2 also try (offset, value) pair codes (kernel 5)
   int dist_p2p;        // multi-GPU: use the peer-memory path (halo push + one-shot all-reduce) when it is connected
