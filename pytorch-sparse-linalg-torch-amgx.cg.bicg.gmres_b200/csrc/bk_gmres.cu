@@ -557,9 +557,7 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
   if constexpr (!Sys::kDist) {
     // launch-bound (L2-resident) systems: the whole solve in ONE cooperative kernel (bk_gmres_persist.cuh)
     const bk_csr* A = sys.A;
-    int coop = 0, per_sm = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device);
-    if (h->persistent && coop && n <= (long long)h->persistent_max_n && A->rowptr && A->col) {
+    if (A->rowptr && A->col) {
       bk_gp_args ga;
       ga.rowptr = A->rowptr;
       ga.col = A->col;
@@ -576,49 +574,8 @@ static int bk_gmres_t(const Sys& sys, const void* b, void* x_user, int has_x0, d
       ga.y = sm.y;
       ga.partials = h->gm_partials;
       ga.m = m;
-      const long long grid = (n + BK_GP_BLOCK - 1) / BK_GP_BLOCK;  // one row per thread
-      if (h->persistent_cluster && grid <= 16) {
-        // one thread-block cluster: hardware barrier instead of the grid barrier
-        const unsigned csize = grid <= 8 ? (unsigned)grid : 16u;  // > 8 CTAs per cluster is the opt-in (non-portable) size
-        auto kern = bk_gmres_persistent_kernel<T, true>;
-        cudaError_t ce = cudaSuccess;
-        if (csize > 8) ce = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (ce == cudaSuccess) {
-          cudaLaunchConfig_t cfg;
-          memset(&cfg, 0, sizeof(cfg));
-          cfg.gridDim = dim3(csize);
-          cfg.blockDim = dim3(BK_GP_BLOCK);
-          cfg.stream = s;
-          cudaLaunchAttribute at[1];
-          at[0].id = cudaLaunchAttributeClusterDimension;
-          at[0].val.clusterDim.x = csize;
-          at[0].val.clusterDim.y = 1;
-          at[0].val.clusterDim.z = 1;
-          cfg.attrs = at;
-          cfg.numAttrs = 1;
-          int nclusters = 0;
-          ce = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
-          if (ce == cudaSuccess && nclusters >= 1) ce = cudaLaunchKernelEx(&cfg, kern, ga);
-          else if (ce == cudaSuccess) ce = cudaErrorInvalidConfiguration;
-        }
-        if (ce == cudaSuccess) {
-          persistent = true;
-          h->last_loop_mode = 3;
-        } else {
-          cudaGetLastError();  // cluster launch unavailable: the cooperative grid version below
-        }
-      }
-      if (!persistent) {
-        BK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bk_gmres_persistent_kernel<T, false>,
-                                                              BK_GP_BLOCK, 0));
-        if (per_sm > 0 && grid <= (long long)per_sm * h->num_sms && grid <= BK_MAXB) {
-          void* args[] = {(void*)&ga};
-          BK_CUDA(cudaLaunchCooperativeKernel((const void*)bk_gmres_persistent_kernel<T, false>, dim3((unsigned)grid),
-                                              dim3(BK_GP_BLOCK), args, 0, s));
-          persistent = true;
-          h->last_loop_mode = 3;
-        }
-      }
+      BK_TRY(bk_launch_persistent(h, bk_gmres_persistent_kernel<T, true>, bk_gmres_persistent_kernel<T, false>, ga, n, s,
+                                  &persistent));
     }
   }
   if (!persistent) BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_cycle, &chunks));

@@ -18,13 +18,8 @@
 // different partition than the multi-kernel path, so results agree to rounding, deterministically.
 #pragma once
 
-#include <cooperative_groups.h>
-
 #include "bk_internal.cuh"
-
-#define BK_GP_BLOCK 1024
-#define BK_GP_WARPS (BK_GP_BLOCK / 32)
-#define BK_GP_NV 8  // projection coefficients reduced per pass
+#include "bk_persist.cuh"
 
 struct bk_gp_args {
   const int* rowptr;
@@ -42,60 +37,6 @@ struct bk_gp_args {
   double* y;         // m
   double* partials;  // [(m + 3)][BK_MAXB]
   int m;
-};
-
-// block-wide sum of NV values per thread -> partials[(base + v) * BK_MAXB + blockIdx.x], v < nv
-template <int NV>
-__device__ __forceinline__ void bk_gp_block_sums(double (&acc)[NV], int nv, double* sh /* NV * BK_GP_WARPS */,
-                                                 double* partials, int base) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[v] += __shfl_down_sync(0xffffffffu, acc[v], o);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int v = 0; v < NV; ++v) sh[v * BK_GP_WARPS + wid] = acc[v];
-  }
-  __syncthreads();
-  if (wid < nv) {
-    double t = sh[wid * BK_GP_WARPS + lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-    if (lane == 0) __stcg(&partials[(size_t)(base + wid) * BK_MAXB + blockIdx.x], t);
-  }
-  __syncthreads();
-}
-
-// s_out[i] = sum over CTAs of partials[(base + i)][cta], i < count — executed by every CTA in the same order
-__device__ __forceinline__ void bk_gp_gather_sums(const double* partials, int base, int count, double* s_out) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = wid; i < count; i += BK_GP_WARPS) {
-    double a = 0.0;
-    for (int c = lane; c < (int)gridDim.x; c += 32) a += __ldcg(&partials[(size_t)(base + i) * BK_MAXB + c]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-    if (lane == 0) s_out[i] = a;
-  }
-  __syncthreads();
-}
-
-// Barrier of the whole kernel.  CLUSTER = false: cooperative-groups grid barrier (an atomic round trip through L2,
-// ~3 us measured).  CLUSTER = true: the grid IS one thread-block cluster (<= 16 CTAs on one GPC, n <= 16384 rows): the
-// hardware cluster barrier (barrier.cluster, ~0.2 us) with release/acquire semantics replaces it — two barriers per
-// Arnoldi step make this the difference between 18 and ~11 us per step on the LDC-100 system.
-template <bool CLUSTER>
-struct bk_gp_barrier {
-  cooperative_groups::grid_group grid;
-  __device__ bk_gp_barrier() : grid(cooperative_groups::this_grid()) {}
-  __device__ __forceinline__ void sync() {
-    if constexpr (CLUSTER) {
-      asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    } else {
-      grid.sync();
-    }
-  }
 };
 
 template <typename T, bool CLUSTER>

@@ -127,18 +127,6 @@ __device__ __forceinline__ float bk_ld_plain(const float* base, int off) {
   return v;
 }
 
-// base[off] and base[off + 256]: the same pattern entry of the two blocks of a pair, one address computation
-__device__ __forceinline__ void bk_ld_pair(const double* base, int off, double& v0, double& v1) {
-  asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %3, 8, %2;\n\tld.global.nc.f64 %0, [a];\n\tld.global.nc.f64 %1, [a+2048];\n\t}"
-      : "=d"(v0), "=d"(v1)
-      : "l"(base), "r"(off));
-}
-__device__ __forceinline__ void bk_ld_pair(const float* base, int off, float& v0, float& v1) {
-  asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %3, 4, %2;\n\tld.global.nc.f32 %0, [a];\n\tld.global.nc.f32 %1, [a+1024];\n\t}"
-      : "=f"(v0), "=f"(v1)
-      : "l"(base), "r"(off));
-}
-
 // one 32-row chunk: y[row] = sum_e [mask bit e] val_e * x[row + off_e]   (+ fused residual / dots).
 // FAST: every row of the chunk has every entry of the pattern (warp-uniform test by the caller; ~3/4 of the chunks of
 // a stencil matrix): no predicates, no zero-fill, no bounds test (a row with a non-empty mask exists).
@@ -176,7 +164,7 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
   const int wid = threadIdx.x >> 5;
   const int n32 = (int)a.n;
   const int nblk = (n32 + 255) >> 8;
-  const int gshift = plan.group;  // log2 of the consecutive 256-row blocks a CTA takes per visit (1..5)
+  const int gshift = plan.group;  // log2 of the consecutive 256-row blocks a CTA takes per visit (0..5)
   const int gmask = (1 << gshift) - 1;
   const int ngroups = (nblk + gmask) >> gshift;
   int reverse = a.reverse;
@@ -192,33 +180,30 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
 
   bk_mask_pat<T> pat;
   int cur = -1;
-  // Groups of 2^gshift (>= 2) consecutive blocks are dealt round-robin to the CTAs (the chip sweeps one window of the
-  // vectors; inside a group neighbouring grid lines are gathered from L1).  A warp takes chunk `wid` of every block of
-  // its groups, TWO consecutive blocks (rows r and r + 256) per step: pair u = 0 .. U-1 of its sequence.  `masks` /
-  // `pids` are padded to 32 whole blocks beyond the matrix (zero masks gather nothing): no tail test.
+  // Groups of 2^gshift consecutive blocks are dealt round-robin to the CTAs (the chip sweeps one window of the vectors;
+  // inside a group neighbouring grid lines are gathered from L1).  A warp takes chunk `wid` of every block of its
+  // groups: chunk t = 0 .. T-1 of its sequence.  `masks` / `pids` are padded to 32 whole blocks beyond the matrix (zero
+  // masks gather nothing), so the tail of the last group needs no test.
   const int my_groups = (ngroups > (int)blockIdx.x) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int U_ = (my_groups << gshift) >> 1;
-  const int pshift = gshift - 1, pmask = (1 << pshift) - 1;
-  auto chunk_at = [&](int u) -> int {  // chunk of the pair's first block
-    const int g = (int)blockIdx.x + (u >> pshift) * (int)gridDim.x;
+  const int T_ = my_groups << gshift;
+  auto chunk_at = [&](int t) -> int {
+    const int g = (int)blockIdx.x + (t >> gshift) * (int)gridDim.x;
     const int gg = reverse ? (ngroups - 1 - g) : g;
-    return (((gg << gshift) + ((u & pmask) << 1)) << 3) + wid;
+    return (((gg << gshift) + (t & gmask)) << 3) + wid;
   };
-  int u = 0;
-  int ch_next = 0, pidA_next = 0, pidB_next = 0;
-  unsigned int mA_next = 0u, mB_next = 0u;
-  if (U_ > 0) {
+  int t = 0;
+  int ch_next = 0, pid_next = 0;
+  unsigned int m_next = 0u;
+  if (T_ > 0) {
     ch_next = chunk_at(0);
-    mA_next = __ldg(masks + (size_t)ch_next * 32 + lane);
-    mB_next = __ldg(masks + (size_t)ch_next * 32 + lane + 256);
-    pidA_next = __ldg(pids + ch_next);
-    pidB_next = __ldg(pids + ch_next + 8);
+    m_next = __ldg(masks + (size_t)ch_next * 32 + lane);
+    pid_next = __ldg(pids + ch_next);
   }
   // L2 prefetch, one visit ahead: ncu showed the kernel waiting on DRAM latency (one first-touch line of x per chunk,
   // ~1700 cycles per chunk with 8 warps per scheduler; DRAM 32 %, issue 44 %).  When a CTA starts a group, one thread
   // asks the L2 for the x range (and the masks) of the group the CTA will visit NEXT with a single bulk-prefetch
   // instruction each (SASS UBLKPF); every gather of that visit — centre lines and the neighbours' lines, which are
-  // other CTAs' centre lines — then hits L2.
+  // other CTAs' centre lines — then hits L2 (measured: 99 -> 84 us).
   auto prefetch_group = [&](int visit) {
     const int g = (int)blockIdx.x + visit * (int)gridDim.x;
     if (g >= ngroups) return;
@@ -233,77 +218,31 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
   };
   const bool pf = plan.prefetch != 0 && threadIdx.x == 0;
   if (pf) prefetch_group(1);
-  while (u < U_) {
-    // a run of pairs with the same pattern: the pattern is (re)loaded here, outside the hot loop
-    const int slot = pidA_next & (BK_MASK_PID_GHOST - 1);
+  while (t < T_) {
+    // a run of chunks with the same pattern: the pattern is (re)loaded here, outside the hot loop
+    const int slot = pid_next & (BK_MASK_PID_GHOST - 1);
     if (slot != cur) {
       bk_mask_load_pattern<T>(plan.ptab, slot, pat);
       cur = slot;
     }
     do {
       const int row = ch_next * 32 + lane;
-      const unsigned int mA = mA_next, mB = mB_next;
-      const int pidA = pidA_next, pidB = pidB_next;
-      ++u;
-      if (pf && (u & pmask) == 0) prefetch_group((u >> pshift) + 1);
-      if (u < U_) {  // the next pair's masks / pattern ids are in flight while this one is computed
-        ch_next = chunk_at(u);
-        mA_next = __ldg(masks + (size_t)ch_next * 32 + lane);
-        mB_next = __ldg(masks + (size_t)ch_next * 32 + lane + 256);
-        pidA_next = __ldg(pids + ch_next);
-        pidB_next = __ldg(pids + ch_next + 8);
+      const unsigned int m = m_next;
+      const bool ghost_chunk = GHOST && (pid_next & BK_MASK_PID_GHOST);
+      ++t;
+      if (pf && (t & gmask) == 0) prefetch_group((t >> gshift) + 1);
+      if (t < T_) {  // the next chunk's mask / pattern id are in flight while this one is computed
+        ch_next = chunk_at(t);
+        m_next = __ldg(masks + (size_t)ch_next * 32 + lane);
+        pid_next = __ldg(pids + ch_next);
       }
-      if (pidA == pidB && !(GHOST && (pidA & BK_MASK_PID_GHOST)) &&
-          __all_sync(0xffffffffu, mA == pat.full && mB == pat.full)) {
-        // ---- both chunks have every entry: one address per pattern entry serves both (the second block's rows sit
-        // 256 elements further: an immediate offset), 16 gathers in flight per warp -------------------------------
-        const T* xr = x + row;
-        T xa[BK_MASK_L], xb[BK_MASK_L];
-#pragma unroll
-        for (int e = 0; e < BK_MASK_L; ++e) bk_ld_pair(xr, pat.off[e], xa[e], xb[e]);
-        T sa = T(0), sb = T(0);
-#pragma unroll
-        for (int e = 0; e < BK_MASK_L; ++e) {
-          sa = fma(pat.val[e], xa[e], sa);
-          sb = fma(pat.val[e], xb[e], sb);
-        }
-        T* yr = static_cast<T*>(a.y) + row;
-        if constexpr (MODE == 1) {
-          const T* br = static_cast<const T*>(a.b) + row;
-          sa = bk_sub(__ldg(br), sa);
-          sb = bk_sub(__ldg(br + 256), sb);
-        }
-        yr[0] = sa;
-        yr[256] = sb;
-        if constexpr ((DOTS & 1) != 0) {
-          const T* wr = static_cast<const T*>(a.w) + row;
-          acc[0] += static_cast<double>(__ldg(wr)) * static_cast<double>(sa);       // (same order as one by one)
-          acc[0] += static_cast<double>(__ldg(wr + 256)) * static_cast<double>(sb);
-        }
-        if constexpr ((DOTS & 2) != 0) {
-          acc[DOTS & 1] += static_cast<double>(sa) * static_cast<double>(sa);
-          acc[DOTS & 1] += static_cast<double>(sb) * static_cast<double>(sb);
-        }
-      } else {
-        if (!(GHOST && (pidA & BK_MASK_PID_GHOST))) {  // (chunks with ghost entries: second phase)
-          if (__all_sync(0xffffffffu, mA == pat.full))
-            bk_mask_chunk<T, MODE, DOTS, false, true>(a, pat, x, xg, row, mA, n32, acc);
-          else
-            bk_mask_chunk<T, MODE, DOTS, false, false>(a, pat, x, xg, row, mA, n32, acc);
-        }
-        if (!(GHOST && (pidB & BK_MASK_PID_GHOST))) {
-          const int slotB = pidB & (BK_MASK_PID_GHOST - 1);
-          if (slotB != cur) {
-            bk_mask_load_pattern<T>(plan.ptab, slotB, pat);
-            cur = slotB;
-          }
-          if (__all_sync(0xffffffffu, mB == pat.full))
-            bk_mask_chunk<T, MODE, DOTS, false, true>(a, pat, x, xg, row + 256, mB, n32, acc);
-          else
-            bk_mask_chunk<T, MODE, DOTS, false, false>(a, pat, x, xg, row + 256, mB, n32, acc);
-        }
+      if (!ghost_chunk) {  // (chunks with ghost entries: second phase)
+        if (__all_sync(0xffffffffu, m == pat.full))
+          bk_mask_chunk<T, MODE, DOTS, false, true>(a, pat, x, xg, row, m, n32, acc);
+        else
+          bk_mask_chunk<T, MODE, DOTS, false, false>(a, pat, x, xg, row, m, n32, acc);
       }
-    } while (u < U_ && (pidA_next & (BK_MASK_PID_GHOST - 1)) == cur);
+    } while (t < T_ && (pid_next & (BK_MASK_PID_GHOST - 1)) == slot);
   }
   if constexpr (GHOST) {
     // ---- second phase: chunks with ghost entries, after the neighbours' halos have landed ---------------------
