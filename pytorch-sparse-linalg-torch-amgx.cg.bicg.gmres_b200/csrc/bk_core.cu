@@ -105,6 +105,8 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->mask_ctas = (int)bk_env_int("BK_MASK_CTAS", 4);
   h->mask_group = (int)bk_env_int("BK_MASK_GROUP", 8);
   h->mask_prefetch = (int)bk_env_int("BK_MASK_PREFETCH", 1);
+  h->mask_window = (int)bk_env_int("BK_MASK_WINDOW", 1);
+  h->mask_wgroup = (int)bk_env_int("BK_MASK_WGROUP", 4);
   h->nvtx = (int)bk_env_int("BK_NVTX", 0);
   h->dist_fuse_push = (int)bk_env_int("BK_DIST_FUSE_PUSH", 1);
   h->dist_fold = (int)bk_env_int("BK_DIST_FOLD", 1);
@@ -206,6 +208,8 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "mask_ctas")) return &h->mask_ctas;
   if (!strcmp(key, "mask_group")) return &h->mask_group;
   if (!strcmp(key, "mask_prefetch")) return &h->mask_prefetch;
+  if (!strcmp(key, "mask_window")) return &h->mask_window;
+  if (!strcmp(key, "mask_wgroup")) return &h->mask_wgroup;
   if (!strcmp(key, "nvtx")) return &h->nvtx;
   if (!strcmp(key, "dist_fuse_push")) return &h->dist_fuse_push;
   if (!strcmp(key, "dist_fold")) return &h->dist_fold;
@@ -958,6 +962,46 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
     return done(BK_OK);
   }
   A->mask_patterns = host[1];
+  {  // window plan of kernel 6W: near half-width W and up to two far offsets, from the (small) pattern table
+    const size_t ne = (size_t)BK_MASK_HT * BK_MASK_L;
+    bk_pair_entry* tab = (bk_pair_entry*)malloc(sizeof(bk_pair_entry) * ne);
+    unsigned long long* hk = (unsigned long long*)malloc(sizeof(unsigned long long) * BK_MASK_HT);
+    A->mw_win = 0;
+    A->mw_nfar = 0;
+    if (tab && hk &&
+        cudaMemcpyAsync(tab, A->mptab, sizeof(bk_pair_entry) * ne, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+        cudaMemcpyAsync(hk, keys, sizeof(unsigned long long) * BK_MASK_HT, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+        cudaStreamSynchronize(s) == cudaSuccess) {
+      const int ea = (int)(16 / bk_dtype_size(A->dtype));
+      int W = 0;
+      int far[64];
+      int nfar_all = 0;
+      for (int slot = 0; slot < BK_MASK_HT; ++slot) {
+        if (!hk[slot]) continue;
+        const bk_pair_entry* pe = tab + (size_t)slot * BK_MASK_L;
+        const int full = (pe[0].pad >> BK_MASK_FULL_SHIFT) & 0x1ff;
+        for (int e = 0; e < BK_MASK_L; ++e) {
+          if (!(full & (1 << e)) || (pe[e].pad & BK_MASK_GHOST)) continue;
+          const int off = pe[e].off, ao = off < 0 ? -off : off;
+          if (ao <= 1040) {
+            if (ao > W) W = ao;
+          } else {
+            bool seen = false;
+            for (int k = 0; k < nfar_all; ++k) seen = seen || far[k] == off;
+            if (!seen && nfar_all < 64) far[nfar_all++] = off;
+          }
+        }
+      }
+      A->mw_win = ((W + 7) / 8) * 8;
+      if (A->mw_win < 8) A->mw_win = 8;
+      for (int k = 0; k < nfar_all && A->mw_nfar < 2; ++k)
+        if (far[k] % ea == 0) A->mw_far[A->mw_nfar++] = far[k];
+    } else {
+      cudaGetLastError();
+    }
+    free(tab);
+    free(hk);
+  }
   if (A->n_cols > A->n) {  // row partition: compact list of the chunks that gather from the ghost vector
     unsigned int* flags = nullptr;
     if (bk_pool_alloc((void**)&flags, sizeof(unsigned int) * (size_t)(nchunks + 1), s) != cudaSuccess) {

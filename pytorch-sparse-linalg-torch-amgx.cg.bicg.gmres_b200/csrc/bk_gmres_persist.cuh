@@ -110,18 +110,18 @@ __global__ void __launch_bounds__(BK_GP_BLOCK, 1) bk_gmres_persistent_kernel(con
         wout[row] = sum;
         wrow = sum;
       }
-      {
+      {  // values 0 .. j+1 of this step: ||w||^2, h_0 .. h_j — reduced 8 at a time
         double acc[BK_GP_NV];
+        for (int g0 = 0; g0 < j + 2; g0 += BK_GP_NV) {
+          const int nv = (j + 2 - g0 < BK_GP_NV) ? (j + 2 - g0) : BK_GP_NV;
 #pragma unroll
-        for (int v = 0; v < BK_GP_NV; ++v) acc[v] = 0.0;
-        acc[0] = (double)wrow * (double)wrow;
-        bk_gp_block_sums<BK_GP_NV>(acc, 1, s_red, P, 0);
-        for (int g0 = 0; g0 <= j; g0 += BK_GP_NV) {
-          const int nv = (j + 1 - g0 < BK_GP_NV) ? (j + 1 - g0) : BK_GP_NV;
-#pragma unroll
-          for (int v = 0; v < BK_GP_NV; ++v)
-            acc[v] = (v < nv && active) ? (double)V[(size_t)(g0 + v) * a.ldv + row] * (double)wrow : 0.0;
-          bk_gp_block_sums<BK_GP_NV>(acc, nv, s_red, P, 1 + g0);
+          for (int v = 0; v < BK_GP_NV; ++v) {
+            const int idx = g0 + v;  // 0: ||w||^2, 1 + i: h_i
+            double t = 0.0;
+            if (v < nv && active) t = (idx == 0) ? (double)wrow : (double)V[(size_t)(idx - 1) * a.ldv + row];
+            acc[v] = t * (double)wrow;
+          }
+          bk_gp_block_sums<BK_GP_NV>(acc, nv, s_red, P, g0);
         }
       }
       grid.sync();
@@ -138,11 +138,8 @@ __global__ void __launch_bounds__(BK_GP_BLOCK, 1) bk_gmres_persistent_kernel(con
         wout[row] = wnew;
       }
       {
-        double acc[BK_GP_NV];
-#pragma unroll
-        for (int v = 0; v < BK_GP_NV; ++v) acc[v] = 0.0;
-        acc[0] = (double)wnew * (double)wnew;
-        bk_gp_block_sums<BK_GP_NV>(acc, 1, s_red, P2, 0);
+        double acc[1] = {(double)wnew * (double)wnew};
+        bk_gp_block_sums<1>(acc, 1, s_red, P2, 0);
       }
       grid.sync();
       // ---- the small dense step, replayed by thread 0 of every CTA (bk_gm_dense_step on shared copies) ---------------
@@ -222,11 +219,8 @@ __global__ void __launch_bounds__(BK_GP_BLOCK, 1) bk_gmres_persistent_kernel(con
       rbuf[row] = rrow;
     }
     {
-      double acc[BK_GP_NV];
-#pragma unroll
-      for (int v = 0; v < BK_GP_NV; ++v) acc[v] = 0.0;
-      acc[0] = (double)rrow * (double)rrow;
-      bk_gp_block_sums<BK_GP_NV>(acc, 1, s_red, P2, 0);
+      double acc[1] = {(double)rrow * (double)rrow};
+      bk_gp_block_sums<1>(acc, 1, s_red, P2, 0);
     }
     grid.sync();
     bk_gp_gather_sums(P2, 0, 1, s_sum);

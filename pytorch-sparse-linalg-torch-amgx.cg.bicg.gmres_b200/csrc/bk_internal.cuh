@@ -123,6 +123,9 @@ struct bk_csr {
   int* mdeferred;            // multi-GPU: chunks with ghost entries (processed after the halo arrived), own
   int n_mdeferred;
   int mask_patterns;         // distinct patterns in the table
+  int mw_win;                // kernel 6W: half-width W of the near window (0: no window plan)
+  int mw_nfar;               // kernel 6W: far windows
+  int mw_far[2];             // their offsets
   int64_t n_cols;            // columns (== n except for the extended local+ghost matrix of a row partition)
   const long long* reg_ghost_gid;  // registration only (n_cols > n): global ids of the ghost columns
   long long reg_row_begin;         // registration only: global id of row 0
@@ -161,6 +164,8 @@ struct bk_handle {
   int mask_ctas;       // CTAs/SM of the row-bitmask SpMV (kernel 6; 2..6)
   int mask_group;      // kernel 6: consecutive 256-row blocks dealt to a CTA at a time
   int mask_prefetch;   // kernel 6: L2 bulk prefetch of the x range of a CTA's next group
+  int mask_window;     // kernel 6W: gathers from TMA-staged shared-memory windows of x (1) instead of LDG (0)
+  int mask_wgroup;     // kernel 6W: consecutive 256-row blocks per stage
   int nvtx;            // emit NVTX ranges around the phases of every solve (BK_NVTX=1)
   int last_loop_mode;  // how the last iteration loop actually ran (bk_result.loop_mode_used)
   int dist_fuse_push;  // multi-GPU CG, peer path: fold the halo push into the kernel that produces p (1)

@@ -11,19 +11,40 @@
 #define BK_GP_WARPS (BK_GP_BLOCK / 32)
 #define BK_GP_NV 8  // projection coefficients reduced per pass
 
-// block-wide sum of NV values per thread -> partials[(base + v) * BK_MAXB + blockIdx.x], v < nv
+// block-wide sum of NV (1 or 8) values per thread -> partials[(base + v) * BK_MAXB + blockIdx.x], v < nv.
+// NV = 8 uses a butterfly: after the exchanges over lane distances 16, 8, 4 every lane holds ONE of the 8 values summed
+// over 8 lanes, two more steps finish the warp sum — 9 double-word shuffles instead of 40.  (With 1024-thread CTAs the
+// shuffle pipe, not the barrier, bounded the first version of the persistent GMRES: 16 of 18 us per Arnoldi step.)
 template <int NV>
 __device__ __forceinline__ void bk_gp_block_sums(double (&acc)[NV], int nv, double* sh /* NV * BK_GP_WARPS */,
                                                  double* partials, int base) {
+  static_assert(NV == 1 || NV == 8, "1 or 8 values");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if constexpr (NV == 1) {
+    double t = acc[0];
 #pragma unroll
-  for (int v = 0; v < NV; ++v) {
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) sh[wid] = t;
+  } else {
+    const bool h1 = (lane & 16) != 0, h2 = (lane & 8) != 0, h3 = (lane & 4) != 0;
+    double a4[4], a2[2];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[v] += __shfl_down_sync(0xffffffffu, acc[v], o);
-  }
-  if (lane == 0) {
+    for (int k = 0; k < 4; ++k) {
+      const double send = h1 ? acc[k] : acc[k + 4];
+      const double keep = h1 ? acc[k + 4] : acc[k];
+      a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
 #pragma unroll
-    for (int v = 0; v < NV; ++v) sh[v * BK_GP_WARPS + wid] = acc[v];
+    for (int k = 0; k < 2; ++k) {
+      const double send = h2 ? a4[k] : a4[k + 2];
+      const double keep = h2 ? a4[k + 2] : a4[k];
+      a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    double a1 = (h3 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h3 ? a2[0] : a2[1], 4);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+    const int vi = (h1 ? 4 : 0) + (h2 ? 2 : 0) + (h3 ? 1 : 0);
+    if ((lane & 3) == 0) sh[vi * BK_GP_WARPS + wid] = a1;
   }
   __syncthreads();
   if (wid < nv) {

@@ -333,6 +333,48 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
         plan.group = gs;
       }
       plan.prefetch = (h->mask_prefetch && bk_aligned16(a.x)) ? 1 : 0;
+      // kernel 6W: gathers from TMA-staged shared-memory windows (x 16-byte aligned, n a multiple of the 16-byte pack)
+      if (h->mask_window && A->mw_win > 0 && bk_aligned16(a.x) && (A->n % (16 / sizeof(T))) == 0) {
+        int gsw = 0;
+        while ((2 << gsw) <= h->mask_wgroup && gsw < 5) ++gsw;
+        const int rows_g = 256 << gsw;
+        bk_maskw_plan wp;
+        wp.win = A->mw_win;
+        wp.nfar = A->mw_nfar;
+        wp.far_off[0] = A->mw_far[0];
+        wp.far_off[1] = A->mw_far[1];
+        const size_t raw = (size_t)(rows_g + 2 * wp.win) * sizeof(T) + (size_t)wp.nfar * rows_g * sizeof(T) + rows_g +
+                           (size_t)(rows_g >> 8) * 32;
+        wp.stage_bytes = (uint32_t)((raw + 127) & ~(size_t)127);
+        int wctas = h->mask_ctas < 2 ? 2 : (h->mask_ctas > 4 ? 4 : h->mask_ctas);
+        int stages = 0;
+        for (; wctas >= 2; --wctas) {
+          stages = (int)(((size_t)224 * 1024 / wctas - 2048) / wp.stage_bytes);
+          if (stages >= 2) break;
+        }
+        if (stages >= 2) {
+          if (stages > BK_TMA_MAX_STAGES) stages = BK_TMA_MAX_STAGES;
+          if (h->tma_stages >= 2 && h->tma_stages < stages) stages = h->tma_stages;
+          wp.stages = stages;
+          plan.group = gsw;
+          const size_t sm = (size_t)stages * wp.stage_bytes;
+          int g = h->num_sms * wctas;
+          if (g > BK_MAXB) g = BK_MAXB;
+          g = bk_grid_rows(g, A->n, rows_g);
+          auto launch = [&](auto k) -> int {
+            BK_TRY(bk_ensure_dyn_smem((const void*)k, sm));
+            k<<<g, BK_TMA_THREADS, sm, s>>>(a, plan, wp, sc, epi);
+            return BK_OK;
+          };
+          switch (wctas) {
+            case 2: BK_TRY(launch(bk_spmv_maskw_kernel<T, MODE, DOTS, false, 2, Epi>)); break;
+            case 3: BK_TRY(launch(bk_spmv_maskw_kernel<T, MODE, DOTS, false, 3, Epi>)); break;
+            default: BK_TRY(launch(bk_spmv_maskw_kernel<T, MODE, DOTS, false, 4, Epi>)); break;
+          }
+          BK_KERNEL_CHECK();
+          return BK_OK;
+        }
+      }
       int ctas = h->mask_ctas < 2 ? 2 : (h->mask_ctas > 6 ? 6 : h->mask_ctas);
       int g = h->num_sms * ctas;
       if (g > BK_MAXB) g = BK_MAXB;

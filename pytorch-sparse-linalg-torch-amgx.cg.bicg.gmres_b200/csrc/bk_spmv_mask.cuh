@@ -288,3 +288,278 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
     bk_grid_reduce<R, Epi, BK_WARPS>(acc, sc, epi);
   }
 }
+
+// =====================================================================================================================
+// Kernel 6W — the same row-bitmask SpMV with its gathers served from SHARED MEMORY: a producer warp stages, per group of
+// 2^gshift consecutive 256-row blocks, the windows of x the group's rows can touch with TMA bulk copies (cp.async.bulk +
+// mbarrier ring, as kernels 2 / 3 / 5 stage the matrix stream):
+//   near window   x[row0 - W, row0 + rows + W)          every offset with |off| <= W (W from the pattern table)
+//   far windows   x[row0 + F_k, row0 + F_k + rows)      up to two far offsets F_k (the +-n^2 planes of a 3-D stencil)
+// plus the group's masks and pattern ids.  Why: ncu on kernel 6 (profiles/r02_ncu_k6_*.txt) shows it bound by the L1TEX
+// pipe, not by HBM — a warp-wide 8-byte gather touches 2-3 cache lines and replays cost ~2 cycles per line, ~40 LSU
+// cycles per 32-row chunk (85 us at 256^3) against an HBM floor of 44 us; bulk copies bypass that pipe, a conflict-free
+// LDS.64 costs 2 cycles flat, and the ring keeps NSTAGE groups of loads in flight per CTA regardless of occupancy.
+// A gather becomes `lds [lane_base + disp_e]` with one per-pattern displacement per entry.  Patterns with an offset that
+// no window covers (and chunks with ghost entries) take the LDG path of kernel 6 inside the same kernel.
+// =====================================================================================================================
+#define BK_MW_MAXFAR 2
+
+struct bk_maskw_plan {
+  int win;                  // W: elements on each side of the near window (multiple of 8)
+  int nfar;
+  int far_off[BK_MW_MAXFAR];  // F_k (multiples of 16 / sizeof(T))
+  int stages;
+  uint32_t stage_bytes;
+};
+
+__device__ __forceinline__ void bk_bulk_g2s_plain(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   bk_smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(bk_smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ double bk_lds_plain(uint32_t addr, double) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float bk_lds_plain(uint32_t addr, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ double bk_lds_masked(uint32_t addr, unsigned int bit, double) {
+  double v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@p ld.shared.f64 %0, [%1];\n\t}"
+               : "=d"(v)
+               : "r"(addr), "r"(bit));
+  return v;
+}
+__device__ __forceinline__ float bk_lds_masked(uint32_t addr, unsigned int bit, float) {
+  float v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@p ld.shared.f32 %0, [%1];\n\t}"
+               : "=f"(v)
+               : "r"(addr), "r"(bit));
+  return v;
+}
+
+// one chunk from the staged windows: xv[e] = smem[lane_base + disp[e]]
+template <typename T, int MODE, int DOTS, bool FAST, int CNT>
+__device__ __forceinline__ void bk_maskw_chunk(const bk_spmv_args& a, const bk_mask_pat<T>& p, const int (&disp)[BK_MASK_L],
+                                               const uint32_t lane_base, const int row, const unsigned int m,
+                                               const int n32, double* acc) {
+  T xv[BK_MASK_L];
+#pragma unroll
+  for (int e = 0; e < BK_MASK_L; ++e) {
+    if (e < CNT) {
+      if (FAST) xv[e] = bk_lds_plain(lane_base + (uint32_t)disp[e], T(0));
+      else xv[e] = bk_lds_masked(lane_base + (uint32_t)disp[e], m & (1u << e), T(0));
+    } else {
+      xv[e] = T(0);
+    }
+  }
+  T sum = T(0);
+#pragma unroll
+  for (int e = 0; e < BK_MASK_L; ++e)
+    if (e < CNT) sum = fma(p.val[e], xv[e], sum);
+  if (FAST || row < n32) {
+    T out = sum;
+    if constexpr (MODE == 1) out = bk_sub(__ldg(static_cast<const T*>(a.b) + row), sum);
+    static_cast<T*>(a.y)[row] = out;
+    if constexpr ((DOTS & 1) != 0)
+      acc[0] += static_cast<double>(__ldg(static_cast<const T*>(a.w) + row)) * static_cast<double>(out);
+    if constexpr ((DOTS & 2) != 0) acc[DOTS & 1] += static_cast<double>(out) * static_cast<double>(out);
+  }
+}
+
+template <typename T, int MODE, int DOTS, bool GHOST, int MINB, typename Epi>
+__global__ void __launch_bounds__(BK_TMA_THREADS, MINB)
+bk_spmv_maskw_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_maskw_plan wp, const bk_scratch sc,
+                     Epi epi) {
+  if (bk_spmv_skip(a)) return;
+  extern __shared__ __align__(128) unsigned char bk_smem_mw[];
+  __shared__ __align__(8) uint64_t full_bar[BK_TMA_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[BK_TMA_MAX_STAGES];
+  constexpr int R = bk_ndots<DOTS>::value;
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int n32 = (int)a.n;
+  const int nblk = (n32 + 255) >> 8;
+  const int gshift = plan.group;
+  const int G = 1 << gshift;
+  const int rows_g = G << 8;
+  const int ngroups = (nblk + G - 1) >> gshift;
+  const int nstage = wp.stages;
+  const int W = wp.win;
+  int reverse = a.reverse;
+  if (a.use_parity) reverse ^= (a.st->parity & 1);
+  const T* x = static_cast<const T*>(a.x);
+  const T* xg = static_cast<const T*>(plan.xg);
+  // stage layout: [near window][far windows][masks][pattern ids]
+  const uint32_t near_bytes = (uint32_t)(rows_g + 2 * W) * (uint32_t)sizeof(T);
+  const uint32_t far_bytes = (uint32_t)rows_g * (uint32_t)sizeof(T);
+  const uint32_t mask_off = near_bytes + (uint32_t)wp.nfar * far_bytes;
+  const uint32_t pid_off = mask_off + (uint32_t)rows_g;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstage; ++s) {
+      bk_mbar_init(&full_bar[s], 1);
+      bk_mbar_init(&empty_bar[s], BK_WARPS);
+    }
+    bk_mbar_fence_init();
+  }
+  __syncthreads();
+
+  double acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.0;
+
+  const int my_groups = (ngroups > (int)blockIdx.x) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto row0_of = [&](int u) -> int {
+    const int g = (int)blockIdx.x + u * (int)gridDim.x;
+    const int gg = reverse ? (ngroups - 1 - g) : g;
+    return (gg << gshift) << 8;
+  };
+
+  bk_mask_pat<T> pat;
+  int cur = -1;
+  if (wid == BK_WARPS) {
+    // ------------------------------ producer warp ------------------------------------------------
+    if (lane == 0) {
+      for (int u = 0; u < my_groups; ++u) {
+        const int stage = u % nstage;
+        if (u >= nstage) bk_mbar_wait(&empty_bar[stage], (uint32_t)(((u / nstage) - 1) & 1));
+        unsigned char* sb = bk_smem_mw + (size_t)stage * wp.stage_bytes;
+        const int row0 = row0_of(u);
+        uint32_t tx = (uint32_t)rows_g + (uint32_t)(G * 32);
+        // windows, clamped to [0, n) (n is a multiple of the 16-byte pack: checked by the launcher)
+        int lo[1 + BK_MW_MAXFAR], hi[1 + BK_MW_MAXFAR], base[1 + BK_MW_MAXFAR];
+        uint32_t soff[1 + BK_MW_MAXFAR];
+        base[0] = row0 - W;
+        lo[0] = max(base[0], 0);
+        hi[0] = min(row0 + rows_g + W, n32);
+        soff[0] = 0u;
+        for (int k = 0; k < wp.nfar; ++k) {
+          base[1 + k] = row0 + wp.far_off[k];
+          lo[1 + k] = max(base[1 + k], 0);
+          hi[1 + k] = min(base[1 + k] + rows_g, n32);
+          soff[1 + k] = near_bytes + (uint32_t)k * far_bytes;
+        }
+        for (int k = 0; k <= wp.nfar; ++k)
+          if (hi[k] > lo[k]) tx += (uint32_t)(hi[k] - lo[k]) * (uint32_t)sizeof(T);
+        bk_mbar_expect_tx(&full_bar[stage], tx);
+        for (int k = 0; k <= wp.nfar; ++k)
+          if (hi[k] > lo[k])
+            bk_bulk_g2s_plain(sb + soff[k] + (size_t)(lo[k] - base[k]) * sizeof(T), x + lo[k],
+                              (uint32_t)(hi[k] - lo[k]) * (uint32_t)sizeof(T), &full_bar[stage]);
+        bk_bulk_g2s_plain(sb + mask_off, plan.masks + row0, (uint32_t)rows_g, &full_bar[stage]);
+        bk_bulk_g2s_plain(sb + pid_off, plan.pids + (row0 >> 5), (uint32_t)(G * 32), &full_bar[stage]);
+      }
+    }
+  } else {
+    // ------------------------------ consumer warps: warp <-> chunk `wid` of every block of the group ------------
+    int disp[BK_MASK_L];      // byte displacement of every pattern entry inside a stage, relative to the lane's slot
+    bool windowed = false;    // every entry of the current pattern is covered by a staged window
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t smem0 = bk_smem_u32(bk_smem_mw);
+    for (int u = 0; u < my_groups; ++u) {
+      bk_mbar_wait(&full_bar[stage], phase);
+      const uint32_t sb = smem0 + (uint32_t)stage * wp.stage_bytes;
+      const int row0 = row0_of(u);
+      for (int j = 0; j < G; ++j) {
+        const int lrow = (j << 8) + (wid << 5) + lane;
+        const int row = row0 + lrow;
+        unsigned int m;
+        int pid;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m) : "r"(sb + mask_off + (uint32_t)lrow));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pid) : "r"(sb + pid_off + (uint32_t)(((j << 3) + wid) << 2)));
+        if (GHOST && (pid & BK_MASK_PID_GHOST)) continue;  // second phase
+        const int slot = pid & (BK_MASK_PID_GHOST - 1);
+        if (slot != cur) {
+          bk_mask_load_pattern<T>(plan.ptab, slot, pat);
+          cur = slot;
+          windowed = true;
+#pragma unroll
+          for (int e = 0; e < BK_MASK_L; ++e) {
+            const int off = pat.off[e];
+            int d = -1;
+            if (!(pat.ghost & (1u << e))) {
+              if (off >= -W && off <= W) d = (W + off) * (int)sizeof(T);
+              for (int k = 0; k < wp.nfar; ++k)
+                if (off == wp.far_off[k]) d = (int)(near_bytes + (uint32_t)k * far_bytes);
+            }
+            if (d < 0 && (pat.full & (1u << e)) && pat.full != 0xffffffffu) windowed = false;  // a real entry nobody stages
+            disp[e] = d < 0 ? 0 : d;
+          }
+        }
+        const bool fast = __all_sync(0xffffffffu, m == pat.full);
+        if (windowed) {
+          const uint32_t lane_base = sb + (uint32_t)lrow * (uint32_t)sizeof(T);
+          const int cnt = __popc(pat.full);  // pattern length (full is (1 << count) - 1)
+          if (fast) {
+            if (cnt <= 5) bk_maskw_chunk<T, MODE, DOTS, true, 5>(a, pat, disp, lane_base, row, m, n32, acc);
+            else if (cnt <= 7) bk_maskw_chunk<T, MODE, DOTS, true, 7>(a, pat, disp, lane_base, row, m, n32, acc);
+            else bk_maskw_chunk<T, MODE, DOTS, true, 8>(a, pat, disp, lane_base, row, m, n32, acc);
+          } else {
+            bk_maskw_chunk<T, MODE, DOTS, false, 8>(a, pat, disp, lane_base, row, m, n32, acc);
+          }
+        } else if (fast) {
+          bk_mask_chunk<T, MODE, DOTS, false, true>(a, pat, x, xg, row, m, n32, acc);
+        } else {
+          bk_mask_chunk<T, MODE, DOTS, false, false>(a, pat, x, xg, row, m, n32, acc);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) bk_mbar_arrive(&empty_bar[stage]);
+      if (++stage == nstage) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  }
+  if constexpr (GHOST) {
+    // ---- second phase: chunks with ghost entries, after the neighbours' halos have landed (LDG path) -----------
+    if (plan.n_deferred > 0 || plan.flags != nullptr) {
+      __shared__ int s_fail;
+      bool ok = true;
+      if (plan.flags != nullptr) {
+        if (threadIdx.x == 0) s_fail = 0;
+        __syncthreads();
+        const unsigned int want = *plan.halo_seq + 1u;
+        if ((int)threadIdx.x < plan.n_flag_peers) {
+          const unsigned long long* flag = plan.flags + plan.flag_peers[threadIdx.x];
+          const long long t0 = clock64();
+          while ((unsigned int)bk_ld_acquire_sys_u64(flag) != want) {
+            if (clock64() - t0 > BK_P2P_TIMEOUT_CYCLES) {
+              s_fail = 1;
+              break;
+            }
+          }
+        }
+        __syncthreads();
+        if (s_fail) {
+          if (threadIdx.x == 0) *plan.err_flag = 1u;
+          ok = false;
+        }
+      }
+      if (ok && wid < BK_WARPS) {
+        const int warps = (int)gridDim.x * BK_WARPS;
+        for (int i = (int)blockIdx.x * BK_WARPS + wid; i < plan.n_deferred; i += warps) {
+          const int c0 = __ldg(plan.deferred + i);
+          const unsigned int m = __ldg(plan.masks + (size_t)c0 * 32 + lane);
+          const int slot = __ldg(plan.pids + c0) & (BK_MASK_PID_GHOST - 1);
+          if (slot != cur) {
+            bk_mask_load_pattern<T>(plan.ptab, slot, pat);
+            cur = slot;
+          }
+          bk_mask_chunk<T, MODE, DOTS, true, false>(a, pat, x, xg, c0 * 32 + lane, m, n32, acc);
+        }
+      }
+    }
+  }
+  if constexpr (DOTS != 0) {
+    bk_grid_reduce<R, Epi, BK_WARPS + 1>(acc, sc, epi);
+  }
+}

@@ -357,7 +357,7 @@ def test_solvers_bitwise_deterministic(ma, manifest, name):
     assert torch.equal(xs[0], xs[1]) and torch.equal(xs[0], xs[2])
 
 
-@pytest.mark.parametrize("opts", [dict(persistent=0), dict(persistent=0, use_compress=2), dict(persistent=0, mask_group=1, mask_ctas=2), dict(persistent=0, mask_group=3, mask_ctas=6, snake=0), dict(persistent=0, fuse_xpay=1), dict(persistent=0, fuse_xpay=0), dict(persistent=0, snake=0), dict(persistent=0, fuse_xpay=1, snake=0), dict(persistent=0, chunk=2), dict(persistent=0, use_tma=0), dict(persistent=0, use_compress=0), dict(persistent=0, use_compress=1),
+@pytest.mark.parametrize("opts", [dict(persistent=0), dict(persistent=0, use_compress=2), dict(persistent=0, mask_window=0), dict(persistent=0, mask_window=0, mask_prefetch=0), dict(persistent=0, mask_wgroup=2, mask_ctas=2, tma_stages=2), dict(persistent=0, mask_wgroup=8, mask_ctas=3), dict(persistent=0, mask_group=1, mask_ctas=2), dict(persistent=0, mask_group=3, mask_ctas=6, snake=0), dict(persistent=0, fuse_xpay=1), dict(persistent=0, fuse_xpay=0), dict(persistent=0, snake=0), dict(persistent=0, fuse_xpay=1, snake=0), dict(persistent=0, chunk=2), dict(persistent=0, use_tma=0), dict(persistent=0, use_compress=0), dict(persistent=0, use_compress=1),
                                   dict(persistent=0, grid_mult_spmv=2, grid_mult_vec=2), dict(persistent=1)])
 def test_cg_kernel_variants(ma, manifest, opts):
     from pytorch_sparse_solver import _native
@@ -1146,10 +1146,20 @@ def test_pair_coded_spmv_stress(n, offsets, drop, pov, expect5, dtype):
         m6 = _native.register_matrix(A, dtype)
         y6, d6 = m6.spmv_dot(x, w)
         k6 = m6.info()["kernel"]
-        b_ = torch.randn(n, dtype=dtype, device="cuda", generator=g)
+        h.set_option("mask_window", 0)           # LDG gathers instead of the TMA-staged windows: same bits
+        y6l, d6l = m6.spmv_dot(x, w)
+        h.set_option("mask_window", 1)
+        h.set_option("mask_wgroup", 2)
+        h.set_option("tma_stages", 2)
+        y6w, d6w = m6.spmv_dot(x, w)
     finally:
         h.set_option("use_compress", 3)
+        h.set_option("mask_window", 1)
+        h.set_option("mask_wgroup", 4)
+        h.set_option("tma_stages", 0)
         _native.clear_cache()
+    assert torch.equal(y6, y6l) and torch.equal(y6, y6w)
+    assert abs(float(d6) - float(d6l)) <= 1e-12 * float(w.abs() @ y6.abs() + 1e-300)
     assert k2 in (0, 2)
     if k2 == 2:
         assert (k5 == 5) == expect5, (k5, expect5)

@@ -66,6 +66,19 @@ def main():
              us_plain=1e3 * ms0, actual_gbs=actual / ms / 1e6, algorithmic_gbs=bytes_alg / ms / 1e6)
         if info["kernel"] == 6 and not args.quick:
             d_ctas, d_grp = h.get_option("mask_ctas"), h.get_option("mask_group")
+            for ctas in (2, 3, 4):
+                for wg in (2, 4, 8):
+                    for st in (0, 2, 3):
+                        h.set_option("mask_window", 1)
+                        h.set_option("mask_ctas", ctas)
+                        h.set_option("mask_wgroup", wg)
+                        h.set_option("tma_stages", st)
+                        ms = time_gpu(lambda: m.spmv_dot(x, x), reps=20)
+                        emit(what="spmv_maskw", mask_ctas=ctas, mask_wgroup=wg, tma_stages=st, us_dot=1e3 * ms,
+                             actual_gbs=actual / ms / 1e6)
+            h.set_option("tma_stages", 0)
+            h.set_option("mask_wgroup", 4)
+            h.set_option("mask_window", 0)
             for ctas in (2, 3, 4, 5):
                 for grp in (2, 4, 8, 16):
                     for pf in (0, 1):
@@ -78,6 +91,7 @@ def main():
             h.set_option("mask_prefetch", 1)
             h.set_option("mask_ctas", d_ctas)
             h.set_option("mask_group", d_grp)
+            h.set_option("mask_window", 1)
         W = args.window
         ms = time_gpu(lambda: m.cg(b, None, 0.0, 0.0, W), reps=3, warm=1)
         emit(what="cg_window", use_compress=uc, kernel=info["kernel"], us_per_iter=1e3 * ms / W, it_s=W / ms * 1e3)
