@@ -17,6 +17,7 @@
 #include "bk_sys.cuh"
 #include "bk_dist.cuh"
 #include "bk_vec.cuh"
+#include "bk_bicgstab_persist.cuh"
 
 template <typename T>
 struct bk_eps_of {
@@ -179,7 +180,7 @@ static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0
   bk_handle* h = sys.h;
   const long long n = sys.n();
   const size_t npad = ((size_t)n + 63) & ~(size_t)63;
-  BK_TRY(bk_ws_reserve(h, (size_t)(diag ? 9 : 7) * npad * sizeof(T)));
+  BK_TRY(bk_ws_reserve(h, (size_t)9 * npad * sizeof(T)));
   bk_bicg_vecs<T> v;
   v.x = (T*)h->ws;
   v.r = v.x + npad;
@@ -230,7 +231,33 @@ static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0
   };
   int64_t chunks = 0;
   bk_call_mark(h, "loop");
-  BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
+  bool persistent = false;
+  if constexpr (!Sys::kDist) {
+    // launch-bound (L2-resident) systems: the whole loop in ONE persistent kernel (bk_bicgstab_persist.cuh);
+    // phat / shat (unused without a preconditioner) serve as the second p / q buffers
+    const bk_csr* A = sys.A;
+    if (diag == nullptr && A->rowptr && A->col) {
+      bk_bp_args ga;
+      ga.rowptr = A->rowptr;
+      ga.col = A->col;
+      ga.val = A->val;
+      ga.n = n;
+      ga.x = v.x;
+      ga.r = v.r;
+      ga.rhat = v.rhat;
+      ga.p0 = v.p;
+      ga.p1 = v.phat;
+      ga.q0 = v.q;
+      ga.q1 = v.shat;
+      ga.s = v.s;
+      ga.t = v.t;
+      ga.st = st;
+      ga.partials = h->partials;
+      BK_TRY(bk_launch_persistent(h, bk_bicgstab_persistent_kernel<T, true>, bk_bicgstab_persistent_kernel<T, false>, ga,
+                                  n, s, &persistent));
+    }
+  }
+  if (!persistent) BK_TRY(bk_run_loop(h, s, use_graph, key, enqueue_chunk, &chunks));
   bk_call_mark(h, "final");
 
   BK_TRY((sys.template matvec<T, 1, 2>(v.x, v.t, nullptr, b, 0, bk_epi_final_r2{st}, s)));
@@ -249,7 +276,7 @@ static int bk_bicgstab_t(const Sys& sys, const void* b, void* x_user, int has_x0
   const bk_dev_state* fin = &h->st_host[3];
   bk_fill_result_isolve(fin, res, 2 * fin->k + (has_x0 ? 1 : 0));
   res->rr_last = fin->rs;
-  res->kernel_launches = chunks * chunk * 5 + 2 + (has_x0 ? 1 : 0) + 2;
+  res->kernel_launches = (persistent ? 1 : chunks * chunk * 5) + 2 + (has_x0 ? 1 : 0) + 2;
   bk_call_finish(h, res);
   return sys.check_comm(fin, "bicgstab");
 }

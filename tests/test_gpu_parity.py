@@ -357,7 +357,7 @@ def test_solvers_bitwise_deterministic(ma, manifest, name):
     assert torch.equal(xs[0], xs[1]) and torch.equal(xs[0], xs[2])
 
 
-@pytest.mark.parametrize("opts", [dict(persistent=0), dict(persistent=0, use_compress=2), dict(persistent=0, mask_window=0), dict(persistent=0, mask_window=0, mask_prefetch=0), dict(persistent=0, mask_wgroup=2, mask_ctas=2, tma_stages=2), dict(persistent=0, mask_wgroup=8, mask_ctas=3), dict(persistent=0, mask_group=1, mask_ctas=2), dict(persistent=0, mask_group=3, mask_ctas=6, snake=0), dict(persistent=0, fuse_xpay=1), dict(persistent=0, fuse_xpay=0), dict(persistent=0, snake=0), dict(persistent=0, fuse_xpay=1, snake=0), dict(persistent=0, chunk=2), dict(persistent=0, use_tma=0), dict(persistent=0, use_compress=0), dict(persistent=0, use_compress=1),
+@pytest.mark.parametrize("opts", [dict(persistent=0), dict(persistent=0, use_compress=2), dict(persistent=0, mask_window=1), dict(persistent=0, mask_prefetch=0), dict(persistent=0, mask_window=1, mask_wgroup=2, mask_ctas=2, tma_stages=2), dict(persistent=0, mask_window=1, mask_wgroup=8, mask_ctas=3), dict(persistent=0, mask_group=1, mask_ctas=2), dict(persistent=0, mask_group=3, mask_ctas=6, snake=0), dict(persistent=0, fuse_xpay=1), dict(persistent=0, fuse_xpay=0), dict(persistent=0, snake=0), dict(persistent=0, fuse_xpay=1, snake=0), dict(persistent=0, chunk=2), dict(persistent=0, use_tma=0), dict(persistent=0, use_compress=0), dict(persistent=0, use_compress=1),
                                   dict(persistent=0, grid_mult_spmv=2, grid_mult_vec=2), dict(persistent=1)])
 def test_cg_kernel_variants(ma, manifest, opts):
     from pytorch_sparse_solver import _native
@@ -771,6 +771,41 @@ def test_gmres_persistent_kernel_vs_multi_kernel(ma, manifest, name):
         assert float(xp.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("name", ["bicgstab_cd3d16_rand", "bicgstab_cd3d16_x0", "bicgstab_cd3d16_fixed10",
+                                  "bicgstab_cd3d16_fixed1", "bicgstab_zero_rhs", "bicgstab_cd3d64_rand_digest"])
+def test_bicgstab_persistent_kernel_vs_multi_kernel(ma, manifest, name):
+    """Launch-bound systems run the whole BiCGStab loop in ONE persistent kernel (bk_bicgstab_persist.cuh: a thread-block
+    cluster with its hardware barrier up to 16384 rows, a cooperative grid above): same iteration counts and info as the
+    graph-launched path, x to rounding, bitwise reproducible."""
+    from pytorch_sparse_solver import _native
+    h = _native.Handle.get(torch.device("cuda"))
+    entry, data, xp, infop = _solve_case(ma, name, manifest)
+    rp = dict(_last())
+    _check_against_golden(entry, data, xp, infop)
+    if entry["n"] <= 200000:
+        assert rp["loop_mode_used"] == 3 or rp["iterations"] == 0
+    _e, _d, xp2, _i = _solve_case(ma, name, manifest)
+    assert torch.equal(xp, xp2)
+    try:
+        h.set_option("persistent", 0)
+        _e, _d, xm, infom = _solve_case(ma, name, manifest)
+        rm = dict(_last())
+        h.set_option("persistent", 1)
+        h.set_option("persistent_cluster", 0)       # cooperative-grid variant
+        _e, _d, xg, infog = _solve_case(ma, name, manifest)
+        rg = dict(_last())
+    finally:
+        h.set_option("persistent", 1)
+        h.set_option("persistent_cluster", 1)
+    assert rm["loop_mode_used"] == 2
+    assert infop == infom == infog == entry["info"]
+    assert abs(rp["iterations"] - rm["iterations"]) <= 1 and rg["iterations"] == rp["iterations"]
+    if float(torch.linalg.norm(xm)) > 0:
+        assert rel_diff(xp, xm) <= 1e-10 and rel_diff(xg, xm) <= 1e-10
+    else:
+        assert float(xp.abs().max()) == 0.0
+
+
 def test_gmres_restart_above_native_limit(ma, manifest):
     """The reference accepts any restart; above the native limit (256) the solve runs on the generic route."""
     entry = manifest["cases"]["gmres_cd3d12_batched"]
@@ -1146,15 +1181,14 @@ def test_pair_coded_spmv_stress(n, offsets, drop, pov, expect5, dtype):
         m6 = _native.register_matrix(A, dtype)
         y6, d6 = m6.spmv_dot(x, w)
         k6 = m6.info()["kernel"]
-        h.set_option("mask_window", 0)           # LDG gathers instead of the TMA-staged windows: same bits
+        h.set_option("mask_window", 1)           # gathers from TMA-staged shared-memory windows instead of LDG: same bits
         y6l, d6l = m6.spmv_dot(x, w)
-        h.set_option("mask_window", 1)
         h.set_option("mask_wgroup", 2)
         h.set_option("tma_stages", 2)
         y6w, d6w = m6.spmv_dot(x, w)
     finally:
         h.set_option("use_compress", 3)
-        h.set_option("mask_window", 1)
+        h.set_option("mask_window", 0)
         h.set_option("mask_wgroup", 4)
         h.set_option("tma_stages", 0)
         _native.clear_cache()
