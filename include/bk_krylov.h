@@ -185,6 +185,18 @@ int bk_axpby(bk_handle* h, int64_t n, int dtype, double a, const void* x, double
  * (the stop test, as in the reference :841) instead of one per dot product. */
 int bk_axpby_dev(bk_handle* h, int64_t n, int dtype, double sa, const double* a_dev, const void* x, double sb,
                  const double* b_dev, const void* y, void* z, void* stream);
+/* z = blockdiag(inv) r: block-Jacobi preconditioner application (what users of the reference write as
+ * M = lambda r: (Binv @ r.view(-1, bs, 1)).view(-1)).  inv: device [ceil(n/bs)][bs][bs] row-major inverses of the
+ * diagonal blocks, dtype as the vectors.  r and z must not alias. */
+int bk_block_apply(bk_handle* h, int64_t n, int bs, int dtype, const void* inv, const void* r, void* z, void* stream);
+/* complex128 vectors stored as interleaved (re, im) doubles, 16-byte aligned (what torch.view_as_real gives):
+ * bk_cdot: out2[0] + i out2[1] = sum conj(x_k) y_k (device, fp64 x 2) — torch.vdot, reference _vdot :86-91;
+ * bk_caxpby: z = (ar + i ai) x + (br + i bi) y.  With the complex matrix registered as its real-equivalent 2n x 2n CSR
+ * ([[re, -im], [im, re]] blocks; module_a/complex_route.py) these serve the reference's complex code path (:100-127,
+ * :1220) on the device. */
+int bk_cdot(bk_handle* h, int64_t n_complex, const void* x, const void* y, double* out2, void* stream);
+int bk_caxpby(bk_handle* h, int64_t n_complex, double ar, double ai, const void* x, double br, double bi,
+              const void* y, void* z, void* stream);
 /* z = x / d — true division, the reference's `y / norm` (_safe_normalize :266-272) */
 int bk_div_scalar(bk_handle* h, int64_t n, int dtype, const void* x, double d, void* z, void* stream);
 

@@ -104,6 +104,32 @@ def main():
             r2[name] = dict(kind=kind, kwargs=kw, n=n, reference_raises=f"{type(e).__name__}: {e}"[:300])
             print(f"  {name}: reference raises {type(e).__name__}: {str(e)[:120]}")
 
+    # ---- block-Jacobi preconditioner written the way users of the reference would (torch.bmm with the block inverses) ---
+    from pytorch_sparse_solver.module_a.preconditioners import BlockJacobiPreconditioner
+    for kind, A, kw, bs in (("cg", problems.scaled_poisson3d_csr(8), dict(tol=1e-10), 4),
+                            ("bicgstab", problems.scaled_convdiff3d_csr(8), dict(tol=1e-10), 8),
+                            ("gmres", problems.scaled_convdiff3d_csr(8), dict(tol=1e-10, restart=20), 3)):
+        Binv = BlockJacobiPreconditioner.diagonal_block_inverses(A, bs)
+        n = A.shape[0]
+        nb = Binv.shape[0]
+
+        def Mb(r, Binv=Binv, bs=bs, n=n, nb=nb):
+            rp = torch.zeros(nb * bs, dtype=r.dtype)
+            rp[:n] = r
+            return torch.bmm(Binv, rp.view(nb, bs, 1)).view(-1)[:n]
+        b0, _ = problems.manufactured_rhs(A, 6)
+        calls = {"n": 0}
+
+        def Aop(v, A=A, calls=calls):
+            calls["n"] += 1
+            return torch.matmul(A, v)
+        x, info = getattr(ref, kind)(Aop, b0, M=Mb, **kw)
+        name = f"{kind}_blockjacobi_bs{bs}"
+        np.savez_compressed(GOLD / f"{name}.npz", b=b0.numpy(), x=x.numpy())
+        r2[name] = dict(kind=kind, info=int(info), kwargs=kw, n=int(n), block_size=bs, matvecs_ref=calls["n"],
+                        gen=dict(matrix="scaled_poisson3d" if kind == "cg" else "scaled_convdiff3d", n=8, seed=7))
+        print(f"  pinned {name}: info {info}, matvecs {calls['n']}")
+
     if "--full" in sys.argv:
         t0 = time.time()
         A = problems.convdiff3d_csr(256)

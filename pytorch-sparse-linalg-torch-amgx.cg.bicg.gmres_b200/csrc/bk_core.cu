@@ -1361,6 +1361,73 @@ extern "C" int bk_div_scalar(bk_handle* h, int64_t n, int dtype, const void* x, 
   return bk_fail(BK_ERR_ARG, "bk_div_scalar: bad dtype %d", dtype);
 }
 
+// ---- block-Jacobi application: z = blockdiag(inv) r, inv = [nblocks][bs][bs] row-major ---------------
+template <typename T>
+__global__ void bk_block_apply_kernel(const T* __restrict__ inv, const T* __restrict__ r, T* __restrict__ z,
+                                      long long n, int bs) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += stride) {
+    const long long blk = row / bs;
+    const int lr = (int)(row - blk * bs);
+    const T* __restrict__ m = inv + ((size_t)blk * bs + lr) * bs;
+    const long long c0 = blk * bs;
+    T sum = T(0);
+    for (int c = 0; c < bs; ++c) {
+      const long long col = c0 + c;
+      if (col < n) sum = fma(m[c], r[col], sum);
+    }
+    z[row] = sum;
+  }
+}
+
+extern "C" int bk_block_apply(bk_handle* h, int64_t n, int bs, int dtype, const void* inv, const void* r, void* z,
+                              void* stream) {
+  if (!h || (n > 0 && (!inv || !r || !z))) return bk_fail(BK_ERR_ARG, "bk_block_apply: null argument");
+  if (bs < 1 || bs > 64) return bk_fail(BK_ERR_ARG, "bk_block_apply: block size must be in [1, 64]");
+  if (r == z) return bk_fail(BK_ERR_ARG, "bk_block_apply: r and z must not alias");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (n == 0) return BK_OK;
+  const int g = bk_grid_rows(h->num_sms * 8, n, 256);
+  if (dtype == BK_F64)
+    bk_block_apply_kernel<double><<<g, 256, 0, (cudaStream_t)stream>>>((const double*)inv, (const double*)r, (double*)z, n, bs);
+  else if (dtype == BK_F32)
+    bk_block_apply_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)inv, (const float*)r, (float*)z, n, bs);
+  else
+    return bk_fail(BK_ERR_ARG, "bk_block_apply: bad dtype %d", dtype);
+  BK_KERNEL_CHECK();
+  return BK_OK;
+}
+
+// ---- complex128 building blocks (reference :86-127, :1220): vectors are interleaved (re, im) fp64 -------
+extern "C" int bk_cdot(bk_handle* h, int64_t n_complex, const void* x, const void* y, double* out2, void* stream) {
+  if (!h || !out2 || (n_complex > 0 && (!x || !y))) return bk_fail(BK_ERR_ARG, "bk_cdot: null argument");
+  if (!bk_aligned16(x) || !bk_aligned16(y)) return bk_fail(BK_ERR_ARG, "bk_cdot: complex vectors must be 16-byte aligned");
+  BK_CUDA(cudaSetDevice(h->device));
+  bk_op_cdot op;
+  op.x = (const double*)x;
+  op.y = (const double*)y;
+  op.out = out2;
+  return bk_launch_ew<double>(h, op, 2 * n_complex, true, bk_slot(h, 0), (cudaStream_t)stream);
+}
+
+extern "C" int bk_caxpby(bk_handle* h, int64_t n_complex, double ar, double ai, const void* x, double br, double bi,
+                         const void* y, void* z, void* stream) {
+  if (!h || (n_complex > 0 && (!x || !y || !z))) return bk_fail(BK_ERR_ARG, "bk_caxpby: null argument");
+  if (!bk_aligned16(x) || !bk_aligned16(y) || !bk_aligned16(z))
+    return bk_fail(BK_ERR_ARG, "bk_caxpby: complex vectors must be 16-byte aligned");
+  BK_CUDA(cudaSetDevice(h->device));
+  if (n_complex == 0) return BK_OK;
+  bk_op_caxpby op;
+  op.x = (const double*)x;
+  op.y = (const double*)y;
+  op.z = (double*)z;
+  op.ar = ar;
+  op.ai = ai;
+  op.br = br;
+  op.bi = bi;
+  return bk_launch_ew<double>(h, op, 2 * n_complex, true, bk_slot(h, 0), (cudaStream_t)stream);
+}
+
 // ---- gradient with respect to the stored entries of A -----------------------------------------
 // For A x = b and a loss L(x):  dL/dA_ij = -(A^-T dL/dx)_i x_j = -g_i x_j, evaluated on the sparsity pattern only
 // (an SDDMM-shaped kernel).  The reference returns no gradient for A (torch_sparse_linalg.py:1248); its Modules B/C

@@ -186,18 +186,20 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
   // masks gather nothing), so the tail of the last group needs no test.
   const int my_groups = (ngroups > (int)blockIdx.x) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int T_ = my_groups << gshift;
-  auto chunk_at = [&](int t) -> int {
+  // this lane's row in chunk t of the warp's sequence; inside a group consecutive chunks are 256 rows apart, so the
+  // hot loop advances with one add and re-derives the row only when it enters a new group
+  auto row_at = [&](int t) -> int {
     const int g = (int)blockIdx.x + (t >> gshift) * (int)gridDim.x;
     const int gg = reverse ? (ngroups - 1 - g) : g;
-    return (((gg << gshift) + (t & gmask)) << 3) + wid;
+    return ((((gg << gshift) + (t & gmask)) << 3) + wid) * 32 + lane;
   };
   int t = 0;
-  int ch_next = 0, pid_next = 0;
+  int row_next = 0, pid_next = 0;
   unsigned int m_next = 0u;
   if (T_ > 0) {
-    ch_next = chunk_at(0);
-    m_next = __ldg(masks + (size_t)ch_next * 32 + lane);
-    pid_next = __ldg(pids + ch_next);
+    row_next = row_at(0);
+    m_next = __ldg(masks + row_next);
+    pid_next = __ldg(pids + (row_next >> 5));
   }
   // L2 prefetch, one visit ahead: ncu showed the kernel waiting on DRAM latency (one first-touch line of x per chunk,
   // ~1700 cycles per chunk with 8 warps per scheduler; DRAM 32 %, issue 44 %).  When a CTA starts a group, one thread
@@ -226,15 +228,19 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
       cur = slot;
     }
     do {
-      const int row = ch_next * 32 + lane;
+      const int row = row_next;
       const unsigned int m = m_next;
       const bool ghost_chunk = GHOST && (pid_next & BK_MASK_PID_GHOST);
       ++t;
-      if (pf && (t & gmask) == 0) prefetch_group((t >> gshift) + 1);
+      if ((t & gmask) != 0) {
+        row_next += 256;
+      } else {  // next group (1 step in 2^gshift)
+        if (pf) prefetch_group((t >> gshift) + 1);
+        row_next = (t < T_) ? row_at(t) : row_next;
+      }
       if (t < T_) {  // the next chunk's mask / pattern id are in flight while this one is computed
-        ch_next = chunk_at(t);
-        m_next = __ldg(masks + (size_t)ch_next * 32 + lane);
-        pid_next = __ldg(pids + ch_next);
+        m_next = __ldg(masks + row_next);
+        pid_next = __ldg(pids + (row_next >> 5));
       }
       if (!ghost_chunk) {  // (chunks with ghost entries: second phase)
         if (__all_sync(0xffffffffu, m == pat.full))

@@ -255,6 +255,74 @@ struct bk_op_div {
   __device__ void epilogue(const double*) const {}
 };
 
+// ---- complex128 vectors as interleaved (re, im) doubles: one fp64 pack (W = 2) is one complex number ----------------
+// out[0] + i out[1] = sum conj(x_k) y_k      (torch.vdot on complex tensors, reference _vdot :86-91)
+struct bk_op_cdot {
+  static constexpr int R = 2;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<double, W> a, b;
+  };
+  const double* x;
+  const double* y;
+  double* out;
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.a = bk_ld<double, W>(x + i);
+    in.b = bk_ld<double, W>(y + i);
+  }
+  template <int W>
+  __device__ void apply(long long, const In<W>& in, const Ctx&, double (&acc)[2]) const {
+    if constexpr (W == 2) {  // one (re, im) pack; the scalar instantiation is never launched (2n is even, aligned)
+      acc[0] += in.a.v[0] * in.b.v[0] + in.a.v[1] * in.b.v[1];
+      acc[1] += in.a.v[0] * in.b.v[1] - in.a.v[1] * in.b.v[0];
+    }
+  }
+  __device__ void epilogue(const double* s) const {
+    out[0] = s[0];
+    out[1] = s[1];
+  }
+};
+
+// z = a x + b y with complex scalars a, b (each product and sum rounded separately, like the reference's torch ops)
+struct bk_op_caxpby {
+  static constexpr int R = 0;
+  using Ctx = bk_noctx;
+  template <int W>
+  struct In {
+    bk_vec<double, W> a, b;
+  };
+  const double* x;
+  const double* y;
+  double* z;
+  double ar, ai, br, bi;
+  __device__ bool skip() const { return false; }
+  __device__ bool reverse() const { return false; }
+  __device__ Ctx prepare() const { return Ctx(); }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.a = bk_ld<double, W>(x + i);
+    in.b = bk_ld<double, W>(y + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx&, double (&)[1]) const {
+    if constexpr (W == 2) {  // one (re, im) pack; the scalar instantiation is never launched (2n is even, aligned)
+      const double xr = in.a.v[0], xi = in.a.v[1], yr = in.b.v[0], yi = in.b.v[1];
+      const double axr = bk_sub(bk_mul(ar, xr), bk_mul(ai, xi)), axi = bk_add(bk_mul(ar, xi), bk_mul(ai, xr));
+      const double byr = bk_sub(bk_mul(br, yr), bk_mul(bi, yi)), byi = bk_add(bk_mul(br, yi), bk_mul(bi, yr));
+      bk_vec<double, W> o;
+      o.v[0] = bk_add(axr, byr);
+      o.v[1] = bk_add(axi, byi);
+      bk_st<double, W>(z + i, o);
+    }
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
 // ---- CG --------------------------------------------------------------------------------------
 // x += alpha p ; r -= alpha Ap ; gamma' = r.r          (_cg_solve :846-850)
 // epilogue: beta = gamma'/gamma, gamma = gamma', k += 1, stop test of :841 for the NEXT iteration.

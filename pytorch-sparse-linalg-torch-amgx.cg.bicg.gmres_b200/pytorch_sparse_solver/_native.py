@@ -87,6 +87,9 @@ _SIGNATURES = {
     "bk_axpby": (C.c_int, [_VP, C.c_int64, C.c_int, C.c_double, _VP, C.c_double, _VP, _VP, _VP]),
     "bk_axpby_dev": (C.c_int, [_VP, C.c_int64, C.c_int, C.c_double, _VP, _VP, C.c_double, _VP, _VP, _VP, _VP]),
     "bk_div_scalar": (C.c_int, [_VP, C.c_int64, C.c_int, _VP, C.c_double, _VP, _VP]),
+    "bk_block_apply": (C.c_int, [_VP, C.c_int64, C.c_int, C.c_int, _VP, _VP, _VP, _VP]),
+    "bk_cdot": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP]),
+    "bk_caxpby": (C.c_int, [_VP, C.c_int64, C.c_double, C.c_double, _VP, C.c_double, C.c_double, _VP, _VP, _VP]),
     "bk_cg": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(bk_result), _VP]),
     "bk_bicgstab": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.c_int64, C.POINTER(bk_result),
                               _VP]),
@@ -485,6 +488,38 @@ def div_scalar(x: torch.Tensor, d: float, out: Optional[torch.Tensor] = None) ->
     with torch.cuda.device(x.device):
         _check(h.lib.bk_div_scalar(h.ptr, x.numel(), _dtype_code(x.dtype), x.data_ptr(), float(d), z.data_ptr(),
                                    _stream_ptr(x.device)), "bk_div_scalar")
+    return z
+
+
+def block_apply(inv: torch.Tensor, r: torch.Tensor, bs: int) -> torch.Tensor:
+    """z = blockdiag(inv) r (bk_block_apply); inv: [nblocks, bs, bs] contiguous, same dtype / device as r."""
+    h = Handle.get(r.device)
+    r = r.contiguous()
+    z = torch.empty_like(r)
+    with torch.cuda.device(r.device):
+        _check(h.lib.bk_block_apply(h.ptr, r.numel(), int(bs), _dtype_code(r.dtype), inv.data_ptr(), r.data_ptr(),
+                                    z.data_ptr(), _stream_ptr(r.device)), "bk_block_apply")
+    return z
+
+
+def cdot(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """sum conj(x) y for complex128 vectors given as interleaved fp64 (2n) tensors; returns a device tensor [re, im]."""
+    h = Handle.get(x.device)
+    out = torch.empty(2, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _check(h.lib.bk_cdot(h.ptr, x.numel() // 2, x.data_ptr(), y.data_ptr(), out.data_ptr(), _stream_ptr(x.device)),
+               "bk_cdot")
+    return out
+
+
+def caxpby(a: complex, x: torch.Tensor, b: complex, y: torch.Tensor) -> torch.Tensor:
+    """z = a x + b y for complex128 vectors given as interleaved fp64 (2n) tensors, complex scalars a, b."""
+    h = Handle.get(x.device)
+    z = torch.empty_like(x)
+    a, b = complex(a), complex(b)
+    with torch.cuda.device(x.device):
+        _check(h.lib.bk_caxpby(h.ptr, x.numel() // 2, a.real, a.imag, x.data_ptr(), b.real, b.imag, y.data_ptr(),
+                               z.data_ptr(), _stream_ptr(x.device)), "bk_caxpby")
     return z
 
 

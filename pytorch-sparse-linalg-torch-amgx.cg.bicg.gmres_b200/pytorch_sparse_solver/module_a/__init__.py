@@ -5,7 +5,8 @@ from .krylov import (
     cg_differentiable, bicgstab_differentiable, gmres_differentiable,
     LinearSolveFunction,
 )
-from .preconditioners import JacobiPreconditioner
+from .preconditioners import BlockJacobiPreconditioner, JacobiPreconditioner
+from .mixed_precision import refined_solve
 from .torch_tree_util import tree_leaves, tree_map, tree_flatten, tree_unflatten, Partial
 
 __all__ = [
@@ -13,6 +14,8 @@ __all__ = [
     'cg_differentiable', 'bicgstab_differentiable', 'gmres_differentiable',
     'LinearSolveFunction',
     'JacobiPreconditioner',   # addition: built-in M that keeps cg() on the device
+    'BlockJacobiPreconditioner',   # addition: block-diagonal M applied by one library kernel
+    'refined_solve',          # addition: mixed-precision iterative refinement
     'tree_leaves', 'tree_map', 'tree_flatten', 'tree_unflatten', 'Partial',
 ]
 

@@ -806,6 +806,92 @@ def test_bicgstab_persistent_kernel_vs_multi_kernel(ma, manifest, name):
         assert float(xp.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("name", ["complex_cg_herm48", "complex_bicgstab_gen48", "complex_gmres_gen48"])
+@pytest.mark.parametrize("layout", ["dense", "csr"])
+def test_complex_systems_vs_reference(ma, manifest, name, layout):
+    """complex128 systems (reference :86-127, :1220) through the real-equivalent registration + bk_cdot / bk_caxpby;
+    goldens: the unmodified reference on the same dense complex matrices."""
+    entry = manifest["round2"][name]
+    data = load_case(name)
+    A = data["A"].cuda()
+    if layout == "csr":
+        A = A.to_sparse_csr()
+    b = data["b"].cuda()
+    x, info = getattr(ma, entry["kind"])(A, b, **entry["kwargs"])
+    assert _last()["route"] == "complex" and info == entry["info"]
+    assert x.dtype == torch.complex128 and x.is_cuda
+    assert float(torch.linalg.norm(x.cpu() - data["x"]) / torch.linalg.norm(data["x"])) <= 1e-9
+    Ad = data["A"].cuda()
+    assert float(torch.linalg.norm(b - Ad @ x) / torch.linalg.norm(b)) <= 1e-9
+    if entry["kind"] == "gmres":
+        xi, infoi = ma.gmres(A, b, solve_method="incremental", **entry["kwargs"])
+        assert infoi == 0 and float(torch.linalg.norm(xi - x) / torch.linalg.norm(x)) <= 1e-7
+    # CPU tensors are staged through the device; the adjoint solve uses A^H
+    xc, infoc = getattr(ma, entry["kind"])(data["A"], data["b"], **entry["kwargs"])
+    assert not xc.is_cuda and infoc == 0 and float(torch.linalg.norm(xc - data["x"]) / torch.linalg.norm(data["x"])) <= 1e-9
+    b1 = b.clone().requires_grad_(True)
+    x1, _ = getattr(ma, entry["kind"])(A, b1, **entry["kwargs"])
+    torch.view_as_real(x1).pow(2).sum().backward()
+    g_exact = torch.linalg.solve(Ad.conj().T, 2 * x1.detach())
+    assert float(torch.linalg.norm(b1.grad - g_exact) / torch.linalg.norm(g_exact)) <= 1e-7
+
+
+@pytest.mark.parametrize("name", ["cg_blockjacobi_bs4", "bicgstab_blockjacobi_bs8", "gmres_blockjacobi_bs3"])
+def test_block_jacobi_preconditioner(ma, manifest, name):
+    """BlockJacobiPreconditioner (one library kernel per application) against the reference run with the equivalent
+    torch.bmm lambda; same matvec counts within the +-2 iteration band, x to 1e-9 (badly scaled systems)."""
+    from pytorch_sparse_solver import _native
+    entry = manifest["round2"][name]
+    data = load_case(name)
+    A_cpu = build_matrix(entry["gen"])
+    A = A_cpu.cuda()
+    bs = entry["block_size"]
+    M = ma.BlockJacobiPreconditioner(A, block_size=bs)
+    # the kernel against a dense product
+    r = torch.randn(A.shape[0], dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    Binv = ma.BlockJacobiPreconditioner.diagonal_block_inverses(A_cpu, bs)
+    ref = torch.block_diag(*Binv)[:A.shape[0], :A.shape[0]] @ r.cpu()
+    assert rel_diff(M(r), ref) <= 1e-14
+    calls = {"n": 0}
+    reg = _native.register_matrix(A)
+
+    def Aop(v):
+        calls["n"] += 1
+        return reg.spmv(v)
+    x, info = getattr(ma, entry["kind"])(Aop, data["b"].cuda(), M=M, **entry["kwargs"])
+    assert info == entry["info"] and _last()["route"] == "generic"
+    per_it = 2 if entry["kind"] == "bicgstab" else 1
+    assert abs(calls["n"] - entry["matvecs_ref"]) <= 2 * per_it + (30 if entry["kind"] == "gmres" else 0)
+    assert rel_diff(x, data["x"]) <= 1e-9
+    # tensor A: the implicit-diff backward re-uses M on A^T
+    b1 = data["b"].cuda().requires_grad_(True)
+    x1, _ = getattr(ma, entry["kind"])(A, b1, M=M, **entry["kwargs"])
+    (x1 ** 2).sum().backward()
+    Ad = A_cpu.to_dense()
+    g_exact = torch.linalg.solve(Ad.T, 2.0 * torch.linalg.solve(Ad, data["b"]))
+    assert rel_diff(b1.grad, g_exact) <= 1e-6
+
+
+@pytest.mark.parametrize("method", ["cg", "bicgstab", "gmres"])
+def test_mixed_precision_iterative_refinement(ma, manifest, method):
+    """fp32 inner solves + fp64 residual: the final fp64 x must meet the fp64 tolerance and agree with
+    the reference's fp64 solution."""
+    name = "cg_p3d64_ones_digest" if method == "cg" else "bicgstab_cd3d64_rand_digest"
+    entry = manifest["cases"][name]
+    data = load_case(name)
+    A_cpu = build_matrix(entry["gen"])
+    A = A_cpu.cuda()
+    from pytorch_sparse_solver import problems
+    b = (torch.ones(entry["n"], dtype=torch.float64) if method == "cg" else problems.manufactured_rhs(A_cpu, 0)[0]).cuda()
+    x, info = ma.refined_solve(A, b, method=method, tol=1e-11, inner_tol=1e-4, restart=30)
+    r = _last()
+    assert info == 0 and x.dtype == torch.float64 and r["refinements"] >= 2
+    assert r["final_residual"] <= 1e-11 * r["b_norm"] * 1.01
+    idx = data["x_sample_idx"]
+    assert rel_diff(x.cpu()[idx], data["x_sample"]) <= 1e-8      # the digests were solved to tol 1e-8 / 1e-10
+    assert abs(float(torch.linalg.norm(x)) - entry["x_norm"]) <= 1e-8 * entry["x_norm"]
+
+
 def test_gmres_restart_above_native_limit(ma, manifest):
     """The reference accepts any restart; above the native limit (256) the solve runs on the generic route."""
     entry = manifest["cases"]["gmres_cd3d12_batched"]
