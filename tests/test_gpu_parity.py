@@ -597,24 +597,36 @@ def test_bicgstab_convdiff3d_256_full_size(ma, manifest):
 
 
 def test_bicgstab_convdiff3d_256_tol1e10_parity_gate(ma, manifest):
-    """Config 3 at the tolerance SURVEY 8c / 8d prescribe for the x gate (tol 1e-10: the reference's self-noise is
-    4e-13 there, against 2e-10 at tol 1e-8): iterations +-2, ||x|| and 4096 sampled entries to 1e-10 against the
-    digest of the unmodified reference (oracle/pin_round2.py --full)."""
+    """Config 3 at the tolerance SURVEY 8c / 8d prescribe for the x gate (tol 1e-10), against the digest of the unmodified
+    reference (oracle/pin_round2.py --full: 477 iterations, ||x||, 4096 sampled entries).
+
+    What the gate can be at this size was MEASURED with the reference itself (oracle/ref_selfnoise.py, manifest
+    round2.ref_selfnoise_bicgstab_cd3d256): run with 8 and with 3 OpenMP threads — i.e. with two summation orders in
+    torch's CPU dot / SpMV — the reference takes 477 vs 475 iterations and its two solutions differ by 1.5e-9 (SURVEY's
+    4e-13 was measured at 128^3 and does not carry over to 256^3).  A third summation order (ours) is held to the same
+    band: iterations within 6 of the digest, x within 5e-9; the TRUE residual meets tol and x is within 1e-8 of the
+    manufactured solution."""
     from pytorch_sparse_solver import problems
     dg = manifest["survey_digests"]["bicgstab_cd3d256_rand_tol1e-10"]
     d2 = manifest["round2"]["digest_bicgstab_cd3d256_tol1e-10"]
+    noise = manifest["round2"]["ref_selfnoise_bicgstab_cd3d256"]
     data = load_case("digest_bicgstab_cd3d256_tol1e-10")
     assert d2["x_norm"] == dg["x_norm"] and d2["info"] == dg["info"] == 0
+    assert noise["rel_diff_between_runs"] > 1e-10 and abs(noise["8"]["iterations_est"] - noise["3"]["iterations_est"]) >= 2
     A = problems.convdiff3d_csr(256, device="cuda")
     b, xt = problems.manufactured_rhs(A, 0)
     x, info = ma.bicgstab(A, b, tol=1e-10)
     res = _last()
     assert info == 0
-    assert abs(res["iterations"] - dg["iterations"]) <= 2, (res["iterations"], dg["iterations"])
-    assert abs(float(torch.linalg.norm(x)) - dg["x_norm"]) <= FP64_TOL * dg["x_norm"]
-    assert rel_diff(x.cpu()[data["x_sample_idx"]], data["x_sample"]) <= FP64_TOL
+    assert abs(res["iterations"] - dg["iterations"]) <= 6, (res["iterations"], dg["iterations"])
+    gate = max(5e-9, 3.0 * noise["rel_diff_between_runs"])
+    assert abs(float(torch.linalg.norm(x)) - dg["x_norm"]) <= gate * dg["x_norm"]
+    assert rel_diff(x.cpu()[data["x_sample_idx"]], data["x_sample"]) <= gate
     assert res["final_residual"] / res["b_norm"] <= 1e-10
     assert rel_diff(x, xt) <= 1e-8
+    # at a size where the reference does not differ from itself the gate is the north star's: 64^3, tol 1e-10
+    entry, data64, x64, info64 = _solve_case(ma, "bicgstab_cd3d64_rand_digest", manifest)
+    _check_against_golden(entry, data64, x64, info64)
 
 
 @pytest.mark.parametrize("kind", ["cg", "bicgstab", "gmres"])
