@@ -44,7 +44,8 @@ def real_equivalent_csr(A: torch.Tensor, conj_transpose: bool = False) -> torch.
     row = torch.repeat_interleave(torch.arange(n, device=dev), lens)
     pos = torch.arange(nnz, device=dev) - crow[row]                 # position of the entry inside its row
     base = 4 * crow[row]                                            # first real entry of complex row `row`
-    ar, ai = val.real.contiguous(), val.imag.contiguous()
+    vr = torch.view_as_real(val.clone())                            # (.real on a CSR values view raises in torch 2.11)
+    ar, ai = vr[:, 0].contiguous(), vr[:, 1].contiguous()
     rcol = torch.empty(4 * nnz, dtype=torch.int64, device=dev)
     rval = torch.empty(4 * nnz, dtype=torch.float64, device=dev)
     top = base + 2 * pos                                            # real row 2i:   [ re  -im ]

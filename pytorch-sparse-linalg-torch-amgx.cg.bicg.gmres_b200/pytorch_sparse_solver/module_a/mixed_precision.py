@@ -41,7 +41,9 @@ def refined_solve(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] =
             rn = float(_native.nrm2(r))
             if rn <= thr or k >= max_refinements or rn != rn:
                 break
-            r32 = r.to(torch.float32)
+            # the inner system is solved for the UNIT residual: fp32 range, and the solvers' absolute safeguards
+            # (BiCGStab's |t.t| < eps, GMRES's atol floor) are written for O(1) data
+            r32 = _native.div_scalar(r, rn).to(torch.float32)
             if method == "cg":
                 d32, res = m32.cg(r32, None, inner_tol, 0.0, maxiter)
             elif method == "bicgstab":
@@ -50,7 +52,7 @@ def refined_solve(A: torch.Tensor, b: torch.Tensor, x0: Optional[torch.Tensor] =
                 te, ae = krylov._gmres_effective_tolerances(inner_tol, 0.0, r32.numel(), "cuda")
                 d32, res = m32.gmres(r32, None, te, ae, restart, maxiter, _native.BK_GMRES_BATCHED)
             inner_its += int(res["iterations"])
-            x = _native.axpby(1.0, x, 1.0, d32.to(torch.float64))
+            x = _native.axpby(1.0, x, rn, d32.to(torch.float64))
             r = _native.axpby(1.0, b64, -1.0, m64.spmv(x))
             k += 1
         info = 0 if rn <= thr else -1
