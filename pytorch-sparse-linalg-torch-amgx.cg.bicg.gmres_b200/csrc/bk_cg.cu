@@ -247,6 +247,7 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
     a.y = v.ap;
     a.guard = 1;
     a.use_parity = h->snake;
+    a.l2_hints = h->l2_hints;
     bk_epi_cg_pAp epi{st};
     BK_TRY((bk_launch_spmv<0, 1, 0>(h, A, a, bk_slot(h, 0), epi, s)));
     pcur = v.p[0];
@@ -267,6 +268,7 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
       op.r = v.r;
       op.st = st;
       op.snake = h->snake;
+      op.hints = h->l2_hints;
       BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
     }
     {
@@ -276,6 +278,7 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
       op.r = v.r;
       op.st = st;
       op.snake = h->snake;
+      op.hints = h->l2_hints;
       BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), s));
     }
   }
@@ -337,7 +340,7 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   const int chunk = bk_pick_chunk(h, bytes_iter, fuse ? 2 : 3);
   const bool use_graph = h->loop_mode != BK_LOOP_STREAM;
   uint64_t key[6] = {1 /*cg*/, A->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
-                     (uint64_t)A->dtype | ((uint64_t)fuse << 8) | ((uint64_t)h->snake << 9) | ((uint64_t)chunk << 16),
+                     (uint64_t)A->dtype | ((uint64_t)fuse << 8) | ((uint64_t)h->snake << 9) | ((uint64_t)(h->l2_hints & 15) << 10) | ((uint64_t)chunk << 16),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   auto enqueue_chunk = [&](cudaStream_t cs) -> int {
     for (int it = 0; it < chunk; ++it) BK_TRY(bk_cg_enqueue_iter<T>(h, A, v, it, fuse, cs));

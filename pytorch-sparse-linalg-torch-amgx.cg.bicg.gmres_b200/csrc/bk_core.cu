@@ -123,6 +123,7 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->chunk = (int)bk_env_int("BK_CHUNK", 0);
   h->fuse_xpay = (int)bk_env_int("BK_FUSE_XPAY", -1);  // -1 auto, 0 off, 1 on
   h->snake = (int)bk_env_int("BK_SNAKE", 1);
+  h->l2_hints = (int)bk_env_int("BK_L2_HINTS", 0);
   h->next_uid = 1;
   cudaError_t e;
   e = cudaMalloc(&h->partials, sizeof(double) * BK_NSLOT * BK_SLOT_ROWS * BK_MAXB);
@@ -226,6 +227,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "chunk")) return &h->chunk;
   if (!strcmp(key, "fuse_xpay")) return &h->fuse_xpay;
   if (!strcmp(key, "snake")) return &h->snake;
+  if (!strcmp(key, "l2_hints")) return &h->l2_hints;
   return nullptr;
 }
 

@@ -183,6 +183,7 @@ struct bk_handle {
   int chunk;
   int fuse_xpay;
   int snake;
+  int l2_hints;  // bit 0: K2 streams Ap | bit 1: K3 streams x | bit 2: K3 streams r | bit 3: SpMV streams masks
   // reduction scratch
   double* partials;        // BK_NSLOT * BK_SLOT_ROWS * BK_MAXB
   unsigned int* counters;  // BK_NSLOT (+ spare)
@@ -335,6 +336,72 @@ __device__ __forceinline__ void bk_st(T* __restrict__ p, const bk_vec<T, W>& r) 
     t.z = r.v[2];
     t.w = r.v[3];
     *reinterpret_cast<float4*>(p) = t;
+  }
+}
+
+// The same with the streaming ("evict first") cache operator: for operands that nobody reads again before the L2 has
+// turned over, so that the vector the NEXT kernel of the iteration starts with keeps its place in the 126 MB L2.
+template <typename T, int W>
+__device__ __forceinline__ bk_vec<T, W> bk_ld_cs(const T* __restrict__ p) {
+  bk_vec<T, W> r;
+  if constexpr (W == 1) {
+    r.v[0] = __ldcs(p);
+  } else if constexpr (sizeof(T) == 8) {
+    double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+  } else {
+    float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    r.v[2] = t.z;
+    r.v[3] = t.w;
+  }
+  return r;
+}
+
+template <typename T, int W>
+__device__ __forceinline__ void bk_st_cs(T* __restrict__ p, const bk_vec<T, W>& r) {
+  if constexpr (W == 1) {
+    __stcs(p, r.v[0]);
+  } else if constexpr (sizeof(T) == 8) {
+    double2 t;
+    t.x = r.v[0];
+    t.y = r.v[1];
+    __stcs(reinterpret_cast<double2*>(p), t);
+  } else {
+    float4 t;
+    t.x = r.v[0];
+    t.y = r.v[1];
+    t.z = r.v[2];
+    t.w = r.v[3];
+    __stcs(reinterpret_cast<float4*>(p), t);
+  }
+}
+
+// ... and with an L2 "evict last" policy: the vector a kernel hands to the next kernel of the iteration.
+__device__ __forceinline__ unsigned long long bk_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bk_st_hint1(double* p, double v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bk_st_hint1(float* p, float v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+template <typename T, int W>
+__device__ __forceinline__ void bk_st_keep(T* __restrict__ p, const bk_vec<T, W>& r, unsigned long long pol) {
+  if constexpr (W == 1) {
+    bk_st_hint1(p, r.v[0], pol);
+  } else if constexpr (sizeof(T) == 8) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(r.v[0]), "d"(r.v[1]), "l"(pol)
+                 : "memory");
+  } else {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(r.v[0]), "f"(r.v[1]),
+                 "f"(r.v[2]), "f"(r.v[3]), "l"(pol)
+                 : "memory");
   }
 }
 

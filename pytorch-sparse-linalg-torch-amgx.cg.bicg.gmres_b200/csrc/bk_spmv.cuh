@@ -42,6 +42,7 @@ struct bk_spmv_args {
   int guard;        // 0 none | 1 st->done | 2 st->done || st->g_cycle_over | 3 st->done || st->exit_early
   int reverse;      // 1: sweep row blocks from the end (snake order for L2 reuse)
   int use_parity;   // 1: reverse ^= st->parity
+  int l2_hints;     // kernel 6: bit 3 masks / pattern ids stream through L2 | bit 4 y is stored "evict last"
 };
 
 __device__ __forceinline__ bool bk_guard_skip(const bk_dev_state* st, int guard) {

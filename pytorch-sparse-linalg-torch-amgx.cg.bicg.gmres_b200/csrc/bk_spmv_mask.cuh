@@ -132,7 +132,8 @@ __device__ __forceinline__ float bk_ld_plain(const float* base, int off) {
 // a stencil matrix): no predicates, no zero-fill, no bounds test (a row with a non-empty mask exists).
 template <typename T, int MODE, int DOTS, bool GHOST, bool FAST>
 __device__ __forceinline__ void bk_mask_chunk(const bk_spmv_args& a, const bk_mask_pat<T>& p, const T* x, const T* xg,
-                                              const int row, const unsigned int m, const int n32, double* acc) {
+                                              const int row, const unsigned int m, const int n32, double* acc,
+                                              const unsigned long long pol = 0ull) {
   const T* xr = x + row;
   const T* xgr = GHOST ? xg + row : nullptr;
   T xv[BK_MASK_L];
@@ -148,7 +149,8 @@ __device__ __forceinline__ void bk_mask_chunk(const bk_spmv_args& a, const bk_ma
   if (FAST || row < n32) {
     T out = sum;
     if constexpr (MODE == 1) out = bk_sub(__ldg(static_cast<const T*>(a.b) + row), sum);
-    static_cast<T*>(a.y)[row] = out;
+    if (pol != 0ull) bk_st_hint1(static_cast<T*>(a.y) + row, out, pol);
+    else static_cast<T*>(a.y)[row] = out;
     if constexpr ((DOTS & 1) != 0)
       acc[0] += static_cast<double>(__ldg(static_cast<const T*>(a.w) + row)) * static_cast<double>(out);
     if constexpr ((DOTS & 2) != 0) acc[DOTS & 1] += static_cast<double>(out) * static_cast<double>(out);
@@ -177,6 +179,7 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
   double acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.0;
+  const unsigned long long pol = (a.l2_hints & 16) ? bk_policy_evict_last() : 0ull;
 
   bk_mask_pat<T> pat;
   int cur = -1;
@@ -244,9 +247,9 @@ bk_spmv_mask_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_scra
       }
       if (!ghost_chunk) {  // (chunks with ghost entries: second phase)
         if (__all_sync(0xffffffffu, m == pat.full))
-          bk_mask_chunk<T, MODE, DOTS, false, true>(a, pat, x, xg, row, m, n32, acc);
+          bk_mask_chunk<T, MODE, DOTS, false, true>(a, pat, x, xg, row, m, n32, acc, pol);
         else
-          bk_mask_chunk<T, MODE, DOTS, false, false>(a, pat, x, xg, row, m, n32, acc);
+          bk_mask_chunk<T, MODE, DOTS, false, false>(a, pat, x, xg, row, m, n32, acc, pol);
       }
     } while (t < T_ && (pid_next & (BK_MASK_PID_GHOST - 1)) == slot);
   }

@@ -398,6 +398,7 @@ struct bk_op_cg_r {
   static constexpr int R = 1;
   struct Ctx {
     T alpha;
+    unsigned long long pol;
   };
   template <int W>
   struct In {
@@ -407,6 +408,7 @@ struct bk_op_cg_r {
   T* r;
   bk_dev_state* st;
   int snake;
+  int hints = 0;  // bit 0: Ap is dead after this pass -> streaming loads | bit 4: r is stored "evict last"
   __device__ bool skip() const {
     if (st->done == 0) return false;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->just_done = 0;
@@ -416,11 +418,12 @@ struct bk_op_cg_r {
   __device__ Ctx prepare() const {
     Ctx c;
     c.alpha = static_cast<T>(st->alpha);
+    c.pol = (hints & 16) ? bk_policy_evict_last() : 0ull;
     return c;
   }
   template <int W>
   __device__ void load(long long i, In<W>& in) const {
-    in.ap = bk_ld<T, W>(ap + i);
+    in.ap = (hints & 1) ? bk_ld_cs<T, W>(ap + i) : bk_ld<T, W>(ap + i);
     in.r = bk_ld<T, W>(r + i);
   }
   template <int W>
@@ -431,7 +434,7 @@ struct bk_op_cg_r {
       ro.v[j] = bk_sub(in.r.v[j], bk_mul(c.alpha, in.ap.v[j]));
       acc[0] += (double)ro.v[j] * (double)ro.v[j];
     }
-    bk_st<T, W>(r + i, ro);
+    if (hints & 16) bk_st_keep<T, W>(r + i, ro, c.pol); else bk_st<T, W>(r + i, ro);
   }
   __device__ void epilogue(const double* s) const {
     const double gamma_new = s[0];
@@ -458,6 +461,7 @@ struct bk_op_cg_xp {
   static constexpr int R = 0;
   struct Ctx {
     T alpha, beta;
+    unsigned long long pol;
   };
   template <int W>
   struct In {
@@ -468,19 +472,21 @@ struct bk_op_cg_xp {
   const T* r;
   const bk_dev_state* st;
   int snake;
+  int hints = 0;  // bit 1: x streams through (next touched one iteration later) | bit 2: so does r
   __device__ bool skip() const { return st->done != 0 && st->just_done == 0; }
   __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
   __device__ Ctx prepare() const {
     Ctx c;
     c.alpha = static_cast<T>(st->alpha);
     c.beta = static_cast<T>(st->beta);
+    c.pol = (hints & 16) ? bk_policy_evict_last() : 0ull;
     return c;
   }
   template <int W>
   __device__ void load(long long i, In<W>& in) const {
-    in.x = bk_ld<T, W>(x + i);
+    in.x = (hints & 2) ? bk_ld_cs<T, W>(x + i) : bk_ld<T, W>(x + i);
     in.p = bk_ld<T, W>(p + i);
-    in.r = bk_ld<T, W>(r + i);
+    in.r = (hints & 4) ? bk_ld_cs<T, W>(r + i) : bk_ld<T, W>(r + i);
   }
   template <int W>
   __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
@@ -490,8 +496,8 @@ struct bk_op_cg_xp {
       xo.v[j] = bk_add(in.x.v[j], bk_mul(c.alpha, in.p.v[j]));
       po.v[j] = bk_add(in.r.v[j], bk_mul(c.beta, in.p.v[j]));
     }
-    bk_st<T, W>(x + i, xo);
-    bk_st<T, W>(p + i, po);
+    if (hints & 2) bk_st_cs<T, W>(x + i, xo); else bk_st<T, W>(x + i, xo);
+    if (hints & 16) bk_st_keep<T, W>(p + i, po, c.pol); else bk_st<T, W>(p + i, po);
   }
   __device__ void epilogue(const double*) const {}
 };
