@@ -77,6 +77,16 @@ def workload_config(n, tol):
             "n": N, "nnz": 7 * N - 6 * n * n, "tol": tol}
 
 
+def dist_workload(n, world, window):
+    """The N>1 workload string (both arms print the same one): n^3 rows per GPU, slabs stacked along the first axis."""
+    npl, ppg = 2 * n, max(n // 4, 1)          # same slab geometry as _dist_problem
+    if ppg * npl * npl != n ** 3:
+        npl, ppg = n, n
+    return (f"CG fp64, 7-pt Poisson {world * ppg}x{npl}x{npl} CSR row-partitioned over {world} GPUs "
+            f"({n}^3 rows per GPU; 8 GPUs = BASELINE configs[4] 512^3 at n=256), b=ones, fixed window of "
+            f"{window} iterations per step")
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -158,7 +168,14 @@ def run_reference(args, rank, world):
         return
     from pytorch_sparse_solver import problems
     n = args.n
-    A = problems.poisson3d_csr(n)
+    if world > 1:   # one slab of this repo's N-GPU workload (same geometry as _dist_problem), as a system of its own
+        npl, ppg = 2 * n, max(n // 4, 1)
+        if ppg * npl * npl != n ** 3:
+            npl, ppg = n, n
+        crow, col, val = problems.stencil3d_rows(npl, ppg, 0, ppg)
+        A = torch.sparse_csr_tensor(crow, col, val, size=(n ** 3, n ** 3))
+    else:
+        A = problems.poisson3d_csr(n)
     b = torch.ones(A.shape[0], dtype=torch.float64)
     from oracle import krylov_oracle as orc
     cores = os.cpu_count() or 1
@@ -175,11 +192,20 @@ def run_reference(args, rank, world):
     value = its / dt
     sample = (f"{args.steps} x fixed window of {window} CG iterations (tol=0, same recurrences as the tol={args.tol:g} "
               f"solve, which takes 611) on P3D-{n}, torch CPU, {cores} threads, {dt:.0f} s")
+    cfg = workload_config(n, args.tol)
+    if world > 1:
+        # N > 1: this repo's arm runs the weak-scaled system (n^3 rows per GPU) and counts n^3-row CG iterations per
+        # second over all ranks.  The reference is single-process: one n^3-row slab is its bounded sample, and its rate
+        # on the slab IS its rate in those units (N times the rows take it N times as long per iteration).
+        cfg = {"workload": dist_workload(n, world, args.dist_window),
+               "value_definition": f"{n}^3-row CG iterations per second"}
+        sample += (f"; the sample is ONE {ppg}x{npl}x{npl} slab of {n}^3 rows (1/{world} of the system) — the metric counts {n}^3-row "
+                   f"iterations, which a single process performs at this rate whatever the number of slabs")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(n, args.tol),
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -569,9 +595,9 @@ def run_dist(args, rank, world):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong_main else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"CG fp64, 7-pt Poisson {world * ppg}x{npl}x{npl} CSR row-partitioned over {world} GPUs "
-                                   f"({n}^3 rows per GPU; 8 GPUs = BASELINE configs[4] 512^3), b=ones, fixed window of "
-                                   f"{window} iterations per step",
+            "config": {"workload": (dist_workload(n, world, window) if not strong_main else
+                                    f"CG fp64, 7-pt Poisson {2 * n}^3 CSR split over {world} GPUs (strong scaling), b=ones, "
+                                    f"fixed window of {window} iterations per step"),
                        "comm": comm,
                        "value_definition": f"{world} x global iterations/s = {n}^3-row CG iterations per second over all ranks",
                        "global_iterations_per_second": it_s, "n_local": rows, "nnz_local": nnz_local,
