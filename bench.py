@@ -416,7 +416,11 @@ def run_single(args):
         pinned = bool(A_h.values().is_pinned() and A_h.col_indices().is_pinned() and b_h.is_pinned())
         h2d = sum(t.numel() * t.element_size() for t in (crow_h, col_h, val_h, b_h))
         d2h = N * 8
-        module_a.cg(A_h, b_h, tol=args.tol)
+        # warm-up in the same pattern as the timed loop (the result of the previous solve stays referenced while the
+        # next one runs, so the pinned result buffers alternate: both must exist before the clock starts — the first
+        # round-2 runs timed one 50 ms cudaHostAlloc in three steps)
+        for _ in range(3):
+            xh, _info = module_a.cg(A_h, b_h, tol=args.tol)
         torch.cuda.synchronize()
         k_e2e = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
@@ -564,18 +568,23 @@ def run_dist(args, rank, world):
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
+    from pytorch_sparse_solver import module_a
+    from pytorch_sparse_solver.module_a import krylov
     D2 = bkd.DistMatrix(crow_h.to(dev, non_blocking=True), col_h.to(dev, non_blocking=True),
                         val_h.to(dev, non_blocking=True), offsets, rank, world)
-    xe, re_ = D2.cg(b_h.to(dev, non_blocking=True), None, 0.0, 0.0, window)
+    xe, info_e = module_a.cg(D2, b_h.to(dev, non_blocking=True), tol=args.tol)   # the call a user makes: a full solve
     xh = xe.cpu()
     torch.cuda.synchronize()
     dist.barrier()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * re_["iterations"] / float(dt), "unit": UNIT, "h2d_bytes_per_step": h2d,
+    its_e = int(krylov.last_result["iterations"])
+    e2e = {"value": world * its_e / float(dt), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": rows * 8, "ms_per_step": 1e3 * float(dt), "steps": 1,
-           "note": "includes partition set-up, halo-plan exchange and IPC window mapping (the NCCL communicator of "
-                   "the process is reused)"}
+           "iterations": its_e, "info": int(info_e),
+           "api": "DistMatrix(slab from pinned host buffers) + pytorch_sparse_solver.module_a.cg(D, b_local, tol) + x to host",
+           "note": "one full tol solve per step; includes H2D of the slab, partition set-up, halo-plan exchange, IPC "
+                   "window mapping, registration (the NCCL communicator of the process is reused)"}
     D2.close()
     del crow_h, col_h, val_h, xh, xe
     # strong-scaling arm: the SAME (2n)^3 system split over the N GPUs

@@ -4,6 +4,9 @@
 // there is no CPU solver in this library.
 #include "bk_internal.cuh"
 
+#include <chrono>
+#include <cstdlib>
+
 extern "C" int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, const void* rowptr, const void* col,
                              int idx_bits, const void* val, int dtype, const void* b, void* x_inout, int has_x0,
                              double tol, double atol, int64_t maxiter, int restart, int gmres_method,
@@ -50,6 +53,17 @@ extern "C" int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, c
   auto cleanup = [&]() {
     if (A) bk_csr_destroy(A);
   };
+  // BK_HOST_TIMING=1: per-phase wall times on stderr (adds stream syncs; diagnosis only)
+  static const bool timing = getenv("BK_HOST_TIMING") != nullptr && atoi(getenv("BK_HOST_TIMING")) != 0;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_prev = timing ? now() : 0.0;
+  auto lap = [&](const char* what) {
+    if (!timing) return;
+    cudaStreamSynchronize(s);
+    const double t = now();
+    fprintf(stderr, "[bk_solve_host] %-14s %8.2f ms\n", what, t - t_prev);
+    t_prev = t;
+  };
   cudaError_t e = cudaMemcpyAsync(d_rp, rowptr, is * (size_t)(n + 1), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_col, col, is * (size_t)nnz, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess && nnz > 0) e = cudaMemcpyAsync(d_val, val, vs * (size_t)nnz, cudaMemcpyHostToDevice, s);
@@ -59,6 +73,7 @@ extern "C" int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, c
     cleanup();
     return bk_fail(BK_ERR_CUDA, "bk_solve_host: H2D copy failed: %s", cudaGetErrorString(e));
   }
+  lap("h2d");
   if (idx_bits == 64) {  // narrow the indices inside the staging area (overlaps the value copy still in flight)
     if (n >= 2147483647LL || nnz >= 2147483647LL) {
       cleanup();
@@ -70,6 +85,7 @@ extern "C" int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, c
   } else {
     rc = bk_csr_create(h, n, nnz, d_rp, d_col, 32, d_val, dtype, 0, s, &A);
   }
+  lap("registration");
   if (rc == BK_OK) {
     if (method == 0)
       rc = bk_cg(h, A, d_b, d_x, has_x0, tol, atol, maxiter, result, s);
@@ -78,9 +94,11 @@ extern "C" int bk_solve_host(bk_handle* h, int method, int64_t n, int64_t nnz, c
     else
       rc = bk_gmres(h, A, d_b, d_x, has_x0, tol, atol, restart, maxiter, gmres_method, result, s);
   }
+  lap("solve");
   if (rc == BK_OK) {
     e = cudaMemcpyAsync(x_inout, d_x, vs * (size_t)n, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    lap("d2h");
     if (e != cudaSuccess) rc = bk_fail(BK_ERR_CUDA, "bk_solve_host: D2H copy failed: %s", cudaGetErrorString(e));
   }
   cleanup();

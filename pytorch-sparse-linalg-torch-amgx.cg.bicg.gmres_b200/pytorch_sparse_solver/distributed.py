@@ -161,8 +161,22 @@ class DistMatrix:
         self.n_global = int(offsets[-1])
         self.device = val.device
         self.dtype = val.dtype
+        import os
+        import time
+        timing = os.environ.get("BK_DIST_TIMING", "0") != "0"   # per-phase set-up times (adds device syncs)
+        self.setup_ms = {}
+        t_last = [time.perf_counter()]
+
+        def mark(name):
+            if timing:
+                torch.cuda.synchronize(self.device)
+                now = time.perf_counter()
+                self.setup_ms[name] = round(1e3 * (now - t_last[0]), 2)
+                t_last[0] = now
         sp = split_local_ghost(crow, col, val, offsets[rank], offsets[rank + 1])
+        mark("split_local_ghost")
         plan = build_halo_plan(sp.ghost_ids, offsets, rank, world, group)
+        mark("build_halo_plan")
         self.split, self.plan = sp, plan
         self.handle = _native.Handle.get(self.device)
         lib = self.handle.lib
@@ -190,15 +204,16 @@ class DistMatrix:
                 sp.ghost_ids.numel(), npeers, peers, sc, rc, self._send_idx.data_ptr(),
                 _native._dtype_code(self.dtype), _native._stream_ptr(self.device), C.byref(p)), "bk_dist_create")
         self.ptr = p
+        mark("bk_dist_create")
         self.p2p = False
         self.folded = False
         self._group = group
         self._src = (crow, col, val)      # the caller's slab (global columns): needed to build the transpose
         self._transpose = None
         self._diag = None
-        import os
         if os.environ.get("BK_DIST_P2P", "1") != "0":
             self._connect_peer_memory(plan, group)
+        mark("connect_peer_memory")
         if self.p2p and os.environ.get("BK_DIST_FOLD", "1") != "0":
             # the rows as one matrix over [local | ghost]: one SpMV kernel per matvec when the row-bitmask plan fits
             folded = C.c_int32(0)
@@ -210,6 +225,7 @@ class DistMatrix:
                     gid.data_ptr() if gid.numel() else None, int(offsets[rank]), _native._stream_ptr(self.device),
                     C.byref(folded)), "bk_dist_set_extended")
             self.folded = bool(folded.value)
+        mark("set_extended")
         sp.ext_col = None                 # only read during registration
         sp.ext_rowptr = None
 
