@@ -565,20 +565,25 @@ def run_dist(args, rank, world):
     b_h = b.cpu().pin_memory()
     h2d = sum(t.numel() * t.element_size() for t in (crow_h, col_h, val_h, b_h))
     del crow, col, val
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
     from pytorch_sparse_solver import module_a
     from pytorch_sparse_solver.module_a import krylov
-    D2 = bkd.DistMatrix(crow_h.to(dev, non_blocking=True), col_h.to(dev, non_blocking=True),
-                        val_h.to(dev, non_blocking=True), offsets, rank, world)
-    xe, info_e = module_a.cg(D2, b_h.to(dev, non_blocking=True), tol=args.tol)   # the call a user makes: a full solve
-    xh = xe.cpu()
-    torch.cuda.synchronize()
-    dist.barrier()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    its_e = int(krylov.last_result["iterations"])
+    xh = torch.empty(rows, dtype=torch.float64).pin_memory()        # the result lands in pinned host memory
+    for rep in range(2):                                            # first pass = warm-up of this code path
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        D2 = bkd.DistMatrix(crow_h.to(dev, non_blocking=True), col_h.to(dev, non_blocking=True),
+                            val_h.to(dev, non_blocking=True), offsets, rank, world)
+        xe, info_e = module_a.cg(D2, b_h.to(dev, non_blocking=True), tol=args.tol)   # the call a user makes: a full solve
+        xh.copy_(xe)
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        its_e = int(krylov.last_result["iterations"])
+        if rep == 0:
+            D2.close()
+            del D2, xe
     e2e = {"value": world * its_e / float(dt), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": rows * 8, "ms_per_step": 1e3 * float(dt), "steps": 1,
            "iterations": its_e, "info": int(info_e),

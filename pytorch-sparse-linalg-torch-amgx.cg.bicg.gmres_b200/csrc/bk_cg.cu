@@ -21,6 +21,7 @@ struct bk_epi_cg_pAp {  // alpha = gamma / (p . Ap)   (:845)
   bk_dev_state* st;
   __device__ __forceinline__ void operator()(const double* s) const {
     st->pAp = s[0];
+    st->alpha_lag = st->alpha;  // lagged-x cut: in an odd iteration the previous alpha is still owed to x
     st->alpha = st->gamma / s[0];
   }
 };
@@ -222,7 +223,7 @@ struct bk_cg_vecs {
 };
 
 template <typename T>
-static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>& v, int it, bool fuse,
+static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>& v, int it, bool fuse, bool lag,
                               cudaStream_t s) {
   const long long n = A->n;
   bk_dev_state* st = h->st;
@@ -241,16 +242,16 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
     BK_TRY((bk_launch_spmv<0, 1, 1>(h, A, a, bk_slot(h, 0), epi, s)));
     pcur = pnew;
   } else {
+    pcur = lag ? v.p[it & 1] : v.p[0];  // lagged-x cut: p ping-pongs (chunks are even-sized and start at an even k)
     bk_spmv_args a = bk_spmv_base(A, st);
-    a.x = v.p[0];
-    a.w = v.p[0];
+    a.x = pcur;
+    a.w = pcur;
     a.y = v.ap;
     a.guard = 1;
     a.use_parity = h->snake;
     a.l2_hints = h->l2_hints;
     bk_epi_cg_pAp epi{st};
     BK_TRY((bk_launch_spmv<0, 1, 0>(h, A, a, bk_slot(h, 0), epi, s)));
-    pcur = v.p[0];
   }
   if (fuse) {
     bk_op_cg_update<T> op;
@@ -271,7 +272,7 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
       op.hints = h->l2_hints;
       BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 1), s));
     }
-    {
+    if (!lag) {
       bk_op_cg_xp<T> op;
       op.x = v.x;
       op.p = v.p[0];
@@ -279,6 +280,24 @@ static int bk_cg_enqueue_iter(bk_handle* h, const bk_csr* A, const bk_cg_vecs<T>
       op.st = st;
       op.snake = h->snake;
       op.hints = h->l2_hints;
+      BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), s));
+    } else if ((it & 1) == 0) {
+      bk_op_cg_p_lag<T> op;
+      op.x = v.x;
+      op.pcur = v.p[0];
+      op.pnext = v.p[1];
+      op.r = v.r;
+      op.st = st;
+      op.snake = h->snake;
+      BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), s));
+    } else {
+      bk_op_cg_xp_lag<T> op;
+      op.x = v.x;
+      op.pprev = v.p[0];
+      op.pcur = v.p[1];
+      op.r = v.r;
+      op.st = st;
+      op.snake = h->snake;
       BK_TRY(bk_launch_ew<T>(h, op, n, true, bk_slot(h, 2), s));
     }
   }
@@ -294,6 +313,7 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   // (measured: -17 % at n = 65k, +13 % at n = 1M), so 'auto' (-1) enables it for small systems only
   const bool persist_ok = h->persistent && n <= (long long)h->persistent_max_n;  // one cooperative kernel runs the loop
   const bool fuse = !persist_ok && A->kernel != 1 && A->split == nullptr && (h->fuse_xpay > 0 || (h->fuse_xpay < 0 && n <= 300000));
+  const bool lag = !fuse && !persist_ok && h->cg_lag_x != 0;
   BK_TRY(bk_ws_reserve(h, (size_t)5 * npad * sizeof(T)));
   bk_cg_vecs<T> v;
   v.x = (T*)h->ws;
@@ -340,10 +360,10 @@ static int bk_cg_t(bk_handle* h, const bk_csr* A, const void* b, void* x_user, i
   const int chunk = bk_pick_chunk(h, bytes_iter, fuse ? 2 : 3);
   const bool use_graph = h->loop_mode != BK_LOOP_STREAM;
   uint64_t key[6] = {1 /*cg*/, A->uid, (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
-                     (uint64_t)A->dtype | ((uint64_t)fuse << 8) | ((uint64_t)h->snake << 9) | ((uint64_t)(h->l2_hints & 15) << 10) | ((uint64_t)chunk << 16),
+                     (uint64_t)A->dtype | ((uint64_t)fuse << 8) | ((uint64_t)h->snake << 9) | ((uint64_t)(h->l2_hints & 31) << 10) | ((uint64_t)lag << 15) | ((uint64_t)chunk << 16),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   auto enqueue_chunk = [&](cudaStream_t cs) -> int {
-    for (int it = 0; it < chunk; ++it) BK_TRY(bk_cg_enqueue_iter<T>(h, A, v, it, fuse, cs));
+    for (int it = 0; it < chunk; ++it) BK_TRY(bk_cg_enqueue_iter<T>(h, A, v, it, fuse, lag, cs));
     return BK_OK;
   };
   int64_t chunks = 0;
@@ -559,11 +579,12 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
   bk_handle* h = sys.h;
   const long long n = sys.n();
   const size_t npad = ((size_t)n + 63) & ~(size_t)63;
-  BK_TRY(bk_ws_reserve(h, (size_t)4 * npad * sizeof(T)));
+  BK_TRY(bk_ws_reserve(h, (size_t)5 * npad * sizeof(T)));
   T* x = (T*)h->ws;
   T* r = x + npad;
   T* p = r + npad;
   T* ap = p + npad;
+  T* p2 = ap + npad;  // second p buffer of the lagged-x cut
   bk_dev_state* st = h->st;
   const size_t vbytes = (size_t)n * sizeof(T);
   bk_call_begin(h, s, "bk_dist_cg");
@@ -590,8 +611,12 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
   const bool fuse_push = sys.can_fuse_push() && h->dist_fuse_push;
   if (fuse_push) BK_TRY(sys.halo_begin<T>(p, 1, true, s));
 
-  auto enqueue_iter = [&](cudaStream_t cs) -> int {
-    BK_TRY((sys.matvec<T, 0, 1>(p, ap, p, nullptr, 1, bk_epi_cg_pAp{st}, cs, fuse_push)));
+  // lagged-x cut (see bk_op_cg_p_lag): x is updated every second iteration, p ping-pongs between p and p2
+  const bool lag = fuse_push && h->cg_lag_x != 0;
+  auto enqueue_iter = [&](int it, cudaStream_t cs) -> int {
+    T* pcur = (lag && (it & 1)) ? p2 : p;
+    T* pnext = (lag && !(it & 1)) ? p2 : p;
+    BK_TRY((sys.matvec<T, 0, 1>(pcur, ap, pcur, nullptr, 1, bk_epi_cg_pAp{st}, cs, fuse_push)));
     {
       bk_op_cg_r<T> op;
       op.ap = ap;
@@ -601,7 +626,7 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
       BK_TRY(sys.ew<T>(op, true, 1, cs));
     }
     if (fuse_push) {
-      BK_TRY(sys.cg_xp_push<T>(x, p, r, cs));
+      BK_TRY(sys.cg_xp_push<T>(x, pcur, pnext, r, lag ? 1 + (it & 1) : 0, cs));
     } else {
       bk_op_cg_xp<T> op;
       op.x = x;
@@ -617,10 +642,10 @@ static int bk_dist_cg_t(const bk_sys_dist& sys, const void* b, void* x_user, int
   const int chunk = bk_pick_chunk(h, bytes_iter, 8);
   const bool use_graph = h->loop_mode != BK_LOOP_STREAM;  // NCCL calls are captured into the iteration graph too
   uint64_t key[6] = {4 /*dist cg*/, sys.uid(), (uint64_t)(uintptr_t)h->ws, (uint64_t)n,
-                     (uint64_t)sys.dtype() | ((uint64_t)fuse_push << 8) | ((uint64_t)sys.snake << 9) | ((uint64_t)chunk << 16),
+                     (uint64_t)sys.dtype() | ((uint64_t)fuse_push << 8) | ((uint64_t)sys.snake << 9) | ((uint64_t)lag << 10) | ((uint64_t)chunk << 16),
                      (uint64_t)bk_grid_spmv(h) | ((uint64_t)bk_grid_vec(h) << 32)};
   auto enqueue_chunk = [&](cudaStream_t cs) -> int {
-    for (int it = 0; it < chunk; ++it) BK_TRY(enqueue_iter(cs));
+    for (int it = 0; it < chunk; ++it) BK_TRY(enqueue_iter(it, cs));
     return BK_OK;
   };
   int64_t chunks = 0;

@@ -124,6 +124,7 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->fuse_xpay = (int)bk_env_int("BK_FUSE_XPAY", -1);  // -1 auto, 0 off, 1 on
   h->snake = (int)bk_env_int("BK_SNAKE", 1);
   h->l2_hints = (int)bk_env_int("BK_L2_HINTS", 0);
+  h->cg_lag_x = (int)bk_env_int("BK_CG_LAG_X", 1);
   h->next_uid = 1;
   cudaError_t e;
   e = cudaMalloc(&h->partials, sizeof(double) * BK_NSLOT * BK_SLOT_ROWS * BK_MAXB);
@@ -228,6 +229,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "fuse_xpay")) return &h->fuse_xpay;
   if (!strcmp(key, "snake")) return &h->snake;
   if (!strcmp(key, "l2_hints")) return &h->l2_hints;
+  if (!strcmp(key, "cg_lag_x")) return &h->cg_lag_x;
   return nullptr;
 }
 

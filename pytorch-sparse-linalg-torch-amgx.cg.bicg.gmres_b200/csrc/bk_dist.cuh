@@ -226,22 +226,31 @@ struct bk_push_ranges {
   T* dst[BK_PUSH_MAXR];
 };
 
+// lag: 0  x += alpha p ; p = r + beta p (in place: pin == pout)
+//      1  even iteration of the lagged-x cut (bk_op_cg_p_lag): pout = r + beta pin — or, when the stop test has just
+//         fired, the pending x += alpha pin instead
+//      2  odd iteration (bk_op_cg_xp_lag): x = (x + alpha_lag pout) + alpha pin ; pout = r + beta pin  (pout held p_{k-1})
 template <typename T>
 __global__ void __launch_bounds__(BK_BLOCK, 3)
-bk_cg_xp_push_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__ r, const long long n,
+bk_cg_xp_push_kernel(T* __restrict__ x, const T* pin, T* pout, const T* __restrict__ r, const long long n,
                      const bk_dev_state* st, const bk_push_ranges<T> pr,
                      unsigned long long* const* __restrict__ remote_flag, const int npeers, unsigned int* counters,
-                     const int snake) {
+                     const int snake, const int lag) {
   const int done = st->done;
   if (done != 0 && st->just_done == 0) return;
   const bool push = (done == 0);
+  const bool flush = (lag == 1) && !push;                // x receives the term the even iteration still owes it
+  const bool upd_x = (lag != 1) || flush;
+  const bool upd_p = !flush;
   const bool rev = snake && ((st->parity & 1) == 0);  // same rule as bk_op_cg_xp::reverse()
   __shared__ int s_last;
   const T alpha = static_cast<T>(st->alpha), beta = static_cast<T>(st->beta);
+  const T alpha_lag = static_cast<T>(st->alpha_lag);
   constexpr int W = bk_native_w<T>::value;
   const long long npack = n / W;
   const long long stride = (long long)gridDim.x * BK_BLOCK;
-  auto one = [&](long long i, T xv, T pv, T rv, T& xo, T& po) {
+  auto one = [&](long long i, T xv, T ppv, T pv, T rv, T& xo, T& po) {
+    if (lag == 2) xv = bk_add(xv, bk_mul(alpha_lag, ppv));
     xo = bk_add(xv, bk_mul(alpha, pv));
     po = bk_add(rv, bk_mul(beta, pv));
     if (push) {
@@ -252,20 +261,26 @@ bk_cg_xp_push_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__
   };
   for (long long k = (long long)blockIdx.x * BK_BLOCK + threadIdx.x; k < npack; k += stride) {
     const long long i = (rev ? (npack - 1 - k) : k) * W;
-    const bk_vec<T, W> xv = bk_ld<T, W>(x + i), pv = bk_ld<T, W>(p + i), rv = bk_ld<T, W>(r + i);
+    bk_vec<T, W> xv, ppv, rv;
+    const bk_vec<T, W> pv = bk_ld<T, W>(pin + i);
+#pragma unroll
+    for (int j = 0; j < W; ++j) xv.v[j] = ppv.v[j] = rv.v[j] = T(0);
+    if (upd_x) xv = bk_ld<T, W>(x + i);
+    if (lag == 2) ppv = bk_ld<T, W>(pout + i);
+    if (upd_p) rv = bk_ld<T, W>(r + i);
     bk_vec<T, W> xo, po;
 #pragma unroll
-    for (int j = 0; j < W; ++j) one(i + j, xv.v[j], pv.v[j], rv.v[j], xo.v[j], po.v[j]);
-    bk_st<T, W>(x + i, xo);
-    bk_st<T, W>(p + i, po);
+    for (int j = 0; j < W; ++j) one(i + j, xv.v[j], ppv.v[j], pv.v[j], rv.v[j], xo.v[j], po.v[j]);
+    if (upd_x) bk_st<T, W>(x + i, xo);
+    if (upd_p) bk_st<T, W>(pout + i, po);
   }
   {
     const long long t = npack * W + (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
     if (t < n) {
       T xo, po;
-      one(t, x[t], p[t], r[t], xo, po);
-      x[t] = xo;
-      p[t] = po;
+      one(t, upd_x ? x[t] : T(0), lag == 2 ? pout[t] : T(0), pin[t], upd_p ? r[t] : T(0), xo, po);
+      if (upd_x) x[t] = xo;
+      if (upd_p) pout[t] = po;
     }
   }
   if (!push) return;
@@ -529,7 +544,7 @@ struct bk_sys_dist {
 
   bool can_fuse_push() const { return p2p && D->npeers > 0 && D->push_nranges >= 0; }
   template <typename T>
-  int cg_xp_push(T* x, T* p, const T* r, cudaStream_t cs) const {
+  int cg_xp_push(T* x, const T* pin, T* pout, const T* r, int lag, cudaStream_t cs) const {
     bk_push_ranges<T> pr;
     pr.nr = D->push_nranges;
     for (int q = 0; q < BK_PUSH_MAXR; ++q) {
@@ -539,8 +554,8 @@ struct bk_sys_dist {
     }
     constexpr int NW = bk_native_w<T>::value;
     const int grid = bk_grid_vec_n(h, n(), 2 * NW);
-    bk_cg_xp_push_kernel<T><<<grid, BK_BLOCK, 0, cs>>>(x, p, r, n(), h->st, pr, D->d_remote_flag, D->npeers,
-                                                      D->p2p.counters, snake ? 1 : 0);
+    bk_cg_xp_push_kernel<T><<<grid, BK_BLOCK, 0, cs>>>(x, pin, pout, r, n(), h->st, pr, D->d_remote_flag, D->npeers,
+                                                      D->p2p.counters, snake ? 1 : 0, lag);
     BK_KERNEL_CHECK();
     return BK_OK;
   }

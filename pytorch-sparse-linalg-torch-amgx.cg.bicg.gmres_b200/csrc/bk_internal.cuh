@@ -61,6 +61,7 @@ struct bk_dev_state {
   double bs;          // b.b
   // CG
   double gamma, pAp, alpha, beta;
+  double alpha_lag;   // CG, lagged-x cut: alpha of the previous (even) iteration, whose x += alpha p is still pending
   // BiCGStab
   double rho, omega, rho_new, rs, rhat_q, ss;
   // final check
@@ -183,6 +184,7 @@ struct bk_handle {
   int chunk;
   int fuse_xpay;
   int snake;
+  int cg_lag_x;  // CG (3-kernel cut): x is updated every second iteration with both pending terms (9n instead of 10n per 2)
   int l2_hints;  // bit 0: K2 streams Ap | bit 1: K3 streams x | bit 2: K3 streams r | bit 3: SpMV streams masks
   // reduction scratch
   double* partials;        // BK_NSLOT * BK_SLOT_ROWS * BK_MAXB

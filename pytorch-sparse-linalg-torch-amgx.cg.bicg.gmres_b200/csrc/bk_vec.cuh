@@ -19,6 +19,21 @@
 #include "bk_internal.cuh"
 #include "bk_p2p.cuh"
 
+#include <type_traits>
+
+// An op that declares `static constexpr bool kCtxLoad = true` gets its Ctx passed to load() as well (ops whose operands
+// depend on a device-side flag).
+template <typename Op, typename = void>
+struct bk_has_ctx_load : std::false_type {};
+template <typename Op>
+struct bk_has_ctx_load<Op, std::void_t<decltype(Op::kCtxLoad)>> : std::true_type {};
+
+template <int W, typename Op, typename In, typename Ctx>
+__device__ __forceinline__ void bk_ew_load(const Op& op, long long i, In& in, const Ctx& ctx) {
+  if constexpr (bk_has_ctx_load<Op>::value) op.template load<W>(i, in, ctx);
+  else op.template load<W>(i, in);
+}
+
 template <typename T, int W, typename Op>
 __global__ void __launch_bounds__(BK_BLOCK, 3) bk_ew_kernel(Op op, const long long n, const bk_scratch sc) {
   if (op.skip()) return;
@@ -39,7 +54,7 @@ __global__ void __launch_bounds__(BK_BLOCK, 3) bk_ew_kernel(Op op, const long lo
     for (int u = 0; u < UN; ++u) {
       p[u] = i + u * stride;
       if (rev) p[u] = npack - 1 - p[u];
-      op.template load<W>(p[u] * W, in[u]);
+      bk_ew_load<W>(op, p[u] * W, in[u], ctx);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) op.template apply<W>(p[u] * W, in[u], ctx, acc);
@@ -47,14 +62,14 @@ __global__ void __launch_bounds__(BK_BLOCK, 3) bk_ew_kernel(Op op, const long lo
   for (; i < npack; i += stride) {
     typename Op::template In<W> in;
     const long long p = rev ? (npack - 1 - i) : i;
-    op.template load<W>(p * W, in);
+    bk_ew_load<W>(op, p * W, in, ctx);
     op.template apply<W>(p * W, in, ctx, acc);
   }
   if constexpr (W > 1) {
     const long long t = npack * W + (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
     if (t < n) {
       typename Op::template In<1> in;
-      op.template load<1>(t, in);
+      bk_ew_load<1>(op, t, in, ctx);
       op.template apply<1>(t, in, ctx, acc);
     }
   }
@@ -498,6 +513,108 @@ struct bk_op_cg_xp {
     }
     if (hints & 2) bk_st_cs<T, W>(x + i, xo); else bk_st<T, W>(x + i, xo);
     if (hints & 16) bk_st_keep<T, W>(p + i, po, c.pol); else bk_st<T, W>(p + i, po);
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
+// The same iteration with x lagging (large systems, option cg_lag_x): x_{k+1} = x_k + alpha_k p_k feeds nothing but the
+// final result, so two consecutive updates are applied together — in the same order, with the same roundings — by the
+// K3 of every second iteration, while p ping-pongs between two buffers so that p_k is still there:
+//   even iteration  K3e  p_{k+1} = r + beta p_k               (reads p_k, r; writes the other buffer)           3n
+//   odd  iteration  K3o  x = (x + alpha_{k-1} p_{k-1}) + alpha_k p_k ; p_{k+1} = r + beta p_k  (into p_{k-1}'s buffer) 6n
+// 9n per two iterations instead of 10n.  If the stop test fires in an even iteration, K3e applies the pending term
+// instead (x += alpha p_k; `just_done`), so x is complete whenever the loop ends.  Bitwise the same x, r, p.
+template <typename T>
+struct bk_op_cg_p_lag {
+  static constexpr int R = 0;
+  static constexpr bool kCtxLoad = true;
+  struct Ctx {
+    T alpha, beta;
+    int flush;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> p, q;
+  };
+  T* x;
+  const T* pcur;
+  T* pnext;
+  const T* r;
+  const bk_dev_state* st;
+  int snake;
+  __device__ bool skip() const { return st->done != 0 && st->just_done == 0; }
+  __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.alpha = static_cast<T>(st->alpha);
+    c.beta = static_cast<T>(st->beta);
+    c.flush = st->just_done;
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in, const Ctx& c) const {
+    in.p = bk_ld<T, W>(pcur + i);
+    in.q = bk_ld<T, W>((c.flush ? static_cast<const T*>(x) : r) + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
+    bk_vec<T, W> o;
+    if (c.flush) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) o.v[j] = bk_add(in.q.v[j], bk_mul(c.alpha, in.p.v[j]));
+      bk_st<T, W>(x + i, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) o.v[j] = bk_add(in.q.v[j], bk_mul(c.beta, in.p.v[j]));
+      bk_st<T, W>(pnext + i, o);
+    }
+  }
+  __device__ void epilogue(const double*) const {}
+};
+
+template <typename T>
+struct bk_op_cg_xp_lag {
+  static constexpr int R = 0;
+  struct Ctx {
+    T alpha, alpha_lag, beta;
+  };
+  template <int W>
+  struct In {
+    bk_vec<T, W> x, pp, pc, r;
+  };
+  T* x;
+  T* pprev;        // p_{k-1}; receives p_{k+1}
+  const T* pcur;   // p_k
+  const T* r;
+  const bk_dev_state* st;
+  int snake;
+  __device__ bool skip() const { return st->done != 0 && st->just_done == 0; }
+  __device__ bool reverse() const { return snake && ((st->parity & 1) == 0); }
+  __device__ Ctx prepare() const {
+    Ctx c;
+    c.alpha = static_cast<T>(st->alpha);
+    c.beta = static_cast<T>(st->beta);
+    c.alpha_lag = static_cast<T>(st->alpha_lag);
+    return c;
+  }
+  template <int W>
+  __device__ void load(long long i, In<W>& in) const {
+    in.x = bk_ld<T, W>(x + i);
+    in.pp = bk_ld<T, W>(pprev + i);
+    in.pc = bk_ld<T, W>(pcur + i);
+    in.r = bk_ld<T, W>(r + i);
+  }
+  template <int W>
+  __device__ void apply(long long i, const In<W>& in, const Ctx& c, double (&)[1]) const {
+    bk_vec<T, W> xo, po;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const T x1 = bk_add(in.x.v[j], bk_mul(c.alpha_lag, in.pp.v[j]));
+      xo.v[j] = bk_add(x1, bk_mul(c.alpha, in.pc.v[j]));
+      po.v[j] = bk_add(in.r.v[j], bk_mul(c.beta, in.pc.v[j]));
+    }
+    bk_st<T, W>(x + i, xo);
+    bk_st<T, W>(pprev + i, po);
   }
   __device__ void epilogue(const double*) const {}
 };

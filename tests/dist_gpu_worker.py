@@ -82,6 +82,14 @@ def main():
             assert rf["info"] == 0 and rf["iterations"] == r["iterations"], (fuse, rf, r)
         assert torch.equal(xs[0], xs[1]), "fused and separate halo push must give identical results"
         D.handle.set_option("dist_fuse_push", 1)
+        # lagged-x cut (x updated every second iteration, p ping-pongs): identical bits, whichever parity the loop stops in
+        for maxit in (1, 2, 3, 4, 5, 8, 9, None):
+            xl = {}
+            for lag in (0, 1):
+                D.handle.set_option("cg_lag_x", lag)
+                xl[lag], rl = D.cg(bg[sl].contiguous(), None, 1e-8, 0.0, maxit)
+            assert torch.equal(xl[0], xl[1]), ("dist cg lagged x", maxit)
+        D.handle.set_option("cg_lag_x", 1)
         # solves that end before / at the first iteration must leave the push/wait counters paired
         xz, rz = D.cg(torch.zeros_like(bg[sl]), None, 1e-8, 0.0, None)
         assert rz["info"] == 0 and rz["iterations"] == 0 and float(xz.abs().max()) == 0.0

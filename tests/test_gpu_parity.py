@@ -754,6 +754,41 @@ def test_result_reports_loop_mode_and_device_time(ma, manifest):
         assert _last()["loop_mode_used"] in (2, 3) and _last()["device_ms"] > 0.0
 
 
+@pytest.mark.parametrize("loop_mode", [0, 1])
+def test_cg_lagged_x_cut_bitwise(loop_mode):
+    """Large systems update x every second iteration with both pending terms (bk_op_cg_p_lag / bk_op_cg_xp_lag): the
+    same additions in the same order, so x must be bit-identical to the plain 3-kernel cut — whatever the parity of the
+    iteration the loop stops in (maxiter 1..7: odd counts end with the flush of K3e, even counts inside K3o), with and
+    without x0, through graphs and plain launches."""
+    from pytorch_sparse_solver import _native, problems
+    dev = torch.device("cuda")
+    h = _native.Handle.get(dev)
+    A = problems.poisson3d_csr(24, device=dev)
+    m = _native.register_matrix(A)
+    g = torch.Generator().manual_seed(5)
+    b = torch.randn(A.shape[0], dtype=torch.float64, generator=g).to(dev)
+    x0 = torch.randn(A.shape[0], dtype=torch.float64, generator=g).to(dev)
+    try:
+        h.set_option("persistent", 0)
+        h.set_option("fuse_xpay", 0)
+        h.set_option("loop_mode", loop_mode)
+        for maxiter in (1, 2, 3, 4, 5, 6, 7, 40, 41, None):
+            for start in (None, x0):
+                out = {}
+                for lag in (0, 1):
+                    h.set_option("cg_lag_x", lag)
+                    x, res = m.cg(b, start, 1e-9, 0.0, maxiter)
+                    out[lag] = (x.clone(), res["iterations"], res["info"], res["final_residual"])
+                assert out[0][1] == out[1][1] and out[0][2] == out[1][2]
+                assert out[0][3] == out[1][3]
+                assert torch.equal(out[0][0], out[1][0]), (maxiter, start is not None)
+    finally:
+        h.set_option("persistent", 1)
+        h.set_option("fuse_xpay", -1)
+        h.set_option("loop_mode", 0)
+        h.set_option("cg_lag_x", 1)
+
+
 @pytest.mark.parametrize("name", ["gmres_ldc100_step1_batched", "gmres_ldc32_step1_incremental", "gmres_cd3d12_x0",
                                   "gmres_scd3d12_jacobi_incremental", "gmres_cd3d12_batched_2cycles", "gmres_zero_rhs"])
 def test_gmres_persistent_kernel_vs_multi_kernel(ma, manifest, name):
