@@ -103,6 +103,9 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->tma_ctas = (int)bk_env_int("BK_TMA_CTAS", 4);
   h->pair_ctas = (int)bk_env_int("BK_PAIR_CTAS", 4);
   h->mask_ctas = (int)bk_env_int("BK_MASK_CTAS", 4);
+  h->mask_cctas = (int)bk_env_int("BK_MASK_CCTAS", 3);
+  h->mask_zmarch = (int)bk_env_int("BK_MASK_ZMARCH", 1);
+  h->mask_zteam = (int)bk_env_int("BK_MASK_ZTEAM", 16);
   h->mask_group = (int)bk_env_int("BK_MASK_GROUP", 8);
   h->mask_prefetch = (int)bk_env_int("BK_MASK_PREFETCH", 1);
   h->mask_window = (int)bk_env_int("BK_MASK_WINDOW", 0);  // measured slower than LDG + L2 prefetch so far (115 vs 84 us)
@@ -125,6 +128,7 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->snake = (int)bk_env_int("BK_SNAKE", 1);
   h->l2_hints = (int)bk_env_int("BK_L2_HINTS", 0);
   h->cg_lag_x = (int)bk_env_int("BK_CG_LAG_X", 1);
+  h->mask_const = (int)bk_env_int("BK_MASK_CONST", 1);
   h->next_uid = 1;
   cudaError_t e;
   e = cudaMalloc(&h->partials, sizeof(double) * BK_NSLOT * BK_SLOT_ROWS * BK_MAXB);
@@ -208,6 +212,9 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "tma_ctas")) return &h->tma_ctas;
   if (!strcmp(key, "pair_ctas")) return &h->pair_ctas;
   if (!strcmp(key, "mask_ctas")) return &h->mask_ctas;
+  if (!strcmp(key, "mask_cctas")) return &h->mask_cctas;
+  if (!strcmp(key, "mask_zmarch")) return &h->mask_zmarch;
+  if (!strcmp(key, "mask_zteam")) return &h->mask_zteam;
   if (!strcmp(key, "mask_group")) return &h->mask_group;
   if (!strcmp(key, "mask_prefetch")) return &h->mask_prefetch;
   if (!strcmp(key, "mask_window")) return &h->mask_window;
@@ -230,6 +237,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "snake")) return &h->snake;
   if (!strcmp(key, "l2_hints")) return &h->l2_hints;
   if (!strcmp(key, "cg_lag_x")) return &h->cg_lag_x;
+  if (!strcmp(key, "mask_const")) return &h->mask_const;
   return nullptr;
 }
 
@@ -890,6 +898,34 @@ __global__ void bk_mask_compact_kernel(const int* __restrict__ pids, long long n
 }
 
 // Try the row-bitmask plan (kernel 6).  ghost_gid / row_begin: see bk_mask_build_kernel (nullptr / 0 on one GPU).
+// kernel 6G: classify every (group of 8 blocks, warp position): one pattern over the 8 chunks?  every row complete?
+struct bk_mask_full16 {
+  unsigned int full[BK_MASK_CP];
+};
+static __global__ void bk_mask_gsum_kernel(const unsigned char* __restrict__ masks, const int* __restrict__ pids,
+                                           const unsigned char* __restrict__ slot2dense, const bk_mask_full16 f,
+                                           const long long n, const int ngroups, int* __restrict__ gsum) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long idx = warp; idx < (long long)ngroups * 8; idx += nwarps) {
+    const long long g = idx >> 3;
+    const int w = (int)(idx & 7);
+    bool mixed = (g + 1) * 2048 > n;  // the matrix ends inside the group
+    bool allfull = true;
+    int pid0 = 0;
+    for (int j = 0; j < 8; ++j) {
+      const long long c = (g * 8 + j) * 8 + w;  // (masks / pids are padded to whole groups)
+      const int pid = (int)slot2dense[pids[c] & (BK_MASK_HT - 1)];
+      if (j == 0) pid0 = pid;
+      if (pid != pid0) mixed = true;
+      const unsigned int m = masks[c * 32 + lane];
+      allfull = allfull && __all_sync(0xffffffffu, m == f.full[pid]);
+    }
+    if (lane == 0) gsum[idx] = pid0 | (allfull ? BK_MASK_GS_FAST : 0) | (mixed ? BK_MASK_GS_MIXED : 0);
+  }
+}
+
 int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long long row_begin, cudaStream_t s) {
   if (h->use_compress < 3 || A->is_view || A->n == 0 || A->nnz == 0 || A->max_row_nnz > BK_MASK_L) return BK_OK;
   const long long nchunks = (A->n + 31) / 32;
@@ -903,6 +939,8 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
     if (A->mpids) bk_pool_free(A->mpids);
     if (A->mptab) bk_pool_free(A->mptab);
     if (A->mdeferred) bk_pool_free(A->mdeferred);
+    if (A->mgsum) bk_pool_free(A->mgsum);
+    A->mgsum = nullptr;
     A->mmasks = nullptr;
     A->mpids = nullptr;
     A->mptab = nullptr;
@@ -1000,6 +1038,70 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
       if (A->mw_win < 8) A->mw_win = 8;
       for (int k = 0; k < nfar_all && A->mw_nfar < 2; ++k)
         if (far[k] % ea == 0) A->mw_far[A->mw_nfar++] = far[k];
+      // kernel 6G: up to BK_MASK_CP patterns, none with ghost entries -> the table as a kernel parameter block and one
+      // summary per (group of 8 blocks, warp position)
+      if (A->mask_patterns <= BK_MASK_CP && A->n_cols == A->n) {
+        unsigned char* s2d = (unsigned char*)calloc(BK_MASK_HT, 1);
+        unsigned char* d_s2d = nullptr;
+        bk_mask_ctab<double>* c64 = (bk_mask_ctab<double>*)A->mctab;
+        bk_mask_ctab<float>* c32 = (bk_mask_ctab<float>*)A->mctab;
+        static_assert(sizeof(bk_mask_ctab<double>) <= sizeof(A->mctab), "parameter block does not fit bk_csr::mctab");
+        memset(A->mctab, 0, sizeof(A->mctab));
+        int np = 0;
+        bool ok = s2d != nullptr;
+        for (int slot = 0; ok && slot < BK_MASK_HT; ++slot) {
+          if (!hk[slot]) continue;
+          if (np >= BK_MASK_CP) {
+            ok = false;
+            break;
+          }
+          const bk_pair_entry* pe = tab + (size_t)slot * BK_MASK_L;
+          unsigned int full = (unsigned int)(pe[0].pad >> BK_MASK_FULL_SHIFT) & 0x1ffu;
+          int len = 0;
+          for (int e = 0; e < BK_MASK_L; ++e) {
+            if (pe[e].pad & BK_MASK_GHOST) ok = false;
+            if (full & (1u << e)) len = e + 1;
+            if (A->dtype == BK_F64) {
+              memcpy(&c64->val[np][e], &pe[e].val, 8);
+              c64->off[np][e] = pe[e].off;
+            } else {
+              memcpy(&c32->val[np][e], &pe[e].val, 4);
+              c32->off[np][e] = pe[e].off;
+            }
+          }
+          if (full == 0u) full = 0xffffffffu;  // empty pattern: no row of the chunk has entries
+          if (A->dtype == BK_F64) {
+            c64->full[np] = full;
+            c64->len[np] = len;
+          } else {
+            c32->full[np] = full;
+            c32->len[np] = len;
+          }
+          s2d[slot] = (unsigned char)np;
+          ++np;
+        }
+        const int ngroups8 = (int)(((A->n + 255) / 256 + 7) / 8);
+        if (ok && bk_pool_alloc((void**)&d_s2d, BK_MASK_HT, s) == cudaSuccess &&
+            bk_pool_alloc((void**)&A->mgsum, sizeof(int) * (size_t)ngroups8 * 8, s) == cudaSuccess) {
+          bk_mask_full16 f16;
+          for (int k = 0; k < BK_MASK_CP; ++k) f16.full[k] = (A->dtype == BK_F64) ? c64->full[k] : c32->full[k];
+          cudaMemcpyAsync(d_s2d, s2d, BK_MASK_HT, cudaMemcpyHostToDevice, s);
+          long long wantw = ((long long)ngroups8 * 8 * 32 + 255) / 256;
+          int gg = (int)(wantw < (long long)h->num_sms * 8 ? wantw : (long long)h->num_sms * 8);
+          if (gg < 1) gg = 1;
+          bk_mask_gsum_kernel<<<gg, 256, 0, s>>>(A->mmasks, A->mpids, d_s2d, f16, A->n, ngroups8, A->mgsum);
+          if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+            bk_pool_free(A->mgsum);
+            A->mgsum = nullptr;
+          }
+        } else {
+          cudaGetLastError();
+          if (A->mgsum) bk_pool_free(A->mgsum);
+          A->mgsum = nullptr;
+        }
+        if (d_s2d) bk_pool_free(d_s2d);
+        free(s2d);
+      }
     } else {
       cudaGetLastError();
     }
@@ -1212,6 +1314,7 @@ extern "C" int bk_csr_destroy(bk_csr* A) {
   if (A->mpids) bk_pool_free(A->mpids);
   if (A->mptab) bk_pool_free(A->mptab);
   if (A->mdeferred) bk_pool_free(A->mdeferred);
+  if (A->mgsum) bk_pool_free(A->mgsum);
   free(A);
   return BK_OK;
 }

@@ -124,6 +124,9 @@ struct bk_csr {
   int* mdeferred;            // multi-GPU: chunks with ghost entries (processed after the halo arrived), own
   int n_mdeferred;
   int mask_patterns;         // distinct patterns in the table
+  // kernel 6G (group-unrolled, patterns as kernel parameters): group summaries + the host copy of the parameter block
+  int* mgsum;                // [ngroups8 * 8] group summaries of kernel 6G (nullptr: > BK_MASK_CP patterns / ghost entries), own
+  unsigned char mctab[2048]; // bk_mask_ctab<T> for the matrix' dtype
   int mw_win;                // kernel 6W: half-width W of the near window (0: no window plan)
   int mw_nfar;               // kernel 6W: far windows
   int mw_far[2];             // their offsets
@@ -184,6 +187,10 @@ struct bk_handle {
   int chunk;
   int fuse_xpay;
   int snake;
+  int mask_cctas;  // kernel 6G: CTAs per SM (2..4)
+  int mask_zteam;  // kernel 6G column order: CTAs per team (adjacent columns)
+  int mask_zmarch; // kernel 6G: column order of the groups (L1 reuse across grid planes)
+  int mask_const;  // kernel 6G (group-unrolled, patterns in the kernel's parameter block) when the matrix has <= 16 patterns
   int cg_lag_x;  // CG (3-kernel cut): x is updated every second iteration with both pending terms (9n instead of 10n per 2)
   int l2_hints;  // bit 0: K2 streams Ap | bit 1: K3 streams x | bit 2: K3 streams r | bit 3: SpMV streams masks
   // reduction scratch

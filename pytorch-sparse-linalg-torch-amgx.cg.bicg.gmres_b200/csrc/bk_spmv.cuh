@@ -376,6 +376,43 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
           return BK_OK;
         }
       }
+      if (h->mask_const && A->mgsum != nullptr) {  // kernel 6G: group-unrolled, pattern table as a kernel parameter
+        bk_mask_ctab<T> ct;
+        memcpy(&ct, A->mctab, sizeof(ct));
+        bk_maskg_plan gp;
+        gp.gsum = A->mgsum;
+        gp.zcols = 0;
+        if (h->mask_zmarch && A->mw_nfar > 0) {  // far offset = a whole number of groups: walk columns of groups
+          int F = 0;
+          for (int k = 0; k < A->mw_nfar; ++k) {
+            const int af = A->mw_far[k] < 0 ? -A->mw_far[k] : A->mw_far[k];
+            if (af > F) F = af;
+          }
+          const long long ngroups = ((A->n + 255) / 256 + 7) / 8;
+          if (F % 2048 == 0 && ngroups >= 4LL * (F / 2048)) gp.zcols = F / 2048;
+        }
+        gp.zteam = 1;
+        if (gp.zcols > 0) {
+          int tw = h->mask_zteam < 1 ? 1 : h->mask_zteam;
+          while (tw > 1 && (gp.zcols % tw) != 0) tw >>= 1;
+          gp.zteam = tw;
+        }
+        const int cctas = h->mask_cctas < 2 ? 2 : (h->mask_cctas > 4 ? 4 : h->mask_cctas);
+        int g = h->num_sms * cctas;
+        if (g > BK_MAXB) g = BK_MAXB;
+        g = bk_grid_rows(g, A->n, BK_BLOCK << 3);
+        if (gp.zcols > 0) {
+          g -= g % gp.zteam;
+          if (g < gp.zteam) gp.zcols = 0, gp.zteam = 1, g = 1;
+        }
+        switch (cctas) {
+          case 2: bk_spmv_maskg_kernel<T, MODE, DOTS, 2, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, gp, ct, sc, epi); break;
+          case 3: bk_spmv_maskg_kernel<T, MODE, DOTS, 3, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, gp, ct, sc, epi); break;
+          default: bk_spmv_maskg_kernel<T, MODE, DOTS, 4, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, gp, ct, sc, epi); break;
+        }
+        BK_KERNEL_CHECK();
+        return BK_OK;
+      }
       int ctas = h->mask_ctas < 2 ? 2 : (h->mask_ctas > 6 ? 6 : h->mask_ctas);
       int g = h->num_sms * ctas;
       if (g > BK_MAXB) g = BK_MAXB;
