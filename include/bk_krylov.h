@@ -94,7 +94,11 @@ typedef struct bk_csr_info {
                            matrices) + ordered per-row reduction | 5 = 2 with 8-bit codes of (column - row, value)
                            PAIRS and no value stream (constant-coefficient stencils; lossless, bit-identical) |
                            6 = one presence BITMASK per row over its 32-row chunk's pattern of (column - row, value)
-                           pairs; the pattern lives in registers (stencils with <= 8 pairs per chunk; bit-identical) */
+                           pairs; the pattern lives in registers (stencils with <= 8 pairs per chunk; bit-identical) |
+                           7 = kernel 6's plan served by the stencil fast path: every pattern is a sub-pattern of one
+                           offset set (7-point 3-D / 5-point 2-D), a lane owns two rows and gathers with 128-bit
+                           loads, offsets and values are constant-bank operands, one summary per 64 rows replaces the
+                           mask bytes of complete rows (fp64; bit-identical) */
   int32_t lanes_per_row;/* for kernel 1 */
   int32_t max_row_nnz;
   double mean_row_nnz;
@@ -118,6 +122,9 @@ int bk_destroy(bk_handle* h);
  *   use_split      1: matrices with a short mean row but a few very long rows are run on a virtual-row view (kernel 4)
  *   use_compress   0: off | 1: stream column indices as 8-bit dictionary codes when the matrix allows it (kernel 3)
  *                  | 2 (default): first try 8-bit codes of (column - row, value) pairs (kernel 5), then kernel 3
+ *                  | 3: first the row-bitmask plan (kernels 6 / 7)
+ *   mask_const     1 (default): matrices that qualify run kernel 7 instead of kernel 6;  mask_cctas: its CTAs per SM (4..6)
+ *   cg_lag_x       1 (default): CG on large systems updates x every second iteration with both pending terms (bit-identical)
  *   tma_ctas       CTAs per SM of the TMA SpMV (2..4), tma_stages: cap on its pipeline depth (0 = fill shared memory)
  *   prefetch_x     kernel 3: L2 bulk prefetch of the forward-diagonal x ranges (experiment, default 0)
  *   grid_mult_vec / grid_mult_spmv   CTAs per SM of the BLAS-1 kernels / the non-TMA SpMV kernels

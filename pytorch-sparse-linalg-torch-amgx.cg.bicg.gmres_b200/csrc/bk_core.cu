@@ -103,9 +103,8 @@ extern "C" int bk_create(int device, bk_handle** out) {
   h->tma_ctas = (int)bk_env_int("BK_TMA_CTAS", 4);
   h->pair_ctas = (int)bk_env_int("BK_PAIR_CTAS", 4);
   h->mask_ctas = (int)bk_env_int("BK_MASK_CTAS", 4);
-  h->mask_cctas = (int)bk_env_int("BK_MASK_CCTAS", 3);
-  h->mask_zmarch = (int)bk_env_int("BK_MASK_ZMARCH", 1);
-  h->mask_zteam = (int)bk_env_int("BK_MASK_ZTEAM", 16);
+  h->mask_cctas = (int)bk_env_int("BK_MASK_CCTAS", 4);
+  h->mask2_prefetch = (int)bk_env_int("BK_MASK2_PREFETCH", 0);
   h->mask_group = (int)bk_env_int("BK_MASK_GROUP", 8);
   h->mask_prefetch = (int)bk_env_int("BK_MASK_PREFETCH", 1);
   h->mask_window = (int)bk_env_int("BK_MASK_WINDOW", 0);  // measured slower than LDG + L2 prefetch so far (115 vs 84 us)
@@ -213,8 +212,7 @@ static int* bk_opt_field(bk_handle* h, const char* key) {
   if (!strcmp(key, "pair_ctas")) return &h->pair_ctas;
   if (!strcmp(key, "mask_ctas")) return &h->mask_ctas;
   if (!strcmp(key, "mask_cctas")) return &h->mask_cctas;
-  if (!strcmp(key, "mask_zmarch")) return &h->mask_zmarch;
-  if (!strcmp(key, "mask_zteam")) return &h->mask_zteam;
+  if (!strcmp(key, "mask2_prefetch")) return &h->mask2_prefetch;
   if (!strcmp(key, "mask_group")) return &h->mask_group;
   if (!strcmp(key, "mask_prefetch")) return &h->mask_prefetch;
   if (!strcmp(key, "mask_window")) return &h->mask_window;
@@ -898,31 +896,47 @@ __global__ void bk_mask_compact_kernel(const int* __restrict__ pids, long long n
 }
 
 // Try the row-bitmask plan (kernel 6).  ghost_gid / row_begin: see bk_mask_build_kernel (nullptr / 0 on one GPU).
-// kernel 6G: classify every (group of 8 blocks, warp position): one pattern over the 8 chunks?  every row complete?
-struct bk_mask_full16 {
-  unsigned int full[BK_MASK_CP];
+// kernel 7: every row's presence bits in UNION numbering, and one summary per 64-row step (two 32-row chunks): pattern
+// id, "some row lacks an entry of its pattern", "two patterns / matrix end within reach of the gathers".
+struct bk_mask_umap {
+  unsigned char pos[BK_MASK_CP][BK_MASK_L];  // union position of entry k of pattern p
+  unsigned int fullu[BK_MASK_CP];            // union bits of a complete row of pattern p
 };
-static __global__ void bk_mask_gsum_kernel(const unsigned char* __restrict__ masks, const int* __restrict__ pids,
-                                           const unsigned char* __restrict__ slot2dense, const bk_mask_full16 f,
-                                           const long long n, const int ngroups, int* __restrict__ gsum) {
+static __global__ void bk_mask_usum_kernel(const unsigned char* __restrict__ masks, const int* __restrict__ pids,
+                                           const unsigned char* __restrict__ slot2dense, const bk_mask_umap um,
+                                           const long long n, const long long nsteps, const long long minoff,
+                                           const long long maxoff, unsigned char* __restrict__ umasks,
+                                           unsigned short* __restrict__ usum, int* __restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long idx = warp; idx < (long long)ngroups * 8; idx += nwarps) {
-    const long long g = idx >> 3;
-    const int w = (int)(idx & 7);
-    bool mixed = (g + 1) * 2048 > n;  // the matrix ends inside the group
-    bool allfull = true;
+  for (long long st = warp; st < nsteps; st += nwarps) {
+    const long long r0 = st * 64;
+    // pairs are loaded with one element of slack on both sides: everything must stay inside [0, n rounded down to a pair)
+    bool mixed = r0 + 64 > n || r0 + minoff - 1 < 0 || r0 + 63 + maxoff + 1 >= (n & ~1LL);
+    bool dirty = false;
     int pid0 = 0;
-    for (int j = 0; j < 8; ++j) {
-      const long long c = (g * 8 + j) * 8 + w;  // (masks / pids are padded to whole groups)
-      const int pid = (int)slot2dense[pids[c] & (BK_MASK_HT - 1)];
-      if (j == 0) pid0 = pid;
+    for (int u = 0; u < 2; ++u) {
+      const long long c = st * 2 + u;  // (masks / pids are padded to whole groups)
+      int pid = (int)slot2dense[pids[c] & (BK_MASK_HT - 1)];
+      if (pid >= BK_MASK_CP) pid = 0;
+      if (u == 0) pid0 = pid;
       if (pid != pid0) mixed = true;
       const unsigned int m = masks[c * 32 + lane];
-      allfull = allfull && __all_sync(0xffffffffu, m == f.full[pid]);
+      unsigned int mu = 0u;
+#pragma unroll
+      for (int k = 0; k < BK_MASK_L; ++k) mu |= ((m >> k) & 1u) << um.pos[pid][k];
+      umasks[c * 32 + lane] = (unsigned char)mu;
+      dirty = dirty || __any_sync(0xffffffffu, (um.fullu[pid] & ~mu) != 0u);
     }
-    if (lane == 0) gsum[idx] = pid0 | (allfull ? BK_MASK_GS_FAST : 0) | (mixed ? BK_MASK_GS_MIXED : 0);
+    if (lane == 0) {
+      // step st = (group g, step j, warp w) in row order; stored as [g][w][j]: a warp reads its four summaries at once
+      const long long g = st >> 5;
+      const int j = (int)((st >> 3) & 3), w = (int)(st & 7);
+      usum[(g * 8 + w) * 4 + j] = (unsigned short)(pid0 | (dirty ? BK_MASK_US_DIRTY : 0) | (mixed ? BK_MASK_US_MIXED : 0));
+      if (mixed) atomicAdd(&counts[1], 1);
+      else if (dirty) atomicAdd(&counts[0], 1);
+    }
   }
 }
 
@@ -939,8 +953,11 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
     if (A->mpids) bk_pool_free(A->mpids);
     if (A->mptab) bk_pool_free(A->mptab);
     if (A->mdeferred) bk_pool_free(A->mdeferred);
-    if (A->mgsum) bk_pool_free(A->mgsum);
-    A->mgsum = nullptr;
+    if (A->musum) bk_pool_free(A->musum);
+    if (A->mumasks) bk_pool_free(A->mumasks);
+    A->musum = nullptr;
+    A->mumasks = nullptr;
+    A->mu_len = 0;
     A->mmasks = nullptr;
     A->mpids = nullptr;
     A->mptab = nullptr;
@@ -1038,17 +1055,50 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
       if (A->mw_win < 8) A->mw_win = 8;
       for (int k = 0; k < nfar_all && A->mw_nfar < 2; ++k)
         if (far[k] % ea == 0) A->mw_far[A->mw_nfar++] = far[k];
-      // kernel 6G: up to BK_MASK_CP patterns, none with ghost entries -> the table as a kernel parameter block and one
-      // summary per (group of 8 blocks, warp position)
-      if (A->mask_patterns <= BK_MASK_CP && A->n_cols == A->n) {
+      // kernel 7 (fp64): up to BK_MASK_CP patterns, all sub-patterns of one set of <= 8 offsets, no ghost entries -> the
+      // union's byte offsets and the per-pattern values as a kernel parameter block, masks in union numbering, one
+      // summary per 64-row step
+      if (A->dtype == BK_F64 && A->mask_patterns <= BK_MASK_CP && A->n_cols == A->n) {
         unsigned char* s2d = (unsigned char*)calloc(BK_MASK_HT, 1);
         unsigned char* d_s2d = nullptr;
-        bk_mask_ctab<double>* c64 = (bk_mask_ctab<double>*)A->mctab;
-        bk_mask_ctab<float>* c32 = (bk_mask_ctab<float>*)A->mctab;
-        static_assert(sizeof(bk_mask_ctab<double>) <= sizeof(A->mctab), "parameter block does not fit bk_csr::mctab");
+        bk_mask_utab* ctb = (bk_mask_utab*)A->mctab;
+        static_assert(sizeof(bk_mask_utab) <= sizeof(A->mctab), "parameter block does not fit bk_csr::mctab");
         memset(A->mctab, 0, sizeof(A->mctab));
-        int np = 0;
+        bk_mask_umap um;
+        memset(&um, 0, sizeof(um));
+        long long uni[BK_MASK_L];
+        int nu = 0;
         bool ok = s2d != nullptr;
+        for (int slot = 0; ok && slot < BK_MASK_HT; ++slot) {  // the union of the offsets, ascending
+          if (!hk[slot]) continue;
+          const bk_pair_entry* pe = tab + (size_t)slot * BK_MASK_L;
+          const unsigned int full = (unsigned int)(pe[0].pad >> BK_MASK_FULL_SHIFT) & 0x1ffu;
+          for (int e = 0; e < BK_MASK_L && ok; ++e) {
+            if (!(full & (1u << e))) continue;
+            if (pe[e].pad & BK_MASK_GHOST) ok = false;
+            const long long off = pe[e].off;
+            int at = 0;
+            while (at < nu && uni[at] < off) ++at;
+            if (at < nu && uni[at] == off) continue;
+            if (nu >= BK_MASK_L) {
+              ok = false;
+              break;
+            }
+            for (int q = nu; q > at; --q) uni[q] = uni[q - 1];
+            uni[at] = off;
+            ++nu;
+          }
+        }
+        int np = 0;
+        unsigned int oddmask = 0u;
+        for (int q = 0; ok && q < nu; ++q) {
+          if (uni[q] & 1) {
+            oddmask |= 1u << q;
+            ctb->offb[q] = 8 * (uni[q] - 1);
+          } else {
+            ctb->offb[q] = 8 * uni[q];
+          }
+        }
         for (int slot = 0; ok && slot < BK_MASK_HT; ++slot) {
           if (!hk[slot]) continue;
           if (np >= BK_MASK_CP) {
@@ -1056,48 +1106,56 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
             break;
           }
           const bk_pair_entry* pe = tab + (size_t)slot * BK_MASK_L;
-          unsigned int full = (unsigned int)(pe[0].pad >> BK_MASK_FULL_SHIFT) & 0x1ffu;
-          int len = 0;
+          const unsigned int full = (unsigned int)(pe[0].pad >> BK_MASK_FULL_SHIFT) & 0x1ffu;
           for (int e = 0; e < BK_MASK_L; ++e) {
-            if (pe[e].pad & BK_MASK_GHOST) ok = false;
-            if (full & (1u << e)) len = e + 1;
-            if (A->dtype == BK_F64) {
-              memcpy(&c64->val[np][e], &pe[e].val, 8);
-              c64->off[np][e] = pe[e].off;
-            } else {
-              memcpy(&c32->val[np][e], &pe[e].val, 4);
-              c32->off[np][e] = pe[e].off;
-            }
-          }
-          if (full == 0u) full = 0xffffffffu;  // empty pattern: no row of the chunk has entries
-          if (A->dtype == BK_F64) {
-            c64->full[np] = full;
-            c64->len[np] = len;
-          } else {
-            c32->full[np] = full;
-            c32->len[np] = len;
+            if (!(full & (1u << e))) continue;
+            int at = 0;
+            while (at < nu && uni[at] != (long long)pe[e].off) ++at;
+            // ONE value per offset and pattern: a chunk whose rows carry different coefficients on the same diagonal
+            // (variable-coefficient operators, e.g. the LDC pressure matrix) has two pairs with one offset -> kernel 6
+            if (um.fullu[np] & (1u << at)) ok = false;
+            memcpy(&ctb->val[np][at], &pe[e].val, 8);
+            um.pos[np][e] = (unsigned char)at;
+            um.fullu[np] |= 1u << at;
           }
           s2d[slot] = (unsigned char)np;
           ++np;
         }
-        const int ngroups8 = (int)(((A->n + 255) / 256 + 7) / 8);
-        if (ok && bk_pool_alloc((void**)&d_s2d, BK_MASK_HT, s) == cudaSuccess &&
-            bk_pool_alloc((void**)&A->mgsum, sizeof(int) * (size_t)ngroups8 * 8, s) == cudaSuccess) {
-          bk_mask_full16 f16;
-          for (int k = 0; k < BK_MASK_CP; ++k) f16.full[k] = (A->dtype == BK_F64) ? c64->full[k] : c32->full[k];
+        const long long ngroups8 = ((A->n + 255) / 256 + 7) / 8;
+        const long long nsteps = ngroups8 * 32;
+        int* dcount = (int*)(h->counters + 8);
+        if (ok && nu >= 1 && bk_pool_alloc((void**)&d_s2d, BK_MASK_HT, s) == cudaSuccess &&
+            bk_pool_alloc((void**)&A->musum, sizeof(unsigned short) * (size_t)nsteps, s) == cudaSuccess &&
+            bk_pool_alloc((void**)&A->mumasks, (size_t)nblk8 * 32, s) == cudaSuccess) {
           cudaMemcpyAsync(d_s2d, s2d, BK_MASK_HT, cudaMemcpyHostToDevice, s);
-          long long wantw = ((long long)ngroups8 * 8 * 32 + 255) / 256;
+          cudaMemsetAsync(A->mumasks, 0, (size_t)nblk8 * 32, s);
+          cudaMemsetAsync(dcount, 0, 2 * sizeof(int), s);
+          long long wantw = (nsteps * 32 + 255) / 256;
           int gg = (int)(wantw < (long long)h->num_sms * 8 ? wantw : (long long)h->num_sms * 8);
           if (gg < 1) gg = 1;
-          bk_mask_gsum_kernel<<<gg, 256, 0, s>>>(A->mmasks, A->mpids, d_s2d, f16, A->n, ngroups8, A->mgsum);
+          bk_mask_usum_kernel<<<gg, 256, 0, s>>>(A->mmasks, A->mpids, d_s2d, um, A->n, nsteps, uni[0], uni[nu - 1],
+                                                 A->mumasks, A->musum, dcount);
+          int cnt[2] = {0, 0};
+          cudaMemcpyAsync(cnt, dcount, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
           if (cudaStreamSynchronize(s) != cudaSuccess || cudaGetLastError() != cudaSuccess) {
-            bk_pool_free(A->mgsum);
-            A->mgsum = nullptr;
+            ok = false;
+          } else {
+            A->mu_len = nu;
+            A->mu_odd = (int)oddmask;
+            // matrix-side bytes of kernel 7: a 2-byte summary per 64 rows, mask bytes of the steps that read them
+            // (kernel 6's share for the mixed steps), the parameter block
+            A->mu_bytes = nsteps * 2 + (int64_t)cnt[0] * 64 + (int64_t)cnt[1] * (64 + 8) + (int64_t)sizeof(bk_mask_utab);
           }
         } else {
+          ok = false;
           cudaGetLastError();
-          if (A->mgsum) bk_pool_free(A->mgsum);
-          A->mgsum = nullptr;
+        }
+        if (!ok) {
+          if (A->musum) bk_pool_free(A->musum);
+          if (A->mumasks) bk_pool_free(A->mumasks);
+          A->musum = nullptr;
+          A->mumasks = nullptr;
+          A->mu_len = 0;
         }
         if (d_s2d) bk_pool_free(d_s2d);
         free(s2d);
@@ -1314,7 +1372,8 @@ extern "C" int bk_csr_destroy(bk_csr* A) {
   if (A->mpids) bk_pool_free(A->mpids);
   if (A->mptab) bk_pool_free(A->mptab);
   if (A->mdeferred) bk_pool_free(A->mdeferred);
-  if (A->mgsum) bk_pool_free(A->mgsum);
+  if (A->musum) bk_pool_free(A->musum);
+  if (A->mumasks) bk_pool_free(A->mumasks);
   free(A);
   return BK_OK;
 }
@@ -1330,6 +1389,10 @@ extern "C" int bk_csr_get_info(const bk_csr* A, bk_csr_info* out) {
   out->mean_row_nnz = A->mean_row_nnz;
   out->bytes_matrix = A->nnz * (int64_t)(bk_dtype_size(A->dtype) + 4) + (A->n + 1) * 4;
   out->bytes_stream = A->bytes_stream;
+  if (A->kernel == 6 && bk_mask2_usable(A->h, A)) {  // the stencil fast path serves this matrix (operands permitting)
+    out->kernel = 7;
+    out->bytes_stream = A->mu_bytes;
+  }
   return BK_OK;
 }
 

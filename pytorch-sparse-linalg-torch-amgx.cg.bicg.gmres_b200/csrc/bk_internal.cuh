@@ -124,9 +124,12 @@ struct bk_csr {
   int* mdeferred;            // multi-GPU: chunks with ghost entries (processed after the halo arrived), own
   int n_mdeferred;
   int mask_patterns;         // distinct patterns in the table
-  // kernel 6G (group-unrolled, patterns as kernel parameters): group summaries + the host copy of the parameter block
-  int* mgsum;                // [ngroups8 * 8] group summaries of kernel 6G (nullptr: > BK_MASK_CP patterns / ghost entries), own
-  unsigned char mctab[2048]; // bk_mask_ctab<T> for the matrix' dtype
+  // kernel 7 (two rows per lane, patterns as kernel parameters): tile summaries + the host copy of the parameter block
+  unsigned short* musum;     // [n / 64, whole groups] step summaries of kernel 7 (nullptr: fp32 / no common offset set / ghosts), own
+  unsigned char* mumasks;    // [nchunks * 32] presence bits in union numbering, own
+  int mu_len, mu_odd;        // union entries, bit mask of the odd offsets
+  int64_t mu_bytes;          // matrix-side bytes kernel 7 reads per SpMV
+  unsigned char mctab[1024]; // bk_mask_utab
   int mw_win;                // kernel 6W: half-width W of the near window (0: no window plan)
   int mw_nfar;               // kernel 6W: far windows
   int mw_far[2];             // their offsets
@@ -187,10 +190,9 @@ struct bk_handle {
   int chunk;
   int fuse_xpay;
   int snake;
-  int mask_cctas;  // kernel 6G: CTAs per SM (2..4)
-  int mask_zteam;  // kernel 6G column order: CTAs per team (adjacent columns)
-  int mask_zmarch; // kernel 6G: column order of the groups (L1 reuse across grid planes)
-  int mask_const;  // kernel 6G (group-unrolled, patterns in the kernel's parameter block) when the matrix has <= 16 patterns
+  int mask_cctas;  // kernel 7: CTAs per SM (4..6)
+  int mask2_prefetch;  // kernel 7: L2 bulk prefetch of the next group's x range (measured: no gain on 3-D stencils; off)
+  int mask_const;  // kernel 7 (two rows per lane, patterns in the kernel's parameter block) when the matrix has <= 12 patterns
   int cg_lag_x;  // CG (3-kernel cut): x is updated every second iteration with both pending terms (9n instead of 10n per 2)
   int l2_hints;  // bit 0: K2 streams Ap | bit 1: K3 streams x | bit 2: K3 streams r | bit 3: SpMV streams masks
   // reduction scratch

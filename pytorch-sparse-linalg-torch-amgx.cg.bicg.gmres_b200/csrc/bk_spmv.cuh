@@ -288,6 +288,13 @@ static inline int bk_set_smem(K kernel, size_t bytes) {
   return BK_OK;
 }
 
+// kernel 7 runs the structures it is instantiated for: 7 union offsets with the 3rd and 5th odd (3-D 7-point stencil, even
+// line length), 5 with the 2nd and 4th odd (2-D 5-point)
+static inline bool bk_mask2_usable(const bk_handle* h, const bk_csr* A) {
+  if (!h->mask_const || A->musum == nullptr || A->dtype != BK_F64) return false;
+  return (A->mu_len == 7 && A->mu_odd == 0x14) || (A->mu_len == 5 && A->mu_odd == 0x0a);
+}
+
 template <typename T, int MODE, int DOTS, int XMODE, typename Epi>
 static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a, const bk_scratch& sc,
                             Epi epi, cudaStream_t s);
@@ -376,53 +383,43 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
           return BK_OK;
         }
       }
-      if (h->mask_const && A->mgsum != nullptr) {  // kernel 6G: group-unrolled, pattern table as a kernel parameter
-        bk_mask_ctab<T> ct;
-        memcpy(&ct, A->mctab, sizeof(ct));
-        bk_maskg_plan gp;
-        gp.gsum = A->mgsum;
-        gp.zcols = 0;
-        if (h->mask_zmarch && A->mw_nfar > 0) {  // far offset = a whole number of groups: walk columns of groups
-          int F = 0;
-          for (int k = 0; k < A->mw_nfar; ++k) {
-            const int af = A->mw_far[k] < 0 ? -A->mw_far[k] : A->mw_far[k];
-            if (af > F) F = af;
+      if constexpr (std::is_same<T, double>::value) {
+        // kernel 7: two rows per lane, 128-bit gathers over the union of the patterns' offsets (operands 16-byte aligned;
+        // instantiated for 7-point 3-D and 5-point 2-D stencils with even line lengths)
+        if (bk_mask2_usable(h, A) && bk_aligned16(a.x) && bk_aligned16(a.y) && (MODE == 0 || bk_aligned16(a.b)) &&
+            ((DOTS & 1) == 0 || bk_aligned16(a.w))) {
+          bk_mask_utab ct;
+          memcpy(&ct, A->mctab, sizeof(ct));
+          bk_mask2_plan up;
+          plan.prefetch = (h->mask2_prefetch && bk_aligned16(a.x)) ? 1 : 0;
+          up.usum = A->musum;
+          up.umasks = A->mumasks;
+          const int cctas = h->mask_cctas < 4 ? 4 : (h->mask_cctas > 6 ? 6 : h->mask_cctas);
+          int g = h->num_sms * cctas;
+          if (g > BK_MAXB) g = BK_MAXB;
+          g = bk_grid_rows(g, A->n, BK_BLOCK << 3);
+          const bool s7 = A->mu_len == 7;
+#define BK_MASK2_LAUNCH(MINB)                                                                                     \
+  if (s7) bk_spmv_mask2_kernel<MODE, DOTS, 7, 0x14u, MINB, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, up, ct, sc, epi);    \
+  else bk_spmv_mask2_kernel<MODE, DOTS, 5, 0x0au, MINB, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, up, ct, sc, epi);
+          switch (cctas) {
+            case 4: BK_MASK2_LAUNCH(4) break;
+            case 5: BK_MASK2_LAUNCH(5) break;
+            default: BK_MASK2_LAUNCH(6) break;
           }
-          const long long ngroups = ((A->n + 255) / 256 + 7) / 8;
-          if (F % 2048 == 0 && ngroups >= 4LL * (F / 2048)) gp.zcols = F / 2048;
+#undef BK_MASK2_LAUNCH
+          BK_KERNEL_CHECK();
+          return BK_OK;
         }
-        gp.zteam = 1;
-        if (gp.zcols > 0) {
-          int tw = h->mask_zteam < 1 ? 1 : h->mask_zteam;
-          while (tw > 1 && (gp.zcols % tw) != 0) tw >>= 1;
-          gp.zteam = tw;
-        }
-        const int cctas = h->mask_cctas < 2 ? 2 : (h->mask_cctas > 4 ? 4 : h->mask_cctas);
-        int g = h->num_sms * cctas;
-        if (g > BK_MAXB) g = BK_MAXB;
-        g = bk_grid_rows(g, A->n, BK_BLOCK << 3);
-        if (gp.zcols > 0) {
-          g -= g % gp.zteam;
-          if (g < gp.zteam) gp.zcols = 0, gp.zteam = 1, g = 1;
-        }
-        switch (cctas) {
-          case 2: bk_spmv_maskg_kernel<T, MODE, DOTS, 2, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, gp, ct, sc, epi); break;
-          case 3: bk_spmv_maskg_kernel<T, MODE, DOTS, 3, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, gp, ct, sc, epi); break;
-          default: bk_spmv_maskg_kernel<T, MODE, DOTS, 4, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, gp, ct, sc, epi); break;
-        }
-        BK_KERNEL_CHECK();
-        return BK_OK;
       }
-      int ctas = h->mask_ctas < 2 ? 2 : (h->mask_ctas > 6 ? 6 : h->mask_ctas);
+      int ctas = h->mask_ctas < 3 ? 3 : (h->mask_ctas > 5 ? 5 : h->mask_ctas);
       int g = h->num_sms * ctas;
       if (g > BK_MAXB) g = BK_MAXB;
       g = bk_grid_rows(g, A->n, BK_BLOCK << plan.group);
       switch (ctas) {
-        case 2: bk_spmv_mask_kernel<T, MODE, DOTS, false, 2, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
         case 3: bk_spmv_mask_kernel<T, MODE, DOTS, false, 3, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
         case 4: bk_spmv_mask_kernel<T, MODE, DOTS, false, 4, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
-        case 5: bk_spmv_mask_kernel<T, MODE, DOTS, false, 5, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
-        default: bk_spmv_mask_kernel<T, MODE, DOTS, false, 6, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
+        default: bk_spmv_mask_kernel<T, MODE, DOTS, false, 5, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, sc, epi); break;
       }
     }
   } else if (A->kernel == 5 && XMODE == 0) {

@@ -574,86 +574,126 @@ bk_spmv_maskw_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_mas
 }
 
 // =====================================================================================================================
-// Kernel 6G — kernel 6 unrolled over a GROUP of 8 consecutive 256-row blocks, for single-GPU pattern matrices with at
-// most BK_MASK_CP patterns.  What the probes of round 2 said about kernel 6 (tools/k6_occupancy.py, ncu summaries in
-// profiles/r02_ncu_k6_*): latency-bound (fp32 at 2/3/4/5 CTAs per SM: 169/120/97/80 us), ~85 issued instructions per
-// 32-row chunk, of which only 7 + 7 are the gathers and the FMAs — the rest is 64-bit address arithmetic (sm_100 has no
-// 64-bit integer add: two instructions per gather), the per-chunk mask / pattern-id loads, the vote and the loop.
-// A warp's chunks inside a group are exactly 256 rows apart, and a stencil matrix keeps ONE pattern over almost every
-// group (P3D-256: a block is a grid line; the pattern changes at the first and last line of a plane), so:
-//   * registration classifies every (group, warp position) once: same pattern in all 8 chunks? every row complete?
-//     (bk_mask_gsum_kernel -> one int per 8 chunks instead of a mask byte per row + a pattern id per chunk);
-//   * the kernel forms the 7-8 gather pointers ONCE per group and walks the 8 chunks with immediate offsets
-//     (`ld [p_e + j * 2048]`): per chunk 7 loads, 7 FMAs, 1 store (+ the fused dot) and nothing else; the loads of two
-//     chunks are issued back to back (14 gathers in flight per warp);
-//   * complete groups (3/4 of a stencil matrix) read no masks at all; groups with incomplete rows (the grid-line ends)
-//     read one mask byte per row and predicate the gathers; mixed groups (pattern changes, the matrix tail) run the
-//     chunk-by-chunk code of kernel 6;
-//   * pattern values / offsets come from the kernel's parameter block (constant bank, indexed by the pattern id).
-// Same FMA chain in the same order => bit-identical to kernels 2 / 3 / 5 / 6 (tested).
+// Kernel 7 — the stencil fast path of the row-bitmask SpMV, rebuilt around what the round-2 probes measured
+// (tools/micro/gather_width.cu, tools/k6_occupancy.py, tools/k6_traffic_probe.py; summaries in profiles/):
+//   * a 7-gather stencil kernel is bound neither by HBM nor by L2 traffic (the same time whether the gathers hit L1, L2
+//     or all read the same line) but by the number of load instructions per row and the warps in flight: a bare 7-point
+//     gather takes 131 / 78 / 62 us at 2 / 4 / 6 CTAs per SM with 64-bit loads, 82 / 56 / 52 us with 128-bit loads
+//     (copy: 48 us); kernel 6 holds the pattern in 26 registers and issues ~85 instructions per 32-row chunk (84-105 us).
+// Hence, for matrices whose patterns are all sub-patterns of ONE offset set (the union; every constant-coefficient
+// stencil — boundary patterns only lack entries):
+//   * a lane owns TWO consecutive rows and gathers with 128-bit loads; an entry with an odd offset takes the aligned
+//     pair one element to the left, the second row's operand comes from the next lane by shuffle, lane 31 loads its own;
+//   * the byte offsets of the union travel in the kernel's parameter block and are constant-bank operands of the 64-bit
+//     address adds; the VALUES of the step's pattern (0 where the pattern lacks a union entry) are fetched from the
+//     parameter block by pattern id — no pattern registers, no per-pattern code, no pattern switches;
+//   * registration classifies every 64-row step once (bk_mask_usum_kernel): pattern id, "some row lacks an entry its
+//     pattern has" (such steps read two mask bytes per lane — in union numbering — and zero the missing operands),
+//     "two patterns / within reach of the matrix ends" (such steps run kernel 6's chunk code; none in the interior);
+//   * the structure (number of union entries, which are odd) is a template parameter: 7-point 3-D and 5-point 2-D
+//     stencils with even line lengths are instantiated; everything else stays on kernel 6.
+// An operand multiplied by a zero value contributes fma(0, x, s) = s, as the padded entries of kernels 5 / 6 do: the row
+// sums are the same FMA chain in CSR order => y is bit-identical to kernels 2 / 3 / 5 / 6 (tested).  fp64, single GPU.
 // =====================================================================================================================
-#define BK_MASK_CP 16       // patterns the parameter block holds
-#define BK_MASK_GS_FAST 0x100   // group summary: every row of the 8 chunks has every entry of the pattern
-#define BK_MASK_GS_MIXED 0x200  // group summary: chunks differ in pattern (or the group is cut by the matrix end)
+#define BK_MASK_CP 12        // patterns the parameter block holds
+#define BK_MASK_US_DIRTY 0x100   // step summary: some row lacks an entry of its pattern -> masks are read
+#define BK_MASK_US_MIXED 0x200   // step summary: two patterns in the 64 rows / matrix end within reach -> chunk code
 
-template <typename T>
-struct bk_mask_ctab {
-  T val[BK_MASK_CP][BK_MASK_L];
-  int off[BK_MASK_CP][BK_MASK_L];
-  unsigned int full[BK_MASK_CP];  // mask of a row that has every entry
-  int len[BK_MASK_CP];            // entries of the pattern
+struct bk_mask_utab {
+  double val[BK_MASK_CP][BK_MASK_L];  // value of union entry e in pattern p (0: the pattern has no such entry)
+  long long offb[BK_MASK_L];          // byte offset of the 16-byte pair to load: 8*off (even off), 8*(off-1) (odd off)
 };
 
-struct bk_maskg_plan {
-  const int* gsum;  // [ngroups8 * 8] summary of chunk position w of group g (BK_MASK_GS_*, low byte: dense pattern id)
-  int zteam;        // column order: CTAs work in teams of zteam on ADJACENT columns (one contiguous span of every plane:
-                    // DRAM rows are interleaved at 256 B, a lone 16 KB tile per CTA opens a row per 256 B — measured 2x slower)
-  int zcols;        // > 0: the far offset of the patterns is zcols groups (a grid plane): a CTA walks a COLUMN of groups
-                    // plane after plane, so the plane it gathered as "z+1" is its centre one visit later and its "z-1"
-                    // two visits later — both from L1 instead of L2 (0: groups dealt round-robin, like kernel 6)
+struct bk_mask2_plan {
+  const unsigned short* usum;     // [ngroups][8 warps][4 steps] step summaries (BK_MASK_US_*, low byte: pattern id)
+  const unsigned char* umasks;    // [rows] presence bits in UNION numbering
 };
 
-// two chunks (j0, j0 + 1) of a uniform group; p[e] = x + row0 + off_e.  MASKED: one presence byte per row.
-template <typename T, int MODE, int DOTS, bool MASKED, int J0>
-__device__ __forceinline__ void bk_maskg_pair(const T* const (&p)[BK_MASK_L], const T (&v)[BK_MASK_L], const int len,
-                                              const unsigned char* __restrict__ pm, T* __restrict__ py,
-                                              const T* __restrict__ pb, const T* __restrict__ pw, double* acc) {
-  T xv[2][BK_MASK_L];
-  unsigned int m[2] = {0xffu, 0xffu};
-  if (MASKED) {
-    m[0] = __ldg(pm + (J0 + 0) * 256);
-    m[1] = __ldg(pm + (J0 + 1) * 256);
-  }
+__device__ __forceinline__ double2 bk_ldg_pair(const double* base, long long byte_off) {
+  return __ldg(reinterpret_cast<const double2*>(reinterpret_cast<const char*>(base) + byte_off));
+}
+
+// One step: rows i, i + 1 of this lane (xr = x + i), every union entry.
+template <int MODE, int DOTS, int LEN, unsigned int ODD, bool DIRTY>
+__device__ __forceinline__ void bk_mask2_step(const bk_mask_utab& ct, const int pat, const double* xr,
+                                              const unsigned char* __restrict__ pm, double* __restrict__ py,
+                                              const double* __restrict__ pb, const double* __restrict__ pw,
+                                              const int lane, double* acc) {
+  double2 P[LEN];
+  double edge[LEN];
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-#pragma unroll
-    for (int e = 0; e < BK_MASK_L; ++e) {
-      xv[u][e] = T(0);
-      if (e < 5 || e < len) {  // (uniform; entries past the pattern's length are not touched)
-        if (!MASKED) xv[u][e] = __ldg(p[e] + (J0 + u) * 256);
-        else if (m[u] & (1u << e)) xv[u][e] = __ldg(p[e] + (J0 + u) * 256);
-      }
+  for (int e = 0; e < LEN; ++e) {
+    P[e] = bk_ldg_pair(xr, ct.offb[e]);
+    if ((ODD >> e) & 1u) {  // lane 31's second row: the element after its pair's neighbour
+      edge[e] = 0.0;
+      if (lane == 31)
+        edge[e] = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(xr) + ct.offb[e]) + 2);
     }
   }
+  unsigned int m2 = 0xffffu;
+  if (DIRTY) m2 = __ldg(reinterpret_cast<const unsigned short*>(pm));  // this lane's two mask bytes
+  double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    T sum = T(0);
-#pragma unroll
-    for (int e = 0; e < BK_MASK_L; ++e)
-      if (e < 5 || e < len) sum = fma(v[e], xv[u][e], sum);
-    T out = sum;
-    if constexpr (MODE == 1) out = bk_sub(__ldg(pb + (J0 + u) * 256), sum);
-    py[(J0 + u) * 256] = out;
-    if constexpr ((DOTS & 1) != 0) acc[0] += static_cast<double>(__ldg(pw + (J0 + u) * 256)) * static_cast<double>(out);
-    if constexpr ((DOTS & 2) != 0) acc[DOTS & 1] += static_cast<double>(out) * static_cast<double>(out);
+  for (int e = 0; e < LEN; ++e) {
+    double a0 = P[e].x, a1 = P[e].y;
+    if ((ODD >> e) & 1u) {  // pair (i + off - 1, i + off): row i takes .y, row i + 1 the next lane's .x
+      a0 = P[e].y;
+      a1 = __shfl_down_sync(0xffffffffu, P[e].x, 1);
+      if (lane == 31) a1 = edge[e];
+    }
+    if (DIRTY) {
+      a0 = (m2 & (1u << e)) ? a0 : 0.0;
+      a1 = (m2 & (0x100u << e)) ? a1 : 0.0;
+    }
+    const double v = ct.val[pat][e];
+    s0 = fma(v, a0, s0);
+    s1 = fma(v, a1, s1);
+  }
+  double o0 = s0, o1 = s1;
+  if constexpr (MODE == 1) {
+    const double2 bv = __ldg(reinterpret_cast<const double2*>(pb));
+    o0 = bk_sub(bv.x, s0);
+    o1 = bk_sub(bv.y, s1);
+  }
+  *reinterpret_cast<double2*>(py) = make_double2(o0, o1);
+  if constexpr ((DOTS & 1) != 0) {
+    const double2 wv = __ldg(reinterpret_cast<const double2*>(pw));
+    acc[0] += wv.x * o0;
+    acc[0] += wv.y * o1;
+  }
+  if constexpr ((DOTS & 2) != 0) {
+    acc[DOTS & 1] += o0 * o0;
+    acc[DOTS & 1] += o1 * o1;
   }
 }
 
-template <typename T, int MODE, int DOTS, int MINB, typename Epi>
+// A step with two patterns / within reach of the matrix ends: kernel 6's chunk code on its two 32-row chunks.
+// Not inlined: its pattern registers must not weigh on the hot path.
+// (returns its dot contributions by value: an accumulator whose address escapes would live in local memory)
+template <int MODE, int DOTS>
+__device__ __noinline__ double2 bk_mask2_mixed_step(const bk_spmv_args a, const bk_mask_plan plan, const int row_first,
+                                                    const int lane) {
+  const double* x = static_cast<const double*>(a.x);
+  const int n32 = (int)a.n;
+  bk_mask_pat<double> pat;
+  double t[2] = {0.0, 0.0};
+#pragma unroll 1
+  for (int u = 0; u < 2; ++u) {
+    const int row = row_first + u * 32 + lane;
+    const unsigned int m = __ldg(plan.masks + row);  // (masks / pids are padded by 32 blocks)
+    const int slot = __ldg(plan.pids + (row >> 5)) & (BK_MASK_PID_GHOST - 1);
+    bk_mask_load_pattern<double>(plan.ptab, slot, pat);
+    bk_mask_chunk<double, MODE, DOTS, false, false>(a, pat, x, nullptr, row, m, n32, t);
+  }
+  return make_double2(t[0], t[1]);
+}
+
+template <int MODE, int DOTS, int LEN, unsigned int ODD, int MINB, typename Epi>
 __global__ void __launch_bounds__(BK_BLOCK, MINB)
-bk_spmv_maskg_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_maskg_plan gp,
-                     const __grid_constant__ bk_mask_ctab<T> ct, const bk_scratch sc, Epi epi) {
+bk_spmv_mask2_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_mask2_plan up,
+                     const __grid_constant__ bk_mask_utab ct, const bk_scratch sc, Epi epi) {
   if (bk_spmv_skip(a)) return;
+  using T = double;
   constexpr int R = bk_ndots<DOTS>::value;
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
@@ -663,102 +703,62 @@ bk_spmv_maskg_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_mas
   int reverse = a.reverse;
   if (a.use_parity) reverse ^= (a.st->parity & 1);
   const T* __restrict__ x = static_cast<const T*>(a.x);
-  const unsigned char* __restrict__ masks = plan.masks;
-  const int* __restrict__ pids = plan.pids;  // hashed pattern-table slots (mixed groups run kernel 6's chunk code)
-  int my_visits, i0 = 0;
-  if (gp.zcols > 0) {  // (super-column, plane) items, column-major, cut into one contiguous piece per team
-    const int np = (ngroups + gp.zcols - 1) / gp.zcols;
-    const int tot = (gp.zcols / gp.zteam) * np;
-    const int nteams = (int)gridDim.x / gp.zteam;  // (the host launches a multiple of zteam CTAs)
-    const int team = (int)blockIdx.x / gp.zteam;
-    const int pr = (tot + nteams - 1) / nteams;
-    i0 = team * pr;
-    my_visits = i0 >= tot ? 0 : (tot - i0 < pr ? tot - i0 : pr);
-  } else {
-    my_visits = (ngroups > (int)blockIdx.x) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  }
 
   double acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.0;
 
-  // visit -> group.  Round-robin (zcols == 0), or column-major over (column, plane) cut into gridDim.x contiguous pieces.
-  const int ncol = gp.zcols;
-  const int nplanes = ncol > 0 ? (ngroups + ncol - 1) / ncol : 0;
-  const int member = ncol > 0 ? (int)blockIdx.x % gp.zteam : 0;
-  auto group_of = [&](int visit) -> int {  // (may be >= ngroups in the column order: a hole of the last plane)
-    if (ncol > 0) {
-      const int idx = i0 + visit;
-      const int sc = idx / nplanes;  // super-column (zteam adjacent columns)
-      return (idx - sc * nplanes) * ncol + sc * gp.zteam + member;
-    }
+  const int my_visits = (ngroups > (int)blockIdx.x) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  auto group_of = [&](int visit) -> int {
     const int g = (int)blockIdx.x + visit * (int)gridDim.x;
     return reverse ? (ngroups - 1 - g) : g;
   };
-  auto prefetch_group = [&](int visit) {  // see kernel 6: the x range of a group this CTA visits soon -> L2
+  auto prefetch_group = [&](int visit) {  // see kernel 6: the x range of the group this CTA visits next -> L2
     if (visit >= my_visits) return;
-    const int gg = group_of(visit);
-    if (gg >= ngroups) return;
-    const long long r0 = (long long)gg * 2048;
+    const long long r0 = (long long)group_of(visit) * 2048;
     long long r1 = r0 + 2048;
-    constexpr long long EA = 16 / sizeof(T);
-    const long long nal = (long long)n32 & ~(EA - 1);
+    const long long nal = (long long)n32 & ~1LL;
     if (r1 > nal) r1 = nal;
     if (r1 > r0) bk_bulk_prefetch_l2(x + r0, (uint32_t)((r1 - r0) * sizeof(T)));
   };
   const bool pf = plan.prefetch != 0 && threadIdx.x == 0;
   if (pf) prefetch_group(1);
-  auto summary = [&](int visit) -> int {
-    const int gg = group_of(visit);
-    return gg < ngroups ? __ldg(gp.gsum + gg * 8 + wid) : -1;
-  };
-  int s_next = my_visits > 0 ? summary(0) : 0;
-  bk_mask_pat<T> pat;  // (mixed groups only)
-  int cur = -1;
+  // the warp's four step summaries of a group are stored together (one 8-byte load); those of the NEXT visit are loaded
+  // one visit ahead
+  uint2 sm_next = make_uint2(0u, 0u);
+  if (my_visits > 0) sm_next = __ldg(reinterpret_cast<const uint2*>(up.usum) + group_of(0) * 8 + wid);
   for (int visit = 0; visit < my_visits; ++visit) {
     const int gg = group_of(visit);
-    const int s = s_next;
-    if (visit + 1 < my_visits) s_next = summary(visit + 1);
     if (pf) prefetch_group(visit + 2);
-    if (s < 0) continue;  // hole of the column order
-    const int row0 = gg * 2048 + wid * 32 + lane;
-    if ((s & BK_MASK_GS_MIXED) == 0) {
-      const int slot = s & 0xff;
-      const int len = ct.len[slot];
-      const T* p[BK_MASK_L];
-      T v[BK_MASK_L];
+    // this lane's rows in step j: row0 + 512 j, row0 + 512 j + 1
+    const int row0 = gg * 2048 + wid * 64 + 2 * lane;
+    const uint2 smq = sm_next;
+    if (visit + 1 < my_visits) sm_next = __ldg(reinterpret_cast<const uint2*>(up.usum) + group_of(visit + 1) * 8 + wid);
+    unsigned int sm[4];
+    sm[0] = smq.x & 0xffffu;
+    sm[1] = smq.x >> 16;
+    sm[2] = smq.y & 0xffffu;
+    sm[3] = smq.y >> 16;
+    const T* xr = x + row0;
+    const unsigned char* pm = up.umasks + row0;
+    T* py = static_cast<T*>(a.y) + row0;
+    const T* pb = MODE == 1 ? static_cast<const T*>(a.b) + row0 : nullptr;
+    const T* pw = (DOTS & 1) ? static_cast<const T*>(a.w) + row0 : nullptr;
 #pragma unroll
-      for (int e = 0; e < BK_MASK_L; ++e) {
-        p[e] = x + row0 + ct.off[slot][e];
-        v[e] = ct.val[slot][e];
-      }
-      T* py = static_cast<T*>(a.y) + row0;
-      const T* pb = MODE == 1 ? static_cast<const T*>(a.b) + row0 : nullptr;
-      const T* pw = (DOTS & 1) ? static_cast<const T*>(a.w) + row0 : nullptr;
-      const unsigned char* pm = masks + row0;
-      if (s & BK_MASK_GS_FAST) {
-        bk_maskg_pair<T, MODE, DOTS, false, 0>(p, v, len, pm, py, pb, pw, acc);
-        bk_maskg_pair<T, MODE, DOTS, false, 2>(p, v, len, pm, py, pb, pw, acc);
-        bk_maskg_pair<T, MODE, DOTS, false, 4>(p, v, len, pm, py, pb, pw, acc);
-        bk_maskg_pair<T, MODE, DOTS, false, 6>(p, v, len, pm, py, pb, pw, acc);
+    for (int j = 0; j < 4; ++j) {
+      const unsigned int s = sm[j];
+      if ((s & (BK_MASK_US_DIRTY | BK_MASK_US_MIXED)) == 0) {
+        bk_mask2_step<MODE, DOTS, LEN, ODD, false>(ct, (int)(s & 0xffu), xr + j * 512, pm + j * 512, py + j * 512,
+                                                  MODE == 1 ? pb + j * 512 : nullptr, (DOTS & 1) ? pw + j * 512 : nullptr,
+                                                  lane, acc);
+      } else if ((s & BK_MASK_US_MIXED) == 0) {
+        bk_mask2_step<MODE, DOTS, LEN, ODD, true>(ct, (int)(s & 0xffu), xr + j * 512, pm + j * 512, py + j * 512,
+                                                 MODE == 1 ? pb + j * 512 : nullptr, (DOTS & 1) ? pw + j * 512 : nullptr,
+                                                 lane, acc);
       } else {
-        bk_maskg_pair<T, MODE, DOTS, true, 0>(p, v, len, pm, py, pb, pw, acc);
-        bk_maskg_pair<T, MODE, DOTS, true, 2>(p, v, len, pm, py, pb, pw, acc);
-        bk_maskg_pair<T, MODE, DOTS, true, 4>(p, v, len, pm, py, pb, pw, acc);
-        bk_maskg_pair<T, MODE, DOTS, true, 6>(p, v, len, pm, py, pb, pw, acc);
-      }
-    } else {
-      // pattern changes inside the group / the matrix ends inside it: kernel 6's chunk-by-chunk code
-#pragma unroll 1
-      for (int j = 0; j < 8; ++j) {
-        const int row = row0 + j * 256;
-        const unsigned int m = __ldg(masks + row);  // (masks / pids are padded by 32 blocks)
-        const int slot = __ldg(pids + (row >> 5)) & (BK_MASK_PID_GHOST - 1);
-        if (slot != cur) {
-          bk_mask_load_pattern<T>(plan.ptab, slot, pat);
-          cur = slot;
-        }
-        bk_mask_chunk<T, MODE, DOTS, false, false>(a, pat, x, nullptr, row, m, n32, acc);
+        const double2 t = bk_mask2_mixed_step<MODE, DOTS>(a, plan, gg * 2048 + j * 512 + wid * 64, lane);
+        if constexpr (DOTS != 0) acc[0] += t.x;
+        if constexpr (R == 2) acc[1] += t.y;
       }
     }
   }

@@ -27,7 +27,7 @@ def time_gpu(fn, reps=30, warm=5):
 
 dev = torch.device("cuda", 0)
 h = _native.Handle.get(dev)
-h.set_option("mask_zmarch", 0)
+h.set_option("mask_cctas", 4)
 for kind in ("p2d_65536x256", "p2d_4096x4096", "p3d_256"):
     if kind == "p2d_65536x256":
         A = problems.poisson2d_csr(65536, 256, device=dev)

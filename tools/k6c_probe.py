@@ -37,18 +37,13 @@ for kind in ("p3d", "cd3d"):
     us0 = 1e3 * time_gpu(lambda: m.spmv_dot(x, x))
     print(json.dumps(dict(what="k6", kind=kind, patterns=m.info().get("mask_patterns"), us=round(us0, 2))), flush=True)
     h.set_option("mask_const", 1)
-    for cctas in (2, 3, 4):
-        for grp in (0, 4, 8, 16, 32):
-            h.set_option("mask_cctas", cctas)
-            h.set_option("mask_zmarch", 1 if grp else 0)
-            h.set_option("mask_zteam", max(grp, 1))
-            y1, d1 = m.spmv_dot(x, x)
-            same = bool(torch.equal(y1, y0))
-            us = 1e3 * time_gpu(lambda: m.spmv_dot(x, x))
-            print(json.dumps(dict(what="k6g", kind=kind, mask_cctas=cctas, zteam=grp, us=round(us, 2), bitwise_y=same,
-                                  dot_rel=float(abs(d1 - d0) / abs(d0)))), flush=True)
-    h.set_option("mask_cctas", 3)
-    h.set_option("mask_zmarch", 1)
-    h.set_option("mask_zteam", 16)
+    for cctas in (4, 5, 6):
+        h.set_option("mask_cctas", cctas)
+        y1, d1 = m.spmv_dot(x, x)
+        same = bool(torch.equal(y1, y0))
+        us = 1e3 * time_gpu(lambda: m.spmv_dot(x, x))
+        print(json.dumps(dict(what="k7", kind=kind, mask_cctas=cctas, us=round(us, 2), bitwise_y=same,
+                              dot_rel=float(abs(d1 - d0) / abs(d0)))), flush=True)
+    h.set_option("mask_cctas", 5)
     del m, A
     _native.clear_cache()
