@@ -918,7 +918,9 @@ static __global__ void bk_mask_usum_kernel(const unsigned char* __restrict__ mas
     int pid0 = 0;
     for (int u = 0; u < 2; ++u) {
       const long long c = st * 2 + u;  // (masks / pids are padded to whole groups)
-      int pid = (int)slot2dense[pids[c] & (BK_MASK_HT - 1)];
+      const int praw = pids[c];
+      if (praw & BK_MASK_PID_GHOST) mixed = true;  // (row partition) ghost entries: the chunk waits for the halo
+      int pid = (int)slot2dense[praw & (BK_MASK_HT - 1)];
       if (pid >= BK_MASK_CP) pid = 0;
       if (u == 0) pid0 = pid;
       if (pid != pid0) mixed = true;
@@ -1058,7 +1060,7 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
       // kernel 7 (fp64): up to BK_MASK_CP patterns, all sub-patterns of one set of <= 8 offsets, no ghost entries -> the
       // union's byte offsets and the per-pattern values as a kernel parameter block, masks in union numbering, one
       // summary per 64-row step
-      if (A->dtype == BK_F64 && A->mask_patterns <= BK_MASK_CP && A->n_cols == A->n) {
+      if (A->dtype == BK_F64) {
         unsigned char* s2d = (unsigned char*)calloc(BK_MASK_HT, 1);
         unsigned char* d_s2d = nullptr;
         bk_mask_utab* ctb = (bk_mask_utab*)A->mctab;
@@ -1073,9 +1075,11 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
           if (!hk[slot]) continue;
           const bk_pair_entry* pe = tab + (size_t)slot * BK_MASK_L;
           const unsigned int full = (unsigned int)(pe[0].pad >> BK_MASK_FULL_SHIFT) & 0x1ffu;
+          bool ghosty = false;  // (row partition) patterns with ghost entries belong to chunks of the second phase
+          for (int e = 0; e < BK_MASK_L; ++e) ghosty = ghosty || ((full & (1u << e)) && (pe[e].pad & BK_MASK_GHOST));
+          if (ghosty) continue;
           for (int e = 0; e < BK_MASK_L && ok; ++e) {
             if (!(full & (1u << e))) continue;
-            if (pe[e].pad & BK_MASK_GHOST) ok = false;
             const long long off = pe[e].off;
             int at = 0;
             while (at < nu && uni[at] < off) ++at;
@@ -1101,12 +1105,15 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
         }
         for (int slot = 0; ok && slot < BK_MASK_HT; ++slot) {
           if (!hk[slot]) continue;
+          const bk_pair_entry* pe = tab + (size_t)slot * BK_MASK_L;
+          const unsigned int full = (unsigned int)(pe[0].pad >> BK_MASK_FULL_SHIFT) & 0x1ffu;
+          bool ghosty = false;
+          for (int e = 0; e < BK_MASK_L; ++e) ghosty = ghosty || ((full & (1u << e)) && (pe[e].pad & BK_MASK_GHOST));
+          if (ghosty) continue;  // (s2d stays 0: steps with such chunks are marked mixed below and never use it)
           if (np >= BK_MASK_CP) {
             ok = false;
             break;
           }
-          const bk_pair_entry* pe = tab + (size_t)slot * BK_MASK_L;
-          const unsigned int full = (unsigned int)(pe[0].pad >> BK_MASK_FULL_SHIFT) & 0x1ffu;
           for (int e = 0; e < BK_MASK_L; ++e) {
             if (!(full & (1u << e))) continue;
             int at = 0;
@@ -1142,6 +1149,7 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
           } else {
             A->mu_len = nu;
             A->mu_odd = (int)oddmask;
+            A->mu_center = (nu >= 3 && uni[nu / 2] == 0 && uni[nu / 2 - 1] == -1 && uni[nu / 2 + 1] == 1) ? 1 : 0;
             // matrix-side bytes of kernel 7: a 2-byte summary per 64 rows, mask bytes of the steps that read them
             // (kernel 6's share for the mixed steps), the parameter block
             A->mu_bytes = nsteps * 2 + (int64_t)cnt[0] * 64 + (int64_t)cnt[1] * (64 + 8) + (int64_t)sizeof(bk_mask_utab);

@@ -473,6 +473,29 @@ struct bk_sys_dist {
         plan.err_flag = D->p2p.counters + 4;
       }
       bk_epi_fold<RF, Epi> fe{epi, gsum(), st, D->npeers > 0 ? 1 : 0};
+      if constexpr (std::is_same<T, double>::value) {
+        // kernel 7 on the interior steps (bk_spmv_mask.cuh), kernel 6's chunk code on the chunks with ghost entries
+        if (bk_mask2_usable(h, E) && bk_aligned16(x) && bk_aligned16(y) && (MODE == 0 || bk_aligned16(b)) &&
+            ((DOTS & 1) == 0 || bk_aligned16(w))) {
+          bk_mask_utab ct;
+          memcpy(&ct, E->mctab, sizeof(ct));
+          bk_mask2_plan up;
+          up.usum = E->musum;
+          up.umasks = E->mumasks;
+          plan.prefetch = 0;
+          int g7 = h->num_sms * 4;
+          if (g7 > BK_MAXB) g7 = BK_MAXB;
+          g7 = bk_grid_rows(g7, E->n, BK_BLOCK << 3);
+          if (E->mu_len == 7)
+            bk_spmv_mask2_kernel<MODE, DOTS, 7, 0x14u, true, 4, bk_epi_fold<RF, Epi>><<<g7, BK_BLOCK, 0, cs>>>(
+                a, plan, up, ct, bk_slot(h, 0), fe);
+          else
+            bk_spmv_mask2_kernel<MODE, DOTS, 5, 0x0au, true, 4, bk_epi_fold<RF, Epi>><<<g7, BK_BLOCK, 0, cs>>>(
+                a, plan, up, ct, bk_slot(h, 0), fe);
+          BK_KERNEL_CHECK();
+          return BK_OK;
+        }
+      }
       int g = h->num_sms * 4;
       if (g > BK_MAXB) g = BK_MAXB;
       g = bk_grid_rows(g, E->n, BK_BLOCK << plan.group);

@@ -128,6 +128,7 @@ struct bk_csr {
   unsigned short* musum;     // [n / 64, whole groups] step summaries of kernel 7 (nullptr: fp32 / no common offset set / ghosts), own
   unsigned char* mumasks;    // [nchunks * 32] presence bits in union numbering, own
   int mu_len, mu_odd;        // union entries, bit mask of the odd offsets
+  int mu_center;             // 1: the union holds -1, 0, +1 at positions len/2 - 1, len/2, len/2 + 1
   int64_t mu_bytes;          // matrix-side bytes kernel 7 reads per SpMV
   unsigned char mctab[1024]; // bk_mask_utab
   int mw_win;                // kernel 6W: half-width W of the near window (0: no window plan)

@@ -292,6 +292,7 @@ static inline int bk_set_smem(K kernel, size_t bytes) {
 // line length), 5 with the 2nd and 4th odd (2-D 5-point)
 static inline bool bk_mask2_usable(const bk_handle* h, const bk_csr* A) {
   if (!h->mask_const || A->musum == nullptr || A->dtype != BK_F64) return false;
+  if (!A->mu_center) return false;  // offsets -1, 0, +1 at the union positions K - 1, K, K + 1
   return (A->mu_len == 7 && A->mu_odd == 0x14) || (A->mu_len == 5 && A->mu_odd == 0x0a);
 }
 
@@ -400,8 +401,8 @@ static int bk_launch_spmv_t(bk_handle* h, const bk_csr* A, const bk_spmv_args& a
           g = bk_grid_rows(g, A->n, BK_BLOCK << 3);
           const bool s7 = A->mu_len == 7;
 #define BK_MASK2_LAUNCH(MINB)                                                                                     \
-  if (s7) bk_spmv_mask2_kernel<MODE, DOTS, 7, 0x14u, MINB, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, up, ct, sc, epi);    \
-  else bk_spmv_mask2_kernel<MODE, DOTS, 5, 0x0au, MINB, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, up, ct, sc, epi);
+  if (s7) bk_spmv_mask2_kernel<MODE, DOTS, 7, 0x14u, false, MINB, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, up, ct, sc, epi);    \
+  else bk_spmv_mask2_kernel<MODE, DOTS, 5, 0x0au, false, MINB, Epi><<<g, BK_BLOCK, 0, s>>>(a, plan, up, ct, sc, epi);
           switch (cctas) {
             case 4: BK_MASK2_LAUNCH(4) break;
             case 5: BK_MASK2_LAUNCH(5) break;

@@ -613,33 +613,41 @@ __device__ __forceinline__ double2 bk_ldg_pair(const double* base, long long byt
   return __ldg(reinterpret_cast<const double2*>(reinterpret_cast<const char*>(base) + byte_off));
 }
 
-// One step: rows i, i + 1 of this lane (xr = x + i), every union entry.
+// One step: rows i, i + 1 of this lane (xr = x + i), every union entry.  The instantiated structures have the offsets
+// -1, 0, +1 at the union positions K - 1, K, K + 1 (K = LEN / 2; checked at registration), so the two odd entries need no
+// loads of their own: x[i - 1] is the previous lane's centre .y, x[i + 2] the next lane's centre .x (lanes 0 / 31 load
+// theirs) — ncu on the first version showed the L1 wavefront pipe at 67 %, the top unit; this removes 8 of ~42 wavefronts.
 template <int MODE, int DOTS, int LEN, unsigned int ODD, bool DIRTY>
 __device__ __forceinline__ void bk_mask2_step(const bk_mask_utab& ct, const int pat, const double* xr,
                                               const unsigned char* __restrict__ pm, double* __restrict__ py,
                                               const double* __restrict__ pb, const double* __restrict__ pw,
                                               const int lane, double* acc) {
+  constexpr int K = LEN / 2;
+  static_assert(ODD == ((1u << (K - 1)) | (1u << (K + 1))), "kernel 7: the odd entries are the centre's two neighbours");
   double2 P[LEN];
-  double edge[LEN];
 #pragma unroll
-  for (int e = 0; e < LEN; ++e) {
-    P[e] = bk_ldg_pair(xr, ct.offb[e]);
-    if ((ODD >> e) & 1u) {  // lane 31's second row: the element after its pair's neighbour
-      edge[e] = 0.0;
-      if (lane == 31)
-        edge[e] = __ldg(reinterpret_cast<const double*>(reinterpret_cast<const char*>(xr) + ct.offb[e]) + 2);
-    }
-  }
+  for (int e = 0; e < LEN; ++e)
+    if (!((ODD >> e) & 1u)) P[e] = bk_ldg_pair(xr, ct.offb[e]);
+  double lo = 0.0, hi = 0.0;
+  if (lane == 0) lo = __ldg(xr - 1);
+  if (lane == 31) hi = __ldg(xr + 2);
   unsigned int m2 = 0xffffu;
   if (DIRTY) m2 = __ldg(reinterpret_cast<const unsigned short*>(pm));  // this lane's two mask bytes
   double s0 = 0.0, s1 = 0.0;
 #pragma unroll
   for (int e = 0; e < LEN; ++e) {
-    double a0 = P[e].x, a1 = P[e].y;
-    if ((ODD >> e) & 1u) {  // pair (i + off - 1, i + off): row i takes .y, row i + 1 the next lane's .x
-      a0 = P[e].y;
-      a1 = __shfl_down_sync(0xffffffffu, P[e].x, 1);
-      if (lane == 31) a1 = edge[e];
+    double a0, a1;
+    if (e == K - 1) {         // offset -1: rows i, i + 1 take x[i - 1], x[i]
+      a0 = __shfl_up_sync(0xffffffffu, P[K].y, 1);
+      if (lane == 0) a0 = lo;
+      a1 = P[K].x;
+    } else if (e == K + 1) {  // offset +1: x[i + 1], x[i + 2]
+      a0 = P[K].y;
+      a1 = __shfl_down_sync(0xffffffffu, P[K].x, 1);
+      if (lane == 31) a1 = hi;
+    } else {
+      a0 = P[e].x;
+      a1 = P[e].y;
     }
     if (DIRTY) {
       a0 = (m2 & (1u << e)) ? a0 : 0.0;
@@ -670,7 +678,7 @@ __device__ __forceinline__ void bk_mask2_step(const bk_mask_utab& ct, const int 
 // A step with two patterns / within reach of the matrix ends: kernel 6's chunk code on its two 32-row chunks.
 // Not inlined: its pattern registers must not weigh on the hot path.
 // (returns its dot contributions by value: an accumulator whose address escapes would live in local memory)
-template <int MODE, int DOTS>
+template <int MODE, int DOTS, bool GHOST>
 __device__ __noinline__ double2 bk_mask2_mixed_step(const bk_spmv_args a, const bk_mask_plan plan, const int row_first,
                                                     const int lane) {
   const double* x = static_cast<const double*>(a.x);
@@ -681,14 +689,67 @@ __device__ __noinline__ double2 bk_mask2_mixed_step(const bk_spmv_args a, const 
   for (int u = 0; u < 2; ++u) {
     const int row = row_first + u * 32 + lane;
     const unsigned int m = __ldg(plan.masks + row);  // (masks / pids are padded by 32 blocks)
-    const int slot = __ldg(plan.pids + (row >> 5)) & (BK_MASK_PID_GHOST - 1);
+    const int pid = __ldg(plan.pids + (row >> 5));
+    if (GHOST && (pid & BK_MASK_PID_GHOST)) continue;  // chunks with ghost entries: second phase, after the halo
+    const int slot = pid & (BK_MASK_PID_GHOST - 1);
     bk_mask_load_pattern<double>(plan.ptab, slot, pat);
     bk_mask_chunk<double, MODE, DOTS, false, false>(a, pat, x, nullptr, row, m, n32, t);
   }
   return make_double2(t[0], t[1]);
 }
 
-template <int MODE, int DOTS, int LEN, unsigned int ODD, int MINB, typename Epi>
+// Multi-GPU (folded SpMV over [local | ghost], bk_dist.cuh): the chunks that gather ghost entries, after the neighbours'
+// halos have landed — kernel 6's second phase (flag poll with acquire loads, then the compact list of those chunks).
+template <int MODE, int DOTS>
+__device__ __noinline__ double2 bk_mask2_ghost_phase(const bk_spmv_args a, const bk_mask_plan plan) {
+  double t[2] = {0.0, 0.0};
+  if (plan.n_deferred == 0 && plan.flags == nullptr) return make_double2(0.0, 0.0);
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  bool ok = true;
+  if (plan.flags != nullptr) {
+    __shared__ int s_fail2;
+    if (threadIdx.x == 0) s_fail2 = 0;
+    __syncthreads();
+    const unsigned int want = *plan.halo_seq + 1u;
+    if ((int)threadIdx.x < plan.n_flag_peers) {
+      const unsigned long long* flag = plan.flags + plan.flag_peers[threadIdx.x];
+      const long long t0 = clock64();
+      while ((unsigned int)bk_ld_acquire_sys_u64(flag) != want) {
+        if (clock64() - t0 > BK_P2P_TIMEOUT_CYCLES) {
+          s_fail2 = 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if (s_fail2) {
+      if (threadIdx.x == 0) *plan.err_flag = 1u;
+      ok = false;
+    }
+  }
+  if (ok) {
+    const double* x = static_cast<const double*>(a.x);
+    const double* xg = static_cast<const double*>(plan.xg);
+    const int n32 = (int)a.n;
+    bk_mask_pat<double> pat;
+    int cur = -1;
+    const int warps = (int)gridDim.x * BK_WARPS;
+    for (int i = (int)blockIdx.x * BK_WARPS + wid; i < plan.n_deferred; i += warps) {
+      const int c0 = __ldg(plan.deferred + i);
+      const unsigned int m = __ldg(plan.masks + (size_t)c0 * 32 + lane);
+      const int slot = __ldg(plan.pids + c0) & (BK_MASK_PID_GHOST - 1);
+      if (slot != cur) {
+        bk_mask_load_pattern<double>(plan.ptab, slot, pat);
+        cur = slot;
+      }
+      bk_mask_chunk<double, MODE, DOTS, true, false>(a, pat, x, xg, c0 * 32 + lane, m, n32, t);
+    }
+  }
+  return make_double2(t[0], t[1]);
+}
+
+template <int MODE, int DOTS, int LEN, unsigned int ODD, bool GHOST, int MINB, typename Epi>
 __global__ void __launch_bounds__(BK_BLOCK, MINB)
 bk_spmv_mask2_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_mask2_plan up,
                      const __grid_constant__ bk_mask_utab ct, const bk_scratch sc, Epi epi) {
@@ -756,11 +817,16 @@ bk_spmv_mask2_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_mas
                                                  MODE == 1 ? pb + j * 512 : nullptr, (DOTS & 1) ? pw + j * 512 : nullptr,
                                                  lane, acc);
       } else {
-        const double2 t = bk_mask2_mixed_step<MODE, DOTS>(a, plan, gg * 2048 + j * 512 + wid * 64, lane);
+        const double2 t = bk_mask2_mixed_step<MODE, DOTS, GHOST>(a, plan, gg * 2048 + j * 512 + wid * 64, lane);
         if constexpr (DOTS != 0) acc[0] += t.x;
         if constexpr (R == 2) acc[1] += t.y;
       }
     }
+  }
+  if constexpr (GHOST) {
+    const double2 t = bk_mask2_ghost_phase<MODE, DOTS>(a, plan);
+    if constexpr (DOTS != 0) acc[0] += t.x;
+    if constexpr (R == 2) acc[1] += t.y;
   }
   if constexpr (DOTS != 0) {
     bk_grid_reduce<R, Epi, BK_WARPS>(acc, sc, epi);
