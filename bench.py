@@ -20,7 +20,8 @@ A "step" is ONE full CG solve of that system (611 iterations) made through the r
                 bytes counted by the library at registration (bk_csr_info.bytes_stream) + one read of x + one write of
                 y — / mean launch time.
   iteration     the whole CG iteration both ways: algorithmic bytes (nnz*12 + 4(n+1) + 11n*8) and actual
-                bytes (bytes_stream + 10n*8: K1 reads p writes Ap, K2 reads Ap,r writes r, K3 reads x,p,r writes x,p).
+                bytes (bytes_stream + 10n*8: K1 reads p writes Ap, K2 reads Ap,r writes r, K3 reads x,p,r writes x,p; 9.5n*8 with
+                the lagged-x cut).
   cpu_baseline  the oracle port of the reference (torch CPU, all host threads) on a bounded fixed-iteration window.
   extra         the other BASELINE configs through the same API: config 3 (BiCGStab, CD3D-256), config 4 (GMRES(30) on
                 the LDC-100 pressure system, forward and forward+backward), config 1 (CG, 2-D Poisson 256^2) and the
@@ -53,7 +54,8 @@ import torch  # noqa: E402
 KERNEL_NAMES = {0: "bk_spmv_stream_kernel", 1: "bk_spmv_vector_kernel", 2: "bk_spmv_tma_kernel<int32 columns>",
                 3: "bk_spmv_tma_kernel<8-bit dictionary-coded columns>", 4: "row-split view + bk_vrow_reduce_kernel",
                 5: "bk_spmv_pair_kernel<8-bit (offset,value) pair codes, SELL-32-4>",
-                6: "bk_spmv_mask_kernel<row bitmasks over chunk patterns>"}
+                6: "bk_spmv_mask_kernel<row bitmasks over chunk patterns>",
+                7: "bk_spmv_mask2_kernel<stencil fast path: two rows per lane, 128-bit gathers, one summary per 64 rows>"}
 
 METRIC = "cg_iterations_per_second"
 UNIT = "it/s"
@@ -394,7 +396,11 @@ def run_single(args):
         "note": "the kernel SURVEY 8d's algorithmic byte count (nnz*12 + (n+1)*4 + 2n*8) describes: every CSR byte is "
                 "streamed; read-dominated, so it can sit slightly above the measured COPY peak. traffic: see profiles/ "
                 "(ncu DRAM bytes are not measurable inside this run)"}
-    actual_iter = minfo["bytes_stream"] + 10 * N * 8
+    # vector passes per iteration: K1 reads p writes Ap (2), K2 reads Ap,r writes r (3), K3 reads x,p,r writes x,p (5) —
+    # or, with the lagged-x cut (cg_lag_x, large systems), K3 alternates 3 and 6 passes: 9.5 per iteration
+    lagged = bool(h.get_option("cg_lag_x")) and N > 300000
+    vec_passes = 9.5 if lagged else 10.0
+    actual_iter = int(minfo["bytes_stream"] + vec_passes * N * 8)
     iteration = {
         "us_per_iteration": 1e3 * ms / its,
         "algorithmic": {"bytes_per_iteration": bytes_iter, "achieved_gbs": bytes_iter * value / 1e9,
@@ -403,7 +409,8 @@ def run_single(args):
                                 "the re-cut iteration move fewer bytes than that plan"},
         "actual": {"bytes_per_iteration": actual_iter, "achieved_gbs": actual_iter * value / 1e9,
                    "frac_of_peak": actual_iter * value / 1e9 / peak,
-                   "note": "bytes the three kernels of an iteration really stream: matrix stream + 10 vector passes"}}
+                   "note": f"bytes the three kernels of an iteration really stream: matrix stream + {vec_passes:g} vector passes"
+                           + (" (lagged-x cut: x is updated every second iteration)" if lagged else "")}}
 
     # ---- e2e: the same API call with HOST tensors (pinned): H2D + registration + solve + D2H inside -----------------
     e2e = None
@@ -457,8 +464,9 @@ def run_single(args):
                     "l2_policy": "inputs (1.4 GB streamed per iteration) exceed L2; no flush needed",
                     "spmv_kernel": minfo["kernel"],
                     "options": {k: h.get_option(k) for k in ("use_tma", "use_compress", "tma_ctas", "pair_ctas", "mask_ctas",
-                                                             "mask_group", "tma_stages", "grid_mult_spmv", "grid_mult_vec",
-                                                             "fuse_xpay", "snake", "loop_mode", "chunk")}},
+                                                             "mask_group", "mask_const", "mask_cctas", "cg_lag_x", "tma_stages",
+                                                             "grid_mult_spmv", "grid_mult_vec", "fuse_xpay", "snake", "loop_mode",
+                                                             "chunk")}},
         "roofline": roofline, "roofline_coded": roofline_coded, "iteration": iteration,
         "e2e": e2e, "cpu_baseline": cpu, "extra": extra, "gpu_launches": int(launches), "clocks": clk.summary(),
     }

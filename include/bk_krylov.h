@@ -288,7 +288,8 @@ int bk_dist_destroy(bk_dist* D);
  * separate boundary-row kernel and the correction of the dot partials disappear.  ghost_gid: device int64[n_ghost],
  * global ids of the ghost entries; row_begin: global id of local row 0 (pattern entries are ordered by global offset,
  * like the single-GPU matrix).  ext_val may be the array the local/ghost blocks were split from.  The arrays are only
- * read during this call.  *folded = 1 when the plan was built (else the two-kernel path stays in use). */
+ * read during this call.  *folded = 1 when the plan was built (2: its interior steps also qualify for kernel 7), else 0
+ * and the two-kernel path stays in use. */
 int bk_dist_set_extended(bk_dist* D, int64_t nnz_ext, const void* ext_rowptr, const void* ext_col, const void* ext_val,
                          const void* ghost_gid, int64_t row_begin, void* stream, int32_t* folded);
 /* Peer-memory path (NVLink/NVSwitch, CUDA IPC).  Each rank exports the 64-byte IPC handle of its communication

@@ -217,7 +217,7 @@ extern "C" int bk_dist_set_extended(bk_dist* D, int64_t nnz_ext, const void* ext
     return rc;
   }
   D->Aext = E;
-  *folded = 1;
+  *folded = bk_mask2_usable(h, E) ? 2 : 1;  // 2: the interior steps run kernel 7 (stencil fast path)
   bk_graphs_invalidate(h);
   return BK_OK;
 }

@@ -207,6 +207,7 @@ class DistMatrix:
         mark("bk_dist_create")
         self.p2p = False
         self.folded = False
+        self.fold_kernel = 0
         self._group = group
         self._src = (crow, col, val)      # the caller's slab (global columns): needed to build the transpose
         self._transpose = None
@@ -225,6 +226,7 @@ class DistMatrix:
                     gid.data_ptr() if gid.numel() else None, int(offsets[rank]), _native._stream_ptr(self.device),
                     C.byref(folded)), "bk_dist_set_extended")
             self.folded = bool(folded.value)
+            self.fold_kernel = 7 if folded.value == 2 else (6 if folded.value else 0)
         mark("set_extended")
         sp.ext_col = None                 # only read during registration
         sp.ext_rowptr = None
@@ -271,7 +273,8 @@ class DistMatrix:
             self.ptr = None
 
     def local_info(self) -> dict:
-        return {"folded_single_kernel_spmv": self.folded, "p2p": self.p2p, "n_local": self.split.n_local,
+        return {"folded_single_kernel_spmv": self.folded, "folded_spmv_kernel": self.fold_kernel, "p2p": self.p2p,
+                "n_local": self.split.n_local,
                 "n_ghost": int(self.split.ghost_ids.numel()), "n_boundary_rows": int(self.split.brow_ids.numel())}
 
     def diagonal(self) -> torch.Tensor:
