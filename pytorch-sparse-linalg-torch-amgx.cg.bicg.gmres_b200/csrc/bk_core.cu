@@ -905,7 +905,7 @@ struct bk_mask_umap {
 static __global__ void bk_mask_usum_kernel(const unsigned char* __restrict__ masks, const int* __restrict__ pids,
                                            const unsigned char* __restrict__ slot2dense, const bk_mask_umap um,
                                            const long long n, const long long nsteps, const long long minoff,
-                                           const long long maxoff, unsigned char* __restrict__ umasks,
+                                           const long long maxoff, const int kc, unsigned char* __restrict__ umasks,
                                            unsigned short* __restrict__ usum, int* __restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -914,7 +914,9 @@ static __global__ void bk_mask_usum_kernel(const unsigned char* __restrict__ mas
     const long long r0 = st * 64;
     // pairs are loaded with one element of slack on both sides: everything must stay inside [0, n rounded down to a pair)
     bool mixed = r0 + 64 > n || r0 + minoff - 1 < 0 || r0 + 63 + maxoff + 1 >= (n & ~1LL);
-    bool dirty = false;
+    bool dirty = false;      // some row lacks an entry of its pattern, other than the two edge cases below
+    bool lo_miss = false;    // the step's first row lacks (only) the -1 neighbour: union position kc - 1
+    bool hi_miss = false;    // the step's last row lacks (only) the +1 neighbour: union position kc + 1
     int pid0 = 0;
     for (int u = 0; u < 2; ++u) {
       const long long c = st * 2 + u;  // (masks / pids are padded to whole groups)
@@ -929,13 +931,27 @@ static __global__ void bk_mask_usum_kernel(const unsigned char* __restrict__ mas
 #pragma unroll
       for (int k = 0; k < BK_MASK_L; ++k) mu |= ((m >> k) & 1u) << um.pos[pid][k];
       umasks[c * 32 + lane] = (unsigned char)mu;
-      dirty = dirty || __any_sync(0xffffffffu, (um.fullu[pid] & ~mu) != 0u);
+      unsigned int miss = um.fullu[pid] & ~mu;
+      if (kc >= 1 && u == 0 && lane == 0 && miss == (1u << (kc - 1))) {
+        lo_miss = true;
+        miss = 0u;
+      }
+      if (kc >= 1 && u == 1 && lane == 31 && miss == (1u << (kc + 1))) {
+        hi_miss = true;
+        miss = 0u;
+      }
+      dirty = dirty || __any_sync(0xffffffffu, miss != 0u);
     }
+    lo_miss = __any_sync(0xffffffffu, lo_miss);
+    hi_miss = __any_sync(0xffffffffu, hi_miss);
     if (lane == 0) {
       // step st = (group g, step j, warp w) in row order; stored as [g][w][j]: a warp reads its four summaries at once
       const long long g = st >> 5;
       const int j = (int)((st >> 3) & 3), w = (int)(st & 7);
-      usum[(g * 8 + w) * 4 + j] = (unsigned short)(pid0 | (dirty ? BK_MASK_US_DIRTY : 0) | (mixed ? BK_MASK_US_MIXED : 0));
+      // (a step that reads masks anyway gets its edge operands zeroed by them: the edge flags are for mask-free steps)
+      usum[(g * 8 + w) * 4 + j] =
+          (unsigned short)(pid0 | (dirty ? BK_MASK_US_DIRTY : 0) | (mixed ? BK_MASK_US_MIXED : 0) |
+                           ((lo_miss && !dirty) ? BK_MASK_US_LO : 0) | ((hi_miss && !dirty) ? BK_MASK_US_HI : 0));
       if (mixed) atomicAdd(&counts[1], 1);
       else if (dirty) atomicAdd(&counts[0], 1);
     }
@@ -1140,7 +1156,9 @@ int bk_csr_plan_mask(bk_handle* h, bk_csr* A, const long long* ghost_gid, long l
           long long wantw = (nsteps * 32 + 255) / 256;
           int gg = (int)(wantw < (long long)h->num_sms * 8 ? wantw : (long long)h->num_sms * 8);
           if (gg < 1) gg = 1;
-          bk_mask_usum_kernel<<<gg, 256, 0, s>>>(A->mmasks, A->mpids, d_s2d, um, A->n, nsteps, uni[0], uni[nu - 1],
+          // union position of offset 0 when its neighbours are -1 and +1 (the structures kernel 7 runs), else -1
+          const int kc = (nu >= 3 && uni[nu / 2] == 0 && uni[nu / 2 - 1] == -1 && uni[nu / 2 + 1] == 1) ? nu / 2 : -1;
+          bk_mask_usum_kernel<<<gg, 256, 0, s>>>(A->mmasks, A->mpids, d_s2d, um, A->n, nsteps, uni[0], uni[nu - 1], kc,
                                                  A->mumasks, A->musum, dcount);
           int cnt[2] = {0, 0};
           cudaMemcpyAsync(cnt, dcount, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);

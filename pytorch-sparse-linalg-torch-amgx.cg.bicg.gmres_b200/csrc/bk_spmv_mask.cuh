@@ -598,6 +598,8 @@ bk_spmv_maskw_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_mas
 #define BK_MASK_CP 12        // patterns the parameter block holds
 #define BK_MASK_US_DIRTY 0x100   // step summary: some row lacks an entry of its pattern -> masks are read
 #define BK_MASK_US_MIXED 0x200   // step summary: two patterns in the 64 rows / matrix end within reach -> chunk code
+#define BK_MASK_US_LO 0x400      // step summary: the ONLY missing entry is the -1 neighbour of the step's first row (a grid
+#define BK_MASK_US_HI 0x800      // line starts there) / the +1 neighbour of its last row: the edge loads return 0, no masks
 
 struct bk_mask_utab {
   double val[BK_MASK_CP][BK_MASK_L];  // value of union entry e in pattern p (0: the pattern has no such entry)
@@ -618,19 +620,22 @@ __device__ __forceinline__ double2 bk_ldg_pair(const double* base, long long byt
 // loads of their own: x[i - 1] is the previous lane's centre .y, x[i + 2] the next lane's centre .x (lanes 0 / 31 load
 // theirs) — ncu on the first version showed the L1 wavefront pipe at 67 %, the top unit; this removes 8 of ~42 wavefronts.
 template <int MODE, int DOTS, int LEN, unsigned int ODD, bool DIRTY>
-__device__ __forceinline__ void bk_mask2_step(const bk_mask_utab& ct, const int pat, const double* xr,
+__device__ __forceinline__ void bk_mask2_step(const bk_mask_utab& ct, const unsigned int summ, const double* xr,
                                               const unsigned char* __restrict__ pm, double* __restrict__ py,
                                               const double* __restrict__ pb, const double* __restrict__ pw,
                                               const int lane, double* acc) {
+  const int pat = (int)(summ & 0xffu);
   constexpr int K = LEN / 2;
   static_assert(ODD == ((1u << (K - 1)) | (1u << (K + 1))), "kernel 7: the odd entries are the centre's two neighbours");
   double2 P[LEN];
 #pragma unroll
   for (int e = 0; e < LEN; ++e)
     if (!((ODD >> e) & 1u)) P[e] = bk_ldg_pair(xr, ct.offb[e]);
+  // the step's first row has no -1 neighbour when a grid line starts there (its last row no +1 when one ends): the usual
+  // reason for an incomplete row, recorded in the summary so that such steps need no masks — the edge operand is 0
   double lo = 0.0, hi = 0.0;
-  if (lane == 0) lo = __ldg(xr - 1);
-  if (lane == 31) hi = __ldg(xr + 2);
+  if (lane == 0 && !(summ & BK_MASK_US_LO)) lo = __ldg(xr - 1);
+  if (lane == 31 && !(summ & BK_MASK_US_HI)) hi = __ldg(xr + 2);
   unsigned int m2 = 0xffffu;
   if (DIRTY) m2 = __ldg(reinterpret_cast<const unsigned short*>(pm));  // this lane's two mask bytes
   double s0 = 0.0, s1 = 0.0;
@@ -809,11 +814,11 @@ bk_spmv_mask2_kernel(const bk_spmv_args a, const bk_mask_plan plan, const bk_mas
     for (int j = 0; j < 4; ++j) {
       const unsigned int s = sm[j];
       if ((s & (BK_MASK_US_DIRTY | BK_MASK_US_MIXED)) == 0) {
-        bk_mask2_step<MODE, DOTS, LEN, ODD, false>(ct, (int)(s & 0xffu), xr + j * 512, pm + j * 512, py + j * 512,
+        bk_mask2_step<MODE, DOTS, LEN, ODD, false>(ct, s, xr + j * 512, pm + j * 512, py + j * 512,
                                                   MODE == 1 ? pb + j * 512 : nullptr, (DOTS & 1) ? pw + j * 512 : nullptr,
                                                   lane, acc);
       } else if ((s & BK_MASK_US_MIXED) == 0) {
-        bk_mask2_step<MODE, DOTS, LEN, ODD, true>(ct, (int)(s & 0xffu), xr + j * 512, pm + j * 512, py + j * 512,
+        bk_mask2_step<MODE, DOTS, LEN, ODD, true>(ct, s, xr + j * 512, pm + j * 512, py + j * 512,
                                                  MODE == 1 ? pb + j * 512 : nullptr, (DOTS & 1) ? pw + j * 512 : nullptr,
                                                  lane, acc);
       } else {
