@@ -93,9 +93,21 @@ def build_halo_plan(ghost_ids: torch.Tensor, offsets: Sequence[int], rank: int, 
     needs = {}
     for o in torch.unique(owner).tolist():
         needs[int(o)] = gids[owner == o]
+
+    def pack(t):  # a contiguous run of ids (the usual case: whole grid planes) travels as (first, count), not as 2 MB
+        n = int(t.numel())
+        if n > 0 and int(t[-1]) - int(t[0]) == n - 1:
+            return ("range", int(t[0]), n)
+        return ("ids", t)
+
+    def unpack(m):
+        if m[0] == "range":
+            return torch.arange(m[1], m[1] + m[2], dtype=torch.int64)
+        return m[1]
     if world > 1:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, needs, group=group)
+        wire = [None] * world
+        dist.all_gather_object(wire, {o: pack(t) for o, t in needs.items()}, group=group)
+        gathered = [{o: unpack(m) for o, m in w.items()} for w in wire]
     else:
         gathered = [needs]
     peers = sorted(set(needs.keys()) | {q for q in range(world) if q != rank and rank in gathered[q]})
