@@ -259,7 +259,35 @@ bk_cg_xp_push_kernel(T* __restrict__ x, const T* pin, T* pout, const T* __restri
         if (q < pr.nr && i >= pr.lo[q] && i < pr.hi[q]) pr.dst[q][i - pr.lo[q]] = po;
     }
   };
-  for (long long k = (long long)blockIdx.x * BK_BLOCK + threadIdx.x; k < npack; k += stride) {
+  // two packs per thread and step, all loads first (like bk_ew_kernel: with one pack in flight the kernel was latency-
+  // bound — the per-phase trace of the 2-GPU iteration showed this kernel ~30 % slower than the plain x/p update)
+  constexpr int UN = 2;
+  long long k = (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
+  for (; k + (UN - 1) * stride < npack; k += UN * stride) {
+    long long ii[UN];
+    bk_vec<T, W> xv[UN], ppv[UN], rv[UN], pv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const long long kk = k + u * stride;
+      ii[u] = (rev ? (npack - 1 - kk) : kk) * W;
+      pv[u] = bk_ld<T, W>(pin + ii[u]);
+#pragma unroll
+      for (int j = 0; j < W; ++j) xv[u].v[j] = ppv[u].v[j] = rv[u].v[j] = T(0);
+      if (upd_x) xv[u] = bk_ld<T, W>(x + ii[u]);
+      if (lag == 2) ppv[u] = bk_ld<T, W>(pout + ii[u]);
+      if (upd_p) rv[u] = bk_ld<T, W>(r + ii[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      bk_vec<T, W> xo, po;
+#pragma unroll
+      for (int j = 0; j < W; ++j)
+        one(ii[u] + j, xv[u].v[j], ppv[u].v[j], pv[u].v[j], rv[u].v[j], xo.v[j], po.v[j]);
+      if (upd_x) bk_st<T, W>(x + ii[u], xo);
+      if (upd_p) bk_st<T, W>(pout + ii[u], po);
+    }
+  }
+  for (; k < npack; k += stride) {
     const long long i = (rev ? (npack - 1 - k) : k) * W;
     bk_vec<T, W> xv, ppv, rv;
     const bk_vec<T, W> pv = bk_ld<T, W>(pin + i);
