@@ -242,13 +242,24 @@ bk_cg_xp_push_kernel(T* __restrict__ x, const T* pin, T* pout, const T* __restri
   const bool flush = (lag == 1) && !push;                // x receives the term the even iteration still owes it
   const bool upd_x = (lag != 1) || flush;
   const bool upd_p = !flush;
-  const bool rev = snake && ((st->parity & 1) == 0);  // same rule as bk_op_cg_xp::reverse()
+  (void)snake;
   __shared__ int s_last;
   const T alpha = static_cast<T>(st->alpha), beta = static_cast<T>(st->beta);
   const T alpha_lag = static_cast<T>(st->alpha_lag);
   constexpr int W = bk_native_w<T>::value;
   const long long npack = n / W;
   const long long stride = (long long)gridDim.x * BK_BLOCK;
+  // Sweep order: the packs of the push ranges FIRST.  The per-phase trace of the 2-GPU iteration (globaltimer stamps)
+  // showed 16 us between the end of this kernel's loop and the start of the next SpMV, 7 of them in the system-scope
+  // fence below: with a plain sweep every CTA stores its share of the trailing boundary plane to the neighbour at the
+  // very END of its loop and then waits for NVLink to acknowledge.  Rotating the sweep so that it starts at the last
+  // range (a suffix of the slab; the first range, a prefix, follows at once) gives those stores the whole kernel to land.
+  long long rot = 0;
+  if (pr.nr > 0 && pr.hi[pr.nr - 1] >= npack * W) rot = pr.lo[pr.nr - 1] / W;
+  auto pack_of = [&](long long kk) -> long long {
+    long long p = kk + rot;
+    return p >= npack ? p - npack : p;
+  };
   auto one = [&](long long i, T xv, T ppv, T pv, T rv, T& xo, T& po) {
     if (lag == 2) xv = bk_add(xv, bk_mul(alpha_lag, ppv));
     xo = bk_add(xv, bk_mul(alpha, pv));
@@ -269,7 +280,7 @@ bk_cg_xp_push_kernel(T* __restrict__ x, const T* pin, T* pout, const T* __restri
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const long long kk = k + u * stride;
-      ii[u] = (rev ? (npack - 1 - kk) : kk) * W;
+      ii[u] = pack_of(kk) * W;
       pv[u] = bk_ld<T, W>(pin + ii[u]);
 #pragma unroll
       for (int j = 0; j < W; ++j) xv[u].v[j] = ppv[u].v[j] = rv[u].v[j] = T(0);
@@ -288,7 +299,7 @@ bk_cg_xp_push_kernel(T* __restrict__ x, const T* pin, T* pout, const T* __restri
     }
   }
   for (; k < npack; k += stride) {
-    const long long i = (rev ? (npack - 1 - k) : k) * W;
+    const long long i = pack_of(k) * W;
     bk_vec<T, W> xv, ppv, rv;
     const bk_vec<T, W> pv = bk_ld<T, W>(pin + i);
 #pragma unroll
