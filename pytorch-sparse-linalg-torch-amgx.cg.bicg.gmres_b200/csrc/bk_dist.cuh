@@ -260,11 +260,24 @@ bk_cg_xp_push_kernel(T* __restrict__ x, const T* pin, T* pout, const T* __restri
     long long p = kk + rot;
     return p >= npack ? p - npack : p;
   };
-  auto one = [&](long long i, T xv, T ppv, T pv, T rv, T& xo, T& po) {
+  // In the rotated order the packs that can hold push elements come first: [0, nbnd); the rest of the sweep runs without
+  // the range tests (the trace showed the loop 10 us slower than the plain x/p update).
+  long long nbnd = npack;
+  if (pr.nr == 0) {
+    nbnd = 0;
+  } else if (rot > 0) {  // the last range is a suffix; a second range that is a prefix follows it in the rotated order
+    nbnd = npack - rot;
+    if (pr.nr >= 2) nbnd = (pr.nr == 2 && pr.lo[0] == 0) ? nbnd + (pr.hi[0] + W - 1) / W : npack;
+    if (nbnd > npack) nbnd = npack;
+  } else if (pr.nr == 1 && pr.lo[0] == 0) {  // a prefix only
+    nbnd = (pr.hi[0] + W - 1) / W;
+    if (nbnd > npack) nbnd = npack;
+  }
+  auto one = [&](long long i, T xv, T ppv, T pv, T rv, T& xo, T& po, const bool chk) {
     if (lag == 2) xv = bk_add(xv, bk_mul(alpha_lag, ppv));
     xo = bk_add(xv, bk_mul(alpha, pv));
     po = bk_add(rv, bk_mul(beta, pv));
-    if (push) {
+    if (chk) {
 #pragma unroll
       for (int q = 0; q < BK_PUSH_MAXR; ++q)
         if (q < pr.nr && i >= pr.lo[q] && i < pr.hi[q]) pr.dst[q][i - pr.lo[q]] = po;
@@ -273,8 +286,12 @@ bk_cg_xp_push_kernel(T* __restrict__ x, const T* pin, T* pout, const T* __restri
   // two packs per thread and step, all loads first (like bk_ew_kernel: with one pack in flight the kernel was latency-
   // bound — the per-phase trace of the 2-GPU iteration showed this kernel ~30 % slower than the plain x/p update)
   constexpr int UN = 2;
-  long long k = (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
-  for (; k + (UN - 1) * stride < npack; k += UN * stride) {
+  const long long tid0 = (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
+  for (int phase = 0; phase < 2; ++phase) {
+  const long long kend = phase == 0 ? nbnd : npack;
+  const bool chk = push && phase == 0;
+  long long k = (phase == 0 ? 0 : nbnd) + tid0;
+  for (; k + (UN - 1) * stride < kend; k += UN * stride) {
     long long ii[UN];
     bk_vec<T, W> xv[UN], ppv[UN], rv[UN], pv[UN];
 #pragma unroll
@@ -293,12 +310,12 @@ bk_cg_xp_push_kernel(T* __restrict__ x, const T* pin, T* pout, const T* __restri
       bk_vec<T, W> xo, po;
 #pragma unroll
       for (int j = 0; j < W; ++j)
-        one(ii[u] + j, xv[u].v[j], ppv[u].v[j], pv[u].v[j], rv[u].v[j], xo.v[j], po.v[j]);
+        one(ii[u] + j, xv[u].v[j], ppv[u].v[j], pv[u].v[j], rv[u].v[j], xo.v[j], po.v[j], chk);
       if (upd_x) bk_st<T, W>(x + ii[u], xo);
       if (upd_p) bk_st<T, W>(pout + ii[u], po);
     }
   }
-  for (; k < npack; k += stride) {
+  for (; k < kend; k += stride) {
     const long long i = pack_of(k) * W;
     bk_vec<T, W> xv, ppv, rv;
     const bk_vec<T, W> pv = bk_ld<T, W>(pin + i);
@@ -309,15 +326,16 @@ bk_cg_xp_push_kernel(T* __restrict__ x, const T* pin, T* pout, const T* __restri
     if (upd_p) rv = bk_ld<T, W>(r + i);
     bk_vec<T, W> xo, po;
 #pragma unroll
-    for (int j = 0; j < W; ++j) one(i + j, xv.v[j], ppv.v[j], pv.v[j], rv.v[j], xo.v[j], po.v[j]);
+    for (int j = 0; j < W; ++j) one(i + j, xv.v[j], ppv.v[j], pv.v[j], rv.v[j], xo.v[j], po.v[j], chk);
     if (upd_x) bk_st<T, W>(x + i, xo);
     if (upd_p) bk_st<T, W>(pout + i, po);
+  }
   }
   {
     const long long t = npack * W + (long long)blockIdx.x * BK_BLOCK + threadIdx.x;
     if (t < n) {
       T xo, po;
-      one(t, upd_x ? x[t] : T(0), lag == 2 ? pout[t] : T(0), pin[t], upd_p ? r[t] : T(0), xo, po);
+      one(t, upd_x ? x[t] : T(0), lag == 2 ? pout[t] : T(0), pin[t], upd_p ? r[t] : T(0), xo, po, push);
       if (upd_x) x[t] = xo;
       if (upd_p) pout[t] = po;
     }
