@@ -218,3 +218,33 @@ def test_oracle_preconditioned_solvers_agree_with_dense_solve():
     x0, info0, st0 = orc.cg(S, bs, None, tol=1e-12)
     assert info == 0 and st["iterations"] < st0["iterations"]
     assert float(torch.linalg.norm(x - xt) / torch.linalg.norm(xt)) <= 1e-8
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` (the oracle port timed on the host cores) runs without a GPU; its JSON line carries the
+    keys the driver reads, at N = 1 and under a torchrun-style environment with N > 1 (rank 0 prints, the others exit 0
+    without work), with the SAME workload string this repo's arm prints for that N."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    def run(extra_env, gpus):
+        env = dict(os.environ, **extra_env)
+        cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", str(gpus), "--n", "12", "--steps", "1",
+               "--warmup", "1", "--ref-window", "5"]
+        p = subprocess.run(cmd, env=env, cwd=str(ROOT), capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        return [json.loads(line) for line in p.stdout.splitlines() if line.startswith("{")]
+
+    (line,) = run({}, 1)
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "cg_iterations_per_second" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    assert "12^3" in line["config"]["workload"]
+    (line2,) = run({"RANK": "0", "WORLD_SIZE": "2", "LOCAL_RANK": "0"}, 2)
+    assert line2["n_gpus"] == 2 and "row-partitioned over 2 GPUs" in line2["config"]["workload"]
+    assert run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, 2) == []
