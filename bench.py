@@ -15,8 +15,8 @@ A "step" is ONE full CG solve of that system (611 iterations) made through the r
   roofline      the GENERAL CSR SpMV kernel that SURVEY 8d's byte formula describes (kernel 2: int32 columns + fp64
                 values streamed by TMA; option use_compress=0) on the same matrix in the same run, timed alone:
                 achieved = algorithmic bytes per launch / mean launch time; frac = achieved / measured copy peak.
-  roofline_coded  the kernel the solve actually uses for this constant-coefficient stencil (kernel 6, row bitmasks
-                over chunk patterns; lossless, bit-identical): achieved = ACTUAL bytes per launch — the matrix-side
+  roofline_coded  the kernel the solve actually uses for this constant-coefficient stencil (kernel 7, the stencil fast
+                path over kernel 6's row-bitmask plan; lossless, bit-identical): achieved = ACTUAL bytes per launch — the matrix-side
                 bytes counted by the library at registration (bk_csr_info.bytes_stream) + one read of x + one write of
                 y — / mean launch time.
   iteration     the whole CG iteration both ways: algorithmic bytes (nnz*12 + 4(n+1) + 11n*8) and actual
